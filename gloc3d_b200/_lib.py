@@ -1,0 +1,116 @@
+"""ctypes binding of libgloc3d.so (the C ABI declared in include/gloc3d.h).
+
+The library is the product: there is no Python or CPU fallback.  If the shared
+object is missing, importing this module raises; if no sm_100 GPU is usable, every
+compute entry point returns GLOC_ERR_CUDA and the wrappers raise GlocError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgloc3d.so")
+
+GLOC_OK = 0
+GLOC_ERR_INVALID = 1
+GLOC_ERR_CUDA = 2
+GLOC_ERR_NOT_BUILT = 3
+GLOC_ERR_RANGE = 4
+GLOC_ERR_NOMEM = 5
+
+KNN_AUTO, KNN_EXACT_SCAN, KNN_SHORTLIST = 0, 1, 2
+
+
+class GlocError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libgloc3d error {code}: {msg}")
+        self.code = code
+
+
+class KnnStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("queries", "kernel_launches", "shortlist_queries",
+                                          "fallback_queries", "shortlist_rows", "last_mode")]
+
+
+class CsmResult(C.Structure):
+    _fields_ = [("found", C.c_int), ("score", C.c_float), ("scan_index", C.c_int),
+                ("x_offset", C.c_int), ("y_offset", C.c_int), ("reserved", C.c_int),
+                ("pose_x", C.c_double), ("pose_y", C.c_double), ("pose_yaw", C.c_double)]
+
+    def as_tuple(self):
+        return (self.found, self.score, self.scan_index, self.x_offset, self.y_offset,
+                self.pose_x, self.pose_y, self.pose_yaw)
+
+
+class Profile(C.Structure):
+    _fields_ = [("dominant_ms", C.c_double), ("dominant_launches", C.c_uint64)]
+
+
+class CsmStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("matches", "kernel_launches", "coarse_candidates",
+                                          "refined_nodes")]
+
+
+# name -> (restype, argtypes); mirrors include/gloc3d.h one to one
+_vp, _sz, _i, _d, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_float
+_ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+SIGNATURES = {
+    "gloc_version": (_i, []),
+    "gloc_last_error": (C.c_char_p, []),
+    "gloc_device_count": (_i, []),
+    "gloc_knn_create": (_i, [C.POINTER(_vp), _sz, _i]),
+    "gloc_knn_destroy": (None, [_vp]),
+    "gloc_knn_set_db": (_i, [_vp, _vp, _sz]),
+    "gloc_knn_set_db_device": (_i, [_vp, _vp, _sz]),
+    "gloc_knn_append": (_i, [_vp, _vp, _sz]),
+    "gloc_knn_size": (_sz, [_vp]),
+    "gloc_knn_dim": (_sz, [_vp]),
+    "gloc_knn_set_search_limit": (_i, [_vp, _sz]),
+    "gloc_knn_set_index_offset": (_i, [_vp, C.c_uint64]),
+    "gloc_knn_set_mode": (_i, [_vp, _i]),
+    "gloc_knn_get_stats": (_i, [_vp, C.POINTER(KnnStats)]),
+    "gloc_knn_set_profiling": (_i, [_vp, _i]),
+    "gloc_knn_get_profile": (_i, [_vp, C.POINTER(Profile)]),
+    "gloc_knn_query": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "gloc_knn_query_device": (_i, [_vp, _vp, _sz, _sz, _vp, _vp, _vp]),
+    "gloc_knn_merge_topk_device": (_i, [_vp, _vp, _sz, _sz, _sz, _vp, _vp, _i, _vp]),
+    "gloc_csm_create": (_i, [C.POINTER(_vp), _i]),
+    "gloc_csm_destroy": (None, [_vp]),
+    "gloc_csm_add_grid_cells": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ip]),
+    "gloc_csm_add_grid_u8": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ip]),
+    "gloc_csm_num_grids": (_i, [_vp]),
+    "gloc_csm_get_precomputation_grid": (_i, [_vp, _i, _i, _vp]),
+    "gloc_csm_match_batch": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f,
+                                  C.POINTER(CsmResult)]),
+    "gloc_csm_discretize": (_i, [_vp, _vp, _i, _d, _d, _d, _i, _d, _d, _d, _d, _vp]),
+    "gloc_csm_search_params": (_i, [_d, _d, _vp, _i, _d, _ip, _ip, _dp]),
+    "gloc_csm_grid_to_points": (_i, [_vp, _i, _i, _d, _d, _d, _vp, _i, _ip]),
+    "gloc_csm_get_stats": (_i, [_vp, C.POINTER(CsmStats)]),
+    "gloc_csm_set_profiling": (_i, [_vp, _i]),
+    "gloc_csm_get_profile": (_i, [_vp, C.POINTER(Profile)]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` or `make -C gloc3d_b200/csrc` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and the binding diverge
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != GLOC_OK:
+        raise GlocError(rc, lib().gloc_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,548 @@
+// csm.cu -- stage 2 kernels: precomputation stack (K5), rotate + discretise (K6),
+// candidate scoring + parallel branch and bound (K7).
+//
+// Replaces, from /root/reference/registration/2d:
+//   PrecomputationGrid2D ctor            fast_correlative_scan_matcher_2d.cpp:112-182
+//   GenerateRotatedScans/DiscretizeScans correlative_scan_matcher_2d.cpp:93-127
+//   SearchParameters::ShrinkToFit        correlative_scan_matcher_2d.cpp:73-91
+//   ScoreCandidates                      fast_correlative_scan_matcher_2d.cpp:372-391
+//   BranchAndBound                       fast_correlative_scan_matcher_2d.cpp:393-438
+//
+// Exactness contract: candidate sums are integers; the score is
+// ToScore(sum / float(P)) in un-fused float32 (fast_..._2d.h:86-88, .cpp:386-387);
+// the answer is the maximum-score (scan, x, y) over the whole shrunk window with
+// ties resolved to the smallest (scan, x, y) -- independent of the order in which
+// the GPU explores the tree (64-bit atomicMax on (score bits, inverted rank)).
+// Point rotation/discretisation is bit-exact with the reference's float/double
+// arithmetic: the quaternion (w, z) per angle comes from the host's libm, the
+// device uses only round-to-nearest intrinsics (no FMA contraction).
+#include <algorithm>
+
+#include "csm_kernels.cuh"
+
+namespace gloc {
+
+namespace {
+
+constexpr int kPointChunk = 4096;  // discretised points cached in shared memory per pass
+constexpr int kCoarseThreads = 256;
+constexpr int kCandPerThread = 4;
+
+// Eigen Quaternionf(AngleAxisf(theta, UnitZ)) * v  with vec = (0, 0, z):
+//   uv = vec x v; uv += uv; v' = v + w*uv + vec x uv      (see oracle/csm_oracle.c)
+__device__ __forceinline__ void rot_z(float w, float z, float vx, float vy, float& rx,
+                                      float& ry) {
+  float ux = -__fmul_rn(z, vy);
+  float uy = __fmul_rn(z, vx);
+  ux = __fadd_rn(ux, ux);
+  uy = __fadd_rn(uy, uy);
+  const float cx = -__fmul_rn(z, uy);
+  const float cy = __fmul_rn(z, ux);
+  rx = __fadd_rn(__fadd_rn(vx, __fmul_rn(w, ux)), cx);
+  ry = __fadd_rn(__fadd_rn(vy, __fmul_rn(w, uy)), cy);
+}
+
+// fast_..._2d.cpp:278-283 (initial yaw), correlative_..._2d.cpp:104-106 (scan angle),
+// :119-121 (translation), map_limits.h:69-76 (GetCellIndex; lround = half away from zero)
+__device__ __forceinline__ int2 discretize_point(const float* __restrict__ p, float w0, float z0,
+                                                 float ws, float zs, float tx, float ty,
+                                                 double res, double max_x, double max_y) {
+  float x0, y0, x1, y1;
+  rot_z(w0, z0, p[0], p[1], x0, y0);
+  rot_z(ws, zs, x0, y0, x1, y1);
+  const float wx = __fadd_rn(x1, tx);
+  const float wy = __fadd_rn(y1, ty);
+  int2 c;
+  c.x = (int)round(__dsub_rn(__ddiv_rn(__dsub_rn(max_y, (double)wy), res), 0.5));
+  c.y = (int)round(__dsub_rn(__ddiv_rn(__dsub_rn(max_x, (double)wx), res), 0.5));
+  return c;
+}
+
+struct LevelView {
+  const uint8_t* cells;
+  int wide_nx, wide_ny, wm1;
+};
+
+__device__ __forceinline__ LevelView level_view(const CsmGridDev& g, int level) {
+  LevelView v;
+  const int w = 1 << level;
+  v.cells = g.stack + g.off[level];
+  v.wide_nx = g.nx + w - 1;
+  v.wide_ny = g.ny + w - 1;
+  v.wm1 = w - 1;
+  return v;
+}
+
+// PrecomputationGrid2D::GetValue, fast_..._2d.h:68-83
+__device__ __forceinline__ int level_val(const LevelView& v, int x, int y) {
+  const unsigned lx = (unsigned)(x + v.wm1), ly = (unsigned)(y + v.wm1);
+  if (lx >= (unsigned)v.wide_nx || ly >= (unsigned)v.wide_ny) return 0;
+  return __ldg(v.cells + (size_t)ly * v.wide_nx + lx);
+}
+
+// ToScore(sum / static_cast<float>(P)), fast_..._2d.cpp:386-387 + .h:86-88
+__device__ __forceinline__ float score_of(int sum, int n_pts, const CsmParams& prm) {
+  const float v = __fdiv_rn((float)sum, (float)n_pts);
+  return __fadd_rn(prm.min_s, __fmul_rn(v, prm.coef));
+}
+
+__device__ __forceinline__ unsigned rank_of(const CsmParams& prm, int s, int xo, int yo) {
+  return ((unsigned)s * prm.W + (unsigned)(xo + prm.n_lin)) * prm.W + (unsigned)(yo + prm.n_lin);
+}
+
+// Larger key = better: higher score, then smaller (scan, x, y).
+__device__ __forceinline__ unsigned long long key_of(float score, unsigned rank) {
+  return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xFFFFFFFFu - rank);
+}
+
+__device__ __forceinline__ unsigned long long ld_best(const unsigned long long* p) {
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------- K5
+
+__global__ void csm_level1_from_cells_kernel(const uint16_t* __restrict__ cells,
+                                             const uint8_t* __restrict__ lut, size_t n,
+                                             uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = lut[cells[i]];
+}
+
+// Width-w grid from the width-w/2 grid: the max over a w x w window is the max of
+// four w/2 x w/2 windows.  Out-of-stack reads are windows outside the map: 0.
+__global__ void csm_build_level_kernel(const uint8_t* __restrict__ prev, int nx, int ny, int w,
+                                       uint8_t* __restrict__ out) {
+  const int wide_nx = nx + w - 1, wide_ny = ny + w - 1;
+  const int lx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ly = blockIdx.y * blockDim.y + threadIdx.y;
+  if (lx >= wide_nx || ly >= wide_ny) return;
+  const int h = w >> 1;
+  const int pnx = nx + h - 1, pny = ny + h - 1;
+  // window origin in map cells, then position in the previous level's local frame
+  const int px = lx - (w - 1) + (h - 1), py = ly - (w - 1) + (h - 1);
+  int m = 0;
+#pragma unroll
+  for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      const int x = px + dx * h, y = py + dy * h;
+      if ((unsigned)x < (unsigned)pnx && (unsigned)y < (unsigned)pny)
+        m = max(m, (int)prev[(size_t)y * pnx + x]);
+    }
+  out[(size_t)ly * wide_nx + lx] = (uint8_t)m;
+}
+
+// ------------------------------------------------------------------------- K6
+
+__global__ void csm_discretize_kernel(const float* __restrict__ pts, int n_pts, float w0, float z0,
+                                      float tx, float ty, const float2* __restrict__ rot, int S,
+                                      double res, double max_x, double max_y,
+                                      int* __restrict__ out_cells) {
+  const int s = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S || p >= n_pts) return;
+  const float2 r = rot[s];
+  const int2 c = discretize_point(pts + 3 * (size_t)p, w0, z0, r.x, r.y, tx, ty, res, max_x, max_y);
+  out_cells[2 * ((size_t)s * n_pts + p)] = c.x;
+  out_cells[2 * ((size_t)s * n_pts + p) + 1] = c.y;
+}
+
+// ------------------------------------------------------------------- K7 coarse
+
+// One CTA per (scan, pair): discretise the scan once into shared memory, shrink the
+// window (ShrinkToFit), score every lattice candidate of this rotation on the coarsest
+// grid, and reduce the best (score, rank) of the rotation bin with warp shuffles.
+__global__ void __launch_bounds__(kCoarseThreads)
+csm_coarse_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
+                  const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
+                  CsmBounds* __restrict__ bounds, int* __restrict__ coarse,
+                  unsigned long long* __restrict__ top_coarse) {
+  __shared__ int2 cells[kPointChunk];
+  __shared__ int red[4][kCoarseThreads / 32];
+  __shared__ unsigned long long redk[kCoarseThreads / 32];
+  __shared__ CsmBounds sb;
+  const int s = blockIdx.x, pi = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const CsmPairDev pr = pairs[pi];
+  const CsmGridDev g = grids[pr.grid];
+  const float2 r = rot[s];
+  const int P = pr.n_pts;
+  const float* sp = pts + 3 * (size_t)pr.pt_begin;
+
+  // ShrinkToFit, correlative_scan_matcher_2d.cpp:77-90
+  int mnx = 0, mny = 0, mxx = 0, mxy = 0;
+  for (int p = tid; p < P; p += kCoarseThreads) {
+    const int2 c = discretize_point(sp + 3 * (size_t)p, pr.w0, pr.z0, r.x, r.y, pr.tx, pr.ty,
+                                    g.resolution, g.max_x, g.max_y);
+    if (p < kPointChunk) cells[p] = c;
+    mnx = min(mnx, -c.x);
+    mny = min(mny, -c.y);
+    mxx = max(mxx, g.nx - 1 - c.x);
+    mxy = max(mxy, g.ny - 1 - c.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if (lane == 0) {
+    red[0][warp] = mnx;
+    red[1][warp] = mny;
+    red[2][warp] = mxx;
+    red[3][warp] = mxy;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w2 = 1; w2 < kCoarseThreads / 32; ++w2) {
+      mnx = min(mnx, red[0][w2]);
+      mny = min(mny, red[1][w2]);
+      mxx = max(mxx, red[2][w2]);
+      mxy = max(mxy, red[3][w2]);
+    }
+    CsmBounds b;
+    b.min_x = max(-prm.n_lin, mnx);
+    b.max_x = min(prm.n_lin, mxx);
+    b.min_y = max(-prm.n_lin, mny);
+    b.max_y = min(prm.n_lin, mxy);
+    sb = b;
+    bounds[(size_t)pi * prm.S + s] = b;
+  }
+  __syncthreads();
+  const CsmBounds b = sb;
+  // GenerateLowestResolutionCandidates, fast_..._2d.cpp:334-370
+  const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
+  const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+  const int ncand = ncx * ncy;
+  const LevelView lv = level_view(g, prm.depth - 1);
+  int* out = coarse + ((size_t)pi * prm.S + s) * prm.maxc;
+  unsigned long long best_key = 0;
+
+  for (int cb = 0; cb < ncand; cb += kCoarseThreads * kCandPerThread) {
+    int sum[kCandPerThread], xo[kCandPerThread], yo[kCandPerThread];
+    bool ok[kCandPerThread];
+#pragma unroll
+    for (int j = 0; j < kCandPerThread; ++j) {
+      const int c = cb + j * kCoarseThreads + tid;  // x fastest: adjacent lanes, adjacent bytes
+      ok[j] = c < ncand;
+      const int iy = ok[j] ? c / ncx : 0, ix = ok[j] ? c % ncx : 0;
+      xo[j] = b.min_x + ix * prm.step;
+      yo[j] = b.min_y + iy * prm.step;
+      sum[j] = 0;
+    }
+    for (int p0 = 0; p0 < P; p0 += kPointChunk) {
+      const int n = min(kPointChunk, P - p0);
+      if (P > kPointChunk) {
+        __syncthreads();
+        for (int p = tid; p < n; p += kCoarseThreads)
+          cells[p] = discretize_point(sp + 3 * (size_t)(p0 + p), pr.w0, pr.z0, r.x, r.y, pr.tx,
+                                      pr.ty, g.resolution, g.max_x, g.max_y);
+        __syncthreads();
+      }
+#pragma unroll 4
+      for (int p = 0; p < n; ++p) {
+        const int2 c = cells[p];
+#pragma unroll
+        for (int j = 0; j < kCandPerThread; ++j)
+          if (ok[j]) sum[j] += level_val(lv, c.x + xo[j], c.y + yo[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kCandPerThread; ++j) {
+      if (!ok[j]) continue;
+      const int ix = (xo[j] - b.min_x) / prm.step, iy = (yo[j] - b.min_y) / prm.step;
+      out[ix * ncy + iy] = sum[j];  // reference enumeration order: x outer, y inner
+      const unsigned long long key =
+          key_of(score_of(sum[j], P, prm), rank_of(prm, s, xo[j], yo[j]));
+      best_key = max(best_key, key);
+    }
+  }
+  // best candidate of this rotation bin -> best coarse candidate of the pair
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    best_key = max(best_key, __shfl_xor_sync(0xffffffffu, best_key, o));
+  if (lane == 0) redk[warp] = best_key;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w2 = 1; w2 < kCoarseThreads / 32; ++w2) best_key = max(best_key, redk[w2]);
+    atomicMax(top_coarse + pi, best_key);
+  }
+}
+
+// --------------------------------------------------------------------- K7 seed
+
+// One CTA per pair: descend greedily from the best coarse candidate to a leaf to get
+// a first incumbent (a real fine score), exactly what the reference's DFS does first.
+__global__ void __launch_bounds__(256)
+csm_seed_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
+                const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
+                const CsmBounds* __restrict__ bounds,
+                const unsigned long long* __restrict__ top_coarse,
+                unsigned long long* __restrict__ best) {
+  __shared__ int red[4][8];
+  __shared__ int s_choice[3];
+  const int pi = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long top = top_coarse[pi];
+  if (top == 0) return;
+  const float top_score = __uint_as_float((unsigned)(top >> 32));
+  if (!(top_score > prm.min_score)) return;  // nothing can beat min_score
+  const unsigned rank = 0xFFFFFFFFu - (unsigned)(top & 0xFFFFFFFFull);
+  const int s = (int)(rank / (prm.W * prm.W));
+  int xo = (int)((rank / prm.W) % prm.W) - prm.n_lin;
+  int yo = (int)(rank % prm.W) - prm.n_lin;
+  if (prm.depth == 1) {
+    if (tid == 0) atomicMax(best + pi, top);
+    return;
+  }
+  const CsmPairDev pr = pairs[pi];
+  const CsmGridDev g = grids[pr.grid];
+  const CsmBounds b = bounds[(size_t)pi * prm.S + s];
+  const float2 r = rot[s];
+  const int P = pr.n_pts;
+  const float* sp = pts + 3 * (size_t)pr.pt_begin;
+  for (int d = prm.depth - 1; d > 0; --d) {
+    const int h = 1 << (d - 1);
+    const LevelView lv = level_view(g, d - 1);
+    int sum[4] = {0, 0, 0, 0};
+    for (int p = tid; p < P; p += 256) {
+      const int2 c = discretize_point(sp + 3 * (size_t)p, pr.w0, pr.z0, r.x, r.y, pr.tx, pr.ty,
+                                      g.resolution, g.max_x, g.max_y);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch)
+        sum[ch] += level_val(lv, c.x + xo + (ch >> 1) * h, c.y + yo + (ch & 1) * h);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) sum[ch] = warp_sum(sum[ch]);
+    if (lane == 0)
+      for (int ch = 0; ch < 4; ++ch) red[ch][warp] = sum[ch];
+    __syncthreads();
+    if (tid == 0) {
+      int bi = -1;
+      unsigned long long bk = 0;
+      for (int ch = 0; ch < 4; ++ch) {
+        const int cx = xo + (ch >> 1) * h, cy = yo + (ch & 1) * h;
+        if (cx > b.max_x || cy > b.max_y) continue;  // fast_..._2d.cpp:415-423
+        int t = 0;
+        for (int w2 = 0; w2 < 8; ++w2) t += red[ch][w2];
+        const unsigned long long k2 = key_of(score_of(t, P, prm), rank_of(prm, s, cx, cy));
+        if (bi < 0 || k2 > bk) {
+          bk = k2;
+          bi = ch;
+        }
+      }
+      s_choice[0] = xo + (bi >> 1) * h;
+      s_choice[1] = yo + (bi & 1) * h;
+      if (d == 1) atomicMax(best + pi, bk);
+    }
+    __syncthreads();
+    xo = s_choice[0];
+    yo = s_choice[1];
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------- K7 filter
+
+// Keep the coarse candidates whose bound can still beat the incumbent.
+__global__ void csm_filter_kernel(const CsmPairDev* __restrict__ pairs, int n_pairs, CsmParams prm,
+                                  const CsmBounds* __restrict__ bounds,
+                                  const int* __restrict__ coarse,
+                                  const unsigned long long* __restrict__ best,
+                                  unsigned* __restrict__ survivors,
+                                  unsigned* __restrict__ n_survivors) {
+  const size_t total = (size_t)n_pairs * prm.S * prm.maxc;
+  for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < total;
+       u += (size_t)gridDim.x * blockDim.x) {
+    const int slot = (int)(u % prm.maxc);
+    const size_t ps = u / prm.maxc;
+    const int s = (int)(ps % prm.S), pi = (int)(ps / prm.S);
+    const CsmBounds b = bounds[ps];
+    const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
+    const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+    if (slot >= ncx * ncy) continue;
+    const int xo = b.min_x + (slot / ncy) * prm.step, yo = b.min_y + (slot % ncy) * prm.step;
+    const float sc = score_of(coarse[u], pairs[pi].n_pts, prm);
+    if (key_of(sc, rank_of(prm, s, xo, yo)) > best[pi]) {
+      const unsigned pos = atomicAdd(n_survivors, 1u);
+      survivors[pos] = (unsigned)u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------- K7 refine
+
+struct Node {
+  int xo, yo, d;
+  float score;
+};
+
+// Persistent warps: each pops a surviving coarse candidate and runs the reference's
+// DFS (children sorted by score, fast_..._2d.cpp:430-436) inside its subtree, pruning
+// against the pair's incumbent shared through global memory.
+__global__ void __launch_bounds__(256)
+csm_refine_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
+                  const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
+                  const CsmBounds* __restrict__ bounds, const int* __restrict__ coarse,
+                  const unsigned* __restrict__ survivors, const unsigned* __restrict__ n_survivors,
+                  unsigned* __restrict__ cursor, unsigned long long* __restrict__ best,
+                  unsigned long long* __restrict__ counters) {
+  const int lane = threadIdx.x & 31;
+  const unsigned total = *n_survivors;
+  unsigned long long expanded = 0;
+  Node stack[3 * kCsmMaxDepth + 4];
+  for (;;) {
+    unsigned i = 0;
+    if (lane == 0) i = atomicAdd(cursor, 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= total) break;
+    const unsigned u = survivors[i];
+    const int slot = (int)(u % prm.maxc);
+    const unsigned ps = u / prm.maxc;
+    const int s = (int)(ps % prm.S), pi = (int)(ps / prm.S);
+    const CsmPairDev pr = pairs[pi];
+    const CsmGridDev g = grids[pr.grid];
+    const CsmBounds b = bounds[ps];
+    const float2 r = rot[s];
+    const int P = pr.n_pts;
+    const float* sp = pts + 3 * (size_t)pr.pt_begin;
+    const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+    int top = 0;
+    stack[0].xo = b.min_x + (slot / ncy) * prm.step;
+    stack[0].yo = b.min_y + (slot % ncy) * prm.step;
+    stack[0].d = prm.depth - 1;
+    stack[0].score = score_of(coarse[u], P, prm);
+    top = 1;
+    while (top > 0) {
+      const Node nd = stack[--top];
+      const unsigned long long nk = key_of(nd.score, rank_of(prm, s, nd.xo, nd.yo));
+      if (!(nk > ld_best(best + pi))) continue;  // bound cannot beat the incumbent
+      if (nd.d == 0) {                           // only when depth == 1
+        if (lane == 0) atomicMax(best + pi, nk);
+        continue;
+      }
+      const int h = 1 << (nd.d - 1);
+      const LevelView lv = level_view(g, nd.d - 1);
+      int sum[4] = {0, 0, 0, 0};
+      for (int p = lane; p < P; p += 32) {
+        const int2 c = discretize_point(sp + 3 * (size_t)p, pr.w0, pr.z0, r.x, r.y, pr.tx, pr.ty,
+                                        g.resolution, g.max_x, g.max_y);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+          sum[ch] += level_val(lv, c.x + nd.xo + (ch >> 1) * h, c.y + nd.yo + (ch & 1) * h);
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) sum[ch] = warp_sum(sum[ch]);
+      ++expanded;
+      Node kids[4];
+      int nk_n = 0;
+      for (int ch = 0; ch < 4; ++ch) {  // x outer, y inner (fast_..._2d.cpp:414-429)
+        const int cx = nd.xo + (ch >> 1) * h, cy = nd.yo + (ch & 1) * h;
+        if (cx > b.max_x || cy > b.max_y) continue;
+        kids[nk_n].xo = cx;
+        kids[nk_n].yo = cy;
+        kids[nk_n].d = nd.d - 1;
+        kids[nk_n].score = score_of(sum[ch], P, prm);
+        ++nk_n;
+      }
+      if (nd.d - 1 == 0) {
+        unsigned long long bk = 0;
+        for (int c2 = 0; c2 < nk_n; ++c2)
+          bk = max(bk, key_of(kids[c2].score, rank_of(prm, s, kids[c2].xo, kids[c2].yo)));
+        if (lane == 0 && bk > ld_best(best + pi)) atomicMax(best + pi, bk);
+      } else {
+        // stable insertion sort, descending score; push worst first so best pops first
+        for (int a = 1; a < nk_n; ++a) {
+          const Node t = kids[a];
+          int c2 = a - 1;
+          while (c2 >= 0 && kids[c2].score < t.score) {
+            kids[c2 + 1] = kids[c2];
+            --c2;
+          }
+          kids[c2 + 1] = t;
+        }
+        for (int c2 = nk_n - 1; c2 >= 0; --c2) stack[top++] = kids[c2];
+      }
+    }
+  }
+  if (lane == 0 && expanded) atomicAdd(counters, expanded);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+
+cudaError_t launch_csm_level1_from_cells(const uint16_t* cells, const uint8_t* lut, size_t n,
+                                         uint8_t* out, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  csm_level1_from_cells_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(cells, lut, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_build_level(const uint8_t* prev, int nx, int ny, int w, uint8_t* out,
+                                   cudaStream_t stream) {
+  dim3 blk(64, 4);
+  dim3 grd((nx + w - 1 + blk.x - 1) / blk.x, (ny + w - 1 + blk.y - 1) / blk.y);
+  csm_build_level_kernel<<<grd, blk, 0, stream>>>(prev, nx, ny, w, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_discretize(const float* pts, int n_pts, float w0, float z0, float tx,
+                                  float ty, const float2* rot, int S, double resolution,
+                                  double max_x, double max_y, int* out_cells, cudaStream_t stream) {
+  if (n_pts == 0 || S == 0) return cudaSuccess;
+  dim3 grd((n_pts + 255) / 256, S);
+  csm_discretize_kernel<<<grd, 256, 0, stream>>>(pts, n_pts, w0, z0, tx, ty, rot, S, resolution,
+                                                 max_x, max_y, out_cells);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                              const float* pts, const float2* rot, CsmParams prm,
+                              CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
+                              cudaStream_t stream) {
+  dim3 grd(prm.S, n_pairs);
+  csm_coarse_kernel<<<grd, kCoarseThreads, 0, stream>>>(grids, pairs, pts, rot, prm, bounds,
+                                                        coarse, top_coarse);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_seed(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                            const float* pts, const float2* rot, CsmParams prm,
+                            const CsmBounds* bounds, const unsigned long long* top_coarse,
+                            unsigned long long* best, cudaStream_t stream) {
+  csm_seed_kernel<<<n_pairs, 256, 0, stream>>>(grids, pairs, pts, rot, prm, bounds, top_coarse,
+                                               best);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_filter(const CsmPairDev* pairs, int n_pairs, CsmParams prm,
+                              const CsmBounds* bounds, const int* coarse,
+                              const unsigned long long* best, unsigned* survivors,
+                              unsigned* n_survivors, cudaStream_t stream) {
+  const size_t total = (size_t)n_pairs * prm.S * prm.maxc;
+  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
+  csm_filter_kernel<<<blocks, 256, 0, stream>>>(pairs, n_pairs, prm, bounds, coarse, best,
+                                                survivors, n_survivors);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_refine(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                              const float* pts, const float2* rot, CsmParams prm,
+                              const CsmBounds* bounds, const int* coarse,
+                              const unsigned* survivors, const unsigned* n_survivors,
+                              unsigned* cursor, unsigned long long* best,
+                              unsigned long long* counters, int n_ctas, cudaStream_t stream) {
+  (void)n_pairs;
+  csm_refine_kernel<<<n_ctas, 256, 0, stream>>>(grids, pairs, pts, rot, prm, bounds, coarse,
+                                                survivors, n_survivors, cursor, best, counters);
+  return cudaGetLastError();
+}
+
+}  // namespace gloc

@@ -1,0 +1,74 @@
+// csm_kernels.cuh -- device-side data model + launchers of the stage-2 kernels
+// (definitions in csm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace gloc {
+
+constexpr int kCsmMaxDepth = 8;  // precomputation widths 1..128
+
+// One map grid on the device: its precomputation stack, level i = width 2^i,
+// (nx+w-1) x (ny+w-1) cells, stride nx+w-1, offset (-w+1,-w+1) -- the layout of
+// PrecomputationGrid2D::cells_ (2d/fast_correlative_scan_matcher_2d.h:113-125).
+struct CsmGridDev {
+  const uint8_t* stack;
+  long long off[kCsmMaxDepth];
+  int nx, ny;
+  double resolution, max_x, max_y;
+};
+
+// One (grid, scan) pair.
+struct CsmPairDev {
+  int grid;            // index into the CsmGridDev array of this batch
+  long long pt_begin;  // first point of the scan in the concatenated xyz array
+  int n_pts;
+  float w0, z0;        // quaternion (w, z) of the float initial yaw (host libm)
+  float tx, ty;        // float initial translation
+};
+
+struct CsmParams {
+  int n_lin, n_ang, S, depth;
+  int step;       // 1 << (depth-1): coarse lattice step = coarsest width
+  int max_side;   // max coarse candidates per axis per scan
+  int maxc;       // max_side^2: slots per scan in the coarse arrays
+  unsigned W;     // 2*n_lin+1 (rank radix)
+  float min_score;
+  float min_s;    // PrecomputationGrid2D::min_score_  (1 - kMaxCorrespondenceCost)
+  float coef;     // (max_score_ - min_score_) / 255.f  (ToScore)
+};
+
+struct CsmBounds {
+  int min_x, max_x, min_y, max_y;
+};
+
+// K5
+cudaError_t launch_csm_level1_from_cells(const uint16_t* cells, const uint8_t* lut, size_t n,
+                                         uint8_t* out, cudaStream_t stream);
+cudaError_t launch_csm_build_level(const uint8_t* prev, int nx, int ny, int w, uint8_t* out,
+                                   cudaStream_t stream);
+// K6 (standalone, for parity tests of GenerateRotatedScans + DiscretizeScans)
+cudaError_t launch_csm_discretize(const float* pts, int n_pts, float w0, float z0, float tx,
+                                  float ty, const float2* rot, int S, double resolution,
+                                  double max_x, double max_y, int* out_cells, cudaStream_t stream);
+// K7 pipeline
+cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                              const float* pts, const float2* rot, CsmParams prm,
+                              CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
+                              cudaStream_t stream);
+cudaError_t launch_csm_seed(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                            const float* pts, const float2* rot, CsmParams prm,
+                            const CsmBounds* bounds, const unsigned long long* top_coarse,
+                            unsigned long long* best, cudaStream_t stream);
+cudaError_t launch_csm_filter(const CsmPairDev* pairs, int n_pairs, CsmParams prm,
+                              const CsmBounds* bounds, const int* coarse,
+                              const unsigned long long* best, unsigned* survivors,
+                              unsigned* n_survivors, cudaStream_t stream);
+cudaError_t launch_csm_refine(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                              const float* pts, const float2* rot, CsmParams prm,
+                              const CsmBounds* bounds, const int* coarse,
+                              const unsigned* survivors, const unsigned* n_survivors,
+                              unsigned* cursor, unsigned long long* best,
+                              unsigned long long* counters, int n_ctas, cudaStream_t stream);
+
+
+}  // namespace gloc

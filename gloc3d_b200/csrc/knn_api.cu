@@ -1,0 +1,411 @@
+// knn_api.cu -- C ABI of stage 1 (retrieval).  See include/gloc3d.h for the
+// reference interfaces each entry point replaces.
+#include <algorithm>
+#include <cfloat>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "knn_kernels.cuh"
+#include "knn_shortlist.cuh"
+
+namespace gloc {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int sm_count(int device) {
+  static std::mutex mu;
+  static std::vector<int> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  if ((int)cache.size() <= device) cache.resize(device + 1, 0);
+  if (cache[device] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || v <= 0)
+      v = 148;
+    cache[device] = v;
+  }
+  return cache[device];
+}
+
+// Device buffer that only grows.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) {
+      cudaError_t e = cudaFree(p);
+      p = nullptr;
+      bytes = 0;
+      if (e != cudaSuccess) return e;
+    }
+    size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      e = cudaMalloc(&p, need);
+      want = need;
+    }
+    if (e == cudaSuccess) bytes = want; else p = nullptr;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace gloc
+
+using namespace gloc;
+
+struct gloc_knn_index {
+  int device = 0;
+  size_t dim = 0;
+  float* d_db = nullptr;  // row-major n x dim float32 (the reference's KeyMat, contiguous)
+  size_t n = 0, cap = 0;
+  size_t search_limit = SIZE_MAX;
+  uint64_t offset = 0;
+  int mode = GLOC_KNN_AUTO;
+  cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+  DevBuf partial;                 // exact-scan per-range lists
+  DevBuf stage_q, stage_idx, stage_d2;
+  ShortlistState* sl = nullptr;   // tensor-shortlist state (bf16 copy, norms, workspaces)
+  gloc_knn_stats stats{};
+  EventProfiler prof;
+};
+
+namespace {
+
+struct RangePlan {
+  int n_ranges;
+  long long rows_per_range;
+};
+
+// Split the searchable rows into ranges so that (query tiles x ranges) fills the SMs in
+// whole waves; each (query tile, range) unit is one CTA of the exact scan.
+RangePlan plan_ranges(long long n_search, int nq, int device) {
+  const int BQ = exact_scan_tile_q(nq), BN = exact_scan_tile_n(nq);
+  const int sms = sm_count(device);
+  const long long n_qtiles = (nq + BQ - 1) / BQ;
+  const long long max_ranges = std::max<long long>(1, std::min<long long>(64, n_search / (BN * 4LL)));
+  double best_score = -1.0;
+  long long best_r = 1;
+  for (long long r = 1; r <= max_ranges; ++r) {
+    const long long units = n_qtiles * r;
+    const long long waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms);
+    const double score = eff - 0.003 * (double)r;
+    if (score > best_score + 1e-12) {
+      best_score = score;
+      best_r = r;
+    }
+  }
+  long long rpr = (n_search + best_r - 1) / best_r;
+  rpr = (rpr + BN - 1) / BN * BN;
+  RangePlan p;
+  p.rows_per_range = rpr;
+  p.n_ranges = (int)((n_search + rpr - 1) / rpr);
+  return p;
+}
+
+int exact_query_device(gloc_knn_index* ix, const float* d_q, size_t nq, size_t k,
+                       uint64_t* d_idx, float* d_d2, size_t n_search, cudaStream_t stream) {
+  const size_t kChunk = 1u << 17;
+  for (size_t q0 = 0; q0 < nq; q0 += kChunk) {
+    const int cq = (int)std::min(kChunk, nq - q0);
+    const RangePlan plan = plan_ranges((long long)n_search, cq, ix->device);
+    GLOC_CUDA_TRY(ix->partial.reserve((size_t)cq * plan.n_ranges * k * sizeof(uint64_t)));
+    ix->prof.begin(stream);
+    cudaError_t le = launch_knn_exact_scan(ix->d_db, (long long)n_search, (int)ix->dim,
+                                           d_q + q0 * ix->dim, cq, (int)k, plan.n_ranges,
+                                           plan.rows_per_range, (uint64_t*)ix->partial.p, stream);
+    ix->prof.end(stream);
+    GLOC_CUDA_TRY(le);
+    GLOC_CUDA_TRY(launch_knn_finalize((const uint64_t*)ix->partial.p, cq, plan.n_ranges, (int)k,
+                                      ix->offset, d_idx + q0 * k, d_d2 + q0 * k, stream));
+    ix->stats.kernel_launches += 2;
+  }
+  return GLOC_OK;
+}
+
+int grow_db(gloc_knn_index* ix, size_t need_rows) {
+  if (need_rows <= ix->cap) return GLOC_OK;
+  size_t new_cap = std::max(need_rows, ix->cap + ix->cap / 2);
+  float* nd = nullptr;
+  cudaError_t e = cudaMalloc((void**)&nd, new_cap * ix->dim * sizeof(float));
+  if (e != cudaSuccess && new_cap != need_rows) {
+    (void)cudaGetLastError();
+    new_cap = need_rows;
+    e = cudaMalloc((void**)&nd, new_cap * ix->dim * sizeof(float));
+  }
+  if (e != cudaSuccess) return fail(GLOC_ERR_NOMEM, std::string("cudaMalloc(db): ") + cudaGetErrorString(e));
+  if (ix->n > 0) {
+    e = cudaMemcpy(nd, ix->d_db, ix->n * ix->dim * sizeof(float), cudaMemcpyDeviceToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(nd);
+      return fail(GLOC_ERR_CUDA, std::string("cudaMemcpy(db grow): ") + cudaGetErrorString(e));
+    }
+  }
+  if (ix->d_db) cudaFree(ix->d_db);
+  ix->d_db = nd;
+  ix->cap = new_cap;
+  return GLOC_OK;
+}
+
+int put_rows(gloc_knn_index* ix, const float* rows, size_t n, size_t at, cudaMemcpyKind kind) {
+  if (n == 0) return GLOC_OK;
+  int rc = grow_db(ix, at + n);
+  if (rc != GLOC_OK) return rc;
+  GLOC_CUDA_TRY(cudaMemcpy(ix->d_db + at * ix->dim, rows, n * ix->dim * sizeof(float), kind));
+  return GLOC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gloc_version(void) { return 100; }
+const char* gloc_last_error(void) { return g_last_error.c_str(); }
+
+int gloc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess &&
+        major == 10)
+      ++ok;
+  }
+  return ok;
+}
+
+int gloc_knn_create(gloc_knn_index** out, size_t dim, int device) {
+  if (!out) return fail(GLOC_ERR_INVALID, "gloc_knn_create: out is null");
+  *out = nullptr;
+  if (dim == 0 || dim > (1u << 20)) return fail(GLOC_ERR_INVALID, "gloc_knn_create: bad dim");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    (void)cudaGetLastError();
+    return fail(GLOC_ERR_CUDA, "gloc_knn_create: no CUDA device (there is no CPU fallback)");
+  }
+  if (device < 0 || device >= ndev) return fail(GLOC_ERR_INVALID, "gloc_knn_create: bad device");
+  int major = 0;
+  GLOC_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+  if (major != 10)
+    return fail(GLOC_ERR_CUDA, "gloc_knn_create: device is not sm_100 (kernels are sm_100a only)");
+  DeviceGuard g(device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_knn_create: cudaSetDevice failed");
+  gloc_knn_index* ix = new (std::nothrow) gloc_knn_index;
+  if (!ix) return fail(GLOC_ERR_NOMEM, "gloc_knn_create: out of host memory");
+  ix->device = device;
+  ix->dim = dim;
+  e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ix;
+    return fail(GLOC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+  }
+  *out = ix;
+  return GLOC_OK;
+}
+
+void gloc_knn_destroy(gloc_knn_index* ix) {
+  if (!ix) return;
+  DeviceGuard g(ix->device);
+  if (ix->stream) {
+    cudaStreamSynchronize(ix->stream);
+    cudaStreamDestroy(ix->stream);
+  }
+  if (ix->d_db) cudaFree(ix->d_db);
+  ix->partial.release();
+  ix->stage_q.release();
+  ix->stage_idx.release();
+  ix->stage_d2.release();
+  shortlist_destroy(ix->sl);
+  delete ix;
+}
+
+int gloc_knn_set_db(gloc_knn_index* ix, const float* rows, size_t n) {
+  if (!ix || (n > 0 && !rows)) return fail(GLOC_ERR_INVALID, "gloc_knn_set_db: null argument");
+  DeviceGuard g(ix->device);
+  GLOC_CUDA_TRY(cudaDeviceSynchronize());
+  ix->n = 0;
+  shortlist_invalidate(ix->sl, 0);
+  int rc = put_rows(ix, rows, n, 0, cudaMemcpyHostToDevice);
+  if (rc == GLOC_OK) ix->n = n;
+  return rc;
+}
+
+int gloc_knn_set_db_device(gloc_knn_index* ix, const float* d_rows, size_t n) {
+  if (!ix || (n > 0 && !d_rows)) return fail(GLOC_ERR_INVALID, "gloc_knn_set_db_device: null argument");
+  DeviceGuard g(ix->device);
+  GLOC_CUDA_TRY(cudaDeviceSynchronize());
+  ix->n = 0;
+  shortlist_invalidate(ix->sl, 0);
+  int rc = put_rows(ix, d_rows, n, 0, cudaMemcpyDeviceToDevice);
+  if (rc == GLOC_OK) ix->n = n;
+  return rc;
+}
+
+int gloc_knn_append(gloc_knn_index* ix, const float* rows, size_t n) {
+  if (!ix || (n > 0 && !rows)) return fail(GLOC_ERR_INVALID, "gloc_knn_append: null argument");
+  DeviceGuard g(ix->device);
+  GLOC_CUDA_TRY(cudaDeviceSynchronize());
+  int rc = put_rows(ix, rows, n, ix->n, cudaMemcpyHostToDevice);
+  if (rc == GLOC_OK) {
+    shortlist_invalidate(ix->sl, ix->n);  // rows [0, n) keep their derived data
+    ix->n += n;
+  }
+  return rc;
+}
+
+size_t gloc_knn_size(const gloc_knn_index* ix) { return ix ? ix->n : 0; }
+size_t gloc_knn_dim(const gloc_knn_index* ix) { return ix ? ix->dim : 0; }
+
+int gloc_knn_set_search_limit(gloc_knn_index* ix, size_t n_search) {
+  if (!ix) return fail(GLOC_ERR_INVALID, "gloc_knn_set_search_limit: null index");
+  ix->search_limit = n_search;
+  return GLOC_OK;
+}
+
+int gloc_knn_set_index_offset(gloc_knn_index* ix, uint64_t offset) {
+  if (!ix) return fail(GLOC_ERR_INVALID, "gloc_knn_set_index_offset: null index");
+  ix->offset = offset;
+  return GLOC_OK;
+}
+
+int gloc_knn_set_mode(gloc_knn_index* ix, int mode) {
+  if (!ix || mode < GLOC_KNN_AUTO || mode > GLOC_KNN_SHORTLIST)
+    return fail(GLOC_ERR_INVALID, "gloc_knn_set_mode: bad argument");
+  ix->mode = mode;
+  return GLOC_OK;
+}
+
+int gloc_knn_get_stats(const gloc_knn_index* ix, gloc_knn_stats* stats) {
+  if (!ix || !stats) return fail(GLOC_ERR_INVALID, "gloc_knn_get_stats: null argument");
+  *stats = ix->stats;
+  return GLOC_OK;
+}
+
+int gloc_knn_set_profiling(gloc_knn_index* ix, int enabled) {
+  if (!ix) return fail(GLOC_ERR_INVALID, "gloc_knn_set_profiling: null index");
+  ix->prof.enabled = enabled != 0;
+  return GLOC_OK;
+}
+
+int gloc_knn_get_profile(gloc_knn_index* ix, gloc_profile* out) {
+  if (!ix || !out) return fail(GLOC_ERR_INVALID, "gloc_knn_get_profile: null argument");
+  DeviceGuard g(ix->device);
+  ix->prof.collect(&out->dominant_ms, &out->dominant_launches);
+  return GLOC_OK;
+}
+
+int gloc_knn_query_device(gloc_knn_index* ix, const float* d_q, size_t nq, size_t k,
+                          uint64_t* d_idx, float* d_d2, void* stream_v) {
+  if (!ix) return fail(GLOC_ERR_INVALID, "gloc_knn_query: null index");
+  if (nq == 0) return GLOC_OK;
+  if (!d_q || !d_idx || !d_d2) return fail(GLOC_ERR_INVALID, "gloc_knn_query: null buffer");
+  if (k == 0 || k > 128) return fail(GLOC_ERR_RANGE, "gloc_knn_query: k must be in [1, 128]");
+  const size_t n_search = std::min(ix->n, ix->search_limit);
+  if (n_search == 0)
+    return fail(GLOC_ERR_NOT_BUILT, "gloc_knn_query: the index holds no searchable rows");
+  if (n_search >= (1ull << 32))
+    return fail(GLOC_ERR_RANGE, "gloc_knn_query: more than 2^32-1 rows per index; shard the database");
+  if (nq > (size_t)INT32_MAX) return fail(GLOC_ERR_RANGE, "gloc_knn_query: too many queries in one call");
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_knn_query: cudaSetDevice failed");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  int mode = ix->mode;
+  if (mode == GLOC_KNN_AUTO)
+    mode = shortlist_applicable(ix->dim, n_search, nq, k) ? GLOC_KNN_SHORTLIST : GLOC_KNN_EXACT_SCAN;
+  int rc;
+  if (mode == GLOC_KNN_SHORTLIST) {
+    if (!shortlist_supported(ix->dim, k))
+      return fail(GLOC_ERR_RANGE, "gloc_knn_query: GLOC_KNN_SHORTLIST needs dim % 64 == 0, dim <= 2048, k <= 128");
+    ShortlistArgs a;
+    a.device = ix->device;
+    a.d_db = ix->d_db;
+    a.n_rows = n_search;
+    a.n_total = ix->n;
+    a.dim = ix->dim;
+    a.d_q = d_q;
+    a.nq = nq;
+    a.k = k;
+    a.offset = ix->offset;
+    a.d_idx = d_idx;
+    a.d_d2 = d_d2;
+    a.stream = stream;
+    a.prof = &ix->prof;
+    uint64_t launches = 0, fallback = 0, rows = 0;
+    rc = shortlist_query(&ix->sl, a, &launches, &fallback, &rows);
+    if (rc != GLOC_OK) return rc;
+    ix->stats.kernel_launches += launches;
+    ix->stats.shortlist_queries += nq;
+    ix->stats.shortlist_rows += rows;
+    if (fallback == UINT64_MAX) {
+      // overflow flags are resolved on the device: overflowed queries are re-run by
+      // the exact scan inside shortlist_query (see knn_shortlist.cu)
+      fallback = 0;
+    }
+    ix->stats.fallback_queries += fallback;
+  } else {
+    rc = exact_query_device(ix, d_q, nq, k, d_idx, d_d2, n_search, stream);
+    if (rc != GLOC_OK) return rc;
+  }
+  ix->stats.queries += nq;
+  ix->stats.last_mode = (uint64_t)mode;
+  return GLOC_OK;
+}
+
+int gloc_knn_query(gloc_knn_index* ix, const float* q, size_t nq, size_t k, uint64_t* out_idx,
+                   float* out_d2) {
+  if (!ix) return fail(GLOC_ERR_INVALID, "gloc_knn_query: null index");
+  if (nq == 0) return GLOC_OK;
+  if (!q || !out_idx || !out_d2) return fail(GLOC_ERR_INVALID, "gloc_knn_query: null buffer");
+  if (k == 0 || k > 128) return fail(GLOC_ERR_RANGE, "gloc_knn_query: k must be in [1, 128]");
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_knn_query: cudaSetDevice failed");
+  GLOC_CUDA_TRY(ix->stage_q.reserve(nq * ix->dim * sizeof(float)));
+  GLOC_CUDA_TRY(ix->stage_idx.reserve(nq * k * sizeof(uint64_t)));
+  GLOC_CUDA_TRY(ix->stage_d2.reserve(nq * k * sizeof(float)));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(ix->stage_q.p, q, nq * ix->dim * sizeof(float),
+                                cudaMemcpyHostToDevice, ix->stream));
+  int rc = gloc_knn_query_device(ix, (const float*)ix->stage_q.p, nq, k,
+                                 (uint64_t*)ix->stage_idx.p, (float*)ix->stage_d2.p, ix->stream);
+  if (rc != GLOC_OK) return rc;
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_idx, ix->stage_idx.p, nq * k * sizeof(uint64_t),
+                                cudaMemcpyDeviceToHost, ix->stream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_d2, ix->stage_d2.p, nq * k * sizeof(float),
+                                cudaMemcpyDeviceToHost, ix->stream));
+  GLOC_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+  return GLOC_OK;
+}
+
+int gloc_knn_merge_topk_device(const uint64_t* d_idx, const float* d_d2, size_t g, size_t nq,
+                               size_t k, uint64_t* d_out_idx, float* d_out_d2, int device,
+                               void* stream) {
+  if (nq == 0 || g == 0) return GLOC_OK;
+  if (!d_idx || !d_d2 || !d_out_idx || !d_out_d2)
+    return fail(GLOC_ERR_INVALID, "gloc_knn_merge_topk_device: null buffer");
+  if (k == 0 || k > 4096 || g > 4096 || nq > (size_t)INT32_MAX)
+    return fail(GLOC_ERR_RANGE, "gloc_knn_merge_topk_device: bad sizes");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(GLOC_ERR_CUDA, "gloc_knn_merge_topk_device: cudaSetDevice failed");
+  GLOC_CUDA_TRY(launch_knn_merge_pairs(d_idx, d_d2, (int)g, (int)nq, (int)k, d_out_idx, d_out_d2,
+                                       (cudaStream_t)stream));
+  return GLOC_OK;
+}
+
+}  // extern "C"

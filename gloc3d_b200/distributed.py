@@ -1,0 +1,96 @@
+"""Multi-GPU retrieval: the database shards by rows across the ranks of one box (one
+process per GPU, torch.distributed / NCCL over NVLink for the plumbing).
+
+Every rank holds rows [lo, hi) of the database, answers all queries against its shard
+(local top-k with GLOBAL indices), the per-rank lists are exchanged with ONE all-gather of
+nq*k*(8+4) bytes per rank, and every rank merges them with K4 (`gloc_knn_merge_topk_device`)
+-- same (d2, idx) order, so the result is identical on every rank and identical to a
+single-GPU search.  The reference has no distributed code at all (F1); this
+is the B200 design for its north-star scaling config.
+
+The host logic (shard bounds, gather layout, merge) is backend-agnostic so that it is
+testable on CPU with gloo by injecting a local-search and a merge function.
+"""
+from __future__ import annotations
+
+from typing import Callable
+
+import numpy as np
+
+
+def shard_bounds(n_rows: int, world_size: int) -> list[int]:
+    """Contiguous, balanced row ranges: rank r owns [b[r], b[r+1])."""
+    return [n_rows * r // world_size for r in range(world_size + 1)]
+
+
+class ShardedRetrieval:
+    """Row-sharded exact top-k over `world_size` ranks.
+
+    local_search(q, k) -> (idx, d2) for this rank's shard with global indices;
+    merge(idx[g, nq, k], d2[g, nq, k]) -> (idx[nq, k], d2[nq, k]).
+    With the defaults both run on the GPU through libgloc3d.so.
+    """
+
+    def __init__(self, rank: int, world_size: int, group=None,
+                 local_search: Callable | None = None, merge: Callable | None = None):
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self._local_search = local_search
+        self._merge = merge
+        self.index = None
+        self.lo = self.hi = 0
+
+    # -- GPU-backed construction ------------------------------------------
+    def load_shard(self, shard_rows, lo: int, device: int, mode: int = 0):
+        """shard_rows: this rank's rows [lo, lo+len) as numpy (host) or CUDA tensor."""
+        from .retrieval import KnnIndex, merge_topk_device
+
+        dim = shard_rows.shape[1]
+        self.index = KnnIndex(dim, device)
+        if isinstance(shard_rows, np.ndarray):
+            self.index.set_db(shard_rows)
+        else:
+            self.index.set_db_device(shard_rows)
+        self.index.set_index_offset(lo)
+        self.index.set_mode(mode)
+        self.lo, self.hi = lo, lo + shard_rows.shape[0]
+        self._local_search = lambda q, k: self.index.query_device(q, k)
+        self._merge = merge_topk_device
+        return self
+
+    # -- query --------------------------------------------------------------
+    def query(self, q, k: int):
+        """q: the full query batch, replicated on every rank (CUDA tensor on the GPU path,
+        CPU tensor under gloo).  Returns the global top-k on every rank."""
+        import torch
+        import torch.distributed as dist
+
+        idx, d2 = self._local_search(q, k)
+        if self.world_size == 1:
+            return idx, d2
+        nq = idx.shape[0]
+        all_idx = torch.empty((self.world_size, nq, k), dtype=idx.dtype, device=idx.device)
+        all_d2 = torch.empty((self.world_size, nq, k), dtype=d2.dtype, device=d2.device)
+        dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
+        dist.all_gather_into_tensor(all_d2, d2.contiguous(), group=self.group)
+        return self._merge(all_idx, all_d2)
+
+    def query_host(self, q_pinned, k: int, out_idx_pinned=None, out_d2_pinned=None):
+        """End-to-end call with HOST buffers: H2D of the queries, sharded search, all-gather,
+        merge, D2H of the result (pinned torch CPU tensors in and out)."""
+        import torch
+
+        dev = torch.device("cuda", self.index.device)
+        q = q_pinned.to(dev, non_blocking=True)
+        idx, d2 = self.query(q, k)
+        if out_idx_pinned is None:
+            out_idx_pinned = torch.empty(idx.shape, dtype=idx.dtype, pin_memory=True)
+            out_d2_pinned = torch.empty(d2.shape, dtype=d2.dtype, pin_memory=True)
+        out_idx_pinned.copy_(idx, non_blocking=True)
+        out_d2_pinned.copy_(d2, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_idx_pinned, out_d2_pinned
+
+    def close(self):
+        if self.index is not None:
+            self.index.close()
+            self.index = None

@@ -1,0 +1,129 @@
+"""Seeded synthetic inputs of KITTI shape: netvlad_fc-like
+descriptors and BEV occupancy grids with planted query scans.  numpy only; the
+same arrays feed the CPU oracle and the GPU path byte for byte.
+
+Conventions follow the reference: descriptors are float32 [n, 512] row-major and
+NOT L2-normalised (model/netvlad_fc.py:99-109); BEV grids are the matcher's
+uint8 width-1 precomputation grid (0 = free ... 255 = occupied,
+registration/2d/fast_correlative_scan_matcher_2d.cpp:184-190) stored
+[num_y_cells][num_x_cells] so that flat index = num_x_cells*y + x
+(registration/2d/grid_2d.cpp:168-171).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DIM = 512
+
+
+def make_descriptors(n: int, dim: int = DIM, seed: int = 1234, dup_run: int = 0,
+                     dup_sigma: float = 0.001) -> np.ndarray:
+    """iid N(0, 1/dim) rows; with dup_run > 1 consecutive rows form random-walk
+    runs of near-duplicates (KITTI-like consecutive frames)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((n, dim), np.float32)
+    chunk = 65536
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        out[s:e] = (rng.standard_normal((e - s, dim)) * (1.0 / np.sqrt(dim))).astype(np.float32)
+    if dup_run > 1:
+        for s in range(0, n, dup_run):
+            e = min(n, s + dup_run)
+            steps = (rng.standard_normal((e - s - 1, dim)) * dup_sigma).astype(np.float32)
+            out[s + 1:e] = out[s] + np.cumsum(steps, axis=0, dtype=np.float32)
+    return out
+
+
+def make_queries(db: np.ndarray, nq: int, seed: int = 5678, sigma: float | None = None) -> np.ndarray:
+    """sigma None: independent draws (set A).  sigma > 0: perturbed copies of
+    random DB rows (set B), the near-tie stress case."""
+    rng = np.random.default_rng(seed)
+    dim = db.shape[1]
+    if sigma is None:
+        return (rng.standard_normal((nq, dim)) * (1.0 / np.sqrt(dim))).astype(np.float32)
+    rows = rng.integers(0, db.shape[0], nq)
+    noise = (np.random.default_rng(91011).standard_normal((nq, dim)) * sigma).astype(np.float32)
+    return (db[rows] + noise).astype(np.float32)
+
+
+def make_bev_grid(nx: int = 800, ny: int = 800, seed: int = 2222, n_segments: int = 60,
+                  n_blobs: int = 40, graded: bool = False) -> np.ndarray:
+    """uint8 [ny, nx] occupancy grid: oblique wall segments + small blobs,
+    about 1.2 % occupied at the default size (about 4.7k cells at 800x800 is reached
+    with the defaults).  graded=True fills occupied cells with values 1..255 instead
+    of 255 (general Cartographer semantics)."""
+    rng = np.random.default_rng(seed)
+    g = np.zeros((ny, nx), np.uint8)
+    scale = np.sqrt(nx * ny) / 800.0
+    for _ in range(n_segments):
+        x0, y0 = rng.uniform(0.08 * nx, 0.92 * nx), rng.uniform(0.08 * ny, 0.92 * ny)
+        ang = rng.uniform(0, np.pi)
+        length = rng.uniform(20, 110) * scale
+        n = int(length * 2) + 2
+        t = np.linspace(0, length, n)
+        xs = np.clip(np.rint(x0 + t * np.cos(ang)).astype(int), 0, nx - 1)
+        ys = np.clip(np.rint(y0 + t * np.sin(ang)).astype(int), 0, ny - 1)
+        g[ys, xs] = 255
+    for _ in range(n_blobs):
+        x0, y0 = rng.integers(10, nx - 10), rng.integers(10, ny - 10)
+        r = rng.integers(1, 4)
+        yy, xx = np.mgrid[-r:r + 1, -r:r + 1]
+        m = (xx * xx + yy * yy) <= r * r
+        ys = np.clip(y0 + yy[m], 0, ny - 1)
+        xs = np.clip(x0 + xx[m], 0, nx - 1)
+        g[ys, xs] = 255
+    if graded:
+        vals = rng.integers(1, 256, size=g.shape).astype(np.uint8)
+        g = np.where(g > 0, vals, 0).astype(np.uint8)
+    return g
+
+
+def centered_limits(nx: int, ny: int, resolution: float = 0.2):
+    """MapLimits::max() that puts the world origin at the grid centre.  Cell x
+    runs along world -y and cell y along world -x (registration/2d/map_limits.h:69-76),
+    hence max_y spans num_x_cells and max_x spans num_y_cells."""
+    return 0.5 * ny * resolution, 0.5 * nx * resolution  # (max_x, max_y)
+
+
+def cells_to_world(cx: np.ndarray, cy: np.ndarray, resolution: float, max_x: float, max_y: float):
+    """Centre of cell (cx, cy) in world coordinates: inverse of GetCellIndex."""
+    y = max_y - (cx.astype(np.float64) + 0.5) * resolution
+    x = max_x - (cy.astype(np.float64) + 0.5) * resolution
+    return x, y
+
+
+def grid_points_world(level1: np.ndarray, resolution: float, max_x: float, max_y: float,
+                      threshold: int = 128) -> np.ndarray:
+    """World-frame (x, y, 0) float32 points at the centres of occupied cells."""
+    cy, cx = np.nonzero(level1 >= threshold)
+    x, y = cells_to_world(cx, cy, resolution, max_x, max_y)
+    return np.stack([x, y, np.zeros_like(x)], axis=1).astype(np.float32)
+
+
+def planted_scan(level1: np.ndarray, resolution: float, max_x: float, max_y: float,
+                 yaw: float, dx: float, dy: float, dropout: float = 0.2,
+                 jitter_cells: float = 0.0, seed: int = 3333) -> np.ndarray:
+    """Sensor-frame scan whose true pose in the map is (dx, dy, yaw): the map's
+    occupied-cell centres m are mapped to s = R(-yaw) (m - t), thinned by
+    `dropout`, optionally jittered by up to +-jitter_cells cells."""
+    rng = np.random.default_rng(seed)
+    m = grid_points_world(level1, resolution, max_x, max_y).astype(np.float64)
+    keep = rng.random(m.shape[0]) >= dropout
+    m = m[keep]
+    if jitter_cells > 0:
+        m[:, :2] += rng.uniform(-jitter_cells, jitter_cells, (m.shape[0], 2)) * resolution
+    c, s = np.cos(-yaw), np.sin(-yaw)
+    px, py = m[:, 0] - dx, m[:, 1] - dy
+    out = np.stack([c * px - s * py, s * px + c * py, np.zeros_like(px)], axis=1)
+    return out.astype(np.float32)
+
+
+def level1_to_cells(level1: np.ndarray) -> np.ndarray:
+    """A uint16 Grid2D cell array whose width-1 precomputation grid is `level1`
+    for binary grids (255 -> cost value 1 = kMinCorrespondenceCost, 0 -> unknown);
+    graded values are mapped through the inverse of ComputeCellValue approximately
+    (used only to exercise the uint16 entry point)."""
+    lv = level1.astype(np.float64) / 255.0
+    v = np.rint((1.0 - lv) * 32766.0).astype(np.int64) + 1
+    v = np.clip(v, 1, 32767).astype(np.uint16)
+    return np.where(level1 == 0, np.uint16(0), v).astype(np.uint16)

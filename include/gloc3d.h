@@ -1,0 +1,215 @@
+/*
+ * gloc3d.h -- C ABI of libgloc3d.so: the B200 (sm_100a) implementation of
+ * GLoc3D's global-localization query path.  Plain pointers and sizes only; no
+ * C++ or torch types cross this boundary.  Every entry point returns an int
+ * status (GLOC_OK == 0) and never throws; gloc_last_error() gives the message
+ * of the last failure on the calling thread.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative
+ * to /root/reference/registration/).  The C++ shims in gloc3d_b200/host/ put
+ * the reference's own class interfaces (InvKeyTree, FastCorrelativeScanMatcher2D)
+ * on top of these functions; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * There is NO CPU fallback: every compute entry point fails with
+ * GLOC_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GLOC3D_H_
+#define GLOC3D_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLOC_OK 0
+#define GLOC_ERR_INVALID 1   /* bad argument (null pointer, k == 0, dim mismatch ...) */
+#define GLOC_ERR_CUDA 2      /* CUDA runtime / driver failure, or no usable device   */
+#define GLOC_ERR_NOT_BUILT 3 /* query on an empty index (nanoflann: runtime_error,    */
+                             /* nanoflann.hpp:1454-1457)                              */
+#define GLOC_ERR_RANGE 4     /* parameter outside the supported range                 */
+#define GLOC_ERR_NOMEM 5
+
+int gloc_version(void);
+const char* gloc_last_error(void);
+/* Number of CUDA devices of compute capability 10.x visible to the process. */
+int gloc_device_count(void);
+
+/* ===================================================================== stage 1
+ * Exhaustive exact top-k L2 retrieval.  Replaces
+ *   InvKeyTree = KDTreeVectorOfVectorsAdaptor<KeyMat, float>
+ *     ctor  (size_t dim, const KeyMat& mat, int leaf_max_size)   KDTreeVectorOfVectorsAdaptor.h:70-84
+ *     query (const float* q, size_t k, size_t* idx, float* d2)   KDTreeVectorOfVectorsAdaptor.h:95-102
+ * as used by RpyPCLoopDetector::detect (loop_detector.cpp:34-37,42-45,66-79).
+ * Results: the k rows with the smallest squared L2 distance, where the distance
+ * is computed in float32 in the operation order of L2_Adaptor::evalMetric
+ * (nanoflann.hpp:453-487: groups of 4, left-associated, no FMA), ascending by
+ * (d2, idx).  Indices and distances are bit-exact with nanoflann's exact search
+ * (ties: nanoflann's order is traversal-dependent, this library's is (d2, idx)).
+ */
+typedef struct gloc_knn_index gloc_knn_index;
+
+/* Search strategy.  All three return identical results. */
+#define GLOC_KNN_AUTO 0      /* tensor shortlist when it applies, else exact scan   */
+#define GLOC_KNN_EXACT_SCAN 1 /* FP32 exact scan of every row (K3 as a full scan)    */
+#define GLOC_KNN_SHORTLIST 2 /* BF16 tcgen05 GEMM shortlist (K1+K2) + FP32 re-rank  */
+                             /* (K3); queries whose shortlist overflows are re-run  */
+                             /* through the exact scan on the GPU                   */
+
+typedef struct {
+  uint64_t queries;            /* queries answered since creation                   */
+  uint64_t kernel_launches;    /* CUDA kernels launched by this index               */
+  uint64_t shortlist_queries;  /* queries answered through the tensor shortlist     */
+  uint64_t fallback_queries;   /* shortlist overflowed -> exact scan on the GPU     */
+  uint64_t shortlist_rows;     /* rows re-ranked in FP32 (sum over queries)         */
+  uint64_t last_mode;          /* strategy used by the last call (GLOC_KNN_*)       */
+} gloc_knn_stats;
+
+int gloc_knn_create(gloc_knn_index** out, size_t dim, int device);
+void gloc_knn_destroy(gloc_knn_index* index);
+
+/* Replace the database with n rows (row-major n x dim float32, host memory).
+ * Copy semantics: the reference adaptor keeps a const& to the caller's KeyMat
+ * (KDTreeVectorOfVectorsAdaptor.h:88) which must stay unmodified, so a copy is
+ * observationally identical.  n == 0 empties the index. */
+int gloc_knn_set_db(gloc_knn_index* index, const float* rows, size_t n);
+/* Same with rows already in device memory of the index's device. */
+int gloc_knn_set_db_device(gloc_knn_index* index, const float* d_rows, size_t n);
+/* Append rows (SLAM mode grows the DB one keyframe at a time,
+ * loop_detector.cpp:9-20); amortised O(1) re-allocation. */
+int gloc_knn_append(gloc_knn_index* index, const float* rows, size_t n);
+size_t gloc_knn_size(const gloc_knn_index* index);
+size_t gloc_knn_dim(const gloc_knn_index* index);
+
+/* Search only rows [0, n_search) -- SLAM mode searches all but the most recent
+ * NUM_EXCLUDE_RECENT=30 keyframes (loop_detector.cpp:66-72).  SIZE_MAX = all. */
+int gloc_knn_set_search_limit(gloc_knn_index* index, size_t n_search);
+/* Returned index = local row + offset (database sharded over GPUs). */
+int gloc_knn_set_index_offset(gloc_knn_index* index, uint64_t offset);
+int gloc_knn_set_mode(gloc_knn_index* index, int mode);
+int gloc_knn_get_stats(const gloc_knn_index* index, gloc_knn_stats* stats);
+
+/* Live kernel timing for bench.py's roofline line: when enabled, the dominant kernel of
+ * every query call (the exact scan, or the shortlist GEMM) is bracketed by CUDA events on
+ * the launching stream.  get_profile waits for them, returns their summed duration and
+ * count since the last call, and resets. */
+typedef struct {
+  double dominant_ms;
+  uint64_t dominant_launches;
+} gloc_profile;
+int gloc_knn_set_profiling(gloc_knn_index* index, int enabled);
+int gloc_knn_get_profile(gloc_knn_index* index, gloc_profile* out);
+
+/* nq queries (row-major nq x dim) -> out_idx / out_d2 (row-major nq x k), all in
+ * HOST memory (caller-allocated, as loop_detector.cpp:42-43).  Slots beyond the
+ * number of searchable rows get idx = UINT64_MAX, d2 = FLT_MAX.  Host<->device
+ * copies happen inside the call. */
+int gloc_knn_query(gloc_knn_index* index, const float* queries, size_t nq, size_t k,
+                   uint64_t* out_idx, float* out_d2);
+/* Same with queries and outputs in DEVICE memory; work is enqueued on `stream`
+ * (a cudaStream_t, NULL = the legacy default stream) and not synchronised. */
+int gloc_knn_query_device(gloc_knn_index* index, const float* d_queries, size_t nq,
+                          size_t k, uint64_t* d_out_idx, float* d_out_d2, void* stream);
+
+/* K4: merge g per-shard top-k lists (device memory, laid out [g][nq][k], each
+ * ascending by (d2, idx) with GLOBAL indices, UINT64_MAX = empty slot) into the
+ * global top-k -- run on every rank after the NCCL all-gather. */
+int gloc_knn_merge_topk_device(const uint64_t* d_idx, const float* d_d2, size_t g,
+                               size_t nq, size_t k, uint64_t* d_out_idx,
+                               float* d_out_d2, int device, void* stream);
+
+/* ===================================================================== stage 2
+ * Correlative / branch-and-bound scan matching of BEV probability grids.
+ * Replaces cartographer::mapping::scan_matching::FastCorrelativeScanMatcher2D
+ * (2d/fast_correlative_scan_matcher_2d.h:137-200) and the pieces it is built
+ * from (PrecomputationGridStack2D, SearchParameters, GenerateRotatedScans,
+ * DiscretizeScans, ScoreCandidates, BranchAndBound).  A store holds many map
+ * grids (one per database keyframe); a match scores one scan against one grid.
+ * The selected discrete pose is the global maximum over every (scan, x, y) of
+ * the shrunk search window -- what BranchAndBound returns -- with ties
+ * resolved to the smallest (scan, x, y).
+ */
+typedef struct gloc_csm_store gloc_csm_store;
+
+typedef struct {
+  int found;        /* best score > min_score                  fast_..._2d.cpp:311  */
+  float score;      /* PrecomputationGrid2D::ToScore of the best candidate          */
+  int scan_index;   /* Candidate2D::scan_index                 correlative_..._2d.h:90 */
+  int x_offset;     /* Candidate2D::x_index_offset                                  */
+  int y_offset;     /* Candidate2D::y_index_offset                                  */
+  int reserved;
+  double pose_x;    /* initial x + (-y_offset * resolution)    correlative_..._2d.h:81-84 */
+  double pose_y;    /* initial y + (-x_offset * resolution)                         */
+  double pose_yaw;  /* initial yaw + (scan_index - n_ang)*step fast_..._2d.cpp:313-317 */
+} gloc_csm_result;
+
+typedef struct {
+  uint64_t matches;          /* (grid, scan) pairs matched                           */
+  uint64_t kernel_launches;
+  uint64_t coarse_candidates; /* candidates scored on the coarsest grid              */
+  uint64_t refined_nodes;     /* branch-and-bound nodes expanded below it            */
+} gloc_csm_stats;
+
+int gloc_csm_create(gloc_csm_store** out, int device);
+void gloc_csm_destroy(gloc_csm_store* store);
+
+/* Add a map grid given as Grid2D's uint16 correspondence-cost cells
+ * (2d/grid_2d.h:100-101, flat index num_x_cells*y + x, 0 = unknown) with its
+ * MapLimits (2d/map_limits.h:40-47).  The width-1 precomputation grid is
+ * derived on the GPU exactly as PrecomputationGrid2D does
+ * (fast_..._2d.cpp:118-119,130-131,184-190). */
+int gloc_csm_add_grid_cells(gloc_csm_store* store, const uint16_t* cells, int nx, int ny,
+                            double resolution, double max_x, double max_y, int* grid_id);
+/* Add a map grid given directly as the uint8 width-1 precomputation grid
+ * (0 = min score ... 255 = max score). */
+int gloc_csm_add_grid_u8(gloc_csm_store* store, const uint8_t* level1, int nx, int ny,
+                         double resolution, double max_x, double max_y, int* grid_id);
+int gloc_csm_num_grids(const gloc_csm_store* store);
+/* Copy the width-`width` precomputation grid of grid_id back to the host
+ * ((nx+width-1)*(ny+width-1) bytes) -- PrecomputationGridStack2D::Get. */
+int gloc_csm_get_precomputation_grid(gloc_csm_store* store, int grid_id, int width,
+                                     uint8_t* out);
+
+/* Match n_pairs independent (grid, scan) pairs.
+ *   pts          concatenated scan points, float32 (x, y, z) triples (sensor::PointCloud)
+ *   scan_offsets n_scans+1 prefix offsets (in points) into pts
+ *   grid_ids, scan_ids, init_xyyaw  per pair: map grid, scan, initial pose estimate
+ *   n_lin, n_ang, ang_step  SearchParameters "for testing" ctor
+ *                 (correlative_scan_matcher_2d.cpp:57-71); use
+ *                 gloc_csm_search_params for the production ctor
+ *   depth        branch_and_bound_depth (fast_..._2d.h:51); only affects speed
+ *   min_score    Match*'s min_score
+ * = MatchWithSearchParameters (fast_..._2d.cpp:270-320) per pair. */
+int gloc_csm_match_batch(gloc_csm_store* store, const float* pts, const int64_t* scan_offsets,
+                         int n_scans, const int* grid_ids, const int* scan_ids,
+                         const double* init_xyyaw, int n_pairs, int n_lin, int n_ang,
+                         double ang_step, int depth, float min_score,
+                         gloc_csm_result* results);
+
+/* K6 on its own: the rotated + discretised scans MatchWithSearchParameters builds
+ * (fast_..._2d.cpp:278-289 = TransformPointCloud by the float initial yaw,
+ * GenerateRotatedScans correlative_scan_matcher_2d.cpp:93-109, DiscretizeScans
+ * :111-127).  out_cells is (2*n_ang+1) x n_pts x 2 int32 (cell x, cell y), host. */
+int gloc_csm_discretize(gloc_csm_store* store, const float* pts, int n_pts, double init_x,
+                        double init_y, double init_yaw, int n_ang, double ang_step,
+                        double resolution, double max_x, double max_y, int32_t* out_cells);
+
+/* SearchParameters production ctor (correlative_scan_matcher_2d.cpp:27-55). */
+int gloc_csm_search_params(double linear_window, double angular_window, const float* pts,
+                           int n_pts, double resolution, int* n_lin, int* n_ang,
+                           double* ang_step);
+/* GridToVirtualPointCloud (fast_..._2d.cpp:78-95): cells with cost < 0.11 ->
+ * (ox + i*res, oy + j*res, 0).  Returns the count through n_out; pts may be
+ * NULL to size the buffer. */
+int gloc_csm_grid_to_points(const uint16_t* cells, int nx, int ny, double resolution,
+                            double ox, double oy, float* pts, int capacity, int* n_out);
+int gloc_csm_get_stats(const gloc_csm_store* store, gloc_csm_stats* stats);
+/* Same live timing for stage 2; the dominant kernel is the coarse-level scorer. */
+int gloc_csm_set_profiling(gloc_csm_store* store, int enabled);
+int gloc_csm_get_profile(gloc_csm_store* store, gloc_profile* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLOC3D_H_ */

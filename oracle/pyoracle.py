@@ -1,0 +1,301 @@
+"""ctypes bindings for the CPU oracles.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl
+reference` legs may import this module; the product package (gloc3d_b200)
+never does.  See oracle/gloc_oracle.h for what each function restates
+(reference file:line) and for the parity status of each stage.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libgloc_oracle.so")
+_REF = os.path.join(_HERE, "_ref", "libnanoflann_ref.so")
+
+_u64p = C.POINTER(C.c_uint64)
+_f32p = C.POINTER(C.c_float)
+
+
+def build(force: bool = False) -> None:
+    """Compile the C restatement (always) and oracle/_ref (when /root/reference exists)."""
+    if force or not os.path.exists(_LIB) or not os.path.exists(_REF):
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+
+
+def _ptr(a: np.ndarray, ty):
+    return a.ctypes.data_as(ty)
+
+
+class MatchResult(C.Structure):
+    _fields_ = [
+        ("found", C.c_int),
+        ("score", C.c_float),
+        ("scan_index", C.c_int),
+        ("x_offset", C.c_int),
+        ("y_offset", C.c_int),
+        ("pose_x", C.c_double),
+        ("pose_y", C.c_double),
+        ("pose_yaw", C.c_double),
+        ("n_scored", C.c_longlong),
+    ]
+
+    def as_tuple(self):
+        return (self.found, self.score, self.scan_index, self.x_offset, self.y_offset,
+                self.pose_x, self.pose_y, self.pose_yaw)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        L.gloc_oracle_l2.restype = C.c_float
+        L.gloc_oracle_l2.argtypes = [_f32p, _f32p, C.c_size_t]
+        L.gloc_oracle_knn.argtypes = [_f32p, C.c_size_t, C.c_size_t, _f32p, C.c_size_t,
+                                      C.c_size_t, _u64p, _f32p]
+        L.gloc_oracle_knn_mt.argtypes = L.gloc_oracle_knn.argtypes + [C.c_int]
+        L.gloc_oracle_topk_merge.argtypes = [_u64p, _f32p, C.c_size_t, C.c_size_t,
+                                             C.c_size_t, _u64p, _f32p]
+        L.gloc_oracle_min_cost.restype = C.c_float
+        L.gloc_oracle_max_cost.restype = C.c_float
+        L.gloc_oracle_value_to_cost.restype = C.c_float
+        L.gloc_oracle_value_to_cost.argtypes = [C.c_uint16]
+        L.gloc_oracle_cost_to_value.restype = C.c_uint16
+        L.gloc_oracle_cost_to_value.argtypes = [C.c_float]
+        L.gloc_oracle_cell_value.restype = C.c_uint8
+        L.gloc_oracle_cell_value.argtypes = [C.c_float]
+        L.gloc_oracle_level1_from_cells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.gloc_oracle_precomp_from_cells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                     C.c_void_p]
+        L.gloc_oracle_precomp_from_level1.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                                      C.c_void_p]
+        L.gloc_oracle_search_params.argtypes = [C.c_double, C.c_double, _f32p, C.c_int,
+                                                C.c_double, C.POINTER(C.c_int),
+                                                C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.gloc_oracle_grid_to_points.restype = C.c_int
+        L.gloc_oracle_grid_to_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                                 C.c_double, C.c_double, C.c_void_p, C.c_int]
+        L.gloc_oracle_discretize.argtypes = [_f32p, C.c_int, C.c_double, C.c_double,
+                                             C.c_double, C.c_int, C.c_double, C.c_double,
+                                             C.c_double, C.c_double, C.c_void_p]
+        L.gloc_oracle_csm_match.restype = C.c_int
+        L.gloc_oracle_csm_match.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double,
+                                            C.c_double, C.c_double, C.c_int, _f32p, C.c_int,
+                                            C.c_double, C.c_double, C.c_double, C.c_int,
+                                            C.c_int, C.c_double, C.c_float, C.c_int,
+                                            C.POINTER(MatchResult)]
+        L.gloc_oracle_csm_match_full_submap.restype = C.c_int
+        L.gloc_oracle_csm_match_full_submap.argtypes = [C.c_void_p, C.c_int, C.c_int,
+                                                        C.c_double, C.c_double, C.c_double,
+                                                        C.c_int, _f32p, C.c_int, C.c_float,
+                                                        C.c_int, C.POINTER(MatchResult)]
+        L.gloc_oracle_csm_match_batch_mt.argtypes = [
+            C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
+            C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int,
+            C.c_int, C.c_int, C.c_double, C.c_float, C.c_int, C.c_int, C.POINTER(MatchResult)]
+        _lib = L
+    return _lib
+
+
+def have_ref() -> bool:
+    if not os.path.exists(_REF):
+        try:
+            build()
+        except Exception:
+            return False
+    return os.path.exists(_REF)
+
+
+def ref():
+    """The reference's own nanoflann, compiled from /root/reference (oracle/_ref)."""
+    global _ref
+    if _ref is None:
+        if not have_ref():
+            raise RuntimeError("oracle/_ref/libnanoflann_ref.so is missing")
+        R = C.CDLL(_REF)
+        R.gloc_ref_knn_build.restype = C.c_void_p
+        R.gloc_ref_knn_build.argtypes = [_f32p, C.c_size_t, C.c_size_t, C.c_int]
+        R.gloc_ref_knn_query.argtypes = [C.c_void_p, _f32p, C.c_size_t, _u64p, _f32p]
+        R.gloc_ref_knn_query_batch.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_size_t,
+                                               _u64p, _f32p, C.c_int]
+        R.gloc_ref_knn_free.argtypes = [C.c_void_p]
+        _ref = R
+    return _ref
+
+
+# ----------------------------------------------------------------- stage 1
+
+def l2(q: np.ndarray, x: np.ndarray) -> np.float32:
+    q = np.ascontiguousarray(q, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    return np.float32(lib().gloc_oracle_l2(_ptr(q, _f32p), _ptr(x, _f32p), q.size))
+
+
+def knn(db: np.ndarray, q: np.ndarray, k: int, nthreads: int = 1):
+    db = np.ascontiguousarray(db, np.float32)
+    q = np.ascontiguousarray(q, np.float32)
+    n, dim = db.shape if db.ndim == 2 else (0, q.shape[1])
+    nq = q.shape[0]
+    idx = np.empty((nq, k), np.uint64)
+    d2 = np.empty((nq, k), np.float32)
+    lib().gloc_oracle_knn_mt(_ptr(db, _f32p), n, dim, _ptr(q, _f32p), nq, k,
+                             _ptr(idx, _u64p), _ptr(d2, _f32p), nthreads)
+    return idx, d2
+
+
+def topk_merge(idx: np.ndarray, d2: np.ndarray):
+    """idx/d2: [g, nq, k] per-shard lists with GLOBAL indices."""
+    idx = np.ascontiguousarray(idx, np.uint64)
+    d2 = np.ascontiguousarray(d2, np.float32)
+    g, nq, k = idx.shape
+    oi = np.empty((nq, k), np.uint64)
+    od = np.empty((nq, k), np.float32)
+    lib().gloc_oracle_topk_merge(_ptr(idx, _u64p), _ptr(d2, _f32p), g, nq, k,
+                                 _ptr(oi, _u64p), _ptr(od, _f32p))
+    return oi, od
+
+
+class RefTree:
+    """The reference's InvKeyTree (nanoflann KD-tree, leaf 10) over a copy of db."""
+
+    def __init__(self, db: np.ndarray, leaf_max_size: int = 10):
+        db = np.ascontiguousarray(db, np.float32)
+        self.n, self.dim = db.shape
+        self._h = ref().gloc_ref_knn_build(_ptr(db, _f32p), self.n, self.dim, leaf_max_size)
+
+    def query(self, q: np.ndarray, k: int, nthreads: int = 1):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)
+        nq = q.shape[0]
+        idx = np.empty((nq, k), np.uint64)
+        d2 = np.empty((nq, k), np.float32)
+        ref().gloc_ref_knn_query_batch(self._h, _ptr(q, _f32p), nq, k, _ptr(idx, _u64p),
+                                       _ptr(d2, _f32p), nthreads)
+        return idx, d2
+
+    def close(self):
+        if self._h:
+            ref().gloc_ref_knn_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ----------------------------------------------------------------- stage 2
+
+def value_to_cost(v: int) -> np.float32:
+    return np.float32(lib().gloc_oracle_value_to_cost(int(v)))
+
+
+def cost_to_value(c: float) -> int:
+    return int(lib().gloc_oracle_cost_to_value(float(np.float32(c))))
+
+
+def cell_value(p: float) -> int:
+    return int(lib().gloc_oracle_cell_value(float(np.float32(p))))
+
+
+def level1_from_cells(cells: np.ndarray) -> np.ndarray:
+    """cells: uint16 [ny, nx] (flat index nx*y + x).  Returns uint8 [ny, nx]."""
+    cells = np.ascontiguousarray(cells, np.uint16)
+    ny, nx = cells.shape
+    out = np.empty((ny, nx), np.uint8)
+    lib().gloc_oracle_level1_from_cells(cells.ctypes.data, nx, ny, out.ctypes.data)
+    return out
+
+
+def precomp_from_cells(cells: np.ndarray, width: int) -> np.ndarray:
+    cells = np.ascontiguousarray(cells, np.uint16)
+    ny, nx = cells.shape
+    out = np.empty((ny + width - 1, nx + width - 1), np.uint8)
+    lib().gloc_oracle_precomp_from_cells(cells.ctypes.data, nx, ny, width, out.ctypes.data)
+    return out
+
+
+def precomp_from_level1(level1: np.ndarray, width: int) -> np.ndarray:
+    level1 = np.ascontiguousarray(level1, np.uint8)
+    ny, nx = level1.shape
+    out = np.empty((ny + width - 1, nx + width - 1), np.uint8)
+    lib().gloc_oracle_precomp_from_level1(level1.ctypes.data, nx, ny, width, out.ctypes.data)
+    return out
+
+
+def search_params(lin_window: float, ang_window: float, pts: np.ndarray, resolution: float):
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    nl, na, st = C.c_int(), C.c_int(), C.c_double()
+    lib().gloc_oracle_search_params(lin_window, ang_window, _ptr(pts, _f32p), pts.shape[0],
+                                    resolution, C.byref(nl), C.byref(na), C.byref(st))
+    return nl.value, na.value, st.value
+
+
+def grid_to_points(cells: np.ndarray, resolution: float, ox: float, oy: float) -> np.ndarray:
+    cells = np.ascontiguousarray(cells, np.uint16)
+    ny, nx = cells.shape
+    n = lib().gloc_oracle_grid_to_points(cells.ctypes.data, nx, ny, resolution, ox, oy, None, 0)
+    pts = np.zeros((n, 3), np.float32)
+    lib().gloc_oracle_grid_to_points(cells.ctypes.data, nx, ny, resolution, ox, oy,
+                                     pts.ctypes.data, n)
+    return pts
+
+
+def discretize(pts, init, n_ang, ang_step, resolution, max_x, max_y) -> np.ndarray:
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    S = 2 * n_ang + 1
+    out = np.empty((S, pts.shape[0], 2), np.int32)
+    lib().gloc_oracle_discretize(_ptr(pts, _f32p), pts.shape[0], init[0], init[1], init[2],
+                                 n_ang, ang_step, resolution, max_x, max_y, out.ctypes.data)
+    return out
+
+
+def csm_match(level1, resolution, max_x, max_y, depth, pts, init, n_lin, n_ang, ang_step,
+              min_score, mode=0) -> MatchResult:
+    level1 = np.ascontiguousarray(level1, np.uint8)
+    ny, nx = level1.shape
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    r = MatchResult()
+    lib().gloc_oracle_csm_match(level1.ctypes.data, nx, ny, resolution, max_x, max_y, depth,
+                                _ptr(pts, _f32p), pts.shape[0], init[0], init[1], init[2],
+                                n_lin, n_ang, ang_step, min_score, mode, C.byref(r))
+    return r
+
+
+def csm_match_full_submap(level1, resolution, max_x, max_y, depth, pts, min_score,
+                          mode=0) -> MatchResult:
+    level1 = np.ascontiguousarray(level1, np.uint8)
+    ny, nx = level1.shape
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    r = MatchResult()
+    lib().gloc_oracle_csm_match_full_submap(level1.ctypes.data, nx, ny, resolution, max_x,
+                                            max_y, depth, _ptr(pts, _f32p), pts.shape[0],
+                                            min_score, mode, C.byref(r))
+    return r
+
+
+def csm_match_batch(grids, resolution, max_x, max_y, depth, pts_list, inits, n_lin, n_ang,
+                    ang_step, min_score, mode=0, nthreads=1):
+    """grids: list of uint8 [ny,nx] (same shape); pts_list: list of [P_i,3] float32."""
+    grids = [np.ascontiguousarray(g, np.uint8) for g in grids]
+    pts_list = [np.ascontiguousarray(p, np.float32).reshape(-1, 3) for p in pts_list]
+    n = len(grids)
+    ny, nx = grids[0].shape
+    gp = (C.c_void_p * n)(*[g.ctypes.data for g in grids])
+    pp = (C.c_void_p * n)(*[p.ctypes.data for p in pts_list])
+    npts = (C.c_int * n)(*[p.shape[0] for p in pts_list])
+    init = np.ascontiguousarray(inits, np.float64).reshape(n, 3)
+    out = (MatchResult * n)()
+    lib().gloc_oracle_csm_match_batch_mt(gp, nx, ny, resolution, max_x, max_y, depth, pp, npts,
+                                         init.ctypes.data_as(C.POINTER(C.c_double)), n, n_lin,
+                                         n_ang, ang_step, min_score, mode, nthreads, out)
+    return list(out)

@@ -1,0 +1,56 @@
+"""Mint the golden fixtures under tests/golden/.  Run from the repo root in the build
+container (needs /root/reference for the nanoflann build under oracle/_ref):
+
+    python tests/golden/make_golden.py
+
+knn_*.npz   outputs of the REFERENCE ITSELF (its nanoflann + adaptor compiled unmodified
+            from /root/reference/registration, oracle/nanoflann_ref.cpp) on seeded inputs;
+            inputs are stored too so the fixtures do not depend on numpy's RNG stream.
+csm_*.npz   outputs of the stage-2 restatement (oracle/csm_oracle.c); the reference's
+            registration/2d cannot be built here, so these pin the restatement against
+            regressions only (parity unpinned, see oracle/gloc_oracle.h).
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from gloc3d_b200 import synth  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def knn_case(name, n, dim, nq, k, seed, dup_run=0, sigma=None):
+    db = synth.make_descriptors(n, dim, seed=seed, dup_run=dup_run)
+    q = synth.make_queries(db, nq, seed=seed + 1, sigma=sigma)
+    tree = po.RefTree(db, 10)
+    idx, d2 = tree.query(q, k)
+    np.savez_compressed(os.path.join(OUT, name), db=db, q=q, k=k, idx=idx, d2=d2)
+    print(name, db.shape, q.shape, k)
+
+
+def csm_case(name, nx, ny, seed, yaw, dx, dy, n_lin, n_ang, step, depth, min_score, graded=False):
+    res = 0.2
+    g = synth.make_bev_grid(nx, ny, seed=seed, n_segments=14, n_blobs=8, graded=graded)
+    mx, my = synth.centered_limits(nx, ny, res)
+    scan = synth.planted_scan(g, res, mx, my, yaw, dx, dy, dropout=0.2, seed=seed + 1)
+    r = po.csm_match(g, res, mx, my, depth, scan, (0.1, -0.05, 0.02), n_lin, n_ang, step,
+                     min_score, 0)
+    cells = po.discretize(scan, (0.1, -0.05, 0.02), n_ang, step, res, mx, my)
+    levels = {f"level{w}": po.precomp_from_level1(g, w) for w in (2, 4, 16)}
+    np.savez_compressed(os.path.join(OUT, name), grid=g, scan=scan, res=res, max_x=mx, max_y=my,
+                        init=np.array([0.1, -0.05, 0.02]), n_lin=n_lin, n_ang=n_ang, step=step,
+                        depth=depth, min_score=min_score, result=np.array(r.as_tuple(), np.float64),
+                        cells_first=cells[0], cells_last=cells[-1], **levels)
+    print(name, r.as_tuple())
+
+
+if __name__ == "__main__":
+    knn_case("knn_d512_k20.npz", 160, 512, 6, 20, 11)                      # reference k (loop_detector.h:98)
+    knn_case("knn_d512_k25_dups.npz", 160, 512, 6, 25, 21, dup_run=8, sigma=0.002)
+    knn_case("knn_d30_tail.npz", 200, 30, 5, 7, 31)                        # dim % 4 != 0 tail path
+    csm_case("csm_binary.npz", 150, 110, 41, 0.35, 1.2, -0.8, 14, 24, np.pi / 90, 4, 0.3)
+    csm_case("csm_graded.npz", 120, 140, 51, -0.6, -1.0, 0.6, 10, 20, np.pi / 60, 3, 0.2, graded=True)

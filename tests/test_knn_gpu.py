@@ -1,0 +1,197 @@
+"""GPU parity tests of stage 1: the CUDA path, called through the C ABI, against the CPU
+oracle (bit-exact indices and distances) on seeded inputs, the golden vectors minted from
+the reference's nanoflann, and size-independent properties at BASELINE.json's full size."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import gloc3d_b200 as g
+from gloc3d_b200 import synth
+from helpers import assert_knn_equal, canonical_ties
+
+pytestmark = pytest.mark.gpu
+
+MODES = [g.KNN_EXACT_SCAN, g.KNN_AUTO]
+U64MAX = np.iinfo(np.uint64).max
+
+
+def run(db, q, k, mode, **kw):
+    ix = g.KnnIndex(db.shape[1], 0)
+    ix.set_db(db)
+    ix.set_mode(mode)
+    for name, v in kw.items():
+        getattr(ix, name)(v)
+    out = ix.query(q, k)
+    ix.close()
+    return out
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("k", [20, 25])
+def test_kitti00_shape(oracle, mode, k):
+    # config 0: 4,541-frame database; reference k = 20 (loop_detector.h:98), BASELINE k = 25
+    db = synth.make_descriptors(4541, seed=1234)
+    q = synth.make_queries(db, 300, seed=5678)
+    idx, d2 = run(db, q, k, mode)
+    assert_knn_equal(idx, d2, *oracle.knn(db, q, k, nthreads=8))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_near_duplicate_runs(oracle, mode):
+    # set B: perturbed copies against runs of near-duplicate frames (near-ties everywhere)
+    db = synth.make_descriptors(6000, seed=1234, dup_run=16)
+    for sigma in (0.002, 0.01):
+        q = synth.make_queries(db, 200, seed=5678, sigma=sigma)
+        idx, d2 = run(db, q, 25, mode)
+        assert_knn_equal(idx, d2, *oracle.knn(db, q, 25, nthreads=8))
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_exact_duplicates_tie_break(oracle, mode):
+    # identical rows -> bit-equal distances; order must be (d2, idx) ascending
+    base = synth.make_descriptors(300, seed=9)
+    db = np.concatenate([base, base[:100], base[50:80]]).astype(np.float32)
+    q = np.concatenate([base[:40] + np.float32(1e-3), base[60:70]]).astype(np.float32)
+    idx, d2 = run(db, q, 25, mode)
+    assert_knn_equal(idx, d2, *oracle.knn(db, q, 25))
+    # all rows identical: every distance ties
+    db2 = np.repeat(base[:1], 200, axis=0)
+    idx, d2 = run(db2, base[:3], 25, mode)
+    assert (idx == np.arange(25, dtype=np.uint64)[None, :]).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (1, 512, 1, 1), (25, 512, 3, 25), (10, 512, 2, 25),      # fewer rows than k
+    (257, 512, 1, 20), (1000, 512, 64, 25), (1000, 512, 65, 25),
+    (513, 128, 17, 5), (700, 30, 9, 7), (300, 3, 5, 4), (300, 1, 5, 4), (2000, 64, 130, 64),
+    (3000, 512, 10, 128), (129, 516, 4, 33),
+])
+def test_shapes_and_edges(oracle, mode, n, dim, nq, k):
+    db = synth.make_descriptors(n, dim, seed=n + dim)
+    q = synth.make_queries(db, nq, seed=nq + k)
+    idx, d2 = run(db, q, k, mode)
+    ridx, rd2 = oracle.knn(db, q, k)
+    assert_knn_equal(idx, d2, ridx, rd2)
+    if n < k:
+        assert (idx[:, n:] == U64MAX).all() and (d2[:, n:] == np.finfo(np.float32).max).all()
+
+
+def test_unnormalised_and_scaled_descriptors(oracle):
+    # netvlad_fc descriptors are not L2-normalised: mixed norms, offsets
+    rng = np.random.default_rng(3)
+    db = synth.make_descriptors(5000, seed=5) * rng.uniform(0.2, 5.0, (5000, 1)).astype(np.float32)
+    db += np.float32(0.05)
+    q = synth.make_queries(db, 128, seed=6) * np.float32(2.5)
+    for mode in MODES:
+        idx, d2 = run(db, q, 25, mode)
+        assert_knn_equal(idx, d2, *oracle.knn(db, q, 25, nthreads=8))
+
+
+def test_golden_vectors_from_reference(golden_dir):
+    for f in sorted(glob.glob(os.path.join(golden_dir, "knn_*.npz"))):
+        z = np.load(f)
+        for mode in MODES:
+            idx, d2 = run(z["db"], z["q"], int(z["k"]), mode)
+            assert np.array_equal(d2.view(np.uint32), z["d2"].view(np.uint32)), f
+            assert np.array_equal(idx, canonical_ties(z["idx"], z["d2"])), f
+
+
+def test_against_compiled_reference(oracle):
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libnanoflann_ref.so not shipped")
+    db = synth.make_descriptors(4541, seed=1234)
+    q = synth.make_queries(db, 100, seed=5678)
+    tree = oracle.RefTree(db, 10)
+    ridx, rd2 = tree.query(q, 20, nthreads=8)
+    idx, d2 = run(db, q, 20, g.KNN_AUTO)
+    assert np.array_equal(d2.view(np.uint32), rd2.view(np.uint32))
+    assert np.array_equal(idx, canonical_ties(ridx, rd2))
+
+
+def test_interface_mirror_and_slam_mode(oracle):
+    db = synth.make_descriptors(400, seed=1)
+    tree = g.InvKeyTree(512, db, 10)                       # loop_detector.cpp:36
+    ret = np.zeros(20, np.uint64)
+    dist = np.zeros(20, np.float32)
+    tree.query(db[7] + np.float32(1e-4), 20, ret, dist)   # loop_detector.cpp:45
+    ridx, rd2 = oracle.knn(db, (db[7] + np.float32(1e-4))[None], 20)
+    assert np.array_equal(ret, ridx[0]) and np.array_equal(dist, rd2[0]) and ret[0] == 7
+    # SLAM mode: append keyframes, search all but the 30 most recent (loop_detector.cpp:66-72)
+    ix = g.KnnIndex(512, 0)
+    for s in range(0, 400, 50):
+        ix.append(db[s:s + 50])
+    assert len(ix) == 400
+    ix.set_search_limit(400 - 30)
+    idx, d2 = ix.query(db[399:400], 20)
+    ridx, rd2 = oracle.knn(db[:370], db[399:400], 20)
+    assert_knn_equal(idx, d2, ridx, rd2)
+    ix.set_search_limit(None)
+    ix.set_index_offset(1_000_000)
+    idx, d2 = ix.query(db[399:400], 5)
+    assert idx[0, 0] == 1_000_399 and d2[0, 0] == 0.0
+    # error behaviour
+    ix.set_db(np.zeros((0, 512), np.float32))
+    with pytest.raises(g.GlocError) as e:
+        ix.query(db[:1], 5)
+    assert e.value.code == g._lib.GLOC_ERR_NOT_BUILT
+    with pytest.raises(g.GlocError):
+        tree.index.query(db[:1], 0)
+    with pytest.raises(ValueError):
+        tree.index.query(np.zeros((1, 100), np.float32), 5)
+    ix.close()
+
+
+def test_device_buffers_and_shard_merge(oracle):
+    import torch
+
+    db = synth.make_descriptors(9000, seed=11, dup_run=4)
+    q = synth.make_queries(db, 333, seed=12, sigma=0.003)
+    full_idx, full_d2 = oracle.knn(db, q, 25, nthreads=8)
+    tq = torch.from_numpy(q).cuda()
+    for shards in (1, 2, 4, 8):
+        b = [9000 * i // shards for i in range(shards + 1)]
+        lists_i, lists_d = [], []
+        for s in range(shards):
+            ix = g.KnnIndex(512, 0)
+            ix.set_db_device(torch.from_numpy(db[b[s]:b[s + 1]]).cuda())
+            ix.set_index_offset(b[s])
+            i, d = ix.query_device(tq, 25)
+            lists_i.append(i)
+            lists_d.append(d)
+            torch.cuda.synchronize()
+            ix.close()
+        mi, md = g.merge_topk_device(torch.stack(lists_i).contiguous(), torch.stack(lists_d).contiguous())
+        torch.cuda.synchronize()
+        assert_knn_equal(mi.cpu().numpy().view(np.uint64), md.cpu().numpy(), full_idx, full_d2)
+
+
+def test_full_size_properties(oracle):
+    # config 1 (BASELINE.json): 100k descriptors, 10k queries, top-25.  The oracle checks a
+    # 48-query sample bit-exactly; the rest is covered by size-independent properties.
+    n, nq, k = 100_000, 10_000, 25
+    db = synth.make_descriptors(n, seed=1234, dup_run=8)
+    q = synth.make_queries(db, nq, seed=5678, sigma=0.01)
+    src = np.random.default_rng(5678).integers(0, n, nq)        # rows the queries were cut from
+    ix = g.KnnIndex(512, 0)
+    ix.set_db(db)
+    idx, d2 = ix.query(q, k)
+    st = ix.stats()
+    ix.close()
+    assert st.queries == nq and st.kernel_launches > 0
+    assert (np.diff(d2.astype(np.float64), axis=1) >= 0).all()             # ascending
+    same = np.diff(d2.view(np.uint32).astype(np.int64), axis=1) == 0
+    assert (np.diff(idx.astype(np.int64), axis=1)[same] > 0).all()          # ties by index
+    assert (idx < n).all() and all(len(set(r)) == k for r in idx[::97])     # distinct rows
+    # returned distances are the reference-order distances of the returned rows
+    for r in range(0, nq, 501):
+        for c in (0, 7, 24):
+            assert oracle.l2(q[r], db[idx[r, c]]).view(np.uint32) == d2[r, c].view(np.uint32)
+    # a query perturbed from db[j] (sigma 0.01 -> d2 ~ 0.05) finds j among its neighbours
+    hit = (idx == src[:, None].astype(np.uint64)).any(axis=1)
+    assert hit.mean() > 0.999
+    sample = np.arange(0, nq, nq // 48)[:48]
+    ridx, rd2 = oracle.knn(db, q[sample], k, nthreads=8)
+    assert_knn_equal(idx[sample], d2[sample], ridx, rd2)
