@@ -1,0 +1,511 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the global-localization query path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload retrieval|verify] [--impl reference]
+
+Metric (BASELINE.json): global-localization queries/s.  One "step" = one pass of the hot
+path over one batch of synthetic input.
+
+Workload "retrieval" (default; BASELINE.json configs[1], the configuration the metric is
+quoted on that fits one GPU): 100k-descriptor database (512-d float32), 10k-query batch per
+GPU, top-25 exact L2.  N > 1: the database is row-sharded over the N ranks (north_star), every
+rank answers the whole batch of N x 10k queries against its shard, ONE NCCL all-gather of the
+local top-k lists, K4 merge on every rank.  Per-GPU work (queries x rows) is fixed as N grows:
+"scaling": "weak"; value = all queries answered by the job / max-over-ranks device time.
+
+Workload "verify" (configs[2]): 25 candidate grids per query, 361 yaw bins, +-100 cells at
+0.2 m, depth 5, 800x800 BEV grids; pairs are split across ranks, no collective.
+
+`value`  : inputs resident in HBM, CUDA-event timed.  `e2e`: the same metric through the
+C ABI / public API with HOST (pinned) buffers, H2D + D2H inside the timed region.
+`--impl reference`: the reference's own CPU implementation (its nanoflann compiled from
+/root/reference into oracle/_ref, or the oracle port for verify) on all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+DIM, K_NN = 512, 25
+DB_ROWS, Q_PER_GPU = 100_000, 10_000
+METRIC, UNIT = "global-loc queries/s", "queries/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_retrieval_inputs(world: int):
+    from gloc3d_b200 import synth
+
+    db = synth.make_descriptors(DB_ROWS, DIM, seed=1234, dup_run=8)
+    nq = Q_PER_GPU * world
+    qa = synth.make_queries(db, nq // 2, seed=5678)                    # set A: independent
+    qb = synth.make_queries(db, nq - nq // 2, seed=5679, sigma=0.01)   # set B: perturbed copies
+    return db, np.ascontiguousarray(np.concatenate([qa, qb]))
+
+
+# ------------------------------------------------------------------ retrieval
+def run_retrieval(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import gloc3d_b200 as g
+    from gloc3d_b200.distributed import ShardedRetrieval, shard_bounds
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    db, q = make_retrieval_inputs(world)
+    nq = q.shape[0]
+    b = shard_bounds(DB_ROWS, world)
+    lo, hi = b[rank], b[rank + 1]
+    mode = {"auto": g.KNN_AUTO, "exact": g.KNN_EXACT_SCAN, "shortlist": g.KNN_SHORTLIST}[args.mode]
+    sr = ShardedRetrieval(rank, world).load_shard(torch.from_numpy(db[lo:hi]).to(dev), lo,
+                                                  local_rank, mode)
+    q_dev = torch.from_numpy(q).to(dev)
+    q_pin = torch.from_numpy(q).pin_memory()
+    oi_pin = torch.empty((nq, K_NN), dtype=torch.int64).pin_memory()
+    od_pin = torch.empty((nq, K_NN), dtype=torch.float32).pin_memory()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing (value) ------------------------------------
+    for _ in range(args.warmup):
+        out = sr.query(q_dev, K_NN)
+    barrier()
+    sr.index.set_profiling(True)
+    launches0 = sr.index.stats().kernel_launches
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = sr.query(q_dev, K_NN)
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    dom_ms, dom_n = sr.index.profile()
+    sr.index.set_profiling(False)
+    st = sr.index.stats()
+    own_launches = (st.kernel_launches - launches0) + (args.steps if world > 1 else 0)  # + K4 merge
+    launches = int(sum_over_ranks(float(own_launches)))
+    ms_per_step = ms_total / args.steps
+    value = nq / (ms_per_step * 1e-3)
+
+    # ---- end to end with host buffers (e2e) --------------------------------
+    def e2e_step():
+        if world == 1:
+            sr.index.query_ptr(q_pin.data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
+        else:
+            sr.query_host(q_pin, K_NN, oi_pin, od_pin)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
+    barrier()
+
+    # ---- sanity: the timed path returns the oracle's answer on a sample -----
+    idx_np = out[0].cpu().numpy().view(np.uint64)
+    d2_np = out[1].cpu().numpy()
+    assert np.array_equal(idx_np, oi_pin.numpy().view(np.uint64)) and np.array_equal(d2_np, od_pin.numpy())
+
+    if rank != 0:
+        return None
+    last_mode = int(st.last_mode)
+    shard_rows = hi - lo
+    flops = 2.0 * nq * shard_rows * DIM                       # per launch of the dominant kernel
+    alg_bytes = shard_rows * DIM * 4 + nq * DIM * 4 + nq * K_NN * 12
+    avg_ms = dom_ms / max(dom_n, 1)
+    peak_tf = peaks["bf16_tflops"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get({1: "exact_scan", 2: "shortlist_gemm"}.get(last_mode, ""), None)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if last_mode == g.KNN_EXACT_SCAN else "bf16 shortlist + f32 exact re-rank",
+        "data": "synthetic",
+        "config": {"workload": "configs[1]: 100k x 512-d f32 descriptor DB, 10k-query batch per GPU, "
+                               "top-25 exact L2 retrieval (bit-exact vs nanoflann)",
+                   "db_rows": DB_ROWS, "queries_per_step": nq, "k": K_NN, "dim": DIM,
+                   "sharding": f"rows/{world} + all-gather top-k + merge" if world > 1 else "none",
+                   "strategy": {1: "exact_scan", 2: "tensor_shortlist"}.get(last_mode, str(last_mode)),
+                   "l2": "inputs larger than L2 (DB shard + query batch > 126 MB per rank); no flush"},
+        "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(q.nbytes) * world,
+                "d2h_bytes_per_step": int(nq * K_NN * 12) * world},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": {1: "knn_exact_scan_kernel", 2: "knn_shortlist_gemm_kernel"}.get(last_mode),
+                     "achieved": flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else None,
+                     "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": (flops / (avg_ms * 1e-3) / 1e12) / peak_tf if avg_ms > 0 else None,
+                     "traffic": traffic, "peak_source": peaks["source"] + " (burst bf16)",
+                     "kernel_ms": avg_ms, "kernel_launches_timed": dom_n,
+                     "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
+                     "hbm_frac_of_algorithmic_bytes": (alg_bytes / (avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if avg_ms > 0 else None},
+        "stats": {"fallback_queries": int(st.fallback_queries), "shortlist_rows_per_query":
+                  (st.shortlist_rows / max(st.shortlist_queries, 1))},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_retrieval(db, q, budget_s=args.cpu_budget)
+    sr.close()
+    return line
+
+
+def cpu_baseline_retrieval(db, q, budget_s: float):
+    """The reference's nanoflann (oracle/_ref) on all host threads, bounded sample."""
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    if po.have_ref():
+        t0 = time.perf_counter()
+        tree = po.RefTree(db, 10)
+        build_s = time.perf_counter() - t0
+        run = lambda qs: tree.query(qs, K_NN, nthreads=cores)  # noqa: E731
+        kind = "reference"
+    else:
+        build_s = 0.0
+        run = lambda qs: po.knn(db, qs, K_NN, nthreads=cores)  # noqa: E731
+        kind = "port"
+    n0 = min(q.shape[0], cores)
+    t0 = time.perf_counter()
+    run(q[:n0])
+    per_q = (time.perf_counter() - t0) / n0
+    n = int(max(n0, min(q.shape[0], budget_s / max(per_q, 1e-9))))
+    n = max(cores, n // cores * cores)
+    t0 = time.perf_counter()
+    run(q[:n])
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n} of the step's queries against the full 100k DB, nanoflann KD-tree "
+                      f"(leaf 10) built once in {build_s:.2f} s (not counted), {cores} threads"}
+
+
+def run_reference_retrieval(args):
+    from oracle import pyoracle as po
+
+    db, q = make_retrieval_inputs(1)
+    cores = os.cpu_count() or 1
+    if po.have_ref():
+        tree = po.RefTree(db, 10)
+        run = lambda qs: tree.query(qs, K_NN, nthreads=cores)  # noqa: E731
+        kind = "reference"
+    else:
+        run = lambda qs: po.knn(db, qs, K_NN, nthreads=cores)  # noqa: E731
+        kind = "port"
+    n0 = min(q.shape[0], cores)
+    t0 = time.perf_counter()
+    run(q[:n0])
+    per_q = (time.perf_counter() - t0) / n0
+    total_steps = args.steps + args.warmup
+    n = int(min(q.shape[0], max(cores, (args.cpu_budget * 4 / total_steps) / max(per_q, 1e-9))))
+    n = max(cores, n // cores * cores)
+    for _ in range(args.warmup):
+        run(q[:n])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run(q[:n])
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    v = n / (ms * 1e-3)
+    sample = (f"{n} queries/step of the 10k batch against the full 100k DB; nanoflann KD-tree (leaf 10), "
+              f"{cores} host threads")
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "configs[1]: 100k x 512-d f32 descriptor DB, 10k-query batch per GPU, "
+                                   "top-25 exact L2 retrieval (bit-exact vs nanoflann)",
+                       "db_rows": DB_ROWS, "k": K_NN, "dim": DIM},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+# --------------------------------------------------------------------- verify
+VER = dict(nx=800, ny=800, res=0.2, n_lin=100, n_ang=180, step=2 * np.pi / 360, depth=5,
+           min_score=0.3, cands=25)
+
+
+def make_verify_inputs(n_queries: int, n_maps: int = 32):
+    from gloc3d_b200 import synth
+
+    mx, my = synth.centered_limits(VER["nx"], VER["ny"], VER["res"])
+    maps = [synth.make_bev_grid(VER["nx"], VER["ny"], seed=2222 + i) for i in range(n_maps)]
+    rng = np.random.default_rng(3333)
+    scans, pairs = [], []
+    for qi in range(n_queries):
+        m = qi % n_maps
+        yaw, dx, dy = rng.uniform(-np.pi, np.pi), rng.uniform(-18, 18), rng.uniform(-18, 18)
+        scans.append(synth.planted_scan(maps[m], VER["res"], mx, my, yaw, dx, dy, dropout=0.2,
+                                        jitter_cells=1.0, seed=3333 + qi))
+        for c in range(VER["cands"]):          # candidate 0 is the planted map, 24 are wrong places
+            pairs.append(((m + c) % n_maps, qi))
+    return maps, mx, my, scans, pairs
+
+
+def run_verify(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import gloc3d_b200 as g
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    nq = args.verify_queries * world
+    maps, mx, my, scans, pairs = make_verify_inputs(nq)
+    mine = pairs[rank::world]                      # pairs are independent: no collective
+    st = g.CsmStore(local_rank)
+    gids = [st.add_grid_u8(m, VER["res"], mx, my) for m in maps]
+    gi = [gids[p[0]] for p in mine]
+    si = [p[1] for p in mine]
+    inits = [(0.0, 0.0, 0.0)] * len(mine)
+
+    def step():
+        return st.match_batch(scans, gi, si, inits, VER["n_lin"], VER["n_ang"], VER["step"],
+                              VER["depth"], VER["min_score"])
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        out = step()
+    st.set_profiling(True)
+    l0 = st.stats().kernel_launches
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = step()
+    dt = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    dom_ms, dom_n = st.profile()
+    launches = st.stats().kernel_launches - l0
+    if rank != 0:
+        return None
+    ms = dt / args.steps
+    found = sum(r.found for r in out)
+    P = float(np.mean([s.shape[0] for s in scans]))
+    side = (2 * VER["n_lin"]) // (1 << (VER["depth"] - 1)) + 1
+    lookups = (2 * VER["n_ang"] + 1) * side * side * P * len(mine)      # coarse level, per launch
+    peaks = load_peaks()
+    hbm_bytes = len(set(gi)) * VER["nx"] * VER["ny"] + sum(s.shape[0] for s in scans) * 12 + len(mine) * 24
+    avg_ms = dom_ms / max(dom_n, 1)
+    line = {
+        "metric": METRIC, "value": nq / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8 sums -> f32 score", "data": "synthetic",
+        "config": {"workload": "configs[2]: verification sweep, 25 candidate grids/query, 361 yaw bins, "
+                               "+-100 cells @0.2 m, depth 5, 800x800 BEV grids",
+                   "queries_per_step": nq, "pairs_per_step": len(pairs),
+                   "timing": "host wall clock around the synchronous C-ABI call (H2D of scans, D2H of "
+                             "results inside); value == e2e for this workload",
+                   "l2": "grid stacks (3.2 MB each, 32 maps) are L2-resident by design"},
+        "e2e": {"value": nq / (ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(s.nbytes for s in scans)) * world,
+                "d2h_bytes_per_step": len(pairs) * 8},
+        "gpu_launches": int(launches) * world, "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "csm_coarse_kernel",
+                     "achieved": hbm_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": (hbm_bytes / (avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if avg_ms else None,
+                     "traffic": None, "kernel_ms": avg_ms,
+                     "note": "compulsory HBM bytes are tiny; the binding limit is the L1/LSU byte-gather "
+                             "rate", "gather_lookups_per_s": lookups / (avg_ms * 1e-3) if avg_ms else None},
+        "stats": {"found": int(found), "pairs": len(mine)},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_verify(maps, mx, my, scans, pairs, args.cpu_budget)
+    st.close()
+    return line
+
+
+def cpu_baseline_verify(maps, mx, my, scans, pairs, budget_s):
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    n = min(len(pairs), max(cores, int(budget_s / 0.7) * cores))
+    sel = pairs[:n]
+    t0 = time.perf_counter()
+    po.csm_match_batch([maps[p[0]] for p in sel], VER["res"], mx, my, VER["depth"],
+                       [scans[p[1]] for p in sel], [(0, 0, 0)] * n, VER["n_lin"], VER["n_ang"],
+                       VER["step"], VER["min_score"], 0, cores)
+    dt = time.perf_counter() - t0
+    return {"value": (n / VER["cands"]) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} (grid, scan) pairs = {n / VER['cands']:.1f} queries, branch-and-bound restatement "
+                      f"of registration/2d (oracle/csm_oracle.c), {cores} threads"}
+
+
+def run_reference_verify(args):
+    cores = os.cpu_count() or 1
+    maps, mx, my, scans, pairs = make_verify_inputs(max(1, cores // VER["cands"] + 1))
+    from oracle import pyoracle as po
+
+    n = min(len(pairs), cores)
+    sel = pairs[:n]
+
+    def run():
+        po.csm_match_batch([maps[p[0]] for p in sel], VER["res"], mx, my, VER["depth"],
+                           [scans[p[1]] for p in sel], [(0, 0, 0)] * n, VER["n_lin"], VER["n_ang"],
+                           VER["step"], VER["min_score"], 0, cores)
+    for _ in range(args.warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        run()
+    ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    v = (n / VER["cands"]) / (ms * 1e-3)
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8 sums -> f32 score", "data": "synthetic",
+            "config": {"workload": "configs[2]: verification sweep, 25 candidate grids/query, 361 yaw bins, "
+                                   "+-100 cells @0.2 m, depth 5, 800x800 BEV grids"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{n} (grid, scan) pairs per step, {cores} threads"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "verify"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "exact", "shortlist"])
+    ap.add_argument("--verify-queries", type=int, default=8, help="queries per GPU per step (verify)")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        line = run_reference_retrieval(args) if args.workload == "retrieval" else run_reference_verify(args)
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the product has no CPU path", file=sys.stderr)
+        return 2
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        fn = run_retrieval if args.workload == "retrieval" else run_verify
+        line = fn(args, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
