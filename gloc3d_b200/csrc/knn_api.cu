@@ -296,6 +296,14 @@ int gloc_knn_set_mode(gloc_knn_index* ix, int mode) {
 int gloc_knn_get_stats(const gloc_knn_index* ix, gloc_knn_stats* stats) {
   if (!ix || !stats) return fail(GLOC_ERR_INVALID, "gloc_knn_get_stats: null argument");
   *stats = ix->stats;
+  if (ix->sl) {  // device-side counters of the shortlist path (synchronises the device)
+    DeviceGuard g(ix->device);
+    uint64_t rows = 0, ovf = 0;
+    int rc = shortlist_counters(ix->sl, &rows, &ovf);
+    if (rc != GLOC_OK) return rc;
+    stats->shortlist_rows = rows;
+    stats->fallback_queries = ovf;
+  }
   return GLOC_OK;
 }
 
@@ -353,13 +361,6 @@ int gloc_knn_query_device(gloc_knn_index* ix, const float* d_q, size_t nq, size_
     if (rc != GLOC_OK) return rc;
     ix->stats.kernel_launches += launches;
     ix->stats.shortlist_queries += nq;
-    ix->stats.shortlist_rows += rows;
-    if (fallback == UINT64_MAX) {
-      // overflow flags are resolved on the device: overflowed queries are re-run by
-      // the exact scan inside shortlist_query (see knn_shortlist.cu)
-      fallback = 0;
-    }
-    ix->stats.fallback_queries += fallback;
   } else {
     rc = exact_query_device(ix, d_q, nq, k, d_idx, d_d2, n_search, stream);
     if (rc != GLOC_OK) return rc;

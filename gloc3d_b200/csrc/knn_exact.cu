@@ -39,7 +39,8 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int ROWS, int NT>
 __device__ __forceinline__ void stage_chunk(float* dst, const float* __restrict__ src,
                                             long long r0, long long r_end, int dim, int c0,
-                                            bool vec_ok, int tid) {
+                                            bool vec_ok, int tid,
+                                            const int* __restrict__ rowmap = nullptr) {
   constexpr int SLOTS = ROWS * (DK / 4);
 #pragma unroll
   for (int s = tid; s < SLOTS; s += NT) {
@@ -48,7 +49,7 @@ __device__ __forceinline__ void stage_chunk(float* dst, const float* __restrict_
     float* d = dst + row * DKP + (s % (DK / 4)) * 4;
     const long long gr = r0 + row;
     if (gr < r_end && col < dim) {
-      const float* g = src + (size_t)gr * dim + col;
+      const float* g = src + (size_t)(rowmap ? (long long)rowmap[gr] : gr) * dim + col;
       if (vec_ok && col + 4 <= dim) {
         cp_async16(d, g);
       } else {
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__(ScanCfg<BQ, BN, TQ, TN, KCAP>::NT, 1)
 knn_exact_scan_kernel(const float* __restrict__ db, long long n_rows, int dim,
                       const float* __restrict__ q, int nq, int k, int n_qtiles,
                       long long rows_per_range, int n_ranges,
-                      uint64_t* __restrict__ partial) {
+                      uint64_t* __restrict__ partial, const int* __restrict__ qmap,
+                      const int* __restrict__ nq_dev) {
   using Cfg = ScanCfg<BQ, BN, TQ, TN, KCAP>;
   constexpr int NT = Cfg::NT, TXN = Cfg::TXN, TYN = Cfg::TYN, QCAP = Cfg::QCAP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -135,6 +137,10 @@ knn_exact_scan_kernel(const float* __restrict__ db, long long n_rows, int dim,
   const int tx = tid % TXN, ty = tid / TXN;
   const int qt = blockIdx.x % n_qtiles, rg = blockIdx.x / n_qtiles;
   const long long q0 = (long long)qt * BQ;
+  // Fallback launches size the grid for the worst case and pass the real query count (and
+  // the compacted query ids) in device memory: surplus CTAs leave before any barrier.
+  if (nq_dev != nullptr) nq = *nq_dev;
+  if (q0 >= nq) return;
   const long long row_begin = (long long)rg * rows_per_range;
   const long long row_end = min(n_rows, row_begin + rows_per_range);
   const bool vec_ok = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0) &&
@@ -153,13 +159,14 @@ knn_exact_scan_kernel(const float* __restrict__ db, long long n_rows, int dim,
 #pragma unroll
       for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-    stage_chunk<BQ, NT>(Qs, q, q0, nq, dim, 0, vec_ok, tid);
+    stage_chunk<BQ, NT>(Qs, q, q0, nq, dim, 0, vec_ok, tid, qmap);
     stage_chunk<BN, NT>(Xs, db, x0, row_end, dim, 0, vec_ok, tid);
     cp_async_commit();
     for (int c = 0; c < n_chunks; ++c) {
       const int st = c & 1;
       if (c + 1 < n_chunks) {
-        stage_chunk<BQ, NT>(Qs + (st ^ 1) * BQ * DKP, q, q0, nq, dim, (c + 1) * DK, vec_ok, tid);
+        stage_chunk<BQ, NT>(Qs + (st ^ 1) * BQ * DKP, q, q0, nq, dim, (c + 1) * DK, vec_ok, tid,
+                            qmap);
         stage_chunk<BN, NT>(Xs + (st ^ 1) * BN * DKP, db, x0, row_end, dim, (c + 1) * DK, vec_ok,
                             tid);
         cp_async_commit();
@@ -261,12 +268,15 @@ knn_exact_scan_kernel(const float* __restrict__ db, long long n_rows, int dim,
 // lower bounds in every other list (keys are distinct: different rows).
 __global__ void knn_finalize_kernel(const uint64_t* __restrict__ partial, int nq, int n_lists,
                                     int k, uint64_t idx_offset, uint64_t* __restrict__ out_idx,
-                                    float* __restrict__ out_d2) {
+                                    float* __restrict__ out_d2, const int* __restrict__ qmap,
+                                    const int* __restrict__ nq_dev) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (nq_dev != nullptr) nq = *nq_dev;
   if (warp >= nq) return;
   const uint64_t* P = partial + (size_t)warp * n_lists * k;
-  uint64_t* oi = out_idx + (size_t)warp * k;
-  float* od = out_d2 + (size_t)warp * k;
+  const size_t orow = qmap ? (size_t)qmap[warp] : (size_t)warp;
+  uint64_t* oi = out_idx + orow * k;
+  float* od = out_d2 + orow * k;
   for (int i = lane; i < k; i += 32) {
     oi[i] = 0xFFFFFFFFFFFFFFFFull;
     od[i] = 3.402823466e+38f;  // FLT_MAX
@@ -344,7 +354,7 @@ __global__ void knn_merge_pairs_kernel(const uint64_t* __restrict__ idx,
 template <int BQ, int BN, int TQ, int TN, int KCAP>
 cudaError_t launch_scan(const float* db, long long n_rows, int dim, const float* q, int nq, int k,
                         int n_ranges, long long rows_per_range, uint64_t* partial,
-                        cudaStream_t stream) {
+                        const int* qmap, const int* nq_dev, cudaStream_t stream) {
   using Cfg = ScanCfg<BQ, BN, TQ, TN, KCAP>;
   auto kern = knn_exact_scan_kernel<BQ, BN, TQ, TN, KCAP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -352,7 +362,8 @@ cudaError_t launch_scan(const float* db, long long n_rows, int dim, const float*
   if (e != cudaSuccess) return e;
   const int n_qtiles = (nq + BQ - 1) / BQ;
   kern<<<n_qtiles * n_ranges, Cfg::NT, Cfg::kSmem, stream>>>(db, n_rows, dim, q, nq, k, n_qtiles,
-                                                            rows_per_range, n_ranges, partial);
+                                                            rows_per_range, n_ranges, partial, qmap,
+                                                            nq_dev);
   return cudaGetLastError();
 }
 
@@ -363,13 +374,14 @@ int exact_scan_tile_n(int nq) { return nq <= 64 ? 256 : 128; }
 
 cudaError_t launch_knn_exact_scan(const float* db, long long n_rows, int dim, const float* q,
                                   int nq, int k, int n_ranges, long long rows_per_range,
-                                  uint64_t* partial, cudaStream_t stream) {
+                                  uint64_t* partial, cudaStream_t stream, const int* qmap,
+                                  const int* nq_dev) {
   const bool small = nq <= 64;
 #define GLOC_SCAN(KC)                                                                       \
   (small ? launch_scan<16, 256, 4, 4, KC>(db, n_rows, dim, q, nq, k, n_ranges,              \
-                                          rows_per_range, partial, stream)                  \
+                                          rows_per_range, partial, qmap, nq_dev, stream)    \
          : launch_scan<128, 128, 8, 8, KC>(db, n_rows, dim, q, nq, k, n_ranges,             \
-                                           rows_per_range, partial, stream))
+                                           rows_per_range, partial, qmap, nq_dev, stream))
   if (k <= 32) return GLOC_SCAN(32);
   if (k <= 64) return GLOC_SCAN(64);
   return GLOC_SCAN(128);
@@ -378,10 +390,10 @@ cudaError_t launch_knn_exact_scan(const float* db, long long n_rows, int dim, co
 
 cudaError_t launch_knn_finalize(const uint64_t* partial, int nq, int n_lists, int k,
                                 uint64_t idx_offset, uint64_t* out_idx, float* out_d2,
-                                cudaStream_t stream) {
+                                cudaStream_t stream, const int* qmap, const int* nq_dev) {
   const int threads = 128, wpb = threads / 32;
-  knn_finalize_kernel<<<(nq + wpb - 1) / wpb, threads, 0, stream>>>(partial, nq, n_lists, k,
-                                                                    idx_offset, out_idx, out_d2);
+  knn_finalize_kernel<<<(nq + wpb - 1) / wpb, threads, 0, stream>>>(
+      partial, nq, n_lists, k, idx_offset, out_idx, out_d2, qmap, nq_dev);
   return cudaGetLastError();
 }
 

@@ -11,10 +11,12 @@ int exact_scan_tile_n(int nq);
 // partial: [nq][n_ranges][k] packed keys, ascending per (query, range), kEmptyKey padded.
 cudaError_t launch_knn_exact_scan(const float* db, long long n_rows, int dim, const float* q,
                                   int nq, int k, int n_ranges, long long rows_per_range,
-                                  uint64_t* partial, cudaStream_t stream);
+                                  uint64_t* partial, cudaStream_t stream,
+                                  const int* qmap = nullptr, const int* nq_dev = nullptr);
 cudaError_t launch_knn_finalize(const uint64_t* partial, int nq, int n_lists, int k,
                                 uint64_t idx_offset, uint64_t* out_idx, float* out_d2,
-                                cudaStream_t stream);
+                                cudaStream_t stream, const int* qmap = nullptr,
+                                const int* nq_dev = nullptr);
 cudaError_t launch_knn_merge_pairs(const uint64_t* idx, const float* d2, int g, int nq, int k,
                                    uint64_t* out_idx, float* out_d2, cudaStream_t stream);
 

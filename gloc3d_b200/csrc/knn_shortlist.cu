@@ -1,14 +1,868 @@
-// knn_shortlist.cu -- placeholder until the tcgen05 shortlist lands: reports "not
-// applicable" so GLOC_KNN_AUTO uses the exact scan.
+// knn_shortlist.cu -- stage 1 on the tensor cores: K1 (norms + BF16 copy), K2 (tcgen05 GEMM
+// shortlist with the selection fused into the TMEM epilogue) and K3 (FP32 exact re-rank in
+// the reference's operation order + top-k).
+//
+// Replaces the leaf loop of nanoflann's searchLevel
+// (/root/reference/registration/nanoflann.hpp:1602-1622) for large query batches.  The
+// Q x N distance matrix never touches HBM: the approximate score
+//     s(q, x) = ||x||^2 - 2 <bf16(q), bf16(x)>        (D_apx = ||q||^2 + s)
+// lives only in tensor memory; each epilogue thread owns one query row, keeps a running
+// upper bound of the k-th smallest score and appends the few rows below it to that query's
+// candidate list.  K3 re-computes the survivors' distances exactly (bit-exact with
+// L2_Adaptor::evalMetric, nanoflann.hpp:453-487) and selects the top-k by (d2, idx).
+//
+// Exactness (proved in DESIGN.md "shortlist bound"): with u = 2^-8 (BF16 round-to-nearest)
+//   |D_apx - D_ref| <= eps(q) = c1 ||q|| Xmax + c2 (||q|| + Xmax)^2 + tiny,
+//   c1 = 2(2u + u^2) + 2^-10,  c2 = 2^-14,  Xmax = max_x ||x||,
+// so every true top-k row has D_apx <= A_k + 2 eps, A_k = k-th smallest D_apx.  A thread's
+// threshold is B + 2 eps with B >= A_k at all times (B = max of 32 disjoint sub-stream
+// minima, k <= 32), hence the candidate list is a superset of the true top-k.  Lists that
+// overflow their capacity are detected and those queries are re-run through the exact scan
+// on the GPU -- never through a CPU path.
+//
+// sm_100a only: tcgen05.mma (kind::f16, M=128, N=256, K=16, cta_group::1), accumulators in
+// TMEM (2 x 256 columns, double buffered against the epilogue), operands staged by TMA
+// (cp.async.bulk.tensor, 128B swizzle) and tracked with mbarriers.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "knn_kernels.cuh"
 #include "knn_shortlist.cuh"
 
 namespace gloc {
-struct ShortlistState {};
-bool shortlist_supported(size_t, size_t) { return false; }
-bool shortlist_applicable(size_t, size_t, size_t, size_t) { return false; }
-void shortlist_invalidate(ShortlistState*, size_t) {}
-void shortlist_destroy(ShortlistState*) {}
-int shortlist_query(ShortlistState**, const ShortlistArgs&, uint64_t*, uint64_t*, uint64_t*) {
-  return fail(GLOC_ERR_RANGE, "tensor shortlist not built");
+
+namespace {
+
+// ------------------------------------------------------------------ tile shape
+constexpr int BM = 128;            // queries per tile = TMEM lanes = UMMA M
+constexpr int BN = 256;            // DB rows per tile = UMMA N = TMEM columns per stage
+constexpr int BK = 64;             // K elements per smem k-block (128 B of bf16: one swizzle row)
+constexpr int UK = 16;             // UMMA K for 16-bit inputs
+constexpr int kStagesB = 3;        // B ring depth
+constexpr int kMaxKBlocks = 8;     // dim <= 512 keeps the whole query tile resident (128 KB)
+constexpr int kABytesPerKB = BM * BK * 2;   // 16 KB
+constexpr int kBBytes = BN * BK * 2;        // 32 KB
+constexpr int kThreads = 256;      // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kTmemCols = 512;
+constexpr int kPrimeTiles = 4;     // dry-run tiles of first-wave units (threshold warm-up)
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kMaxKBlocks * kABytesPerKB +
+                              (size_t)kStagesB * kBBytes + 256 /*barriers*/;
+
+// shortlist error-bound constants (see header comment)
+constexpr float kC1 = 2.f * (2.f / 256.f + 1.f / 65536.f) + 1.f / 1024.f;
+constexpr float kC2 = 1.f / 16384.f;
+
+// monotone float <-> uint map so that unsigned atomicMin orders like the float
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+__device__ __forceinline__ float ord2f(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (error surfaces on the host) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();  // ~2 s
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar,
+                                            int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, BF16 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms 1024 B apart (SBO).
+// cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
+// [46,48), layout_type SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                       // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;             // SBO
+  d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 [4,6)=1, a/b_format BF16 [7,10),
+// [10,13)=1, a/b K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29).
+constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+        "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ K1: norms + bf16 copy
+// One warp per row: ||x||^2 in FP32 (tree order; only the shortlist uses it) and the BF16
+// copy the GEMM streams.  Rows in [n, n_pad) get norm = +inf so that padded tile columns can
+// never be short-listed.
+__global__ void knn_prep_rows_kernel(const float* __restrict__ src, long long n, long long n_pad,
+                                     int dim, __nv_bfloat16* __restrict__ dst,
+                                     float* __restrict__ norms, unsigned* __restrict__ max_norm2_bits) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_pad) return;
+  if (row >= n) {
+    if (lane == 0 && norms) norms[row] = __int_as_float(0x7f800000);
+    return;
+  }
+  const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)row * dim);
+  __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + (size_t)row * dim);
+  float acc = 0.f;
+  for (int i = lane; i < dim / 4; i += 32) {
+    const float4 v = __ldg(s4 + i);
+    acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    d2[2 * i] = __floats2bfloat162_rn(v.x, v.y);
+    d2[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) {
+    if (norms) norms[row] = acc;
+    if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(acc));
+  }
+}
+
+// ------------------------------------------------------------------ K2: GEMM shortlist
+struct GemmArgs {
+  int nq, n_qtiles, n_ranges, tiles_per_range, n_kb, k, cap, r_big;
+  long long n_rows;                 // searchable rows
+  const float* xn;                  // [n_pad] row norms (+inf beyond n_rows... see prep)
+  const float* qn;                  // [nq]
+  const unsigned* max_norm2_bits;   // Xmax^2
+  unsigned* thr_ord;                // [nq] shared running threshold (ordered-uint of s-space)
+  float* eps2;                      // [nq] 2*eps, written by the epilogue (read by K3)
+  unsigned* cand_idx;               // [nq][n_ranges][cap]
+  float* cand_s;                    // [nq][n_ranges][cap]
+  unsigned* unit_cnt;               // [nq][n_ranges]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
+                          const __grid_constant__ CUtensorMap map_db, GemmArgs a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  unsigned char* sA = smem;                                          // n_kb x 16 KB (resident)
+  unsigned char* sB = smem + (size_t)kMaxKBlocks * kABytesPerKB;     // kStagesB x 32 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kStagesB * kBBytes);
+  uint64_t* full_b = bars;                   // [kStagesB]
+  uint64_t* empty_b = bars + kStagesB;       // [kStagesB]
+  uint64_t* a_full = bars + 2 * kStagesB;    // [1]
+  uint64_t* a_empty = a_full + 1;            // [1]
+  uint64_t* tm_full = a_empty + 1;           // [2]
+  uint64_t* tm_empty = tm_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = a.n_qtiles * a.n_ranges;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_db) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStagesB; ++s) {
+      mbar_init(full_b + s, 1);
+      mbar_init(empty_b + s, 1);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tm_full + s, 1);
+      mbar_init(tm_empty + s, 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "n"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // Tiles a unit runs: first-wave units dry-run their first kPrimeTiles tiles (no emission)
+  // to warm the threshold up, then start over -- every role computes the same schedule.
+  auto unit_tiles = [&](int u, int& qt, int& rg, int& t_begin, int& t_count, int& prime) {
+    qt = u % a.n_qtiles;
+    rg = u / a.n_qtiles;
+    t_begin = rg * a.tiles_per_range;
+    const long long total_tiles = (a.n_rows + BN - 1) / BN;
+    t_count = (int)min((long long)a.tiles_per_range, total_tiles - t_begin);
+    prime = (rg < a.r_big) ? min(kPrimeTiles, t_count) : 0;
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, uphase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int qt, rg, t_begin, t_count, prime;
+        unit_tiles(u, qt, rg, t_begin, t_count, prime);
+        mbar_wait(a_empty, uphase ^ 1);  // previous unit's MMAs no longer read the query tile
+        mbar_expect_tx(a_full, (uint32_t)(a.n_kb * kABytesPerKB));
+        for (int kb = 0; kb < a.n_kb; ++kb)
+          tma_load_2d(sA + (size_t)kb * kABytesPerKB, &map_q, a_full, kb * BK, qt * BM);
+        uphase ^= 1;
+        for (int it = 0; it < prime + t_count; ++it) {
+          const int t = t_begin + (it < prime ? it : it - prime);
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            mbar_wait(empty_b + stage, phase ^ 1);
+            mbar_expect_tx(full_b + stage, kBBytes);
+            tma_load_2d(sB + (size_t)stage * kBBytes, &map_db, full_b + stage, kb * BK, t * BN);
+            if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+      mbar_wait(a_empty, uphase ^ 1);  // the last unit's commit has landed before the CTA exits
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0, uphase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int qt, rg, t_begin, t_count, prime;
+        unit_tiles(u, qt, rg, t_begin, t_count, prime);
+        mbar_wait(a_full, uphase);
+        uphase ^= 1;
+        for (int it = 0; it < prime + t_count; ++it) {
+          mbar_wait(tm_empty + as, aphase ^ 1);  // epilogue drained this accumulator stage
+          tcgen05_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+          for (int kb = 0; kb < a.n_kb; ++kb) {
+            mbar_wait(full_b + stage, phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(sA + (size_t)kb * kABytesPerKB);
+            const uint32_t b_addr = smem_u32(sB + (size_t)stage * kBBytes);
+#pragma unroll
+            for (int k4 = 0; k4 < BK / UK; ++k4) {
+              umma_bf16(d_tmem, make_sw128_desc(a_addr + k4 * UK * 2),
+                        make_sw128_desc(b_addr + k4 * UK * 2), kInstrDesc,
+                        (kb | k4) != 0 ? 1u : 0u);
+            }
+            tcgen05_commit(empty_b + stage);  // B slot reusable once these MMAs retire
+            if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+          }
+          tcgen05_commit(tm_full + as);       // accumulator ready for the epilogue
+          if (++as == 2) { as = 0; aphase ^= 1; }
+        }
+        tcgen05_commit(a_empty);              // query tile may be overwritten
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue: selection out of TMEM
+    const int ew = warp - 4;                  // == warp % 4: this warp's TMEM lane quadrant
+    const int row = ew * 32 + lane;           // query row inside the tile = TMEM lane
+    int as = 0;
+    uint32_t aphase = 0;
+    const float xmax = sqrtf(__uint_as_float(*a.max_norm2_bits)) * (1.f + 1.f / 1024.f);
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      int qt, rg, t_begin, t_count, prime;
+      unit_tiles(u, qt, rg, t_begin, t_count, prime);
+      const int q = qt * BM + row;
+      const bool q_ok = q < a.nq;
+      float eps2 = 0.f;
+      if (q_ok) {
+        const float qnorm = sqrtf(a.qn[q]) * (1.f + 1.f / 1024.f);
+        const float e = kC1 * qnorm * xmax + kC2 * (qnorm + xmax) * (qnorm + xmax) + 1e-30f;
+        eps2 = 2.f * e;
+        if (rg == 0) a.eps2[q] = eps2;
+      }
+      float thr = q_ok ? ord2f(a.thr_ord[q]) : -INFINITY;   // shared across this query's units
+      float smin[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) smin[j] = INFINITY;
+      unsigned cnt = 0;
+      const size_t list_base = ((size_t)(q_ok ? q : 0) * a.n_ranges + rg) * (size_t)a.cap;
+      for (int it = 0; it < prime + t_count; ++it) {
+        const bool emit = (it >= prime) && q_ok;
+        const int t = t_begin + (it < prime ? it : it - prime);
+        mbar_wait(tm_full + as, aphase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+        const float4* xn4 = reinterpret_cast<const float4*>(a.xn + (size_t)t * BN);
+        // rows >= n_rows (search limit / tile padding) must neither be short-listed nor
+        // tighten the bound
+        const int valid_cols = (int)min((long long)BN, a.n_rows - (long long)t * BN);
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 x4 = __ldg(xn4 + c * 8 + j4);
+            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const int j = j4 * 4 + jj;
+              float s = fmaf(-2.f, __uint_as_float(v[j]), xs[jj]);
+              if (c * 32 + j >= valid_cols) s = INFINITY;
+              smin[j] = fminf(smin[j], s);
+              if (emit && s <= thr) {
+                if (cnt < (unsigned)a.cap) {
+                  a.cand_idx[list_base + cnt] = (unsigned)(t * BN + c * 32 + j);
+                  a.cand_s[list_base + cnt] = s;
+                }
+                ++cnt;
+              }
+            }
+          }
+        }
+        // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tm_empty + as);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+        // tighten: max of the 32 sub-stream minima bounds the 32nd (hence k-th) smallest score
+        float tb = smin[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) tb = fmaxf(tb, smin[j]);
+        if (q_ok) {
+          const float mine = tb + eps2;
+          if (mine < thr) {
+            thr = mine;
+            atomicMin(a.thr_ord + q, f2ord(mine));
+          }
+          thr = fminf(thr, ord2f(*reinterpret_cast<volatile unsigned*>(a.thr_ord + q)));
+        }
+      }
+      if (q_ok) a.unit_cnt[(size_t)q * a.n_ranges + rg] = cnt;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(kTmemCols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ K3: select + exact re-rank
+constexpr int kSurvMax = 2048;   // candidates below the final threshold, per query
+constexpr int kFinalMax = 256;   // candidates re-ranked exactly, per query
+constexpr int kRerankThreads = 128;
+
+struct RerankArgs {
+  const float* db;
+  const float* q;
+  int nq, dim, k, n_ranges, cap;
+  const unsigned* cand_idx;
+  const float* cand_s;
+  const unsigned* unit_cnt;
+  const unsigned* thr_ord;
+  const float* eps2;
+  uint64_t offset;
+  uint64_t* out_idx;
+  float* out_d2;
+  int* overflow_list;     // compacted ids of queries that must be re-run exactly
+  int* overflow_count;
+  unsigned long long* rows_reranked;   // [0] rows re-ranked, [1] overflowed queries (cumulative)
+};
+
+__global__ void __launch_bounds__(kRerankThreads)
+knn_shortlist_rerank_kernel(RerankArgs a) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  float* surv_s = reinterpret_cast<float*>(sm_raw);                       // [kSurvMax]
+  unsigned* surv_i = reinterpret_cast<unsigned*>(surv_s + kSurvMax);      // [kSurvMax]
+  unsigned* fin_i = surv_i + kSurvMax;                                    // [kFinalMax]
+  float* fin_d = reinterpret_cast<float*>(fin_i + kFinalMax);             // [kFinalMax]
+  float* qs = fin_d + kFinalMax;                                          // [dim]
+  float* G = qs + a.dim;                                                  // [32][dim/4 + 1]
+  __shared__ int n_surv, n_fin, bad;
+  __shared__ float s_ak;
+  const int q = blockIdx.x, tid = threadIdx.x;
+  const int groups = a.dim / 4, gstride = groups + 1;
+  if (tid == 0) { n_surv = 0; n_fin = 0; bad = 0; }
+  for (int i = tid; i < a.dim; i += kRerankThreads) qs[i] = a.q[(size_t)q * a.dim + i];
+  __syncthreads();
+  const float tau = ord2f(a.thr_ord[q]);
+  const float eps2 = a.eps2[q];
+  // 1. gather the candidates below the final threshold from every unit list of this query
+  for (int r = 0; r < a.n_ranges; ++r) {
+    const unsigned cnt = a.unit_cnt[(size_t)q * a.n_ranges + r];
+    if (cnt > (unsigned)a.cap) { if (tid == 0) bad = 1; }
+    const unsigned c = min(cnt, (unsigned)a.cap);
+    const size_t base = ((size_t)q * a.n_ranges + r) * (size_t)a.cap;
+    for (unsigned i = tid; i < c; i += kRerankThreads) {
+      const float s = a.cand_s[base + i];
+      if (s <= tau) {
+        const int pos = atomicAdd(&n_surv, 1);
+        if (pos < kSurvMax) { surv_s[pos] = s; surv_i[pos] = a.cand_idx[base + i]; }
+      }
+    }
+  }
+  __syncthreads();
+  int ns = n_surv;
+  if (ns > kSurvMax) { if (tid == 0) bad = 1; ns = kSurvMax; }
+  __syncthreads();
+  if (!bad) {
+    // 2. A_k = k-th smallest approximate score among the survivors (all of the k smallest
+    //    approximate scores are survivors), then keep s <= A_k + 2 eps.
+    if (tid == 0) s_ak = INFINITY;
+    __syncthreads();
+    if (ns >= a.k) {
+      for (int i = tid; i < ns; i += kRerankThreads) {
+        const float si = surv_s[i];
+        int rank = 0;
+        for (int j = 0; j < ns; ++j) {
+          const float sj = surv_s[j];
+          rank += (sj < si || (sj == si && j < i)) ? 1 : 0;
+        }
+        if (rank == a.k - 1) s_ak = si;
+      }
+    }
+    __syncthreads();
+    const float tau2 = s_ak + eps2;
+    for (int i = tid; i < ns; i += kRerankThreads) {
+      if (surv_s[i] <= tau2) {
+        const int pos = atomicAdd(&n_fin, 1);
+        if (pos < kFinalMax) fin_i[pos] = surv_i[i];
+      }
+    }
+    __syncthreads();
+    if (n_fin > kFinalMax && tid == 0) bad = 1;
+    __syncthreads();
+  }
+  if (bad) {
+    if (tid == 0) {
+      const int pos = atomicAdd(a.overflow_count, 1);
+      a.overflow_list[pos] = q;
+      if (a.rows_reranked) atomicAdd(a.rows_reranked + 1, 1ull);
+    }
+    return;
+  }
+  const int nf = n_fin;
+  // 3. exact distances, reference operation order (nanoflann.hpp:453-487): the per-group
+  //    sums ((d0^2+d1^2)+d2^2)+d3^2 are independent (computed by all threads, coalesced row
+  //    reads); the running sum over groups is a serial chain done by one thread per row.
+  for (int b0 = 0; b0 < nf; b0 += 32) {
+    const int nb = min(32, nf - b0);
+    for (int c = 0; c < nb; ++c) {
+      const float4* x4 = reinterpret_cast<const float4*>(a.db + (size_t)fin_i[b0 + c] * a.dim);
+      for (int g = tid; g < groups; g += kRerankThreads) {
+        const float4 x = __ldg(x4 + g);
+        const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * g);
+        const float d0 = __fsub_rn(qq.x, x.x), d1 = __fsub_rn(qq.y, x.y);
+        const float d2 = __fsub_rn(qq.z, x.z), d3 = __fsub_rn(qq.w, x.w);
+        float s = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
+        s = __fadd_rn(s, __fmul_rn(d2, d2));
+        s = __fadd_rn(s, __fmul_rn(d3, d3));
+        G[c * gstride + g] = s;
+      }
+    }
+    __syncthreads();
+    if (tid < nb) {
+      float r = 0.f;
+      const float* gr = G + tid * gstride;
+      for (int g = 0; g < groups; ++g) r = __fadd_rn(r, gr[g]);
+      fin_d[b0 + tid] = r;
+    }
+    __syncthreads();
+  }
+  // 4. top-k by (d2, idx)
+  uint64_t* oi = a.out_idx + (size_t)q * a.k;
+  float* od = a.out_d2 + (size_t)q * a.k;
+  for (int i = tid; i < a.k; i += kRerankThreads) {
+    oi[i] = 0xFFFFFFFFFFFFFFFFull;
+    od[i] = 3.402823466e+38f;
+  }
+  __syncthreads();
+  for (int i = tid; i < nf; i += kRerankThreads) {
+    const uint64_t ki = pack_key(fin_d[i], fin_i[i]);
+    int rank = 0;
+    for (int j = 0; j < nf; ++j) rank += (pack_key(fin_d[j], fin_i[j]) < ki) ? 1 : 0;
+    if (rank < a.k) {
+      oi[rank] = (uint64_t)fin_i[i] + a.offset;
+      od[rank] = fin_d[i];
+    }
+  }
+  if (tid == 0 && a.rows_reranked) atomicAdd(a.rows_reranked, (unsigned long long)nf);
+}
+
+__global__ void knn_fill_u32_kernel(unsigned* p, size_t n, unsigned v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 matrix [rows][dim] (K-major), box = BK x box_rows, 128B swizzle, OOB rows read as 0
+bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t dim, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {dim, rows};
+  cuuint64_t gstride[1] = {dim * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Buf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    const size_t want = need + need / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) bytes = want; else p = nullptr;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace
+
+struct ShortlistState {
+  // database-derived (valid for rows [0, prepared_rows))
+  Buf db_bf16, xn, max_norm2;
+  size_t prepared_rows = 0, prepared_pad = 0;
+  const float* prepared_src = nullptr;
+  // per-call workspaces
+  Buf q_bf16, qn, thr, eps2, cand_idx, cand_s, unit_cnt, ovf_list, ovf_count, rows_ctr, partial;
+};
+
+bool shortlist_supported(size_t dim, size_t k) {
+  return dim % BK == 0 && dim >= BK && dim <= (size_t)kMaxKBlocks * BK && k >= 1 && k <= 32;
+}
+
+bool shortlist_applicable(size_t dim, size_t n_rows, size_t nq, size_t k) {
+  // the GEMM wins once the batch fills tensor tiles; tiny batches stay on the exact scan
+  return shortlist_supported(dim, k) && nq >= 64 && n_rows >= 1024;
+}
+
+void shortlist_invalidate(ShortlistState* s, size_t first_dirty_row) {
+  if (s) s->prepared_rows = std::min(s->prepared_rows, first_dirty_row);
+}
+
+void shortlist_destroy(ShortlistState* s) {
+  if (!s) return;
+  for (Buf* b : {&s->db_bf16, &s->xn, &s->max_norm2, &s->q_bf16, &s->qn, &s->thr, &s->eps2,
+                 &s->cand_idx, &s->cand_s, &s->unit_cnt, &s->ovf_list, &s->ovf_count, &s->rows_ctr,
+                 &s->partial})
+    b->release();
+  delete s;
+}
+
+namespace {
+
+struct Plan {
+  int n_ranges, tiles_per_range, r_big, cap;
+};
+
+Plan make_plan(long long n_rows, int nq, int sms) {
+  const long long tiles = (n_rows + BN - 1) / BN;
+  const int n_qtiles = (nq + BM - 1) / BM;
+  const long long max_r = std::max<long long>(1, std::min<long long>(16, tiles / 8));
+  double best = -1;
+  long long best_r = 1;
+  for (long long r = 1; r <= max_r; ++r) {
+    const long long units = (long long)n_qtiles * r;
+    const long long waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms);
+    const double score = eff - 0.004 * (double)r;
+    if (score > best + 1e-12) { best = score; best_r = r; }
+  }
+  Plan p;
+  p.tiles_per_range = (int)((tiles + best_r - 1) / best_r);
+  p.n_ranges = (int)((tiles + p.tiles_per_range - 1) / p.tiles_per_range);
+  p.r_big = std::min<int>(p.n_ranges, (sms + n_qtiles - 1) / n_qtiles);
+  p.cap = 1024;
+  return p;
+}
+
+}  // namespace
+
+int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launches,
+                    uint64_t* fallback, uint64_t* rows_reranked) {
+  if (!*sp) *sp = new ShortlistState;
+  ShortlistState* S = *sp;
+  cudaStream_t st = A.stream;
+  const int dim = (int)A.dim, k = (int)A.k;
+  const int sms = sm_count(A.device);
+  (void)fallback;
+  (void)rows_reranked;
+
+  // ---- K1 (cached): bf16 copy + norms of the database rows
+  const size_t n_total = A.n_total;
+  const size_t n_pad = (n_total + BN - 1) / BN * BN + BN;
+  if (S->prepared_src != A.d_db || S->prepared_pad < n_pad) S->prepared_rows = 0;
+  if (S->prepared_rows < n_total) {
+    if (S->prepared_rows == 0) {
+      GLOC_CUDA_TRY(S->db_bf16.reserve(n_pad * dim * 2));
+      GLOC_CUDA_TRY(S->xn.reserve(n_pad * sizeof(float)));
+      GLOC_CUDA_TRY(S->max_norm2.reserve(4));
+      GLOC_CUDA_TRY(cudaMemsetAsync(S->max_norm2.p, 0, 4, st));
+      S->prepared_pad = std::min(S->db_bf16.bytes / ((size_t)dim * 2), S->xn.bytes / sizeof(float));
+    } else if (S->prepared_pad < n_pad) {
+      S->prepared_rows = 0;
+      return shortlist_query(sp, A, launches, fallback, rows_reranked);
+    }
+    const size_t r0 = S->prepared_rows;
+    const long long rows = (long long)(n_pad - r0);
+    const int wpb = 8;
+    knn_prep_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        A.d_db + r0 * dim, (long long)(n_total - r0), rows, dim,
+        (__nv_bfloat16*)S->db_bf16.p + r0 * dim, (float*)S->xn.p + r0, (unsigned*)S->max_norm2.p);
+    GLOC_CUDA_TRY(cudaGetLastError());
+    ++*launches;
+    S->prepared_rows = n_total;
+    S->prepared_src = A.d_db;
+  }
+
+  CUtensorMap map_db;
+  if (!make_map(&map_db, S->db_bf16.p, A.n_rows, (uint64_t)dim, BN))
+    return fail(GLOC_ERR_CUDA, "cuTensorMapEncodeTiled(db) failed");
+
+  const size_t kChunk = 16384;  // bounds the candidate workspace
+  for (size_t q0 = 0; q0 < A.nq; q0 += kChunk) {
+    const int nq = (int)std::min(kChunk, A.nq - q0);
+    const Plan plan = make_plan((long long)A.n_rows, nq, sms);
+    const int n_qtiles = (nq + BM - 1) / BM;
+    const size_t lists = (size_t)nq * plan.n_ranges;
+    GLOC_CUDA_TRY(S->q_bf16.reserve((size_t)n_qtiles * BM * dim * 2));
+    GLOC_CUDA_TRY(S->qn.reserve((size_t)nq * 4));
+    GLOC_CUDA_TRY(S->thr.reserve((size_t)nq * 4));
+    GLOC_CUDA_TRY(S->eps2.reserve((size_t)nq * 4));
+    GLOC_CUDA_TRY(S->cand_idx.reserve(lists * plan.cap * 4));
+    GLOC_CUDA_TRY(S->cand_s.reserve(lists * plan.cap * 4));
+    GLOC_CUDA_TRY(S->unit_cnt.reserve(lists * 4));
+    GLOC_CUDA_TRY(S->ovf_list.reserve((size_t)nq * 4));
+    GLOC_CUDA_TRY(S->ovf_count.reserve(4));
+    if (!S->rows_ctr.p) {
+      GLOC_CUDA_TRY(S->rows_ctr.reserve(16));
+      GLOC_CUDA_TRY(cudaMemsetAsync(S->rows_ctr.p, 0, 16, st));
+    }
+    const float* dq = A.d_q + q0 * dim;
+
+    // K1 for the queries
+    {
+      const int wpb = 8;
+      knn_prep_rows_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+          dq, nq, nq, dim, (__nv_bfloat16*)S->q_bf16.p, (float*)S->qn.p, nullptr);
+      GLOC_CUDA_TRY(cudaGetLastError());
+      knn_fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>((unsigned*)S->thr.p, (size_t)nq,
+                                                          0xFF800000u);  // f2ord(+inf)
+      GLOC_CUDA_TRY(cudaGetLastError());
+      GLOC_CUDA_TRY(cudaMemsetAsync(S->ovf_count.p, 0, 4, st));
+      *launches += 2;
+    }
+    CUtensorMap map_q;
+    if (!make_map(&map_q, S->q_bf16.p, (uint64_t)nq, (uint64_t)dim, BM))
+      return fail(GLOC_ERR_CUDA, "cuTensorMapEncodeTiled(queries) failed");
+
+    // K2
+    GemmArgs g;
+    g.nq = nq;
+    g.n_qtiles = n_qtiles;
+    g.n_ranges = plan.n_ranges;
+    g.tiles_per_range = plan.tiles_per_range;
+    g.n_kb = dim / BK;
+    g.k = k;
+    g.cap = plan.cap;
+    g.r_big = plan.r_big;
+    g.n_rows = (long long)A.n_rows;
+    g.xn = (const float*)S->xn.p;
+    g.qn = (const float*)S->qn.p;
+    g.max_norm2_bits = (const unsigned*)S->max_norm2.p;
+    g.thr_ord = (unsigned*)S->thr.p;
+    g.eps2 = (float*)S->eps2.p;
+    g.cand_idx = (unsigned*)S->cand_idx.p;
+    g.cand_s = (float*)S->cand_s.p;
+    g.unit_cnt = (unsigned*)S->unit_cnt.p;
+    static bool attr_set = false;
+    if (!attr_set) {
+      GLOC_CUDA_TRY(cudaFuncSetAttribute(knn_shortlist_gemm_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBytes));
+      attr_set = true;
+    }
+    const int n_units = n_qtiles * plan.n_ranges;
+    const int grid = std::min(n_units, sms);
+    if (A.prof) A.prof->begin(st);
+    knn_shortlist_gemm_kernel<<<grid, kThreads, kSmemBytes, st>>>(map_q, map_db, g);
+    cudaError_t ge = cudaGetLastError();
+    if (A.prof) A.prof->end(st);
+    GLOC_CUDA_TRY(ge);
+
+    // K3
+    RerankArgs r;
+    r.db = A.d_db;
+    r.q = dq;
+    r.nq = nq;
+    r.dim = dim;
+    r.k = k;
+    r.n_ranges = plan.n_ranges;
+    r.cap = plan.cap;
+    r.cand_idx = g.cand_idx;
+    r.cand_s = g.cand_s;
+    r.unit_cnt = g.unit_cnt;
+    r.thr_ord = g.thr_ord;
+    r.eps2 = g.eps2;
+    r.offset = A.offset;
+    r.out_idx = A.d_idx + q0 * k;
+    r.out_d2 = A.d_d2 + q0 * k;
+    r.overflow_list = (int*)S->ovf_list.p;
+    r.overflow_count = (int*)S->ovf_count.p;
+    r.rows_reranked = (unsigned long long*)S->rows_ctr.p;
+    const size_t rr_smem = (size_t)kSurvMax * 8 + (size_t)kFinalMax * 8 + (size_t)dim * 4 +
+                           (size_t)32 * (dim / 4 + 1) * 4;
+    static bool attr2 = false;
+    if (!attr2) {
+      GLOC_CUDA_TRY(cudaFuncSetAttribute(knn_shortlist_rerank_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr2 = true;
+    }
+    knn_shortlist_rerank_kernel<<<nq, kRerankThreads, rr_smem, st>>>(r);
+    GLOC_CUDA_TRY(cudaGetLastError());
+    *launches += 2;
+
+    // overflowed queries: exact scan on the device, sized for the worst case, count read on
+    // the device (surplus CTAs exit immediately; usually every CTA does)
+    {
+      const int BQs = exact_scan_tile_q(nq), BNs = exact_scan_tile_n(nq);
+      (void)BQs;
+      const int n_r = (int)std::max<long long>(1, std::min<long long>(8, (long long)A.n_rows / (BNs * 4LL)));
+      long long rpr = ((long long)A.n_rows + n_r - 1) / n_r;
+      rpr = (rpr + BNs - 1) / BNs * BNs;
+      const int n_ranges = (int)(((long long)A.n_rows + rpr - 1) / rpr);
+      GLOC_CUDA_TRY(S->partial.reserve((size_t)nq * n_ranges * k * 8));
+      GLOC_CUDA_TRY(launch_knn_exact_scan(A.d_db, (long long)A.n_rows, dim, dq, nq, k, n_ranges, rpr,
+                                          (uint64_t*)S->partial.p, st, (const int*)S->ovf_list.p,
+                                          (const int*)S->ovf_count.p));
+      GLOC_CUDA_TRY(launch_knn_finalize((const uint64_t*)S->partial.p, nq, n_ranges, k, A.offset,
+                                        A.d_idx + q0 * k, A.d_d2 + q0 * k, st,
+                                        (const int*)S->ovf_list.p, (const int*)S->ovf_count.p));
+      *launches += 2;
+    }
+  }
+  return GLOC_OK;
+}
+
+// Cumulative device-side counters (rows re-ranked exactly, queries that overflowed and were
+// re-run by the exact scan).  Synchronises the device.
+int shortlist_counters(ShortlistState* s, uint64_t* rows, uint64_t* overflow) {
+  *overflow = 0;
+  *rows = 0;
+  if (!s || !s->rows_ctr.p) return GLOC_OK;
+  unsigned long long c[2] = {0, 0};
+  GLOC_CUDA_TRY(cudaDeviceSynchronize());
+  GLOC_CUDA_TRY(cudaMemcpy(c, s->rows_ctr.p, 16, cudaMemcpyDeviceToHost));
+  *rows = c[0];
+  *overflow = c[1];
+  return GLOC_OK;
+}
+
 }  // namespace gloc

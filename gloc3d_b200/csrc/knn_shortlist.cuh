@@ -35,4 +35,8 @@ void shortlist_destroy(ShortlistState* s);
 int shortlist_query(ShortlistState** s, const ShortlistArgs& a, uint64_t* launches,
                     uint64_t* fallback, uint64_t* rows_reranked);
 
+// Cumulative counters kept on the device (synchronises): rows re-ranked in FP32 and queries
+// whose shortlist overflowed (re-run by the exact scan).
+int shortlist_counters(ShortlistState* s, uint64_t* rows_reranked, uint64_t* overflowed);
+
 }  // namespace gloc

@@ -13,11 +13,14 @@ from helpers import assert_knn_equal, canonical_ties
 
 pytestmark = pytest.mark.gpu
 
-MODES = [g.KNN_EXACT_SCAN, g.KNN_AUTO]
+MODES = [g.KNN_EXACT_SCAN, g.KNN_AUTO, g.KNN_SHORTLIST]
 U64MAX = np.iinfo(np.uint64).max
 
 
 def run(db, q, k, mode, **kw):
+    dim = db.shape[1]
+    if mode == g.KNN_SHORTLIST and (dim % 64 or dim > 512 or k > 32):
+        pytest.skip("tensor shortlist needs dim % 64 == 0, dim <= 512, k <= 32")
     ix = g.KnnIndex(db.shape[1], 0)
     ix.set_db(db)
     ix.set_mode(mode)
@@ -88,6 +91,42 @@ def test_unnormalised_and_scaled_descriptors(oracle):
     for mode in MODES:
         idx, d2 = run(db, q, 25, mode)
         assert_knn_equal(idx, d2, *oracle.knn(db, q, 25, nthreads=8))
+
+
+def test_shortlist_overflow_falls_back_on_gpu(oracle):
+    # adversarial: thousands of identical rows make every shortlist overflow its capacity;
+    # those queries must be re-run by the exact scan on the GPU and still be bit-exact
+    base = synth.make_descriptors(64, seed=21)
+    db = np.concatenate([np.repeat(base[:2], 3000, axis=0), synth.make_descriptors(3000, seed=22)])
+    q = np.concatenate([base[:2] + np.float32(1e-4), synth.make_queries(db, 126, seed=23)]).astype(np.float32)
+    ix = g.KnnIndex(512, 0)
+    ix.set_db(db)
+    ix.set_mode(g.KNN_SHORTLIST)
+    idx, d2 = ix.query(q, 25)
+    st = ix.stats()
+    ix.close()
+    assert_knn_equal(idx, d2, *oracle.knn(db, q, 25, nthreads=8))
+    assert st.fallback_queries >= 2 and st.last_mode == g.KNN_SHORTLIST
+
+
+def test_shortlist_stats_and_search_limit(oracle):
+    db = synth.make_descriptors(20000, seed=31, dup_run=4)
+    q = synth.make_queries(db, 700, seed=32, sigma=0.004)
+    ix = g.KnnIndex(512, 0)
+    ix.set_db(db)
+    ix.set_mode(g.KNN_SHORTLIST)
+    ix.set_search_limit(20000 - 300)          # a limit inside a tile: masked columns
+    idx, d2 = ix.query(q, 25)
+    assert_knn_equal(idx, d2, *oracle.knn(db[:19700], q, 25, nthreads=8))
+    ix.set_search_limit(None)
+    ix.append(synth.make_descriptors(500, seed=33))   # derived data of old rows is kept
+    idx, d2 = ix.query(q, 20)
+    full = np.concatenate([db, synth.make_descriptors(500, seed=33)])
+    assert_knn_equal(idx, d2, *oracle.knn(full, q, 20, nthreads=8))
+    st = ix.stats()
+    assert st.shortlist_queries == 1400 and st.fallback_queries == 0
+    assert 20 <= st.shortlist_rows / st.shortlist_queries <= 256
+    ix.close()
 
 
 def test_golden_vectors_from_reference(golden_dir):
