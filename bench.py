@@ -212,7 +212,7 @@ def run_retrieval(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if last_mode == g.KNN_EXACT_SCAN else "bf16 shortlist + f32 exact re-rank",
+        "dtype": "f32" if last_mode == g.KNN_EXACT_SCAN else "fp16 tensor shortlist + f32 exact re-rank",
         "data": "synthetic",
         "config": {"workload": "configs[1]: 100k x 512-d f32 descriptor DB, 10k-query batch per GPU, "
                                "top-25 exact L2 retrieval (bit-exact vs nanoflann)",

@@ -375,8 +375,8 @@ int exact_scan_tile_n(int nq) { return nq <= 64 ? 256 : 128; }
 cudaError_t launch_knn_exact_scan(const float* db, long long n_rows, int dim, const float* q,
                                   int nq, int k, int n_ranges, long long rows_per_range,
                                   uint64_t* partial, cudaStream_t stream, const int* qmap,
-                                  const int* nq_dev) {
-  const bool small = nq <= 64;
+                                  const int* nq_dev, bool force_small) {
+  const bool small = force_small || nq <= 64;
 #define GLOC_SCAN(KC)                                                                       \
   (small ? launch_scan<16, 256, 4, 4, KC>(db, n_rows, dim, q, nq, k, n_ranges,              \
                                           rows_per_range, partial, qmap, nq_dev, stream)    \

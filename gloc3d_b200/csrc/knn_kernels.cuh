@@ -12,7 +12,8 @@ int exact_scan_tile_n(int nq);
 cudaError_t launch_knn_exact_scan(const float* db, long long n_rows, int dim, const float* q,
                                   int nq, int k, int n_ranges, long long rows_per_range,
                                   uint64_t* partial, cudaStream_t stream,
-                                  const int* qmap = nullptr, const int* nq_dev = nullptr);
+                                  const int* qmap = nullptr, const int* nq_dev = nullptr,
+                                  bool force_small = false);
 cudaError_t launch_knn_finalize(const uint64_t* partial, int nq, int n_lists, int k,
                                 uint64_t idx_offset, uint64_t* out_idx, float* out_d2,
                                 cudaStream_t stream, const int* qmap = nullptr,

@@ -1,34 +1,42 @@
-// knn_shortlist.cu -- stage 1 on the tensor cores: K1 (norms + BF16 copy), K2 (tcgen05 GEMM
+// knn_shortlist.cu -- stage 1 on the tensor cores: K1 (norms + FP16 copy), K2 (tcgen05 GEMM
 // shortlist with the selection fused into the TMEM epilogue) and K3 (FP32 exact re-rank in
 // the reference's operation order + top-k).
 //
 // Replaces the leaf loop of nanoflann's searchLevel
 // (/root/reference/registration/nanoflann.hpp:1602-1622) for large query batches.  The
 // Q x N distance matrix never touches HBM: the approximate score
-//     s(q, x) = ||x||^2 - 2 <bf16(q), bf16(x)>        (D_apx = ||q||^2 + s)
+//     s(q, x) = ||x||^2 - 2 <fp16(q), fp16(x)>        (D_apx = ||q||^2 + s)
 // lives only in tensor memory; each epilogue thread owns one query row, keeps a running
 // upper bound of the k-th smallest score and appends the few rows below it to that query's
 // candidate list.  K3 re-computes the survivors' distances exactly (bit-exact with
 // L2_Adaptor::evalMetric, nanoflann.hpp:453-487) and selects the top-k by (d2, idx).
 //
-// Exactness (proved in DESIGN.md "shortlist bound"): with u = 2^-8 (BF16 round-to-nearest)
-//   |D_apx - D_ref| <= eps(q) = c1 ||q|| Xmax + c2 (||q|| + Xmax)^2 + tiny,
-//   c1 = 2(2u + u^2) + 2^-10,  c2 = 2^-14,  Xmax = max_x ||x||,
-// so every true top-k row has D_apx <= A_k + 2 eps, A_k = k-th smallest D_apx.  A thread's
-// threshold is B + 2 eps with B >= A_k at all times (B = max of 32 disjoint sub-stream
-// minima, k <= 32), hence the candidate list is a superset of the true top-k.  Lists that
-// overflow their capacity are detected and those queries are re-run through the exact scan
-// on the GPU -- never through a CPU path.
+// Operand precision: FP16 (11-bit significand, u = 2^-11; same tensor rate as BF16, 8x
+// tighter) after an exact power-of-two scaling (one scale for the database, one per query
+// row) that keeps every element inside FP16's normal range.
+//
+// Exactness (proved in DESIGN.md "shortlist bound"): with dq = q - fp16(q), dx = x - fp16(x)
+// (exact residuals, norms computed in K1),
+//   |D_apx - D_ref| <= eps(q) = 2 (||dq|| Xmax + (1+u) ||q|| DXmax)     operand rounding (Cauchy-Schwarz)
+//                              + 2^-11 ||q|| Xmax                        tensor-core FP32 accumulation
+//                              + 2^-16 (||q|| + Xmax)^2 + tiny           FP32 norms / FFMA / reference rounding
+// with Xmax = max ||x||, DXmax = max ||dx||.  Every true top-k row therefore has
+// D_apx <= A_k + 2 eps, A_k = k-th smallest D_apx.  A thread's threshold is B + 2 eps with
+// B >= A_k at all times (B = 32nd smallest minimum of disjoint 32-row chunks, k <= 32), hence
+// the candidate list is a superset of the true top-k.  Lists that overflow their capacity are
+// detected and those queries are re-run through the exact scan on the GPU -- never on a CPU.
 //
 // sm_100a only: tcgen05.mma (kind::f16, M=128, N=256, K=16, cta_group::1), accumulators in
 // TMEM (2 x 256 columns, double buffered against the epilogue), operands staged by TMA
 // (cp.async.bulk.tensor, 128B swizzle) and tracked with mbarriers.
 #include <cuda.h>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "knn_kernels.cuh"
 #include "knn_shortlist.cuh"
@@ -40,7 +48,7 @@ namespace {
 // ------------------------------------------------------------------ tile shape
 constexpr int BM = 128;            // queries per tile = TMEM lanes = UMMA M
 constexpr int BN = 256;            // DB rows per tile = UMMA N = TMEM columns per stage
-constexpr int BK = 64;             // K elements per smem k-block (128 B of bf16: one swizzle row)
+constexpr int BK = 64;             // K elements per smem k-block (128 B of fp16: one swizzle row)
 constexpr int UK = 16;             // UMMA K for 16-bit inputs
 constexpr int kStagesB = 3;        // B ring depth
 constexpr int kMaxKBlocks = 8;     // dim <= 512 keeps the whole query tile resident (128 KB)
@@ -48,13 +56,14 @@ constexpr int kABytesPerKB = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;        // 32 KB
 constexpr int kThreads = 256;      // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
 constexpr int kTmemCols = 512;
-constexpr int kPrimeTiles = 4;     // dry-run tiles of first-wave units (threshold warm-up)
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kMaxKBlocks * kABytesPerKB +
                               (size_t)kStagesB * kBBytes + 256 /*barriers*/;
 
 // shortlist error-bound constants (see header comment)
-constexpr float kC1 = 2.f * (2.f / 256.f + 1.f / 65536.f) + 1.f / 1024.f;
-constexpr float kC2 = 1.f / 16384.f;
+constexpr float kU = 1.f / 2048.f;          // FP16 unit roundoff
+constexpr float kCAcc = 1.f / 2048.f;       // tensor-core accumulation, relative to ||q|| ||x||
+constexpr float kC2 = 1.f / 65536.f;        // FP32 side computations, relative to (||q||+||x||)^2
+constexpr float kInfl = 1.f + 1.f / 1024.f; // covers the rounding of the norms themselves
 
 // monotone float <-> uint map so that unsigned atomicMin orders like the float
 __device__ __forceinline__ unsigned f2ord(float f) {
@@ -124,8 +133,8 @@ __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
                    smem_u32(bar))
                : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, BF16 inputs, FP32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+// D[tmem] (+)= A[smem desc] * B[smem desc]^T, FP16 inputs, FP32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
                                           uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -146,10 +155,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
   return d;
 }
-// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 [4,6)=1, a/b_format BF16 [7,10),
-// [10,13)=1, a/b K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29).
-constexpr uint32_t kInstrDesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                ((uint32_t)(BM >> 4) << 24);
+// cute::UMMA::InstrDescriptor for kind::f16: c_format F32 [4,6)=1, a/b_format F16 [7,10),
+// [10,13)=0, a/b K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29).
+constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -168,34 +176,126 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ------------------------------------------------------------------ K1: norms + bf16 copy
-// One warp per row: ||x||^2 in FP32 (tree order; only the shortlist uses it) and the BF16
-// copy the GEMM streams.  Rows in [n, n_pad) get norm = +inf so that padded tile columns can
-// never be short-listed.
-__global__ void knn_prep_rows_kernel(const float* __restrict__ src, long long n, long long n_pad,
-                                     int dim, __nv_bfloat16* __restrict__ dst,
-                                     float* __restrict__ norms, unsigned* __restrict__ max_norm2_bits) {
+// ------------------------------------------------------------------ K1: norms + FP16 copy
+// power of two that maps max|v| into [2^13, 2^14): far from FP16 overflow (65504) and
+// underflow (2^-14) for every element that matters
+__host__ __device__ inline float pow2_scale_for(float max_abs) {
+  if (!(max_abs > 0.f) || !(max_abs < 3.0e38f)) return 1.f;
+  int e;
+#ifdef __CUDA_ARCH__
+  frexpf(max_abs, &e);
+  return scalbnf(1.f, 14 - e);  // exact power of two
+#else
+  std::frexp(max_abs, &e);
+  return std::ldexp(1.f, 14 - e);
+#endif
+}
+
+// Database pass 1: ||x||^2 (FP32, tree order -- only the shortlist uses it), max ||x||^2 and
+// max |x_i|.  One warp per row.
+__global__ void knn_db_stats_kernel(const float* __restrict__ src, long long n, int dim,
+                                    float* __restrict__ norms, unsigned* __restrict__ max_norm2_bits,
+                                    unsigned* __restrict__ max_abs_bits) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  if (row >= n_pad) return;
-  if (row >= n) {
-    if (lane == 0 && norms) norms[row] = __int_as_float(0x7f800000);
-    return;
-  }
+  if (row >= n) return;
   const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)row * dim);
-  __nv_bfloat162* d2 = reinterpret_cast<__nv_bfloat162*>(dst + (size_t)row * dim);
-  float acc = 0.f;
+  float acc = 0.f, mx = 0.f;
   for (int i = lane; i < dim / 4; i += 32) {
     const float4 v = __ldg(s4 + i);
     acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    d2[2 * i] = __floats2bfloat162_rn(v.x, v.y);
-    d2[2 * i + 1] = __floats2bfloat162_rn(v.z, v.w);
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
   if (lane == 0) {
-    if (norms) norms[row] = acc;
-    if (max_norm2_bits) atomicMax(max_norm2_bits, __float_as_uint(acc));
+    norms[row] = acc;
+    atomicMax(max_norm2_bits, __float_as_uint(acc));
+    atomicMax(max_abs_bits, __float_as_uint(mx));
+  }
+}
+
+// Database pass 2: FP16 copy of scale*x and the exact residual norm ||x - fp16(scale x)/scale||^2.
+// Rows in [n, n_pad) are zero with norm = +inf so that padded tile columns are never listed.
+__global__ void knn_db_convert_kernel(const float* __restrict__ src, long long n, long long n_pad,
+                                      int dim, float scale, __half* __restrict__ dst,
+                                      float* __restrict__ norms, unsigned* __restrict__ max_dx2_bits) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_pad) return;
+  __half2* d2 = reinterpret_cast<__half2*>(dst + (size_t)row * dim);
+  if (row >= n) {
+    for (int i = lane; i < dim / 2; i += 32) d2[i] = __floats2half2_rn(0.f, 0.f);
+    if (lane == 0) norms[row] = __int_as_float(0x7f800000);
+    return;
+  }
+  const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)row * dim);
+  const float inv = 1.f / scale;
+  float res = 0.f;
+  for (int i = lane; i < dim / 4; i += 32) {
+    const float4 v = __ldg(s4 + i);
+    const __half2 h0 = __floats2half2_rn(v.x * scale, v.y * scale);
+    const __half2 h1 = __floats2half2_rn(v.z * scale, v.w * scale);
+    d2[2 * i] = h0;
+    d2[2 * i + 1] = h1;
+    const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+    const float r0 = v.x - f0.x * inv, r1 = v.y - f0.y * inv, r2 = v.z - f1.x * inv, r3 = v.w - f1.y * inv;
+    res += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+  if (lane == 0) atomicMax(max_dx2_bits, __float_as_uint(res));
+}
+
+// Queries: one warp per row, everything in one pass with a per-row power-of-two scale (no
+// host round trip): FP16 copy, ||q||^2, ||dq||^2 and 1/scale.
+__global__ void knn_query_prep_kernel(const float* __restrict__ src, int n, int dim,
+                                      __half* __restrict__ dst, float* __restrict__ qn,
+                                      float* __restrict__ qe, float* __restrict__ qinv) {
+  const int row = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float4* s4 = reinterpret_cast<const float4*>(src + (size_t)row * dim);
+  __half2* d2 = reinterpret_cast<__half2*>(dst + (size_t)row * dim);
+  float4 v[kMaxKBlocks * BK / 128];  // dim <= 512: at most 4 float4 per lane
+  float acc = 0.f, mx = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxKBlocks * BK / 128; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = (i < dim / 4) ? __ldg(s4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v[j].x), fabsf(v[j].y)), fmaxf(fabsf(v[j].z), fabsf(v[j].w))));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const float scale = pow2_scale_for(mx), inv = 1.f / scale;
+  float res = 0.f;
+#pragma unroll
+  for (int j = 0; j < kMaxKBlocks * BK / 128; ++j) {
+    const int i = lane + 32 * j;
+    if (i < dim / 4) {
+      const __half2 h0 = __floats2half2_rn(v[j].x * scale, v[j].y * scale);
+      const __half2 h1 = __floats2half2_rn(v[j].z * scale, v[j].w * scale);
+      d2[2 * i] = h0;
+      d2[2 * i + 1] = h1;
+      const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+      const float r0 = v[j].x - f0.x * inv, r1 = v[j].y - f0.y * inv;
+      const float r2 = v[j].z - f1.x * inv, r3 = v[j].w - f1.y * inv;
+      res += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) res += __shfl_xor_sync(0xffffffffu, res, o);
+  if (lane == 0) {
+    qn[row] = acc;
+    qe[row] = res;
+    qinv[row] = inv;
   }
 }
 
@@ -204,8 +304,12 @@ struct GemmArgs {
   int nq, n_qtiles, n_ranges, tiles_per_range, n_kb, k, cap, r_big;
   long long n_rows;                 // searchable rows
   const float* xn;                  // [n_pad] row norms (+inf beyond n_rows... see prep)
-  const float* qn;                  // [nq]
+  const float* qn;                  // [nq] ||q||^2
+  const float* qe;                  // [nq] ||q - fp16(q)||^2
+  const float* qinv;                // [nq] 1 / (per-row power-of-two scale)
+  float inv_sx;                     // 1 / (database power-of-two scale)
   const unsigned* max_norm2_bits;   // Xmax^2
+  const unsigned* max_dx2_bits;     // DXmax^2
   unsigned* thr_ord;                // [nq] shared running threshold (ordered-uint of s-space)
   float* eps2;                      // [nq] 2*eps, written by the epilogue (read by K3)
   unsigned* cand_idx;               // [nq][n_ranges][cap]
@@ -263,15 +367,13 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // Tiles a unit runs: first-wave units dry-run their first kPrimeTiles tiles (no emission)
-  // to warm the threshold up, then start over -- every role computes the same schedule.
-  auto unit_tiles = [&](int u, int& qt, int& rg, int& t_begin, int& t_count, int& prime) {
+  // Tiles a unit runs -- every role computes the same schedule.
+  auto unit_tiles = [&](int u, int& qt, int& rg, int& t_begin, int& t_count) {
     qt = u % a.n_qtiles;
     rg = u / a.n_qtiles;
     t_begin = rg * a.tiles_per_range;
     const long long total_tiles = (a.n_rows + BN - 1) / BN;
     t_count = (int)min((long long)a.tiles_per_range, total_tiles - t_begin);
-    prime = (rg < a.r_big) ? min(kPrimeTiles, t_count) : 0;
   };
 
   if (warp == 0) {
@@ -280,15 +382,15 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
       int stage = 0;
       uint32_t phase = 0, uphase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        int qt, rg, t_begin, t_count, prime;
-        unit_tiles(u, qt, rg, t_begin, t_count, prime);
+        int qt, rg, t_begin, t_count;
+        unit_tiles(u, qt, rg, t_begin, t_count);
         mbar_wait(a_empty, uphase ^ 1);  // previous unit's MMAs no longer read the query tile
         mbar_expect_tx(a_full, (uint32_t)(a.n_kb * kABytesPerKB));
         for (int kb = 0; kb < a.n_kb; ++kb)
           tma_load_2d(sA + (size_t)kb * kABytesPerKB, &map_q, a_full, kb * BK, qt * BM);
         uphase ^= 1;
-        for (int it = 0; it < prime + t_count; ++it) {
-          const int t = t_begin + (it < prime ? it : it - prime);
+        for (int it = 0; it < t_count; ++it) {
+          const int t = t_begin + it;
           for (int kb = 0; kb < a.n_kb; ++kb) {
             mbar_wait(empty_b + stage, phase ^ 1);
             mbar_expect_tx(full_b + stage, kBBytes);
@@ -305,11 +407,11 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0, uphase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        int qt, rg, t_begin, t_count, prime;
-        unit_tiles(u, qt, rg, t_begin, t_count, prime);
+        int qt, rg, t_begin, t_count;
+        unit_tiles(u, qt, rg, t_begin, t_count);
         mbar_wait(a_full, uphase);
         uphase ^= 1;
-        for (int it = 0; it < prime + t_count; ++it) {
+        for (int it = 0; it < t_count; ++it) {
           mbar_wait(tm_empty + as, aphase ^ 1);  // epilogue drained this accumulator stage
           tcgen05_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -320,7 +422,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             const uint32_t b_addr = smem_u32(sB + (size_t)stage * kBBytes);
 #pragma unroll
             for (int k4 = 0; k4 < BK / UK; ++k4) {
-              umma_bf16(d_tmem, make_sw128_desc(a_addr + k4 * UK * 2),
+              umma_f16(d_tmem, make_sw128_desc(a_addr + k4 * UK * 2),
                         make_sw128_desc(b_addr + k4 * UK * 2), kInstrDesc,
                         (kb | k4) != 0 ? 1u : 0u);
             }
@@ -335,60 +437,89 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: selection out of TMEM
+    // Thread = one query row.  Fast path per 32-column chunk: scores s = ||x||^2 - 2 dot
+    // (32 FFMA) and their minimum (FMNMX tree); a chunk whose minimum is above the threshold
+    // is done.  Otherwise (rare) every score under the threshold is appended to the candidate
+    // list AND inserted into the thread's sorted list of the 32 smallest scores seen, whose
+    // largest entry B = lst[31] bounds the 32nd (hence k-th, k <= 32) smallest score of the
+    // whole database from above; the threshold is B + 2 eps, shared between the units of a
+    // query through global memory.  Every score <= B passes the test, so the list is exact.
     const int ew = warp - 4;                  // == warp % 4: this warp's TMEM lane quadrant
     const int row = ew * 32 + lane;           // query row inside the tile = TMEM lane
     int as = 0;
     uint32_t aphase = 0;
-    const float xmax = sqrtf(__uint_as_float(*a.max_norm2_bits)) * (1.f + 1.f / 1024.f);
+    const float xmax = sqrtf(__uint_as_float(*a.max_norm2_bits)) * kInfl;
+    const float dxmax = sqrtf(__uint_as_float(*a.max_dx2_bits)) * kInfl;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      int qt, rg, t_begin, t_count, prime;
-      unit_tiles(u, qt, rg, t_begin, t_count, prime);
+      int qt, rg, t_begin, t_count;
+      unit_tiles(u, qt, rg, t_begin, t_count);
       const int q = qt * BM + row;
       const bool q_ok = q < a.nq;
-      float eps2 = 0.f;
+      float eps2 = 0.f, cm = 0.f;
       if (q_ok) {
-        const float qnorm = sqrtf(a.qn[q]) * (1.f + 1.f / 1024.f);
-        const float e = kC1 * qnorm * xmax + kC2 * (qnorm + xmax) * (qnorm + xmax) + 1e-30f;
+        const float qnorm = sqrtf(a.qn[q]) * kInfl, dq = sqrtf(a.qe[q]) * kInfl;
+        const float e = 2.f * (dq * xmax + (1.f + kU) * qnorm * dxmax) + kCAcc * qnorm * xmax +
+                        kC2 * (qnorm + xmax) * (qnorm + xmax) + 1e-30f;
         eps2 = 2.f * e;
         if (rg == 0) a.eps2[q] = eps2;
+        cm = -2.f * a.inv_sx * a.qinv[q];   // undoes both power-of-two scales (exact)
       }
       float thr = q_ok ? ord2f(a.thr_ord[q]) : -INFINITY;   // shared across this query's units
-      float smin[32];
+      float lst[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) smin[j] = INFINITY;
+      for (int j = 0; j < 32; ++j) lst[j] = INFINITY;
       unsigned cnt = 0;
       const size_t list_base = ((size_t)(q_ok ? q : 0) * a.n_ranges + rg) * (size_t)a.cap;
-      for (int it = 0; it < prime + t_count; ++it) {
-        const bool emit = (it >= prime) && q_ok;
-        const int t = t_begin + (it < prime ? it : it - prime);
+      for (int it = 0; it < t_count; ++it) {
+        const int t = t_begin + it;
         mbar_wait(tm_full + as, aphase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
         const float4* xn4 = reinterpret_cast<const float4*>(a.xn + (size_t)t * BN);
-        // rows >= n_rows (search limit / tile padding) must neither be short-listed nor
-        // tighten the bound
+        // rows >= n_rows (search limit inside this tile) must neither be short-listed nor
+        // tighten the bound; rows >= n_total already carry ||x||^2 = +inf
         const int valid_cols = (int)min((long long)BN, a.n_rows - (long long)t * BN);
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
+          float4 xr[8];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) xr[j4] = __ldg(xn4 + c * 8 + j4);
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + c * 32, v);
           tmem_ld_wait();
+          float sc[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 x4 = __ldg(xn4 + c * 8 + j4);
-            const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+            sc[4 * j4 + 0] = fmaf(cm, __uint_as_float(v[4 * j4 + 0]), xr[j4].x);
+            sc[4 * j4 + 1] = fmaf(cm, __uint_as_float(v[4 * j4 + 1]), xr[j4].y);
+            sc[4 * j4 + 2] = fmaf(cm, __uint_as_float(v[4 * j4 + 2]), xr[j4].z);
+            sc[4 * j4 + 3] = fmaf(cm, __uint_as_float(v[4 * j4 + 3]), xr[j4].w);
+          }
+          if (valid_cols < BN) {  // warp-uniform, last tile of a limited search only
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const int j = j4 * 4 + jj;
-              float s = fmaf(-2.f, __uint_as_float(v[j]), xs[jj]);
-              if (c * 32 + j >= valid_cols) s = INFINITY;
-              smin[j] = fminf(smin[j], s);
-              if (emit && s <= thr) {
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j >= valid_cols) sc[j] = INFINITY;
+          }
+          float m = fminf(sc[0], sc[1]);
+#pragma unroll
+          for (int j = 2; j < 32; j += 2) m = fminf(m, fminf(sc[j], sc[j + 1]));
+          if (q_ok && m <= thr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (sc[j] <= thr && sc[j] < INFINITY) {   // +inf = masked / padded row
                 if (cnt < (unsigned)a.cap) {
                   a.cand_idx[list_base + cnt] = (unsigned)(t * BN + c * 32 + j);
-                  a.cand_s[list_base + cnt] = s;
+                  a.cand_s[list_base + cnt] = sc[j];
                 }
                 ++cnt;
+                float w = sc[j];   // sorted insertion; the largest of the 33 values drops out
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  const float lo = fminf(lst[i], w);
+                  w = fmaxf(lst[i], w);
+                  lst[i] = lo;
+                }
+                thr = fminf(thr, lst[31] + eps2);
               }
             }
           }
@@ -398,17 +529,11 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
         __syncwarp();
         if (lane == 0) mbar_arrive(tm_empty + as);
         if (++as == 2) { as = 0; aphase ^= 1; }
-        // tighten: max of the 32 sub-stream minima bounds the 32nd (hence k-th) smallest score
-        float tb = smin[0];
-#pragma unroll
-        for (int j = 1; j < 32; ++j) tb = fmaxf(tb, smin[j]);
-        if (q_ok) {
-          const float mine = tb + eps2;
-          if (mine < thr) {
-            thr = mine;
-            atomicMin(a.thr_ord + q, f2ord(mine));
-          }
-          thr = fminf(thr, ord2f(*reinterpret_cast<volatile unsigned*>(a.thr_ord + q)));
+        if (q_ok) {  // publish / pick up the bound shared by all units of this query
+          const unsigned mine = f2ord(thr);
+          const unsigned seen = *reinterpret_cast<volatile unsigned*>(a.thr_ord + q);
+          if (mine < seen) atomicMin(a.thr_ord + q, mine);
+          else thr = ord2f(seen);
         }
       }
       if (q_ok) a.unit_cnt[(size_t)q * a.n_ranges + rg] = cnt;
@@ -466,10 +591,15 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   const float tau = ord2f(a.thr_ord[q]);
   const float eps2 = a.eps2[q];
   // 1. gather the candidates below the final threshold from every unit list of this query
-  for (int r = 0; r < a.n_ranges; ++r) {
+  __shared__ unsigned s_cnt[64];
+  for (int r = tid; r < a.n_ranges; r += kRerankThreads) {
     const unsigned cnt = a.unit_cnt[(size_t)q * a.n_ranges + r];
-    if (cnt > (unsigned)a.cap) { if (tid == 0) bad = 1; }
-    const unsigned c = min(cnt, (unsigned)a.cap);
+    if (cnt > (unsigned)a.cap) bad = 1;
+    s_cnt[r] = min(cnt, (unsigned)a.cap);
+  }
+  __syncthreads();
+  for (int r = 0; r < a.n_ranges; ++r) {
+    const unsigned c = s_cnt[r];
     const size_t base = ((size_t)q * a.n_ranges + r) * (size_t)a.cap;
     for (unsigned i = tid; i < c; i += kRerankThreads) {
       const float s = a.cand_s[base + i];
@@ -525,17 +655,26 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   //    reads); the running sum over groups is a serial chain done by one thread per row.
   for (int b0 = 0; b0 < nf; b0 += 32) {
     const int nb = min(32, nf - b0);
-    for (int c = 0; c < nb; ++c) {
-      const float4* x4 = reinterpret_cast<const float4*>(a.db + (size_t)fin_i[b0 + c] * a.dim);
-      for (int g = tid; g < groups; g += kRerankThreads) {
-        const float4 x = __ldg(x4 + g);
-        const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * g);
-        const float d0 = __fsub_rn(qq.x, x.x), d1 = __fsub_rn(qq.y, x.y);
-        const float d2 = __fsub_rn(qq.z, x.z), d3 = __fsub_rn(qq.w, x.w);
-        float s = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
-        s = __fadd_rn(s, __fmul_rn(d2, d2));
-        s = __fadd_rn(s, __fmul_rn(d3, d3));
-        G[c * gstride + g] = s;
+    for (int g = tid; g < groups; g += kRerankThreads) {
+      const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * g);
+      for (int c0 = 0; c0 < nb; c0 += 8) {
+        float4 x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {   // 8 independent row reads in flight per thread
+          const int c = min(c0 + u, nb - 1);
+          x[u] = __ldg(reinterpret_cast<const float4*>(a.db + (size_t)fin_i[b0 + c] * a.dim) + g);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          if (c0 + u < nb) {
+            const float d0 = __fsub_rn(qq.x, x[u].x), d1 = __fsub_rn(qq.y, x[u].y);
+            const float d2 = __fsub_rn(qq.z, x[u].z), d3 = __fsub_rn(qq.w, x[u].w);
+            float sg = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
+            sg = __fadd_rn(sg, __fmul_rn(d2, d2));
+            sg = __fadd_rn(sg, __fmul_rn(d3, d3));
+            G[(c0 + u) * gstride + g] = sg;
+          }
+        }
       }
     }
     __syncthreads();
@@ -590,7 +729,7 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// bf16 matrix [rows][dim] (K-major), box = BK x box_rows, 128B swizzle, OOB rows read as 0
+// fp16 matrix [rows][dim] (K-major), box = BK x box_rows, 128B swizzle, OOB rows read as 0
 bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t dim, uint32_t box_rows) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
@@ -598,7 +737,7 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t rows, uint64_t dim, u
   cuuint64_t gstride[1] = {dim * 2};
   cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -627,11 +766,12 @@ struct Buf {
 
 struct ShortlistState {
   // database-derived (valid for rows [0, prepared_rows))
-  Buf db_bf16, xn, max_norm2;
+  Buf db_h, xn, dbstats;   // dbstats: [0] max ||x||^2, [1] max |x_i|, [2] max ||dx||^2 (float bits)
   size_t prepared_rows = 0, prepared_pad = 0;
   const float* prepared_src = nullptr;
+  float scale_x = 1.f;
   // per-call workspaces
-  Buf q_bf16, qn, thr, eps2, cand_idx, cand_s, unit_cnt, ovf_list, ovf_count, rows_ctr, partial;
+  Buf q_h, qn, qe, qinv, thr, eps2, cand_idx, cand_s, unit_cnt, ovf_list, ovf_count, rows_ctr, partial;
 };
 
 bool shortlist_supported(size_t dim, size_t k) {
@@ -649,7 +789,7 @@ void shortlist_invalidate(ShortlistState* s, size_t first_dirty_row) {
 
 void shortlist_destroy(ShortlistState* s) {
   if (!s) return;
-  for (Buf* b : {&s->db_bf16, &s->xn, &s->max_norm2, &s->q_bf16, &s->qn, &s->thr, &s->eps2,
+  for (Buf* b : {&s->db_h, &s->xn, &s->dbstats, &s->q_h, &s->qn, &s->qe, &s->qinv, &s->thr, &s->eps2,
                  &s->cand_idx, &s->cand_s, &s->unit_cnt, &s->ovf_list, &s->ovf_count, &s->rows_ctr,
                  &s->partial})
     b->release();
@@ -695,35 +835,47 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
   (void)fallback;
   (void)rows_reranked;
 
-  // ---- K1 (cached): bf16 copy + norms of the database rows
+  // ---- K1 (cached): FP16 copy + norms of the database rows
   const size_t n_total = A.n_total;
   const size_t n_pad = (n_total + BN - 1) / BN * BN + BN;
   if (S->prepared_src != A.d_db || S->prepared_pad < n_pad) S->prepared_rows = 0;
   if (S->prepared_rows < n_total) {
-    if (S->prepared_rows == 0) {
-      GLOC_CUDA_TRY(S->db_bf16.reserve(n_pad * dim * 2));
+    const bool fresh = S->prepared_rows == 0;
+    if (fresh) {
+      GLOC_CUDA_TRY(S->db_h.reserve(n_pad * dim * 2));
       GLOC_CUDA_TRY(S->xn.reserve(n_pad * sizeof(float)));
-      GLOC_CUDA_TRY(S->max_norm2.reserve(4));
-      GLOC_CUDA_TRY(cudaMemsetAsync(S->max_norm2.p, 0, 4, st));
-      S->prepared_pad = std::min(S->db_bf16.bytes / ((size_t)dim * 2), S->xn.bytes / sizeof(float));
-    } else if (S->prepared_pad < n_pad) {
-      S->prepared_rows = 0;
-      return shortlist_query(sp, A, launches, fallback, rows_reranked);
+      GLOC_CUDA_TRY(S->dbstats.reserve(16));
+      GLOC_CUDA_TRY(cudaMemsetAsync(S->dbstats.p, 0, 16, st));
+      S->prepared_pad = std::min(S->db_h.bytes / ((size_t)dim * 2), S->xn.bytes / sizeof(float));
     }
     const size_t r0 = S->prepared_rows;
-    const long long rows = (long long)(n_pad - r0);
+    unsigned* stats = (unsigned*)S->dbstats.p;
     const int wpb = 8;
-    knn_prep_rows_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-        A.d_db + r0 * dim, (long long)(n_total - r0), rows, dim,
-        (__nv_bfloat16*)S->db_bf16.p + r0 * dim, (float*)S->xn.p + r0, (unsigned*)S->max_norm2.p);
+    const long long new_rows = (long long)(n_total - r0);
+    knn_db_stats_kernel<<<(unsigned)((new_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        A.d_db + r0 * dim, new_rows, dim, (float*)S->xn.p + r0, stats, stats + 1);
     GLOC_CUDA_TRY(cudaGetLastError());
-    ++*launches;
+    float max_abs = 0.f;  // one-time host round trip: the scale is a launch parameter
+    GLOC_CUDA_TRY(cudaMemcpyAsync(&max_abs, stats + 1, 4, cudaMemcpyDeviceToHost, st));
+    GLOC_CUDA_TRY(cudaStreamSynchronize(st));
+    if (fresh) {
+      S->scale_x = pow2_scale_for(max_abs);
+    } else if (!(max_abs * S->scale_x < 32768.f)) {
+      S->prepared_rows = 0;  // appended rows outgrew the scale: convert everything again
+      return shortlist_query(sp, A, launches, fallback, rows_reranked);
+    }
+    const long long conv_rows = (long long)(n_pad - r0);
+    knn_db_convert_kernel<<<(unsigned)((conv_rows + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        A.d_db + r0 * dim, new_rows, conv_rows, dim, S->scale_x, (__half*)S->db_h.p + r0 * dim,
+        (float*)S->xn.p + r0, stats + 2);
+    GLOC_CUDA_TRY(cudaGetLastError());
+    *launches += 2;
     S->prepared_rows = n_total;
     S->prepared_src = A.d_db;
   }
 
   CUtensorMap map_db;
-  if (!make_map(&map_db, S->db_bf16.p, A.n_rows, (uint64_t)dim, BN))
+  if (!make_map(&map_db, S->db_h.p, A.n_rows, (uint64_t)dim, BN))
     return fail(GLOC_ERR_CUDA, "cuTensorMapEncodeTiled(db) failed");
 
   const size_t kChunk = 16384;  // bounds the candidate workspace
@@ -732,8 +884,10 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     const Plan plan = make_plan((long long)A.n_rows, nq, sms);
     const int n_qtiles = (nq + BM - 1) / BM;
     const size_t lists = (size_t)nq * plan.n_ranges;
-    GLOC_CUDA_TRY(S->q_bf16.reserve((size_t)n_qtiles * BM * dim * 2));
+    GLOC_CUDA_TRY(S->q_h.reserve((size_t)n_qtiles * BM * dim * 2));
     GLOC_CUDA_TRY(S->qn.reserve((size_t)nq * 4));
+    GLOC_CUDA_TRY(S->qe.reserve((size_t)nq * 4));
+    GLOC_CUDA_TRY(S->qinv.reserve((size_t)nq * 4));
     GLOC_CUDA_TRY(S->thr.reserve((size_t)nq * 4));
     GLOC_CUDA_TRY(S->eps2.reserve((size_t)nq * 4));
     GLOC_CUDA_TRY(S->cand_idx.reserve(lists * plan.cap * 4));
@@ -750,8 +904,8 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     // K1 for the queries
     {
       const int wpb = 8;
-      knn_prep_rows_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, 0, st>>>(
-          dq, nq, nq, dim, (__nv_bfloat16*)S->q_bf16.p, (float*)S->qn.p, nullptr);
+      knn_query_prep_kernel<<<(nq + wpb - 1) / wpb, wpb * 32, 0, st>>>(
+          dq, nq, dim, (__half*)S->q_h.p, (float*)S->qn.p, (float*)S->qe.p, (float*)S->qinv.p);
       GLOC_CUDA_TRY(cudaGetLastError());
       knn_fill_u32_kernel<<<(nq + 255) / 256, 256, 0, st>>>((unsigned*)S->thr.p, (size_t)nq,
                                                           0xFF800000u);  // f2ord(+inf)
@@ -760,7 +914,7 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
       *launches += 2;
     }
     CUtensorMap map_q;
-    if (!make_map(&map_q, S->q_bf16.p, (uint64_t)nq, (uint64_t)dim, BM))
+    if (!make_map(&map_q, S->q_h.p, (uint64_t)nq, (uint64_t)dim, BM))
       return fail(GLOC_ERR_CUDA, "cuTensorMapEncodeTiled(queries) failed");
 
     // K2
@@ -776,7 +930,11 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     g.n_rows = (long long)A.n_rows;
     g.xn = (const float*)S->xn.p;
     g.qn = (const float*)S->qn.p;
-    g.max_norm2_bits = (const unsigned*)S->max_norm2.p;
+    g.qe = (const float*)S->qe.p;
+    g.qinv = (const float*)S->qinv.p;
+    g.inv_sx = 1.f / S->scale_x;
+    g.max_norm2_bits = (const unsigned*)S->dbstats.p;
+    g.max_dx2_bits = (const unsigned*)S->dbstats.p + 2;
     g.thr_ord = (unsigned*)S->thr.p;
     g.eps2 = (float*)S->eps2.p;
     g.cand_idx = (unsigned*)S->cand_idx.p;
@@ -829,19 +987,39 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     GLOC_CUDA_TRY(cudaGetLastError());
     *launches += 2;
 
+    if (getenv("GLOC_DEBUG_SHORTLIST")) {  // tuning aid: candidate-list statistics of this chunk
+      cudaStreamSynchronize(st);
+      std::vector<unsigned> hc(lists), ht(nq);
+      std::vector<float> he(nq);
+      int ovf = 0;
+      cudaMemcpy(hc.data(), S->unit_cnt.p, lists * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ht.data(), S->thr.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(he.data(), S->eps2.p, (size_t)nq * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(&ovf, S->ovf_count.p, 4, cudaMemcpyDeviceToHost);
+      unsigned long long sum = 0, mx = 0, over = 0;
+      for (unsigned c : hc) { sum += c; mx = std::max<unsigned long long>(mx, c); over += c > (unsigned)plan.cap; }
+      unsigned long long sum_first = 0;
+      for (int qi = 0; qi < nq; ++qi) sum_first += hc[(size_t)qi * plan.n_ranges];
+      fprintf(stderr, "[shortlist] nq=%d ranges=%d tiles/range=%d r_big=%d cap=%d | emitted/query=%.1f "
+                      "(range0 %.1f) max/list=%llu lists_over_cap=%llu | overflowed queries=%d | thr[0]=%08x eps2[0]=%g\n",
+              nq, plan.n_ranges, plan.tiles_per_range, plan.r_big, plan.cap, (double)sum / nq,
+              (double)sum_first / nq, mx, over, ovf, ht[0], he[0]);
+    }
+
     // overflowed queries: exact scan on the device, sized for the worst case, count read on
     // the device (surplus CTAs exit immediately; usually every CTA does)
     {
-      const int BQs = exact_scan_tile_q(nq), BNs = exact_scan_tile_n(nq);
-      (void)BQs;
-      const int n_r = (int)std::max<long long>(1, std::min<long long>(8, (long long)A.n_rows / (BNs * 4LL)));
+      // small-tile configuration (16 queries x 256 rows per CTA) over many row ranges: a
+      // handful of overflowed queries still spreads over the whole GPU
+      const int BNs = 256;
+      const int n_r = (int)std::max<long long>(1, std::min<long long>(32, (long long)A.n_rows / (BNs * 4LL)));
       long long rpr = ((long long)A.n_rows + n_r - 1) / n_r;
       rpr = (rpr + BNs - 1) / BNs * BNs;
       const int n_ranges = (int)(((long long)A.n_rows + rpr - 1) / rpr);
       GLOC_CUDA_TRY(S->partial.reserve((size_t)nq * n_ranges * k * 8));
       GLOC_CUDA_TRY(launch_knn_exact_scan(A.d_db, (long long)A.n_rows, dim, dq, nq, k, n_ranges, rpr,
                                           (uint64_t*)S->partial.p, st, (const int*)S->ovf_list.p,
-                                          (const int*)S->ovf_count.p));
+                                          (const int*)S->ovf_count.p, /*force_small=*/true));
       GLOC_CUDA_TRY(launch_knn_finalize((const uint64_t*)S->partial.p, nq, n_ranges, k, A.offset,
                                         A.d_idx + q0 * k, A.d_d2 + q0 * k, st,
                                         (const int*)S->ovf_list.p, (const int*)S->ovf_count.p));

@@ -53,7 +53,7 @@ typedef struct gloc_knn_index gloc_knn_index;
 /* Search strategy.  All three return identical results. */
 #define GLOC_KNN_AUTO 0      /* tensor shortlist when it applies, else exact scan   */
 #define GLOC_KNN_EXACT_SCAN 1 /* FP32 exact scan of every row (K3 as a full scan)    */
-#define GLOC_KNN_SHORTLIST 2 /* BF16 tcgen05 GEMM shortlist (K1+K2) + FP32 re-rank  */
+#define GLOC_KNN_SHORTLIST 2 /* FP16 tcgen05 GEMM shortlist (K1+K2) + FP32 re-rank  */
                              /* (K3); queries whose shortlist overflows are re-run  */
                              /* through the exact scan on the GPU                   */
 
