@@ -54,8 +54,9 @@ constexpr int kStagesB = 3;        // B ring depth
 constexpr int kMaxKBlocks = 8;     // dim <= 512 keeps the whole query tile resident (128 KB)
 constexpr int kABytesPerKB = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;        // 32 KB
-constexpr int kThreads = 256;      // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kThreads = 384;      // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
 constexpr int kTmemCols = 512;
+constexpr int kWarmChunks = 8;     // chunks whose scores all enter the threshold list (per warpgroup)
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kMaxKBlocks * kABytesPerKB +
                               (size_t)kStagesB * kBBytes + 256 /*barriers*/;
 
@@ -312,9 +313,9 @@ struct GemmArgs {
   const unsigned* max_dx2_bits;     // DXmax^2
   unsigned* thr_ord;                // [nq] shared running threshold (ordered-uint of s-space)
   float* eps2;                      // [nq] 2*eps, written by the epilogue (read by K3)
-  unsigned* cand_idx;               // [nq][n_ranges][cap]
-  float* cand_s;                    // [nq][n_ranges][cap]
-  unsigned* unit_cnt;               // [nq][n_ranges]
+  unsigned* cand_idx;               // [nq][2*n_ranges][cap]  (two epilogue warpgroups)
+  float* cand_s;                    // [nq][2*n_ranges][cap]
+  unsigned* unit_cnt;               // [nq][2*n_ranges]
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -350,7 +351,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(tm_full + s, 1);
-      mbar_init(tm_empty + s, 4);  // one arrive per epilogue warp
+      mbar_init(tm_empty + s, 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -444,7 +445,12 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     // largest entry B = lst[31] bounds the 32nd (hence k-th, k <= 32) smallest score of the
     // whole database from above; the threshold is B + 2 eps, shared between the units of a
     // query through global memory.  Every score <= B passes the test, so the list is exact.
-    const int ew = warp - 4;                  // == warp % 4: this warp's TMEM lane quadrant
+    // Two warpgroups (warps 4-7 and 8-11) share every tile: group wg takes the chunks with
+    // c % 2 == wg, so each scheduler has two epilogue warps to hide TMEM/L1 latency.  Both
+    // threads of a query row keep their own list / candidate list (list index 2*range + wg)
+    // and meet in the shared threshold.
+    const int ew = warp & 3;                  // this warp's TMEM lane quadrant
+    const int wg = (warp - 4) >> 2;           // 0 or 1
     const int row = ew * 32 + lane;           // query row inside the tile = TMEM lane
     int as = 0;
     uint32_t aphase = 0;
@@ -461,7 +467,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
         const float e = 2.f * (dq * xmax + (1.f + kU) * qnorm * dxmax) + kCAcc * qnorm * xmax +
                         kC2 * (qnorm + xmax) * (qnorm + xmax) + 1e-30f;
         eps2 = 2.f * e;
-        if (rg == 0) a.eps2[q] = eps2;
+        if (rg == 0 && wg == 0) a.eps2[q] = eps2;
         cm = -2.f * a.inv_sx * a.qinv[q];   // undoes both power-of-two scales (exact)
       }
       float thr = q_ok ? ord2f(a.thr_ord[q]) : -INFINITY;   // shared across this query's units
@@ -469,9 +475,47 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 #pragma unroll
       for (int j = 0; j < 32; ++j) lst[j] = INFINITY;
       unsigned cnt = 0;
-      const size_t list_base = ((size_t)(q_ok ? q : 0) * a.n_ranges + rg) * (size_t)a.cap;
+      // scores emitted since the last flush and not yet in lst (FIFO; extra ones are only
+      // emitted -- lst then holds a subset of the rows seen, which is still a valid bound)
+      float pend[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pend[i] = INFINITY;
+      int npend = 0;
+      // No bound yet anywhere in the warp (first units of a query): the first kWarmChunks
+      // chunks insert every score into lst with one warp-uniform instruction stream.
+      int warm_left = __any_sync(0xffffffffu, q_ok && thr == INFINITY) ? kWarmChunks : 0;
+      const int n_lists = 2 * a.n_ranges;
+      const size_t list_base = ((size_t)(q_ok ? q : 0) * n_lists + 2 * rg + wg) * (size_t)a.cap;
+
+      // sorted insertion of one score; the largest of the 33 values drops out (+inf: no-op)
+      auto lst_insert = [&](float w) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float lo = fminf(lst[i], w);
+          w = fmaxf(lst[i], w);
+          lst[i] = lo;
+        }
+      };
+      // warp-uniform: every lane inserts its pending scores (lanes with fewer insert +inf)
+      auto flush_pending = [&]() {
+        const int mp = __reduce_max_sync(0xffffffffu, npend);
+#pragma unroll 1
+        for (int p = 0; p < mp; ++p) {
+          const float w = pend[0];
+#pragma unroll
+          for (int i = 0; i < 7; ++i) pend[i] = pend[i + 1];
+          pend[7] = INFINITY;
+          lst_insert(w);
+        }
+        npend = 0;
+        thr = fminf(thr, lst[31] + eps2);
+      };
+
       for (int it = 0; it < t_count; ++it) {
         const int t = t_begin + it;
+        // bound published by the other units of this query: read now, used after the tile
+        unsigned seen = 0xFFFFFFFFu;
+        if (q_ok) seen = *reinterpret_cast<volatile unsigned*>(a.thr_ord + q);
         mbar_wait(tm_full + as, aphase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
@@ -480,7 +524,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
         // tighten the bound; rows >= n_total already carry ||x||^2 = +inf
         const int valid_cols = (int)min((long long)BN, a.n_rows - (long long)t * BN);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = wg; c < BN / 32; c += 2) {
           float4 xr[8];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) xr[j4] = __ldg(xn4 + c * 8 + j4);
@@ -500,30 +544,59 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             for (int j = 0; j < 32; ++j)
               if (c * 32 + j >= valid_cols) sc[j] = INFINITY;
           }
-          float m = fminf(sc[0], sc[1]);
+          const bool warm = warm_left > 0;   // warp-uniform
+          if (warm) {
+            --warm_left;
 #pragma unroll
-          for (int j = 2; j < 32; j += 2) m = fminf(m, fminf(sc[j], sc[j + 1]));
-          if (q_ok && m <= thr) {
+            for (int g = 0; g < 4; ++g) {
+              float r0 = sc[8 * g], r1 = sc[8 * g + 1], r2 = sc[8 * g + 2], r3 = sc[8 * g + 3];
+              float r4 = sc[8 * g + 4], r5 = sc[8 * g + 5], r6 = sc[8 * g + 6], r7 = sc[8 * g + 7];
+#pragma unroll 1
+              for (int jj = 0; jj < 8; ++jj) {   // rolled: one copy of the insertion per group
+                lst_insert(r0);
+                r0 = r1; r1 = r2; r2 = r3; r3 = r4; r4 = r5; r5 = r6; r6 = r7;
+              }
+            }
+            thr = fminf(thr, lst[31] + eps2);
+          }
+          float mg[4];   // minima of the four 8-column groups
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (sc[j] <= thr && sc[j] < INFINITY) {   // +inf = masked / padded row
-                if (cnt < (unsigned)a.cap) {
-                  a.cand_idx[list_base + cnt] = (unsigned)(t * BN + c * 32 + j);
-                  a.cand_s[list_base + cnt] = sc[j];
+          for (int g = 0; g < 4; ++g) {
+            mg[g] = fminf(fminf(fminf(sc[8 * g], sc[8 * g + 1]), fminf(sc[8 * g + 2], sc[8 * g + 3])),
+                          fminf(fminf(sc[8 * g + 4], sc[8 * g + 5]), fminf(sc[8 * g + 6], sc[8 * g + 7])));
+          }
+          const float m = fminf(fminf(mg[0], mg[1]), fminf(mg[2], mg[3]));
+          if (q_ok && m <= thr) {   // lane-divergent slow path, all in registers
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (mg[g] <= thr) {
+                float r0 = sc[8 * g], r1 = sc[8 * g + 1], r2 = sc[8 * g + 2], r3 = sc[8 * g + 3];
+                float r4 = sc[8 * g + 4], r5 = sc[8 * g + 5], r6 = sc[8 * g + 6], r7 = sc[8 * g + 7];
+#pragma unroll 1
+                for (int jj = 0; jj < 8; ++jj) {   // rolled: one compact copy per group
+                  const float vj = r0;
+                  r0 = r1; r1 = r2; r2 = r3; r3 = r4; r4 = r5; r5 = r6; r6 = r7;
+                  if (vj <= thr && vj < INFINITY) {   // +inf = masked / padded row
+                    if (cnt < (unsigned)a.cap) {
+                      a.cand_idx[list_base + cnt] = (unsigned)(t * BN + c * 32 + 8 * g + jj);
+                      a.cand_s[list_base + cnt] = vj;
+                    }
+                    ++cnt;
+                    if (!warm && npend < 8) {
+#pragma unroll
+                      for (int i = 7; i > 0; --i) pend[i] = pend[i - 1];
+                      pend[0] = vj;
+                      ++npend;
+                    }
+                  }
                 }
-                ++cnt;
-                float w = sc[j];   // sorted insertion; the largest of the 33 values drops out
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  const float lo = fminf(lst[i], w);
-                  w = fmaxf(lst[i], w);
-                  lst[i] = lo;
-                }
-                thr = fminf(thr, lst[31] + eps2);
               }
             }
           }
+          // flush as soon as some lane's pending buffer is full (warp-uniform, no divergence)
+          if (__any_sync(0xffffffffu, npend >= 8)) flush_pending();
         }
+        if (__any_sync(0xffffffffu, npend > 0)) flush_pending();
         // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA
         tcgen05_fence_before();
         __syncwarp();
@@ -531,12 +604,11 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
         if (++as == 2) { as = 0; aphase ^= 1; }
         if (q_ok) {  // publish / pick up the bound shared by all units of this query
           const unsigned mine = f2ord(thr);
-          const unsigned seen = *reinterpret_cast<volatile unsigned*>(a.thr_ord + q);
           if (mine < seen) atomicMin(a.thr_ord + q, mine);
           else thr = ord2f(seen);
         }
       }
-      if (q_ok) a.unit_cnt[(size_t)q * a.n_ranges + rg] = cnt;
+      if (q_ok) a.unit_cnt[(size_t)q * n_lists + 2 * rg + wg] = cnt;
     }
   }
 
@@ -819,7 +891,7 @@ Plan make_plan(long long n_rows, int nq, int sms) {
   p.tiles_per_range = (int)((tiles + best_r - 1) / best_r);
   p.n_ranges = (int)((tiles + p.tiles_per_range - 1) / p.tiles_per_range);
   p.r_big = std::min<int>(p.n_ranges, (sms + n_qtiles - 1) / n_qtiles);
-  p.cap = 1024;
+  p.cap = 512;
   return p;
 }
 
@@ -883,7 +955,7 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     const int nq = (int)std::min(kChunk, A.nq - q0);
     const Plan plan = make_plan((long long)A.n_rows, nq, sms);
     const int n_qtiles = (nq + BM - 1) / BM;
-    const size_t lists = (size_t)nq * plan.n_ranges;
+    const size_t lists = (size_t)nq * plan.n_ranges * 2;  // two epilogue warpgroups per unit
     GLOC_CUDA_TRY(S->q_h.reserve((size_t)n_qtiles * BM * dim * 2));
     GLOC_CUDA_TRY(S->qn.reserve((size_t)nq * 4));
     GLOC_CUDA_TRY(S->qe.reserve((size_t)nq * 4));
@@ -962,7 +1034,7 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     r.nq = nq;
     r.dim = dim;
     r.k = k;
-    r.n_ranges = plan.n_ranges;
+    r.n_ranges = plan.n_ranges * 2;   // lists per query
     r.cap = plan.cap;
     r.cand_idx = g.cand_idx;
     r.cand_s = g.cand_s;
@@ -999,7 +1071,7 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
       unsigned long long sum = 0, mx = 0, over = 0;
       for (unsigned c : hc) { sum += c; mx = std::max<unsigned long long>(mx, c); over += c > (unsigned)plan.cap; }
       unsigned long long sum_first = 0;
-      for (int qi = 0; qi < nq; ++qi) sum_first += hc[(size_t)qi * plan.n_ranges];
+      for (int qi = 0; qi < nq; ++qi) sum_first += hc[(size_t)qi * plan.n_ranges * 2] + hc[(size_t)qi * plan.n_ranges * 2 + 1];
       fprintf(stderr, "[shortlist] nq=%d ranges=%d tiles/range=%d r_big=%d cap=%d | emitted/query=%.1f "
                       "(range0 %.1f) max/list=%llu lists_over_cap=%llu | overflowed queries=%d | thr[0]=%08x eps2[0]=%g\n",
               nq, plan.n_ranges, plan.tiles_per_range, plan.r_big, plan.cap, (double)sum / nq,
