@@ -15,6 +15,8 @@
 //
 // Roofline: this kernel is FP32-issue bound (12 non-fusable ops per 4 dims per
 // (query,row) pair = 3 ops/dim), not HBM bound, for any query batch above ~16.
+#include <algorithm>
+
 #include "knn_kernels.cuh"
 
 namespace gloc {
@@ -135,12 +137,13 @@ knn_exact_scan_kernel(const float* __restrict__ db, long long n_rows, int dim,
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tx = tid % TXN, ty = tid / TXN;
-  const int qt = blockIdx.x % n_qtiles, rg = blockIdx.x / n_qtiles;
-  const long long q0 = (long long)qt * BQ;
-  // Fallback launches size the grid for the worst case and pass the real query count (and
-  // the compacted query ids) in device memory: surplus CTAs leave before any barrier.
+  // n_qtiles is the number of query tiles in the GRID; a CTA strides over the real tiles.
+  // Fallback launches bound the grid and pass the real query count (and the compacted query
+  // ids) in device memory: surplus CTAs leave before any barrier.
+  const int rg = blockIdx.x / n_qtiles;
   if (nq_dev != nullptr) nq = *nq_dev;
-  if (q0 >= nq) return;
+  for (int qt = blockIdx.x % n_qtiles; (long long)qt * BQ < nq; qt += n_qtiles) {
+  const long long q0 = (long long)qt * BQ;
   const long long row_begin = (long long)rg * rows_per_range;
   const long long row_end = min(n_rows, row_begin + rows_per_range);
   const bool vec_ok = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(db) & 15) == 0) &&
@@ -148,6 +151,7 @@ knn_exact_scan_kernel(const float* __restrict__ db, long long n_rows, int dim,
   const int n_chunks = (dim + DK - 1) / DK;
   const int full_groups = dim / 4, tail = dim % 4;
 
+  __syncthreads();  // previous query tile of this CTA fully written out
   for (int i = tid; i < BQ * KCAP; i += NT) list[i] = kEmptyKey;
   for (int i = tid; i < BQ; i += NT) qcnt[i] = 0;
   __syncthreads();
@@ -260,6 +264,7 @@ knn_exact_scan_kernel(const float* __restrict__ db, long long n_rows, int dim,
     if (q0 + qr < nq)
       partial[((size_t)(q0 + qr) * n_ranges + rg) * k + s] = list[qr * KCAP + s];
   }
+  }  // query-tile loop
 }
 
 // ---------------------------------------------------------------------------
@@ -360,7 +365,8 @@ cudaError_t launch_scan(const float* db, long long n_rows, int dim, const float*
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)Cfg::kSmem);
   if (e != cudaSuccess) return e;
-  const int n_qtiles = (nq + BQ - 1) / BQ;
+  int n_qtiles = (nq + BQ - 1) / BQ;
+  if (nq_dev != nullptr) n_qtiles = std::min(n_qtiles, 64);  // fallback: bounded grid, CTAs stride
   kern<<<n_qtiles * n_ranges, Cfg::NT, Cfg::kSmem, stream>>>(db, n_rows, dim, q, nq, k, n_qtiles,
                                                             rows_per_range, n_ranges, partial, qmap,
                                                             nq_dev);

@@ -663,21 +663,33 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   const float tau = ord2f(a.thr_ord[q]);
   const float eps2 = a.eps2[q];
   // 1. gather the candidates below the final threshold from every unit list of this query
-  __shared__ unsigned s_cnt[64];
+  __shared__ unsigned s_cnt[64], s_off[65];
   for (int r = tid; r < a.n_ranges; r += kRerankThreads) {
     const unsigned cnt = a.unit_cnt[(size_t)q * a.n_ranges + r];
     if (cnt > (unsigned)a.cap) bad = 1;
     s_cnt[r] = min(cnt, (unsigned)a.cap);
   }
   __syncthreads();
-  for (int r = 0; r < a.n_ranges; ++r) {
-    const unsigned c = s_cnt[r];
-    const size_t base = ((size_t)q * a.n_ranges + r) * (size_t)a.cap;
-    for (unsigned i = tid; i < c; i += kRerankThreads) {
-      const float s = a.cand_s[base + i];
+  if (tid == 0) {
+    unsigned o = 0;
+    for (int r = 0; r < a.n_ranges; ++r) { s_off[r] = o; o += s_cnt[r]; }
+    s_off[a.n_ranges] = o;
+  }
+  __syncthreads();
+  {  // one flat pass over all lists: every load is independent of the others
+    const unsigned total = s_off[a.n_ranges];
+    const size_t qbase = (size_t)q * a.n_ranges * (size_t)a.cap;
+    for (unsigned e = tid; e < total; e += kRerankThreads) {
+      int lo = 0, hi = a.n_ranges - 1;   // largest r with s_off[r] <= e
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
+      }
+      const size_t at = qbase + (size_t)lo * a.cap + (e - s_off[lo]);
+      const float s = a.cand_s[at];
       if (s <= tau) {
         const int pos = atomicAdd(&n_surv, 1);
-        if (pos < kSurvMax) { surv_s[pos] = s; surv_i[pos] = a.cand_idx[base + i]; }
+        if (pos < kSurvMax) { surv_s[pos] = s; surv_i[pos] = a.cand_idx[at]; }
       }
     }
   }
