@@ -70,8 +70,12 @@ class ShardedRetrieval:
         nq = idx.shape[0]
         all_idx = torch.empty((self.world_size, nq, k), dtype=idx.dtype, device=idx.device)
         all_d2 = torch.empty((self.world_size, nq, k), dtype=d2.dtype, device=d2.device)
-        dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_d2, d2.contiguous(), group=self.group)
+        if idx.is_cuda:   # NCCL: one fused gather per array, straight into the merge layout
+            dist.all_gather_into_tensor(all_idx, idx.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(all_d2, d2.contiguous(), group=self.group)
+        else:             # gloo (CPU tests of the host logic)
+            dist.all_gather(list(all_idx.unbind(0)), idx.contiguous(), group=self.group)
+            dist.all_gather(list(all_d2.unbind(0)), d2.contiguous(), group=self.group)
         return self._merge(all_idx, all_d2)
 
     def query_host(self, q_pinned, k: int, out_idx_pinned=None, out_d2_pinned=None):

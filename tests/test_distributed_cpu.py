@@ -1,0 +1,73 @@
+"""CPU: the multi-GPU host logic (row sharding, all-gather layout, merge) with world_size 2
+over gloo.  The GPU kernels are replaced by injected functions (the oracle as the local
+searcher and as the merge) -- only the plumbing of gloc3d_b200.distributed is under test."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gloc3d_b200 import synth
+    from gloc3d_b200.distributed import ShardedRetrieval, shard_bounds
+    from oracle import pyoracle as po
+
+    n, nq, k = 3001, 37, 25
+    db = synth.make_descriptors(n, 64, seed=7, dup_run=4)
+    q = synth.make_queries(db, nq, seed=8, sigma=0.002)
+    b = shard_bounds(n, world)
+    lo, hi = b[rank], b[rank + 1]
+
+    def local_search(qt, kk):
+        idx, d2 = po.knn(db[lo:hi], qt.numpy(), kk)
+        idx = np.where(idx == np.iinfo(np.uint64).max, idx, idx + np.uint64(lo))
+        return torch.from_numpy(idx.view(np.int64)), torch.from_numpy(d2)
+
+    def merge(all_idx, all_d2):
+        mi, md = po.topk_merge(all_idx.numpy().view(np.uint64), all_d2.numpy())
+        return torch.from_numpy(mi.view(np.int64)), torch.from_numpy(md)
+
+    sr = ShardedRetrieval(rank, world, local_search=local_search, merge=merge)
+    idx, d2 = sr.query(torch.from_numpy(q), k)
+    ref_idx, ref_d2 = po.knn(db, q, k)
+    ok = np.array_equal(idx.numpy().view(np.uint64), ref_idx) and np.array_equal(d2.numpy(), ref_d2)
+    open(os.path.join(out_dir, f"rank{rank}.txt"), "w").write("ok" if ok else "mismatch")
+    dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    from gloc3d_b200.distributed import shard_bounds
+
+    for n in (0, 1, 7, 100_000, 1_000_003):
+        for g in (1, 2, 4, 8):
+            b = shard_bounds(n, g)
+            assert b[0] == 0 and b[-1] == n and len(b) == g + 1
+            sizes = np.diff(b)
+            assert (sizes >= 0).all() and sizes.max() - sizes.min() <= 1
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_query_gloo(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(tmp_path / f"rank{r}.txt").read() == "ok"
