@@ -200,8 +200,10 @@ def run_retrieval(args, rank, world, local_rank):
         return None
     last_mode = int(st.last_mode)
     shard_rows = hi - lo
-    flops = 2.0 * nq * shard_rows * DIM                       # per launch of the dominant kernel
-    alg_bytes = shard_rows * DIM * 4 + nq * DIM * 4 + nq * K_NN * 12
+    # the library may split a batch into several launches: algorithmic work per LAUNCH
+    launches_per_step = max(dom_n, 1) / args.steps
+    flops = 2.0 * nq * shard_rows * DIM / launches_per_step
+    alg_bytes = shard_rows * DIM * 4 + (nq * DIM * 4 + nq * K_NN * 12) / launches_per_step
     avg_ms = dom_ms / max(dom_n, 1)
     peak_tf = peaks["bf16_tflops"]
     traffic = None

@@ -962,7 +962,14 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
   if (!make_map(&map_db, S->db_h.p, A.n_rows, (uint64_t)dim, BN))
     return fail(GLOC_ERR_CUDA, "cuTensorMapEncodeTiled(db) failed");
 
-  const size_t kChunk = 16384;  // bounds the candidate workspace
+  // queries per pass: bounded so that the candidate workspace (2 lists per unit, 8 B per
+  // slot) stays under ~6 GB
+  size_t kChunk = 65536;
+  {
+    const Plan p0 = make_plan((long long)A.n_rows, (int)std::min<size_t>(A.nq, kChunk), sms);
+    const size_t per_query = (size_t)p0.n_ranges * 2 * p0.cap * 8;
+    kChunk = std::max<size_t>(BM, std::min<size_t>(kChunk, ((size_t)6 << 30) / per_query / BM * BM));
+  }
   for (size_t q0 = 0; q0 < A.nq; q0 += kChunk) {
     const int nq = (int)std::min(kChunk, A.nq - q0);
     const Plan plan = make_plan((long long)A.n_rows, nq, sms);

@@ -1,0 +1,112 @@
+// gloc_loop_detector.hpp -- the hot-path half of RpyPCLoopDetector
+// (/root/reference/registration/loop_detector.{h,cpp}) on top of the GPU path: same member
+// names, constants and guards for detect()/match(); descriptors and BEV grids are handed in
+// (the CNN forward and the BEV projection are outside the north-star path).
+#ifndef GLOC_LOOP_DETECTOR_HPP_
+#define GLOC_LOOP_DETECTOR_HPP_
+
+#include <iostream>
+#include <memory>
+#include <vector>
+
+#include "gloc_fast_csm_2d.hpp"
+#include "gloc_inv_key_tree.hpp"
+
+class RpyPCLoopDetectorGpu {
+ public:
+  using Grid2DView = cartographer::mapping::Grid2DView;
+  using Matcher = cartographer::mapping::scan_matching::FastCorrelativeScanMatcher2D;
+  using Options = cartographer::mapping::scan_matching::FastCorrelativeScanMatcherOptions2D;
+  using Rigid2d = cartographer::mapping::scan_matching::Rigid2d;
+  using SearchParameters = cartographer::mapping::scan_matching::SearchParameters;
+
+  const int NUM_EXCLUDE_RECENT = 30;  // loop_detector.h:77
+
+  explicit RpyPCLoopDetectorGpu(int device = 0) : device_(device) {}
+
+  // add_keyframe (loop_detector.cpp:9-20) with the descriptor and the BEV grid already computed.
+  // `cells` must stay alive as long as the detector (the reference keeps cv::Mat copies).
+  void add_keyframe(const std::vector<float>& feat, const Grid2DView& grid) {
+    db_features_.push_back(feat);
+    db_grids_.push_back(grid);
+    if (kdtree_) kdtree_->append(feat);
+  }
+
+  // for global localization (loop_detector.cpp:22-46)
+  void detect(const std::vector<float>& q_feat, std::vector<size_t>& loop_indices,
+              std::vector<float>& out_dists_sqr) {
+    if (db_features_.size() <= num_exclude_recent_ + top_k_) {
+      std::cout << "Not enough keyframes in database." << std::endl;
+      return;
+    }
+    ensure_tree();
+    kdtree_->set_search_limit(db_features_.size());
+    loop_indices.resize(top_k_);
+    out_dists_sqr.resize(top_k_);
+    kdtree_->query(&q_feat[0], top_k_, &loop_indices[0], &out_dists_sqr[0]);
+  }
+
+  // for slam, using the last frame as query (loop_detector.cpp:48-81): searches all but the
+  // NUM_EXCLUDE_RECENT most recent keyframes; the reference rebuilds its KD-tree every 30
+  // calls over that set, the GPU index just moves its search limit.
+  bool detect(size_t& q_idx, size_t& loop_idx) {
+    if (db_features_.size() <= num_exclude_recent_ + top_k_) return false;
+    ensure_tree();
+    if (tree_making_period_counter_ % tree_making_period_ == 0)
+      search_rows_ = db_features_.size() - num_exclude_recent_;
+    tree_making_period_counter_ = tree_making_period_counter_ + 1;
+    kdtree_->set_search_limit(search_rows_);
+    const size_t cur_idx = db_features_.size() - 1;
+    std::vector<size_t> ret_indexes(top_k_);
+    std::vector<float> out_dists_sqr(top_k_);
+    kdtree_->query(&db_features_[cur_idx][0], top_k_, &ret_indexes[0], &out_dists_sqr[0]);
+    if (out_dists_sqr[0] < loop_metric_dist_th_) {
+      q_idx = cur_idx;
+      loop_idx = ret_indexes[0];
+      return true;
+    }
+    return false;
+  }
+
+  // match (loop_detector.h:73-75): verify candidate db_idx against the query grid by
+  // correlative / branch-and-bound scan matching of the BEV grids (the north-star verifier
+  // that takes the place of the SURF + RANSAC body, loop_detector.cpp:183-288).
+  // xy_yaw receives (x, y, yaw); estimated_scale is 1 (rigid).
+  bool match(const Grid2DView& q_grid, const size_t db_idx, float xy_yaw[3], double& estimated_scale,
+             int n_lin = 100, int n_ang = 180, double ang_step = 2. * M_PI / 360., float min_score = 0.3f) {
+    if (db_idx >= db_grids_.size()) return false;
+    Matcher matcher(db_grids_[db_idx], options_, device_);
+    const auto cloud = Matcher::GridToVirtualPointCloud(q_grid);
+    float score = 0.f;
+    Rigid2d pose;
+    const SearchParameters sp(n_lin, n_ang, ang_step, db_grids_[db_idx].limits.resolution);
+    if (!matcher.MatchWithSearchParameters(sp, Rigid2d(), cloud, min_score, &score, &pose)) return false;
+    xy_yaw[0] = static_cast<float>(pose.x);
+    xy_yaw[1] = static_cast<float>(pose.y);
+    xy_yaw[2] = static_cast<float>(pose.yaw);
+    estimated_scale = 1.;
+    last_score_ = score;
+    return true;
+  }
+  float last_score() const { return last_score_; }
+
+ private:
+  void ensure_tree() {
+    if (!kdtree_) kdtree_ = std::make_unique<InvKeyTree>(k_dim_, db_features_, 10, device_);
+  }
+  const size_t k_dim_ = 512;                 // loop_detector.h:97-103
+  const size_t top_k_ = 20;
+  const size_t num_exclude_recent_ = 30;
+  const size_t tree_making_period_ = 30;
+  size_t tree_making_period_counter_ = 0;
+  const float loop_metric_dist_th_ = 0.8f;
+  size_t search_rows_ = 0;
+  int device_;
+  float last_score_ = 0.f;
+  KeyMat db_features_;
+  std::unique_ptr<InvKeyTree> kdtree_;
+  std::vector<Grid2DView> db_grids_;
+  Options options_;
+};
+
+#endif  // GLOC_LOOP_DETECTOR_HPP_
