@@ -351,9 +351,11 @@ def run_verify(args, rank, world, local_rank):
     si = [p[1] for p in mine]
     inits = [(0.0, 0.0, 0.0)] * len(mine)
 
+    gpu_depth = args.verify_depth or VER["depth"]
+
     def step():
         return st.match_batch(scans, gi, si, inits, VER["n_lin"], VER["n_ang"], VER["step"],
-                              VER["depth"], VER["min_score"])
+                              gpu_depth, VER["min_score"])
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -474,6 +476,9 @@ def main():
     ap.add_argument("--workload", default="retrieval", choices=["retrieval", "verify"])
     ap.add_argument("--mode", default="auto", choices=["auto", "exact", "shortlist"])
     ap.add_argument("--verify-queries", type=int, default=8, help="queries per GPU per step (verify)")
+    ap.add_argument("--verify-depth", type=int, default=0,
+                    help="internal branch-and-bound depth of the GPU verifier (0 = the reference's 5); "
+                         "the result does not depend on it")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

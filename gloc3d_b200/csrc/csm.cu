@@ -276,6 +276,179 @@ csm_coarse_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
   }
 }
 
+// ------------------------------------------------------------- K7 coarse (phase-major)
+
+__global__ void csm_build_pm_kernel(const uint8_t* __restrict__ level, int wide_nx, int wide_ny,
+                                    int pad, int log2w, int pw, int ph, uint8_t* __restrict__ out) {
+  const int w = 1 << log2w;
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;   // padded coordinates
+  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
+  if (X >= pw * w || Y >= ph * w) return;
+  const int lx = X - pad, ly = Y - pad;
+  uint8_t v = 0;
+  if ((unsigned)lx < (unsigned)wide_nx && (unsigned)ly < (unsigned)wide_ny)
+    v = level[(size_t)ly * wide_nx + lx];
+  const size_t plane = (size_t)((Y & (w - 1)) * w + (X & (w - 1)));
+  out[(plane * ph + (Y >> log2w)) * pw + (X >> log2w)] = v;
+}
+
+constexpr int kPmThreads = 512;
+
+// One CTA per (scan, pair).  Phase 1: discretise the scan into shared memory and shrink the
+// window (ShrinkToFit).  Phase 2: points inside the padded grid become one int32 base offset
+// into the phase-major coarse level (compacted; border points keep their cell for a checked
+// path).  Phase 3: thread = (lattice candidate, point slice); the inner loop is
+// base + candidate offset -> one byte load -> add, no bounds checks, adjacent lanes read
+// adjacent bytes.  Slices are combined with shared-memory atomics; the best (score, rank) of
+// the rotation bin is reduced with warp shuffles.
+__global__ void __launch_bounds__(kPmThreads)
+csm_coarse_pm_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
+                     const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
+                     CsmBounds* __restrict__ bounds, int* __restrict__ coarse,
+                     unsigned long long* __restrict__ top_coarse) {
+  extern __shared__ __align__(16) unsigned char csm_smem[];
+  int2* cells = reinterpret_cast<int2*>(csm_smem);                        // [kPointChunk]
+  int* bases = reinterpret_cast<int*>(cells + kPointChunk);               // [kPointChunk]
+  int2* border = reinterpret_cast<int2*>(bases + kPointChunk);            // [kPointChunk]
+  int* sums = reinterpret_cast<int*>(border + kPointChunk);               // [prm.maxc]
+  __shared__ int red[4][kPmThreads / 32];
+  __shared__ unsigned long long redk[kPmThreads / 32];
+  __shared__ CsmBounds sb;
+  __shared__ int n_in, n_bd;
+  const int s = blockIdx.x, pi = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const CsmPairDev pr = pairs[pi];
+  const CsmGridDev g = grids[pr.grid];
+  const float2 r = rot[s];
+  const int P = pr.n_pts;
+  const float* sp = pts + 3 * (size_t)pr.pt_begin;
+
+  int mnx = 0, mny = 0, mxx = 0, mxy = 0;
+  for (int p = tid; p < P; p += kPmThreads) {
+    const int2 c = discretize_point(sp + 3 * (size_t)p, pr.w0, pr.z0, r.x, r.y, pr.tx, pr.ty,
+                                    g.resolution, g.max_x, g.max_y);
+    if (p < kPointChunk) cells[p] = c;
+    mnx = min(mnx, -c.x);
+    mny = min(mny, -c.y);
+    mxx = max(mxx, g.nx - 1 - c.x);
+    mxy = max(mxy, g.ny - 1 - c.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+    mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+    mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if (lane == 0) {
+    red[0][warp] = mnx;
+    red[1][warp] = mny;
+    red[2][warp] = mxx;
+    red[3][warp] = mxy;
+  }
+  for (int i = tid; i < prm.maxc; i += kPmThreads) sums[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w2 = 1; w2 < kPmThreads / 32; ++w2) {
+      mnx = min(mnx, red[0][w2]);
+      mny = min(mny, red[1][w2]);
+      mxx = max(mxx, red[2][w2]);
+      mxy = max(mxy, red[3][w2]);
+    }
+    CsmBounds b;
+    b.min_x = max(-prm.n_lin, mnx);
+    b.max_x = min(prm.n_lin, mxx);
+    b.min_y = max(-prm.n_lin, mny);
+    b.max_y = min(prm.n_lin, mxy);
+    sb = b;
+    bounds[(size_t)pi * prm.S + s] = b;
+  }
+  __syncthreads();
+  const CsmBounds b = sb;
+  const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
+  const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+  const int ncand = ncx * ncy;
+  const int wm1 = prm.step - 1, log2w = g.pm_log2w, pad = g.pm_pad;
+  const int wide_nx = g.nx + wm1, wide_ny = g.ny + wm1;
+  const int plane_sz = g.pm_ph * g.pm_pw;
+  const LevelView lv = level_view(g, prm.depth - 1);
+
+  // thread -> (candidate, point slice)
+  const int slots = ((ncand + 31) / 32) * 32;             // whole warps share a slice
+  const int n_slices = max(1, kPmThreads / slots);
+  const int my_slice = tid / slots, my_c = tid % slots;
+  const bool active = my_slice < n_slices && (slots <= kPmThreads);
+  int* out = coarse + ((size_t)pi * prm.S + s) * prm.maxc;
+
+  for (int cb = 0; cb < ncand; cb += kPmThreads) {          // > 512 candidates: extra rounds
+    const int c = (slots <= kPmThreads) ? my_c : cb + tid;
+    const bool c_ok = c < ncand && (slots <= kPmThreads ? active : true);
+    const int iy = c_ok ? c / ncx : 0, ix = c_ok ? c % ncx : 0;   // x fastest across lanes
+    const int coff = iy * g.pm_pw + ix;
+    const int xo = b.min_x + ix * prm.step, yo = b.min_y + iy * prm.step;
+    int sum = 0;
+    for (int p0 = 0; p0 < P; p0 += kPointChunk) {
+      const int n = min(kPointChunk, P - p0);
+      __syncthreads();
+      if (tid == 0) { n_in = 0; n_bd = 0; }
+      if (P > kPointChunk) {
+        for (int p = tid; p < n; p += kPmThreads)
+          cells[p] = discretize_point(sp + 3 * (size_t)(p0 + p), pr.w0, pr.z0, r.x, r.y, pr.tx,
+                                      pr.ty, g.resolution, g.max_x, g.max_y);
+      }
+      __syncthreads();
+      for (int p = tid; p < n; p += kPmThreads) {
+        const int lx = cells[p].x + wm1, ly = cells[p].y + wm1;     // wide-grid coordinates
+        if ((unsigned)lx < (unsigned)wide_nx && (unsigned)ly < (unsigned)wide_ny) {
+          const int X = lx + b.min_x + pad, Y = ly + b.min_y + pad;  // >= 0: |min| <= n_lin <= pad
+          const int plane = (Y & wm1) * prm.step + (X & wm1);
+          bases[atomicAdd(&n_in, 1)] = plane * plane_sz + (Y >> log2w) * g.pm_pw + (X >> log2w);
+        } else if (lx >= -prm.n_lin && ly >= -prm.n_lin && lx < wide_nx + prm.n_lin &&
+                   ly < wide_ny + prm.n_lin) {
+          border[atomicAdd(&n_bd, 1)] = cells[p];                    // may reach the grid: checked path
+        }                                                            // else: never lands on the grid
+      }
+      __syncthreads();
+      if (c_ok) {
+        const uint8_t* L = g.pm + coff;
+        const int ni = n_in, stride = (slots <= kPmThreads) ? n_slices : 1;
+        int p = (slots <= kPmThreads) ? my_slice : 0;
+        for (; p + 3 * stride < ni; p += 4 * stride) {
+          const int b0 = bases[p], b1 = bases[p + stride], b2 = bases[p + 2 * stride],
+                    b3 = bases[p + 3 * stride];
+          sum += (int)__ldg(L + b0) + (int)__ldg(L + b1) + (int)__ldg(L + b2) + (int)__ldg(L + b3);
+        }
+        for (; p < ni; p += stride) sum += (int)__ldg(L + bases[p]);
+        const int nb = n_bd;
+        for (int q = (slots <= kPmThreads) ? my_slice : 0; q < nb; q += stride)
+          sum += level_val(lv, border[q].x + xo, border[q].y + yo);
+      }
+    }
+    if (c_ok) {
+      if (slots <= kPmThreads && n_slices > 1) atomicAdd(&sums[c], sum);
+      else sums[c] = sum;
+    }
+  }
+  __syncthreads();
+  unsigned long long best_key = 0;
+  for (int c = tid; c < ncand; c += kPmThreads) {
+    const int iy = c / ncx, ix = c % ncx;
+    const int xo = b.min_x + ix * prm.step, yo = b.min_y + iy * prm.step;
+    const int sm = sums[c];
+    out[ix * ncy + iy] = sm;                                // reference order: x outer, y inner
+    best_key = max(best_key, key_of(score_of(sm, P, prm), rank_of(prm, s, xo, yo)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    best_key = max(best_key, __shfl_xor_sync(0xffffffffu, best_key, o));
+  if (lane == 0) redk[warp] = best_key;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w2 = 1; w2 < kPmThreads / 32; ++w2) best_key = max(best_key, redk[w2]);
+    atomicMax(top_coarse + pi, best_key);
+  }
+}
+
 // --------------------------------------------------------------------- K7 seed
 
 // One CTA per pair: descend greedily from the best coarse candidate to a leaf to get
@@ -503,13 +676,34 @@ cudaError_t launch_csm_discretize(const float* pts, int n_pts, float w0, float z
   return cudaGetLastError();
 }
 
+cudaError_t launch_csm_build_pm(const uint8_t* level, int wide_nx, int wide_ny, int pad, int log2w,
+                                int pw, int ph, uint8_t* out, cudaStream_t stream) {
+  dim3 blk(64, 4);
+  dim3 grd(((pw << log2w) + blk.x - 1) / blk.x, ((ph << log2w) + blk.y - 1) / blk.y);
+  csm_build_pm_kernel<<<grd, blk, 0, stream>>>(level, wide_nx, wide_ny, pad, log2w, pw, ph, out);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                               const float* pts, const float2* rot, CsmParams prm,
                               CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool phase_major) {
   dim3 grd(prm.S, n_pairs);
-  csm_coarse_kernel<<<grd, kCoarseThreads, 0, stream>>>(grids, pairs, pts, rot, prm, bounds,
-                                                        coarse, top_coarse);
+  if (phase_major) {
+    const size_t smem = (size_t)kPointChunk * (8 + 4 + 8) + (size_t)prm.maxc * 4;
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(csm_coarse_pm_kernel,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      if (e != cudaSuccess) return e;
+      attr = true;
+    }
+    csm_coarse_pm_kernel<<<grd, kPmThreads, smem, stream>>>(grids, pairs, pts, rot, prm, bounds,
+                                                            coarse, top_coarse);
+  } else {
+    csm_coarse_kernel<<<grd, kCoarseThreads, 0, stream>>>(grids, pairs, pts, rot, prm, bounds,
+                                                          coarse, top_coarse);
+  }
   return cudaGetLastError();
 }
 

@@ -2,6 +2,7 @@
 // for the reference interfaces each entry point replaces.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -34,6 +35,9 @@ struct HostGrid {
   int depth = 0;               // levels currently built
   size_t bytes = 0;
   long long off[kCsmMaxDepth] = {0};
+  // padded phase-major copy of the coarsest level used by the last batches (CsmGridDev::pm)
+  uint8_t* d_pm = nullptr;
+  int pm_level = -1, pm_pad = 0, pm_pw = 0, pm_ph = 0;
 };
 
 size_t stack_bytes(int nx, int ny, int depth, long long* off) {
@@ -174,8 +178,10 @@ void gloc_csm_destroy(gloc_csm_store* st) {
     cudaStreamSynchronize(st->stream);
     cudaStreamDestroy(st->stream);
   }
-  for (auto& gr : st->grids)
+  for (auto& gr : st->grids) {
     if (gr.d_stack) cudaFree(gr.d_stack);
+    if (gr.d_pm) cudaFree(gr.d_pm);
+  }
   if (st->d_lut) cudaFree(st->d_lut);
   for (Buf* b : {&st->pts, &st->pairs, &st->gridtab, &st->rot, &st->bounds, &st->coarse, &st->top,
                  &st->best, &st->survivors, &st->misc, &st->cells16, &st->disc})
@@ -295,6 +301,7 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
 
   // validate + device tables
   std::vector<CsmPairDev> hp((size_t)n_pairs);
+  bool use_pm = std::getenv("GLOC_CSM_NO_PM") == nullptr;
   std::map<int, int> grid_slot;
   std::vector<CsmGridDev> hg;
   for (int i = 0; i < n_pairs; ++i) {
@@ -314,6 +321,24 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
       d.stack = g.d_stack;
       std::memcpy(d.off, g.off, sizeof(d.off));
       d.nx = g.nx; d.ny = g.ny; d.resolution = g.resolution; d.max_x = g.max_x; d.max_y = g.max_y;
+      {  // padded phase-major coarsest level (rebuilt when depth or window change)
+        const int level = depth - 1, w = 1 << level, pad = n_lin;
+        const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1;
+        const int pw = (wide_nx + 2 * pad + w - 1) / w, ph = (wide_ny + 2 * pad + w - 1) / w;
+        const size_t cells = (size_t)pw * ph * w * w;
+        if (cells > ((size_t)1 << 27)) use_pm = false;  // absurd windows: bounds-checked kernel
+        if (use_pm && (g.pm_level != level || g.pm_pad != pad)) {
+          if (g.d_pm) cudaFree(g.d_pm);
+          g.d_pm = nullptr;
+          g.pm_level = -1;
+          GLOC_CUDA_TRY(cudaMalloc((void**)&g.d_pm, cells));
+          GLOC_CUDA_TRY(launch_csm_build_pm(g.d_stack + g.off[level], wide_nx, wide_ny, pad, level,
+                                            pw, ph, g.d_pm, st->stream));
+          st->stats.kernel_launches++;
+          g.pm_level = level; g.pm_pad = pad; g.pm_pw = pw; g.pm_ph = ph;
+        }
+        d.pm = g.d_pm; d.pm_pad = g.pm_pad; d.pm_pw = g.pm_pw; d.pm_ph = g.pm_ph; d.pm_log2w = level;
+      }
       it = grid_slot.emplace(gi, (int)hg.size()).first;
       hg.push_back(d);
     }
@@ -376,7 +401,8 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
     st->prof.begin(stream);
     cudaError_t ce = launch_csm_coarse(dg, dp, np, (const float*)st->pts.p,
                                        (const float2*)st->rot.p, prm, (CsmBounds*)st->bounds.p,
-                                       (int*)st->coarse.p, (unsigned long long*)st->top.p, stream);
+                                       (int*)st->coarse.p, (unsigned long long*)st->top.p, stream,
+                                       use_pm && (size_t)prm.maxc * 4 + 20 * 4096 <= 150 * 1024);
     st->prof.end(stream);
     GLOC_CUDA_TRY(ce);
     GLOC_CUDA_TRY(launch_csm_seed(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,

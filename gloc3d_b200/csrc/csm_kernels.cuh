@@ -15,6 +15,12 @@ struct CsmGridDev {
   long long off[kCsmMaxDepth];
   int nx, ny;
   double resolution, max_x, max_y;
+  // Coarsest level re-laid for the bulk scorer: zero border of `pm_pad` cells, then split
+  // into w*w phase planes (w = coarsest width = lattice step) of PH x PW bytes each, plane
+  // (ry, rx) holding the cells with (y % w, x % w) == (ry, rx).  Lattice neighbours of a
+  // point are adjacent bytes, and no lookup of an in-grid point needs a bounds check.
+  const uint8_t* pm;
+  int pm_pad, pm_pw, pm_ph, pm_log2w;
 };
 
 // One (grid, scan) pair.
@@ -50,11 +56,14 @@ cudaError_t launch_csm_build_level(const uint8_t* prev, int nx, int ny, int w, u
 cudaError_t launch_csm_discretize(const float* pts, int n_pts, float w0, float z0, float tx,
                                   float ty, const float2* rot, int S, double resolution,
                                   double max_x, double max_y, int* out_cells, cudaStream_t stream);
+// coarsest level -> padded phase-major layout (see CsmGridDev::pm)
+cudaError_t launch_csm_build_pm(const uint8_t* level, int wide_nx, int wide_ny, int pad, int log2w,
+                                int pw, int ph, uint8_t* out, cudaStream_t stream);
 // K7 pipeline
 cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                               const float* pts, const float2* rot, CsmParams prm,
                               CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool phase_major);
 cudaError_t launch_csm_seed(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                             const float* pts, const float2* rot, CsmParams prm,
                             const CsmBounds* bounds, const unsigned long long* top_coarse,
