@@ -407,6 +407,8 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     if (lane == 0) {
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0, uphase = 0;
+      const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA));
+      const uint64_t b_desc0 = make_sw128_desc(smem_u32(sB));
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         int qt, rg, t_begin, t_count;
         unit_tiles(u, qt, rg, t_begin, t_count);
@@ -419,13 +421,13 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
           for (int kb = 0; kb < a.n_kb; ++kb) {
             mbar_wait(full_b + stage, phase);
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(sA + (size_t)kb * kABytesPerKB);
-            const uint32_t b_addr = smem_u32(sB + (size_t)stage * kBBytes);
+            // descriptors differ only in the 14-bit start-address field (units of 16 B)
+            const uint64_t ad = a_desc0 + (uint64_t)(kb * (kABytesPerKB >> 4));
+            const uint64_t bd = b_desc0 + (uint64_t)(stage * (kBBytes >> 4));
 #pragma unroll
             for (int k4 = 0; k4 < BK / UK; ++k4) {
-              umma_f16(d_tmem, make_sw128_desc(a_addr + k4 * UK * 2),
-                        make_sw128_desc(b_addr + k4 * UK * 2), kInstrDesc,
-                        (kb | k4) != 0 ? 1u : 0u);
+              umma_f16(d_tmem, ad + (uint64_t)(k4 * (UK * 2 >> 4)), bd + (uint64_t)(k4 * (UK * 2 >> 4)),
+                       kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
             }
             tcgen05_commit(empty_b + stage);  // B slot reusable once these MMAs retire
             if (++stage == kStagesB) { stage = 0; phase ^= 1; }
@@ -484,6 +486,11 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
       // No bound yet anywhere in the warp (first units of a query): the first kWarmChunks
       // chunks insert every score into lst with one warp-uniform instruction stream.
       int warm_left = __any_sync(0xffffffffu, q_ok && thr == INFINITY) ? kWarmChunks : 0;
+      // Only units that start without any bound build a list of their own (warp-uniform): a
+      // unit that starts under another unit's bound sees too few scores below it to ever fill
+      // 32 entries, so maintaining one would be pure overhead.  It still emits every score
+      // under the shared bound, which is all exactness needs.
+      const bool own_list = warm_left > 0;
       const int n_lists = 2 * a.n_ranges;
       const size_t list_base = ((size_t)(q_ok ? q : 0) * n_lists + 2 * rg + wg) * (size_t)a.cap;
 
@@ -582,7 +589,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
                       a.cand_s[list_base + cnt] = vj;
                     }
                     ++cnt;
-                    if (!warm && npend < 8) {
+                    if (own_list && !warm && npend < 8 && vj < lst[31]) {
 #pragma unroll
                       for (int i = 7; i > 0; --i) pend[i] = pend[i - 1];
                       pend[0] = vj;
@@ -594,9 +601,9 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             }
           }
           // flush as soon as some lane's pending buffer is full (warp-uniform, no divergence)
-          if (__any_sync(0xffffffffu, npend >= 8)) flush_pending();
+          if (own_list && __any_sync(0xffffffffu, npend >= 8)) flush_pending();
         }
-        if (__any_sync(0xffffffffu, npend > 0)) flush_pending();
+        if (own_list && __any_sync(0xffffffffu, npend > 0)) flush_pending();
         // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA
         tcgen05_fence_before();
         __syncwarp();
@@ -623,7 +630,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 }
 
 // ------------------------------------------------------------------ K3: select + exact re-rank
-constexpr int kSurvMax = 2048;   // candidates below the final threshold, per query
+constexpr int kSurvMax = 4096;   // candidates below the final threshold, per query
 constexpr int kFinalMax = 256;   // candidates re-ranked exactly, per query
 constexpr int kRerankThreads = 128;
 
@@ -703,15 +710,25 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
     if (tid == 0) s_ak = INFINITY;
     __syncthreads();
     if (ns >= a.k) {
-      for (int i = tid; i < ns; i += kRerankThreads) {
-        const float si = surv_s[i];
-        int rank = 0;
-        for (int j = 0; j < ns; ++j) {
-          const float sj = surv_s[j];
-          rank += (sj < si || (sj == si && j < i)) ? 1 : 0;
-        }
-        if (rank == a.k - 1) s_ak = si;
+      // k-th smallest score by bisection on the order-preserving 32-bit key: the smallest
+      // key K with |{s : key(s) <= K}| >= k.  32 rounds of count + block reduce, O(ns) each.
+      __shared__ int s_count[kRerankThreads / 32];
+      unsigned lo = 0u, hi = 0xFFFFFFFFu;
+      while (lo < hi) {
+        const unsigned mid = lo + ((hi - lo) >> 1);
+        int c = 0;
+        for (int i = tid; i < ns; i += kRerankThreads) c += f2ord(surv_s[i]) <= mid ? 1 : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((tid & 31) == 0) s_count[tid >> 5] = c;
+        __syncthreads();
+        int total = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) total += s_count[w2];
+        __syncthreads();
+        if (total >= a.k) hi = mid; else lo = mid + 1;
       }
+      if (tid == 0) s_ak = ord2f(lo);
     }
     __syncthreads();
     const float tau2 = s_ak + eps2;
