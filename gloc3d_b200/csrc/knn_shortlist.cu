@@ -659,7 +659,7 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   unsigned* fin_i = surv_i + kSurvMax;                                    // [kFinalMax]
   float* fin_d = reinterpret_cast<float*>(fin_i + kFinalMax);             // [kFinalMax]
   float* qs = fin_d + kFinalMax;                                          // [dim]
-  float* G = qs + a.dim;                                                  // [32][dim/4 + 1]
+  float* G = surv_s;   // [32][dim/4 + 1]: reuses the survivor arrays, dead once the finalists are chosen
   __shared__ int n_surv, n_fin, bad;
   __shared__ float s_ak;
   const int q = blockIdx.x, tid = threadIdx.x;
@@ -694,9 +694,10 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
       }
       const size_t at = qbase + (size_t)lo * a.cap + (e - s_off[lo]);
       const float s = a.cand_s[at];
+      const unsigned ci = a.cand_idx[at];   // issued with the score: one memory round trip
       if (s <= tau) {
         const int pos = atomicAdd(&n_surv, 1);
-        if (pos < kSurvMax) { surv_s[pos] = s; surv_i[pos] = a.cand_idx[at]; }
+        if (pos < kSurvMax) { surv_s[pos] = s; surv_i[pos] = ci; }
       }
     }
   }
@@ -711,22 +712,44 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
     __syncthreads();
     if (ns >= a.k) {
       // k-th smallest score by bisection on the order-preserving 32-bit key: the smallest
-      // key K with |{s : key(s) <= K}| >= k.  32 rounds of count + block reduce, O(ns) each.
-      __shared__ int s_count[kRerankThreads / 32];
-      unsigned lo = 0u, hi = 0xFFFFFFFFu;
+      // key K with |{s : key(s) <= K}| >= k.  Keys live in registers, the range starts at
+      // [min key, max key], one barrier per round (double-buffered partial counts).
+      __shared__ int s_count[2][kRerankThreads / 32];
+      __shared__ unsigned s_mm[2][kRerankThreads / 32];
+      constexpr int kPer = kSurvMax / kRerankThreads;
+      unsigned keys[kPer];
+      unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+      for (int j = 0; j < kPer; ++j) {
+        const int i = tid + j * kRerankThreads;
+        keys[j] = i < ns ? f2ord(surv_s[i]) : 0xFFFFFFFFu;
+        if (i < ns) { kmin = min(kmin, keys[j]); kmax = max(kmax, keys[j]); }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+      }
+      if ((tid & 31) == 0) { s_mm[0][tid >> 5] = kmin; s_mm[1][tid >> 5] = kmax; }
+      __syncthreads();
+      unsigned lo = 0xFFFFFFFFu, hi = 0u;
+#pragma unroll
+      for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) { lo = min(lo, s_mm[0][w2]); hi = max(hi, s_mm[1][w2]); }
+      int round = 0;
       while (lo < hi) {
         const unsigned mid = lo + ((hi - lo) >> 1);
         int c = 0;
-        for (int i = tid; i < ns; i += kRerankThreads) c += f2ord(surv_s[i]) <= mid ? 1 : 0;
+#pragma unroll
+        for (int j = 0; j < kPer; ++j) c += keys[j] <= mid ? 1 : 0;   // padding keys are 0xFFFFFFFF > mid
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if ((tid & 31) == 0) s_count[tid >> 5] = c;
+        if ((tid & 31) == 0) s_count[round & 1][tid >> 5] = c;
         __syncthreads();
         int total = 0;
 #pragma unroll
-        for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) total += s_count[w2];
-        __syncthreads();
+        for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) total += s_count[round & 1][w2];
         if (total >= a.k) hi = mid; else lo = mid + 1;
+        ++round;
       }
       if (tid == 0) s_ak = ord2f(lo);
     }
@@ -1083,8 +1106,8 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     r.overflow_list = (int*)S->ovf_list.p;
     r.overflow_count = (int*)S->ovf_count.p;
     r.rows_reranked = (unsigned long long*)S->rows_ctr.p;
-    const size_t rr_smem = (size_t)kSurvMax * 8 + (size_t)kFinalMax * 8 + (size_t)dim * 4 +
-                           (size_t)32 * (dim / 4 + 1) * 4;
+    const size_t rr_smem = std::max((size_t)kSurvMax * 8, (size_t)32 * (dim / 4 + 1) * 4) +
+                           (size_t)kFinalMax * 8 + (size_t)dim * 4;
     static bool attr2 = false;
     if (!attr2) {
       GLOC_CUDA_TRY(cudaFuncSetAttribute(knn_shortlist_rerank_kernel,
