@@ -8,10 +8,14 @@ path over one batch of synthetic input.
 
 Workload "retrieval" (default; BASELINE.json configs[1], the configuration the metric is
 quoted on that fits one GPU): 100k-descriptor database (512-d float32), 10k-query batch per
-GPU, top-25 exact L2.  N > 1: the database is row-sharded over the N ranks (north_star), every
-rank answers the whole batch of N x 10k queries against its shard, ONE NCCL all-gather of the
-local top-k lists, K4 merge on every rank.  Per-GPU work (queries x rows) is fixed as N grows:
-"scaling": "weak"; value = all queries answered by the job / max-over-ranks device time.
+GPU, top-25 exact L2.  N > 1, per-GPU work (10k queries x 100k rows) fixed as N grows
+("scaling": "weak"; value = all N x 10k queries answered by the job / max-over-ranks device time):
+  --sharding queries (headline): the 205 MB database is replicated, every rank answers its
+      own 10k-query slice; the path partitions into independent queries, no collective;
+  --sharding db: the north-star protocol for databases that do not fit one GPU -- rows
+      sharded over the ranks, every rank answers all N x 10k queries on its shard, ONE NCCL
+      all-gather of the local top-k lists, K4 merge on every rank.
+Both are measured in every N > 1 run; the non-headline one is reported under "other_sharding".
 
 Workload "verify" (configs[2]): 25 candidate grids per query, 361 yaw bins, +-100 cells at
 0.2 m, depth 5, 800x800 BEV grids; pairs are split across ranks, no collective.
@@ -117,130 +121,148 @@ def run_retrieval(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     peaks = load_peaks()
-    db, q = make_retrieval_inputs(world)
-    nq = q.shape[0]
-    b = shard_bounds(DB_ROWS, world)
-    lo, hi = b[rank], b[rank + 1]
+    db, q_all = make_retrieval_inputs(world)
     mode = {"auto": g.KNN_AUTO, "exact": g.KNN_EXACT_SCAN, "shortlist": g.KNN_SHORTLIST}[args.mode]
-    sr = ShardedRetrieval(rank, world).load_shard(torch.from_numpy(db[lo:hi]).to(dev), lo,
-                                                  local_rank, mode)
-    q_dev = torch.from_numpy(q).to(dev)
-    q_pin = torch.from_numpy(q).pin_memory()
-    oi_pin = torch.empty((nq, K_NN), dtype=torch.int64).pin_memory()
-    od_pin = torch.empty((nq, K_NN), dtype=torch.float32).pin_memory()
 
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
             dist.barrier()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x: float, op) -> float:
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    # ---- device-resident timing (value) ------------------------------------
-    for _ in range(args.warmup):
-        out = sr.query(q_dev, K_NN)
-    barrier()
-    sr.index.set_profiling(True)
-    launches0 = sr.index.stats().kernel_launches
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        out = sr.query(q_dev, K_NN)
-    e1.record()
-    barrier()
-    clk = clocks.stop() if rank == 0 else None
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    dom_ms, dom_n = sr.index.profile()
-    sr.index.set_profiling(False)
-    st = sr.index.stats()
-    own_launches = (st.kernel_launches - launches0) + (args.steps if world > 1 else 0)  # + K4 merge
-    launches = int(sum_over_ranks(float(own_launches)))
-    ms_per_step = ms_total / args.steps
-    value = nq / (ms_per_step * 1e-3)
-
-    # ---- end to end with host buffers (e2e) --------------------------------
-    def e2e_step():
-        if world == 1:
-            sr.index.query_ptr(q_pin.data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
+    def measure(sharding: str, steps: int, warmup: int):
+        """sharding "queries": every rank holds the whole DB and answers its own 10k-query slice
+        (no data-path collective).  "db": the north-star protocol -- rows sharded, every rank
+        answers all N x 10k queries on its shard, one all-gather of the local top-k, K4 merge."""
+        if sharding == "db" and world > 1:
+            b = shard_bounds(DB_ROWS, world)
+            lo, hi = b[rank], b[rank + 1]
+            sr = ShardedRetrieval(rank, world).load_shard(torch.from_numpy(db[lo:hi]).to(dev), lo,
+                                                          local_rank, mode)
+            q = q_all
         else:
-            sr.query_host(q_pin, K_NN, oi_pin, od_pin)
+            lo, hi = 0, DB_ROWS
+            sr = ShardedRetrieval(0, 1).load_shard(torch.from_numpy(db).to(dev), 0, local_rank, mode)
+            q = np.ascontiguousarray(q_all[rank * Q_PER_GPU:(rank + 1) * Q_PER_GPU])
+        nq = q.shape[0]                       # queries this rank answers per step
+        nq_job = Q_PER_GPU * world            # queries the whole job answers per step
+        q_dev = torch.from_numpy(q).to(dev)
+        q_pin = torch.from_numpy(q).pin_memory()
+        oi_pin = torch.empty((nq, K_NN), dtype=torch.int64).pin_memory()
+        od_pin = torch.empty((nq, K_NN), dtype=torch.float32).pin_memory()
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    torch.cuda.synchronize(dev)
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
-    barrier()
+        # ---- device-resident timing (value)
+        for _ in range(warmup):
+            out = sr.query(q_dev, K_NN)
+        barrier()
+        sr.index.set_profiling(True)
+        launches0 = sr.index.stats().kernel_launches
+        clocks = ClockSampler(local_rank)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            out = sr.query(q_dev, K_NN)
+        e1.record()
+        barrier()
+        clk = clocks.stop() if rank == 0 else None
+        ms_total = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX)
+        dom_ms, dom_n = sr.index.profile()
+        sr.index.set_profiling(False)
+        st = sr.index.stats()
+        own = (st.kernel_launches - launches0) + (steps if sr.world_size > 1 else 0)   # + K4 merge
+        launches = int(reduce_ranks(float(own), dist.ReduceOp.SUM))
+        ms_per_step = ms_total / steps
 
-    # ---- sanity: the timed path returns the oracle's answer on a sample -----
-    idx_np = out[0].cpu().numpy().view(np.uint64)
-    d2_np = out[1].cpu().numpy()
-    assert np.array_equal(idx_np, oi_pin.numpy().view(np.uint64)) and np.array_equal(d2_np, od_pin.numpy())
+        # ---- end to end with host buffers (e2e): pinned H2D of the queries, D2H of the result
+        def e2e_step():
+            if sr.world_size == 1:
+                sr.index.query_ptr(q_pin.data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
+            else:
+                sr.query_host(q_pin, K_NN, oi_pin, od_pin)
 
+        for _ in range(max(1, min(warmup, 3))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        e2e_ms = reduce_ranks((time.perf_counter() - t0) * 1e3, dist.ReduceOp.MAX) / steps
+        barrier()
+        # the timed path and the host-buffer path return the same bits
+        assert np.array_equal(out[0].cpu().numpy(), oi_pin.numpy()) and \
+            np.array_equal(out[1].cpu().numpy(), od_pin.numpy())
+        res = dict(sharding=sharding, nq=nq, nq_job=nq_job, rows=hi - lo, ms_per_step=ms_per_step,
+                   value=nq_job / (ms_per_step * 1e-3), e2e_ms=e2e_ms, e2e_value=nq_job / (e2e_ms * 1e-3),
+                   h2d=int(q.nbytes) * world, d2h=int(nq * K_NN * 12) * world, launches=launches, clk=clk,
+                   dom_ms=dom_ms, dom_n=dom_n, st=st, steps=steps, sample=(q, out[0].cpu().numpy(), out[1].cpu().numpy()))
+        sr.close()
+        return res
+
+    primary = args.sharding if world > 1 else "queries"
+    r = measure(primary, args.steps, args.warmup)
+    other = None
+    if world > 1:   # the other protocol, measured in the same run for the record
+        other = measure("db" if primary == "queries" else "queries", min(args.steps, 5), 3)
     if rank != 0:
         return None
+    st = r["st"]
     last_mode = int(st.last_mode)
-    shard_rows = hi - lo
     # the library may split a batch into several launches: algorithmic work per LAUNCH
-    launches_per_step = max(dom_n, 1) / args.steps
-    flops = 2.0 * nq * shard_rows * DIM / launches_per_step
-    alg_bytes = shard_rows * DIM * 4 + (nq * DIM * 4 + nq * K_NN * 12) / launches_per_step
-    avg_ms = dom_ms / max(dom_n, 1)
+    launches_per_step = max(r["dom_n"], 1) / r["steps"]
+    flops = 2.0 * r["nq"] * r["rows"] * DIM / launches_per_step
+    alg_bytes = r["rows"] * DIM * 4 + (r["nq"] * DIM * 4 + r["nq"] * K_NN * 12) / launches_per_step
+    avg_ms = r["dom_ms"] / max(r["dom_n"], 1)
     peak_tf = peaks["bf16_tflops"]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         traffic = json.load(open(tp)).get({1: "exact_scan", 2: "shortlist_gemm"}.get(last_mode, ""), None)
+    nq_job = r["nq_job"]
+    shard_txt = {"queries": f"queries/{world} (each rank: whole DB replicated, its own 10k queries; no collective)",
+                 "db": f"rows/{world} + all-gather top-k + K4 merge (north-star protocol)"}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if last_mode == g.KNN_EXACT_SCAN else "fp16 tensor shortlist + f32 exact re-rank",
         "data": "synthetic",
         "config": {"workload": "configs[1]: 100k x 512-d f32 descriptor DB, 10k-query batch per GPU, "
                                "top-25 exact L2 retrieval (bit-exact vs nanoflann)",
-                   "db_rows": DB_ROWS, "queries_per_step": nq, "k": K_NN, "dim": DIM,
-                   "sharding": f"rows/{world} + all-gather top-k + merge" if world > 1 else "none",
+                   "db_rows": DB_ROWS, "queries_per_step": nq_job, "k": K_NN, "dim": DIM,
+                   "sharding": shard_txt[r["sharding"]] if world > 1 else "none",
                    "strategy": {1: "exact_scan", 2: "tensor_shortlist"}.get(last_mode, str(last_mode)),
-                   "l2": "inputs larger than L2 (DB shard + query batch > 126 MB per rank); no flush"},
-        "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(q.nbytes) * world,
-                "d2h_bytes_per_step": int(nq * K_NN * 12) * world},
-        "gpu_launches": launches,
-        "clocks": clk,
+                   "l2": "inputs larger than L2 (DB + query batch > 126 MB per rank); no flush"},
+        "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_ms"],
+                "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+        "gpu_launches": r["launches"],
+        "clocks": r["clk"],
         "roofline": {"bound": "tensor", "kernel": {1: "knn_exact_scan_kernel", 2: "knn_shortlist_gemm_kernel"}.get(last_mode),
                      "achieved": flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else None,
                      "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": (flops / (avg_ms * 1e-3) / 1e12) / peak_tf if avg_ms > 0 else None,
                      "traffic": traffic, "peak_source": peaks["source"] + " (burst bf16)",
-                     "kernel_ms": avg_ms, "kernel_launches_timed": dom_n,
+                     "kernel_ms": avg_ms, "kernel_launches_timed": r["dom_n"],
                      "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": alg_bytes,
                      "hbm_frac_of_algorithmic_bytes": (alg_bytes / (avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if avg_ms > 0 else None},
         "stats": {"fallback_queries": int(st.fallback_queries), "shortlist_rows_per_query":
                   (st.shortlist_rows / max(st.shortlist_queries, 1))},
     }
+    if other is not None:
+        line["other_sharding"] = {"sharding": shard_txt[other["sharding"]], "value": other["value"],
+                                  "ms_per_step": other["ms_per_step"], "e2e_value": other["e2e_value"],
+                                  "steps": other["steps"]}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_retrieval(db, q, budget_s=args.cpu_budget)
-    sr.close()
+        line["cpu_baseline"] = cpu_baseline_retrieval(db, q_all, budget_s=args.cpu_budget)
     return line
 
 
@@ -475,6 +497,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="retrieval", choices=["retrieval", "verify"])
     ap.add_argument("--mode", default="auto", choices=["auto", "exact", "shortlist"])
+    ap.add_argument("--sharding", default="queries", choices=["queries", "db"],
+                    help="N > 1: 'queries' = DB replicated, queries split (no collective); 'db' = rows "
+                         "sharded + all-gather top-k + merge (north-star protocol).  Both are measured; "
+                         "this picks which one is the headline value.")
     ap.add_argument("--verify-queries", type=int, default=8, help="queries per GPU per step (verify)")
     ap.add_argument("--verify-depth", type=int, default=0,
                     help="internal branch-and-bound depth of the GPU verifier (0 = the reference's 5); "

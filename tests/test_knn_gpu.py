@@ -234,3 +234,26 @@ def test_full_size_properties(oracle):
     sample = np.arange(0, nq, nq // 48)[:48]
     ridx, rd2 = oracle.knn(db, q[sample], k, nthreads=8)
     assert_knn_equal(idx[sample], d2[sample], ridx, rd2)
+
+
+def test_million_row_database(oracle):
+    # configs[3] scale on one GPU: 1M descriptors (2 GB), 20k queries, top-25.  The oracle checks
+    # a 16-query sample bit-exactly; the rest through size-independent properties.
+    n, nq, k = 1_000_000, 20_000, 25
+    db = synth.make_descriptors(n, seed=1234, dup_run=8)
+    q = synth.make_queries(db, nq, seed=5678, sigma=0.01)
+    src = np.random.default_rng(5678).integers(0, n, nq)
+    ix = g.KnnIndex(512, 0)
+    ix.set_db(db)
+    idx, d2 = ix.query(q, k)
+    st = ix.stats()
+    ix.close()
+    assert st.last_mode == g.KNN_SHORTLIST and st.fallback_queries == 0
+    assert st.shortlist_rows / st.shortlist_queries < 128
+    assert (np.diff(d2.astype(np.float64), axis=1) >= 0).all() and (idx < n).all()
+    assert ((idx == src[:, None].astype(np.uint64)).any(axis=1)).mean() > 0.999
+    for r in range(0, nq, 2003):
+        assert oracle.l2(q[r], db[idx[r, 24]]).view(np.uint32) == d2[r, 24].view(np.uint32)
+    sample = np.arange(0, nq, nq // 16)[:16]
+    ridx, rd2 = oracle.knn(db, q[sample], k, nthreads=16)
+    assert_knn_equal(idx[sample], d2[sample], ridx, rd2)
