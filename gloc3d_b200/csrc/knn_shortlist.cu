@@ -313,8 +313,9 @@ struct GemmArgs {
   const unsigned* max_dx2_bits;     // DXmax^2
   unsigned* thr_ord;                // [nq] shared running threshold (ordered-uint of s-space)
   float* eps2;                      // [nq] 2*eps, written by the epilogue (read by K3)
-  unsigned* cand_idx;               // [nq][2*n_ranges][cap]  (two epilogue warpgroups)
-  float* cand_s;                    // [nq][2*n_ranges][cap]
+  // candidate lists, [nq][2*n_ranges] lists (two epilogue warpgroups per unit) of cap groups
+  unsigned* cand_g;                 // [list][cap]     base row of an 8-row group
+  float4* cand_v;                   // [list][cap][2]  the group's 8 scores
   unsigned* unit_cnt;               // [nq][2*n_ranges]
 };
 
@@ -493,6 +494,8 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
       const bool own_list = warm_left > 0;
       const int n_lists = 2 * a.n_ranges;
       const size_t list_base = ((size_t)(q_ok ? q : 0) * n_lists + 2 * rg + wg) * (size_t)a.cap;
+      unsigned* const cand_g = a.cand_g + list_base;
+      float4* const cand_v = a.cand_v + 2 * list_base;
 
       // sorted insertion of one score; the largest of the 33 values drops out (+inf: no-op)
       auto lst_insert = [&](float w) {
@@ -572,29 +575,37 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             mg[g] = fminf(fminf(fminf(sc[8 * g], sc[8 * g + 1]), fminf(sc[8 * g + 2], sc[8 * g + 3])),
                           fminf(fminf(sc[8 * g + 4], sc[8 * g + 5]), fminf(sc[8 * g + 6], sc[8 * g + 7])));
           }
-          const float m = fminf(fminf(mg[0], mg[1]), fminf(mg[2], mg[3]));
-          if (q_ok && m <= thr) {   // lane-divergent slow path, all in registers
+          // Emission, group-granular and fully predicated (no divergence, no per-score work):
+          // a lane whose 8-column group holds a score under its threshold stores the group's
+          // base row and all 8 scores (one aligned 32-byte sector); K3 filters the individual
+          // scores.  With ~1e3 hits per query some lane of the warp hits in nearly every
+          // group, so any per-score or lane-divergent handling here would run all the time.
+          const unsigned col0 = (unsigned)(t * BN + c * 32);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (mg[g] <= thr) {   // thr = -inf on rows beyond nq
+              if (cnt < (unsigned)a.cap) {
+                cand_g[cnt] = col0 + 8 * g;
+                cand_v[2 * cnt] = make_float4(sc[8 * g], sc[8 * g + 1], sc[8 * g + 2], sc[8 * g + 3]);
+                cand_v[2 * cnt + 1] = make_float4(sc[8 * g + 4], sc[8 * g + 5], sc[8 * g + 6], sc[8 * g + 7]);
+              }
+              ++cnt;
+            }
+          }
+          if (own_list && !warm) {
+            // units that maintain their own bound: scores entering the sorted list go through
+            // the pending FIFO (visited only where some lane has one: warp-uniform branch)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (mg[g] <= thr) {
-                float r0 = sc[8 * g], r1 = sc[8 * g + 1], r2 = sc[8 * g + 2], r3 = sc[8 * g + 3];
-                float r4 = sc[8 * g + 4], r5 = sc[8 * g + 5], r6 = sc[8 * g + 6], r7 = sc[8 * g + 7];
-#pragma unroll 1
-                for (int jj = 0; jj < 8; ++jj) {   // rolled: one compact copy per group
-                  const float vj = r0;
-                  r0 = r1; r1 = r2; r2 = r3; r3 = r4; r4 = r5; r5 = r6; r6 = r7;
-                  if (vj <= thr && vj < INFINITY) {   // +inf = masked / padded row
-                    if (cnt < (unsigned)a.cap) {
-                      a.cand_idx[list_base + cnt] = (unsigned)(t * BN + c * 32 + 8 * g + jj);
-                      a.cand_s[list_base + cnt] = vj;
-                    }
-                    ++cnt;
-                    if (own_list && !warm && npend < 8 && vj < lst[31]) {
+              if (__any_sync(0xffffffffu, mg[g] < lst[31])) {
 #pragma unroll
-                      for (int i = 7; i > 0; --i) pend[i] = pend[i - 1];
-                      pend[0] = vj;
-                      ++npend;
-                    }
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float vj = sc[8 * g + jj];
+                  if (vj < lst[31] && npend < 8) {
+#pragma unroll
+                    for (int i = 7; i > 0; --i) pend[i] = pend[i - 1];
+                    pend[0] = vj;
+                    ++npend;
                   }
                 }
               }
@@ -638,8 +649,8 @@ struct RerankArgs {
   const float* db;
   const float* q;
   int nq, dim, k, n_ranges, cap;
-  const unsigned* cand_idx;
-  const float* cand_s;
+  const unsigned* cand_g;
+  const float* cand_v;
   const unsigned* unit_cnt;
   const unsigned* thr_ord;
   const float* eps2;
@@ -683,19 +694,20 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
     s_off[a.n_ranges] = o;
   }
   __syncthreads();
-  {  // one flat pass over all lists: every load is independent of the others
-    const unsigned total = s_off[a.n_ranges];
+  {  // one flat pass over all lists (8 scores per group entry): every load is independent
+    const unsigned total = s_off[a.n_ranges] * 8u;
     const size_t qbase = (size_t)q * a.n_ranges * (size_t)a.cap;
-    for (unsigned e = tid; e < total; e += kRerankThreads) {
+    for (unsigned e8 = tid; e8 < total; e8 += kRerankThreads) {
+      const unsigned e = e8 >> 3, j = e8 & 7u;
       int lo = 0, hi = a.n_ranges - 1;   // largest r with s_off[r] <= e
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
         if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
       }
       const size_t at = qbase + (size_t)lo * a.cap + (e - s_off[lo]);
-      const float s = a.cand_s[at];
-      const unsigned ci = a.cand_idx[at];   // issued with the score: one memory round trip
-      if (s <= tau) {
+      const float s = a.cand_v[at * 8 + j];
+      const unsigned ci = a.cand_g[at] + j;   // issued with the score: one memory round trip
+      if (s <= tau && s < INFINITY) {         // +inf = masked / padded row
         const int pos = atomicAdd(&n_surv, 1);
         if (pos < kSurvMax) { surv_s[pos] = s; surv_i[pos] = ci; }
       }
@@ -895,7 +907,7 @@ struct ShortlistState {
   const float* prepared_src = nullptr;
   float scale_x = 1.f;
   // per-call workspaces
-  Buf q_h, qn, qe, qinv, thr, eps2, cand_idx, cand_s, unit_cnt, ovf_list, ovf_count, rows_ctr, partial;
+  Buf q_h, qn, qe, qinv, thr, eps2, cand_g, cand_v, unit_cnt, ovf_list, ovf_count, rows_ctr, partial;
 };
 
 bool shortlist_supported(size_t dim, size_t k) {
@@ -914,7 +926,7 @@ void shortlist_invalidate(ShortlistState* s, size_t first_dirty_row) {
 void shortlist_destroy(ShortlistState* s) {
   if (!s) return;
   for (Buf* b : {&s->db_h, &s->xn, &s->dbstats, &s->q_h, &s->qn, &s->qe, &s->qinv, &s->thr, &s->eps2,
-                 &s->cand_idx, &s->cand_s, &s->unit_cnt, &s->ovf_list, &s->ovf_count, &s->rows_ctr,
+                 &s->cand_g, &s->cand_v, &s->unit_cnt, &s->ovf_list, &s->ovf_count, &s->rows_ctr,
                  &s->partial})
     b->release();
   delete s;
@@ -1002,13 +1014,13 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
   if (!make_map(&map_db, S->db_h.p, A.n_rows, (uint64_t)dim, BN))
     return fail(GLOC_ERR_CUDA, "cuTensorMapEncodeTiled(db) failed");
 
-  // queries per pass: bounded so that the candidate workspace (2 lists per unit, 8 B per
-  // slot) stays under ~6 GB
+  // queries per pass: bounded so that the candidate workspace (2 lists per unit, 36 B per
+  // group slot) stays under ~16 GB
   size_t kChunk = 65536;
   {
     const Plan p0 = make_plan((long long)A.n_rows, (int)std::min<size_t>(A.nq, kChunk), sms);
-    const size_t per_query = (size_t)p0.n_ranges * 2 * p0.cap * 8;
-    kChunk = std::max<size_t>(BM, std::min<size_t>(kChunk, ((size_t)6 << 30) / per_query / BM * BM));
+    const size_t per_query = (size_t)p0.n_ranges * 2 * p0.cap * 36;
+    kChunk = std::max<size_t>(BM, std::min<size_t>(kChunk, ((size_t)16 << 30) / per_query / BM * BM));
   }
   for (size_t q0 = 0; q0 < A.nq; q0 += kChunk) {
     const int nq = (int)std::min(kChunk, A.nq - q0);
@@ -1021,8 +1033,8 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     GLOC_CUDA_TRY(S->qinv.reserve((size_t)nq * 4));
     GLOC_CUDA_TRY(S->thr.reserve((size_t)nq * 4));
     GLOC_CUDA_TRY(S->eps2.reserve((size_t)nq * 4));
-    GLOC_CUDA_TRY(S->cand_idx.reserve(lists * plan.cap * 4));
-    GLOC_CUDA_TRY(S->cand_s.reserve(lists * plan.cap * 4));
+    GLOC_CUDA_TRY(S->cand_g.reserve(lists * plan.cap * 4));
+    GLOC_CUDA_TRY(S->cand_v.reserve(lists * plan.cap * 32));
     GLOC_CUDA_TRY(S->unit_cnt.reserve(lists * 4));
     GLOC_CUDA_TRY(S->ovf_list.reserve((size_t)nq * 4));
     GLOC_CUDA_TRY(S->ovf_count.reserve(4));
@@ -1068,8 +1080,8 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     g.max_dx2_bits = (const unsigned*)S->dbstats.p + 2;
     g.thr_ord = (unsigned*)S->thr.p;
     g.eps2 = (float*)S->eps2.p;
-    g.cand_idx = (unsigned*)S->cand_idx.p;
-    g.cand_s = (float*)S->cand_s.p;
+    g.cand_g = (unsigned*)S->cand_g.p;
+    g.cand_v = (float4*)S->cand_v.p;
     g.unit_cnt = (unsigned*)S->unit_cnt.p;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1095,8 +1107,8 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     r.k = k;
     r.n_ranges = plan.n_ranges * 2;   // lists per query
     r.cap = plan.cap;
-    r.cand_idx = g.cand_idx;
-    r.cand_s = g.cand_s;
+    r.cand_g = g.cand_g;
+    r.cand_v = (const float*)g.cand_v;
     r.unit_cnt = g.unit_cnt;
     r.thr_ord = g.thr_ord;
     r.eps2 = g.eps2;
