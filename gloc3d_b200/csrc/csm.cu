@@ -449,6 +449,263 @@ csm_coarse_pm_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __r
   }
 }
 
+// ------------------------------------------------- K7 coarse (binary grids, bit-sliced)
+//
+// BEV grids of this code base are binary (a pixel is occupied or free: SURVEY F5,
+// 3d/submap_3d.cpp:312-324, :412-424), hence every precomputation level holds only
+// {0, 255} and a candidate's sum is 255 x (number of scan points on occupied cells).
+// For such grids the coarsest level is kept as bit planes: plane (ry, rx) row r is one
+// 64-bit word whose bit c is the cell (16 c + rx - px, 16 r + ry - py) (w = 16 as example).
+// The whole structure (~170 KB for an 800 x 800 map) lives in shared memory.
+//
+// Thread = one rotation (scan), looping over all points: a point contributes, per candidate
+// row, the `ncx` adjacent bits of one plane row -- one 8-byte shared-memory load and a
+// shift -- and two rows are packed into one 32-bit word whose 16-bit halves are column
+// masks.  The per-candidate counts are bit-sliced counters across those words: 16 points
+// are folded by a carry-save adder tree (15 full adders = 30 LOP3 per word) into one
+// weight-16 carry that ripples into 8 high planes, i.e. ~3 logic instructions per point per
+// 26 candidates instead of 26 loads + 26 adds.  No cross-thread reduction, no atomics.
+//
+// Exactness: the cell of a point is the reference's double-precision GetCellIndex; a float
+// evaluation is used only when it is provably on the same side of every rounding boundary
+// (fractional part further than `delta` from 0 and 1, delta bounding the float error), else
+// the double path runs.  ShrinkToFit needs min/max cell indices only, and the cell index is
+// a monotone function of the world coordinate, so the bounds come from the exact cells of
+// the four extreme coordinates.
+
+constexpr int kBitChunk = 4080;     // points per pass: 16 x 255, so 8 high planes cannot overflow
+constexpr int kBitRowSlack = 17;    // zero rows after the last data row (candidate rows read past it)
+
+__global__ void csm_build_pmb_kernel(const uint8_t* __restrict__ level, int wide_nx, int wide_ny,
+                                     int px, int py, int log2w, int rows,
+                                     unsigned long long* __restrict__ out, int* __restrict__ not_binary) {
+  const int w = 1 << log2w;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= w * w * rows) return;
+  const int plane = idx / rows, r = idx % rows;
+  const int ry = plane >> log2w, rx = plane & (w - 1);
+  const int ly = (r << log2w) + ry - py;
+  unsigned long long bits = 0;
+  bool odd = false;
+  if ((unsigned)ly < (unsigned)wide_ny) {
+    for (int c = 0; c < 64; ++c) {
+      const int lx = (c << log2w) + rx - px;
+      if ((unsigned)lx < (unsigned)wide_nx) {
+        const unsigned v = level[(size_t)ly * wide_nx + lx];
+        if (v) bits |= 1ull << c;
+        odd |= (v != 0u && v != 255u);
+      }
+    }
+  }
+  out[idx] = bits;
+  if (odd) atomicOr(not_binary, 1);
+}
+
+// map_limits.h:69-76 on an already transformed point (double arithmetic, lround)
+__device__ __forceinline__ int cell_exact(float wv, double res, double mx) {
+  return (int)round(__dsub_rn(__ddiv_rn(__dsub_rn(mx, (double)wv), res), 0.5));
+}
+
+__device__ __noinline__ int2 cells_exact(float wx, float wy, double res, double max_x, double max_y) {
+  return make_int2(cell_exact(wy, res, max_y), cell_exact(wx, res, max_x));
+}
+
+template <int NP>
+__global__ void __launch_bounds__(192, 1)
+csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
+                       const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
+                       CsmBounds* __restrict__ bounds, int* __restrict__ coarse,
+                       unsigned long long* __restrict__ top_coarse) {
+  extern __shared__ __align__(16) unsigned char csm_smem[];
+  const int pi = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const CsmPairDev pr = pairs[pi];
+  const CsmGridDev g = grids[pr.grid];
+  const int log2w = g.pmb_log2w, w = 1 << log2w, wm = w - 1;
+  const int rows = g.pmb_rows;
+  const int n_words = (w * w) * rows;
+  unsigned long long* bits = reinterpret_cast<unsigned long long*>(csm_smem);
+  float2* P0 = reinterpret_cast<float2*>(bits + n_words);
+  for (int i = tid; i < n_words; i += blockDim.x) bits[i] = __ldg(g.pmb + i);
+
+  const int P = pr.n_pts;
+  const float* sp = pts + 3 * (size_t)pr.pt_begin;
+  const int s = blockIdx.x * blockDim.x + tid;
+  const bool s_ok = s < prm.S;
+  const float2 r = rot[s_ok ? s : 0];
+  // points after the initial-yaw rotation (fast_..._2d.cpp:278-283), shared by all rotations
+  auto stage = [&](int p0, int n) {
+    __syncthreads();
+    for (int p = tid; p < n; p += blockDim.x) {
+      float x0, y0;
+      rot_z(pr.w0, pr.z0, sp[3 * (size_t)(p0 + p)], sp[3 * (size_t)(p0 + p) + 1], x0, y0);
+      P0[p] = make_float2(x0, y0);
+    }
+    __syncthreads();
+  };
+  // ---- pass 1: extreme world coordinates of this rotation -> ShrinkToFit bounds
+  float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+  for (int p0 = 0; p0 < P; p0 += kBitChunk) {
+    const int n = min(kBitChunk, P - p0);
+    stage(p0, n);
+#pragma unroll 4
+    for (int p = 0; p < n; ++p) {
+      const float2 q = P0[p];
+      float x1, y1;
+      rot_z(r.x, r.y, q.x, q.y, x1, y1);
+      const float wx = __fadd_rn(x1, pr.tx), wy = __fadd_rn(y1, pr.ty);
+      mnx = fminf(mnx, wx); mxx = fmaxf(mxx, wx);
+      mny = fminf(mny, wy); mxy = fmaxf(mxy, wy);
+    }
+  }
+  CsmBounds b;
+  {
+    // cell.x = f(wy), cell.y = f(wx), both monotone non-increasing
+    const int cx_max = cell_exact(mny, g.resolution, g.max_y), cx_min = cell_exact(mxy, g.resolution, g.max_y);
+    const int cy_max = cell_exact(mnx, g.resolution, g.max_x), cy_min = cell_exact(mxx, g.resolution, g.max_x);
+    // correlative_scan_matcher_2d.cpp:77-90
+    b.min_x = max(-prm.n_lin, min(0, -cx_max));
+    b.max_x = min(prm.n_lin, max(0, g.nx - 1 - cx_min));
+    b.min_y = max(-prm.n_lin, min(0, -cy_max));
+    b.max_y = min(prm.n_lin, max(0, g.ny - 1 - cy_min));
+  }
+  if (s_ok) bounds[(size_t)pi * prm.S + s] = b;
+  const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
+  const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+
+  // ---- pass 2: bit-sliced scoring
+  const int wide_nx = g.nx + wm, wide_ny = g.ny + wm;
+  const float mx_f = (float)g.max_x, my_f = (float)g.max_y, ir = (float)(1.0 / g.resolution);
+  // |float cell coordinate - exact| <= 2^-24 (|max|/res + 3 |u|) for |u| <= U; 4x safety
+  const float U = (float)(max(wide_nx, wide_ny) + 2 * prm.n_lin + 32);
+  const float delta = 2.3841858e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
+  const int offx = wm + b.min_x + g.pmb_px, offy = wm + b.min_y + g.pmb_py;
+  const unsigned span_x = (unsigned)(wide_nx + 2 * prm.n_lin), span_y = (unsigned)(wide_ny + 2 * prm.n_lin);
+  const int hx0 = wm + prm.n_lin, hy0 = wm + prm.n_lin;
+
+  // the NP packed words (two candidate rows each) a point adds to the counters
+  auto point_words = [&](int p, uint32_t (&v)[NP]) {
+    const float2 q = P0[p];
+    float x1, y1;
+    rot_z(r.x, r.y, q.x, q.y, x1, y1);
+    const float wx = __fadd_rn(x1, pr.tx), wy = __fadd_rn(y1, pr.ty);
+    const float uy = (my_f - wy) * ir, ux = (mx_f - wx) * ir;
+    const float fy = floorf(uy), fx = floorf(ux);
+    const float dy = uy - fy, dx = ux - fx;
+    int cx = (int)fy, cy = (int)fx;
+    const float hi1 = 1.f - delta;
+    if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < 1e7f && fabsf(ux) < 1e7f)) {
+      const int2 ce = cells_exact(wx, wy, g.resolution, g.max_x, g.max_y);   // rare: near a rounding boundary
+      cx = ce.x;
+      cy = ce.y;
+    }
+    // can the point land on the grid for some offset of the window at all?
+    const bool hitable = (unsigned)(cx + hx0) < span_x && (unsigned)(cy + hy0) < span_y && s_ok;
+    const int X = cx + offx, Y = cy + offy;           // Y >= 0 for hitable points
+    const int ax = X >> log2w, ay = hitable ? (Y >> log2w) : 0;
+    const int plane = hitable ? (((Y & wm) << log2w) | (X & wm)) : 0;
+    const int shl = hitable ? max(0, -ax) : 0, axc = min(max(ax, 0), 63);
+    const int nbits = (hitable && ax < 64) ? max(ncx - shl, 0) : 0;
+    const uint32_t m1 = (1u << nbits) - 1u, m2 = m1 | (m1 << 16);
+    const unsigned long long* rowp = bits + plane * rows + ay;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const uint32_t w0 = (uint32_t)(rowp[2 * j] >> axc), w1 = (uint32_t)(rowp[2 * j + 1] >> axc);
+      v[j] = (__byte_perm(w0, w1, 0x5410) & m2) << shl;
+    }
+  };
+  auto csa = [](uint32_t (&h)[NP], uint32_t (&l)[NP], const uint32_t (&x)[NP], const uint32_t (&y)[NP]) {
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const uint32_t u = l[j] ^ x[j];
+      h[j] = (l[j] & x[j]) | (u & y[j]);
+      l[j] = u ^ y[j];
+    }
+  };
+
+  int* out = coarse + ((size_t)pi * prm.S + (s_ok ? s : 0)) * prm.maxc;
+  unsigned long long best_key = 0;
+  for (int p0 = 0; p0 < P; p0 += kBitChunk) {
+    const int n = min(kBitChunk, P - p0);
+    if (P > kBitChunk) stage(p0, n);
+    uint32_t ones[NP], twos[NP], fours[NP], eights[NP], hi[8][NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      ones[j] = twos[j] = fours[j] = eights[j] = 0u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) hi[i][j] = 0u;
+    }
+    auto pair_words = [&](int p, uint32_t (&ta)[NP]) {   // two points -> carry ta, sum into ones
+      uint32_t v0[NP], v1[NP];
+      if (p < n) point_words(p, v0);
+      else {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) v0[j] = 0u;
+      }
+      if (p + 1 < n) point_words(p + 1, v1);
+      else {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) v1[j] = 0u;
+      }
+      csa(ta, ones, v0, v1);
+    };
+    auto quad_words = [&](int p, uint32_t (&fa)[NP]) {
+      uint32_t ta[NP], tb[NP];
+      pair_words(p, ta);
+      pair_words(p + 2, tb);
+      csa(fa, twos, ta, tb);
+    };
+    auto oct_words = [&](int p, uint32_t (&ea)[NP]) {
+      uint32_t fa[NP], fb[NP];
+      quad_words(p, fa);
+      quad_words(p + 4, fb);
+      csa(ea, fours, fa, fb);
+    };
+#pragma unroll 1
+    for (int p = 0; p < n; p += 16) {
+      uint32_t ea[NP], eb[NP], c16[NP];
+      oct_words(p, ea);
+      oct_words(p + 8, eb);
+      csa(c16, eights, ea, eb);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+          const uint32_t t = hi[i][j] & c16[j];
+          hi[i][j] ^= c16[j];
+          c16[j] = t;
+        }
+      }
+    }
+    // counters -> integer sums (255 per hit), accumulated over the passes in `coarse`
+    if (s_ok) {
+      const bool first = p0 == 0, last = p0 + n >= P;
+#pragma unroll
+      for (int iy = 0; iy < 2 * NP; ++iy) {
+        if (iy < ncy) {
+          const int j = iy >> 1, sh0 = (iy & 1) * 16;
+          for (int ix = 0; ix < ncx; ++ix) {
+            const int bp = sh0 + ix;
+            int cnt = (int)((ones[j] >> bp) & 1u) | (int)(((twos[j] >> bp) & 1u) << 1) |
+                      (int)(((fours[j] >> bp) & 1u) << 2) | (int)(((eights[j] >> bp) & 1u) << 3);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cnt |= (int)(((hi[i][j] >> bp) & 1u) << (4 + i));
+            int* o = out + ix * ncy + iy;   // reference enumeration order: x outer, y inner
+            const int sum = 255 * cnt + (first ? 0 : *o);
+            *o = sum;
+            if (last)
+              best_key = max(best_key, key_of(score_of(sum, P, prm),
+                                              rank_of(prm, s, b.min_x + ix * prm.step, b.min_y + iy * prm.step)));
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    best_key = max(best_key, __shfl_xor_sync(0xffffffffu, best_key, o));
+  if (lane == 0 && best_key) atomicMax(top_coarse + pi, best_key);
+}
+
 // --------------------------------------------------------------------- K7 seed
 
 // One CTA per pair: descend greedily from the best coarse candidate to a leaf to get
@@ -705,6 +962,63 @@ cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, 
                                                           coarse, top_coarse);
   }
   return cudaGetLastError();
+}
+
+cudaError_t launch_csm_build_pmb(const uint8_t* level, int wide_nx, int wide_ny, int px, int py,
+                                 int log2w, int rows, unsigned long long* out, int* not_binary,
+                                 cudaStream_t stream) {
+  const int n = (1 << (2 * log2w)) * rows;
+  csm_build_pmb_kernel<<<(n + 127) / 128, 128, 0, stream>>>(level, wide_nx, wide_ny, px, py, log2w,
+                                                            rows, out, not_binary);
+  return cudaGetLastError();
+}
+
+int csm_pmb_rows(int wide_ny, int n_lin, int log2w) {
+  return ((wide_ny + 3 * n_lin - 1) >> log2w) + 1 + kBitRowSlack;
+}
+
+size_t csm_coarse_bits_smem(int log2w, int rows) {
+  return ((size_t)(1 << (2 * log2w)) * rows + kBitChunk) * 8;
+}
+
+namespace {
+template <int NP>
+cudaError_t launch_bits_np(dim3 grd, int threads, size_t smem, cudaStream_t stream,
+                           const CsmGridDev* grids, const CsmPairDev* pairs, const float* pts,
+                           const float2* rot, CsmParams prm, CsmBounds* bounds, int* coarse,
+                           unsigned long long* top_coarse) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(csm_coarse_bits_kernel<NP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  csm_coarse_bits_kernel<NP><<<grd, threads, smem, stream>>>(grids, pairs, pts, rot, prm, bounds,
+                                                             coarse, top_coarse);
+  return cudaGetLastError();
+}
+}  // namespace
+
+// All grids of the batch must carry bit planes built for prm.depth-1 / prm.n_lin and share
+// the largest shared-memory footprint `smem`.
+cudaError_t launch_csm_coarse_bits(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                                   const float* pts, const float2* rot, CsmParams prm,
+                                   CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
+                                   size_t smem, int warps, cudaStream_t stream) {
+  const int threads = 32 * warps;
+  dim3 grd((prm.S + threads - 1) / threads, n_pairs);
+  const int np = (prm.max_side + 1) / 2;
+#define GLOC_BITS_CASE(N)                                                                       \
+  case N:                                                                                       \
+    return launch_bits_np<N>(grd, threads, smem, stream, grids, pairs, pts, rot, prm, bounds,   \
+                             coarse, top_coarse);
+  switch (np) {
+    GLOC_BITS_CASE(1) GLOC_BITS_CASE(2) GLOC_BITS_CASE(3) GLOC_BITS_CASE(4)
+    GLOC_BITS_CASE(5) GLOC_BITS_CASE(6) GLOC_BITS_CASE(7) GLOC_BITS_CASE(8)
+    default: return cudaErrorInvalidValue;
+  }
+#undef GLOC_BITS_CASE
 }
 
 cudaError_t launch_csm_seed(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,

@@ -38,6 +38,10 @@ struct HostGrid {
   // padded phase-major copy of the coarsest level used by the last batches (CsmGridDev::pm)
   uint8_t* d_pm = nullptr;
   int pm_level = -1, pm_pad = 0, pm_pw = 0, pm_ph = 0;
+  // bit planes of the coarsest level (binary grids; CsmGridDev::pmb)
+  unsigned long long* d_pmb = nullptr;
+  int pmb_level = -1, pmb_nlin = -1, pmb_rows = 0;
+  int binary = -1;   // -1 unknown, 0 some cell is neither 0 nor 255, 1 binary
 };
 
 size_t stack_bytes(int nx, int ny, int depth, long long* off) {
@@ -181,6 +185,7 @@ void gloc_csm_destroy(gloc_csm_store* st) {
   for (auto& gr : st->grids) {
     if (gr.d_stack) cudaFree(gr.d_stack);
     if (gr.d_pm) cudaFree(gr.d_pm);
+    if (gr.d_pmb) cudaFree(gr.d_pmb);
   }
   if (st->d_lut) cudaFree(st->d_lut);
   for (Buf* b : {&st->pts, &st->pairs, &st->gridtab, &st->rot, &st->bounds, &st->coarse, &st->top,
@@ -302,6 +307,10 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
   // validate + device tables
   std::vector<CsmPairDev> hp((size_t)n_pairs);
   bool use_pm = std::getenv("GLOC_CSM_NO_PM") == nullptr;
+  // bit-sliced coarse scorer: binary grids whose coarsest level fits 64 columns per plane
+  // row and shared memory, at most 16 lattice candidates per axis
+  bool use_bits = std::getenv("GLOC_CSM_NO_BITS") == nullptr && prm.max_side <= 16;
+  size_t bits_smem = 0;
   std::map<int, int> grid_slot;
   std::vector<CsmGridDev> hg;
   for (int i = 0; i < n_pairs; ++i) {
@@ -338,6 +347,43 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
           g.pm_level = level; g.pm_pad = pad; g.pm_pw = pw; g.pm_ph = ph;
         }
         d.pm = g.d_pm; d.pm_pad = g.pm_pad; d.pm_pw = g.pm_pw; d.pm_ph = g.pm_ph; d.pm_log2w = level;
+      }
+      d.pmb = nullptr; d.pmb_rows = 0; d.pmb_px = 0; d.pmb_py = 0; d.pmb_log2w = 0;
+      if (use_bits && g.binary != 0) {
+        const int level = depth - 1, w = 1 << level;
+        const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1;
+        const int rows = csm_pmb_rows(wide_ny, n_lin, level);
+        const size_t smem = csm_coarse_bits_smem(level, rows);
+        if (((wide_nx + n_lin - 1) >> level) >= 64 || smem > (size_t)225 * 1024) {
+          use_bits = false;
+        } else {
+          if (g.pmb_level != level || g.pmb_nlin != n_lin) {
+            if (g.d_pmb) cudaFree(g.d_pmb);
+            g.d_pmb = nullptr;
+            g.pmb_level = -1;
+            GLOC_CUDA_TRY(cudaMalloc((void**)&g.d_pmb, (size_t)w * w * rows * 8));
+            GLOC_CUDA_TRY(st->misc.reserve(64));
+            GLOC_CUDA_TRY(cudaMemsetAsync(st->misc.p, 0, 4, st->stream));
+            GLOC_CUDA_TRY(launch_csm_build_pmb(g.d_stack + g.off[level], wide_nx, wide_ny, n_lin,
+                                               2 * n_lin, level, rows, g.d_pmb, (int*)st->misc.p,
+                                               st->stream));
+            int not_binary = 0;
+            GLOC_CUDA_TRY(cudaMemcpyAsync(&not_binary, st->misc.p, 4, cudaMemcpyDeviceToHost, st->stream));
+            GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
+            st->stats.kernel_launches++;
+            g.binary = not_binary ? 0 : 1;
+            g.pmb_level = level; g.pmb_nlin = n_lin; g.pmb_rows = rows;
+          }
+          if (g.binary == 1) {
+            d.pmb = g.d_pmb; d.pmb_rows = g.pmb_rows; d.pmb_px = n_lin; d.pmb_py = 2 * n_lin;
+            d.pmb_log2w = level;
+            bits_smem = std::max(bits_smem, smem);
+          } else {
+            use_bits = false;
+          }
+        }
+      } else {
+        use_bits = false;
       }
       it = grid_slot.emplace(gi, (int)hg.size()).first;
       hg.push_back(d);
@@ -377,6 +423,8 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
   }
   std::vector<unsigned long long> hbest((size_t)n_pairs);
   const int n_ctas = sm_count(st->device) * 4;
+  int bits_warps = 6;   // rotations per CTA = 32 x warps
+  if (const char* e = std::getenv("GLOC_CSM_BITS_WARPS")) bits_warps = std::min(6, std::max(1, std::atoi(e)));
   for (long long p0 = 0; p0 < n_pairs; p0 += sub) {
     const int np = (int)std::min<long long>(sub, n_pairs - p0);
     GLOC_CUDA_TRY(st->pairs.reserve((size_t)np * sizeof(CsmPairDev)));
@@ -399,10 +447,16 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
     const CsmGridDev* dg = (const CsmGridDev*)st->gridtab.p;
     const CsmPairDev* dp = (const CsmPairDev*)st->pairs.p;
     st->prof.begin(stream);
-    cudaError_t ce = launch_csm_coarse(dg, dp, np, (const float*)st->pts.p,
-                                       (const float2*)st->rot.p, prm, (CsmBounds*)st->bounds.p,
-                                       (int*)st->coarse.p, (unsigned long long*)st->top.p, stream,
-                                       use_pm && (size_t)prm.maxc * 4 + 20 * 4096 <= 150 * 1024);
+    cudaError_t ce;
+    if (use_bits)
+      ce = launch_csm_coarse_bits(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p, prm,
+                                  (CsmBounds*)st->bounds.p, (int*)st->coarse.p,
+                                  (unsigned long long*)st->top.p, bits_smem, bits_warps, stream);
+    else
+      ce = launch_csm_coarse(dg, dp, np, (const float*)st->pts.p,
+                             (const float2*)st->rot.p, prm, (CsmBounds*)st->bounds.p,
+                             (int*)st->coarse.p, (unsigned long long*)st->top.p, stream,
+                             use_pm && (size_t)prm.maxc * 4 + 20 * 4096 <= 150 * 1024);
     st->prof.end(stream);
     GLOC_CUDA_TRY(ce);
     GLOC_CUDA_TRY(launch_csm_seed(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,

@@ -21,6 +21,11 @@ struct CsmGridDev {
   // point are adjacent bytes, and no lookup of an in-grid point needs a bounds check.
   const uint8_t* pm;
   int pm_pad, pm_pw, pm_ph, pm_log2w;
+  // Binary grids only: the coarsest level as bit planes (csm.cu "bit-sliced").  Plane
+  // (ry, rx), row r = one 64-bit word, bit c = cell (w c + rx - pmb_px, w r + ry - pmb_py)
+  // of the level's own (wide) frame; pmb_rows rows per plane, zero outside the grid.
+  const unsigned long long* pmb;
+  int pmb_rows, pmb_px, pmb_py, pmb_log2w;
 };
 
 // One (grid, scan) pair.
@@ -59,6 +64,16 @@ cudaError_t launch_csm_discretize(const float* pts, int n_pts, float w0, float z
 // coarsest level -> padded phase-major layout (see CsmGridDev::pm)
 cudaError_t launch_csm_build_pm(const uint8_t* level, int wide_nx, int wide_ny, int pad, int log2w,
                                 int pw, int ph, uint8_t* out, cudaStream_t stream);
+// coarsest level -> bit planes; *not_binary is set when a cell is neither 0 nor 255
+cudaError_t launch_csm_build_pmb(const uint8_t* level, int wide_nx, int wide_ny, int px, int py,
+                                 int log2w, int rows, unsigned long long* out, int* not_binary,
+                                 cudaStream_t stream);
+int csm_pmb_rows(int wide_ny, int n_lin, int log2w);
+size_t csm_coarse_bits_smem(int log2w, int rows);
+cudaError_t launch_csm_coarse_bits(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+                                   const float* pts, const float2* rot, CsmParams prm,
+                                   CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
+                                   size_t smem, int warps, cudaStream_t stream);
 // K7 pipeline
 cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                               const float* pts, const float2* rot, CsmParams prm,

@@ -641,14 +641,16 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 }
 
 // ------------------------------------------------------------------ K3: select + exact re-rank
-constexpr int kSurvMax = 4096;   // candidates below the final threshold, per query
+constexpr int kEntMax = 4096;    // group entries per query handled by K3 (more: exact-scan fallback)
+constexpr int kSurvMax = 2048;   // candidates below the tightened threshold, per query
 constexpr int kFinalMax = 256;   // candidates re-ranked exactly, per query
 constexpr int kRerankThreads = 128;
+constexpr int kMaxLists = 64;    // 2 * n_ranges
 
 struct RerankArgs {
   const float* db;
   const float* q;
-  int nq, dim, k, n_ranges, cap;
+  int nq, dim, k, n_ranges, cap;   // n_ranges here = lists per query (2 per GEMM range)
   const unsigned* cand_g;
   const float* cand_v;
   const unsigned* unit_cnt;
@@ -662,120 +664,203 @@ struct RerankArgs {
   unsigned long long* rows_reranked;   // [0] rows re-ranked, [1] overflowed queries (cumulative)
 };
 
+// k-th smallest (k >= 1, k <= n) of the n floats vals[0..n) in shared memory, n <= 8 * threads.
+// Small n: rank by counting on the unique (value, position) key.  Large n: bisection on the
+// order-preserving 32-bit key (smallest K with |{v : key(v) <= K}| >= k), one barrier per
+// round.  Called by all threads of the CTA; `scratch` is 16 words of shared memory.
+__device__ float kth_smallest_smem(const float* vals, int n, int k, unsigned* scratch, float* result) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (n <= 2 * kRerankThreads) {
+    uint64_t key[2];
+    int rank[2] = {0, 0};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = tid + u * kRerankThreads;
+      key[u] = i < n ? (((uint64_t)f2ord(vals[i]) << 32) | (unsigned)i) : ~0ull;
+    }
+    for (int j = 0; j < n; ++j) {
+      const uint64_t kj = ((uint64_t)f2ord(vals[j]) << 32) | (unsigned)j;
+      rank[0] += kj < key[0] ? 1 : 0;
+      rank[1] += kj < key[1] ? 1 : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = tid + u * kRerankThreads;
+      if (i < n && rank[u] == k - 1) *result = vals[i];
+    }
+    __syncthreads();
+    return *result;
+  }
+  unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+  for (int i = tid; i < n; i += kRerankThreads) {
+    const unsigned key = f2ord(vals[i]);
+    kmin = min(kmin, key);
+    kmax = max(kmax, key);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+  }
+  if (lane == 0) { scratch[warp] = kmin; scratch[4 + warp] = kmax; }
+  __syncthreads();
+  unsigned lo = 0xFFFFFFFFu, hi = 0u;
+#pragma unroll
+  for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) { lo = min(lo, scratch[w2]); hi = max(hi, scratch[4 + w2]); }
+  int round = 0;
+  while (lo < hi) {
+    const unsigned mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+    for (int i = tid; i < n; i += kRerankThreads) c += f2ord(vals[i]) <= mid ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) scratch[8 + (round & 1) * 4 + warp] = (unsigned)c;
+    __syncthreads();
+    int total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) total += (int)scratch[8 + (round & 1) * 4 + w2];
+    if (total >= k) hi = mid; else lo = mid + 1;
+    ++round;
+  }
+  __syncthreads();
+  return ord2f(lo);
+}
+
+// One CTA per query.  The kernel is a chain of dependent global round trips (list sizes ->
+// group entries -> candidate rows), so it is organised to issue every load of a stage at once
+// and to keep its shared-memory footprint small enough for ~10 CTAs per SM.
 __global__ void __launch_bounds__(kRerankThreads)
 knn_shortlist_rerank_kernel(RerankArgs a) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   float* surv_s = reinterpret_cast<float*>(sm_raw);                       // [kSurvMax]
   unsigned* surv_i = reinterpret_cast<unsigned*>(surv_s + kSurvMax);      // [kSurvMax]
-  unsigned* fin_i = surv_i + kSurvMax;                                    // [kFinalMax]
+  float* gmin = surv_s;   // [kEntMax] group minima: dead before the survivors are written
+  float* G = surv_s;      // [32][dim/4 + 1]: reuses the survivor arrays, dead once the finalists are chosen
+  const int groups = a.dim / 4, gstride = groups + 1;
+  const size_t g_bytes = (size_t)32 * gstride * 4, s_bytes = (size_t)kSurvMax * 8;
+  unsigned char* after = sm_raw + (g_bytes > s_bytes ? g_bytes : s_bytes);
+  unsigned* fin_i = reinterpret_cast<unsigned*>(after);                   // [kFinalMax]
   float* fin_d = reinterpret_cast<float*>(fin_i + kFinalMax);             // [kFinalMax]
   float* qs = fin_d + kFinalMax;                                          // [dim]
-  float* G = surv_s;   // [32][dim/4 + 1]: reuses the survivor arrays, dead once the finalists are chosen
   __shared__ int n_surv, n_fin, bad;
-  __shared__ float s_ak;
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const int groups = a.dim / 4, gstride = groups + 1;
+  __shared__ float s_kth;
+  __shared__ unsigned s_cnt[kMaxLists], s_off[kMaxLists + 1], scratch[16];
+  const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) { n_surv = 0; n_fin = 0; bad = 0; }
-  for (int i = tid; i < a.dim; i += kRerankThreads) qs[i] = a.q[(size_t)q * a.dim + i];
-  __syncthreads();
+  // stage 0: everything that only depends on q, issued together
+  unsigned my_cnt = 0;
+  if (tid < a.n_ranges) my_cnt = a.unit_cnt[(size_t)q * a.n_ranges + tid];
   const float tau = ord2f(a.thr_ord[q]);
   const float eps2 = a.eps2[q];
-  // 1. gather the candidates below the final threshold from every unit list of this query
-  __shared__ unsigned s_cnt[64], s_off[65];
-  for (int r = tid; r < a.n_ranges; r += kRerankThreads) {
-    const unsigned cnt = a.unit_cnt[(size_t)q * a.n_ranges + r];
-    if (cnt > (unsigned)a.cap) bad = 1;
-    s_cnt[r] = min(cnt, (unsigned)a.cap);
+  for (int i = tid; i < groups; i += kRerankThreads)
+    reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(a.q + (size_t)q * a.dim) + i);
+  __syncthreads();
+  if (tid < a.n_ranges) {
+    if (my_cnt > (unsigned)a.cap) bad = 1;
+    s_cnt[tid] = min(my_cnt, (unsigned)a.cap);
   }
   __syncthreads();
-  if (tid == 0) {
-    unsigned o = 0;
-    for (int r = 0; r < a.n_ranges; ++r) { s_off[r] = o; o += s_cnt[r]; }
-    s_off[a.n_ranges] = o;
+  if (warp == 0) {   // exclusive prefix over <= 64 lists
+    const unsigned c0 = lane < a.n_ranges ? s_cnt[lane] : 0u;
+    const unsigned c1 = lane + 32 < a.n_ranges ? s_cnt[lane + 32] : 0u;
+    unsigned x0 = c0, x1 = c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y0 = __shfl_up_sync(0xffffffffu, x0, o), y1 = __shfl_up_sync(0xffffffffu, x1, o);
+      if (lane >= o) { x0 += y0; x1 += y1; }
+    }
+    const unsigned t0 = __shfl_sync(0xffffffffu, x0, 31);
+    s_off[lane] = x0 - c0;
+    s_off[lane + 32] = t0 + x1 - c1;
+    if (lane == 31) {
+      s_off[kMaxLists] = t0 + x1;
+      if (t0 + x1 > (unsigned)kEntMax) bad = 1;
+    }
   }
   __syncthreads();
-  {  // one flat pass over all lists (8 scores per group entry): every load is independent
-    const unsigned total = s_off[a.n_ranges] * 8u;
+  if (!bad) {
+    // stage 1: one thread per group entry (base row + 8 scores); the first two entries of a
+    // thread stay in registers for the second pass
+    const int total = (int)s_off[kMaxLists];
     const size_t qbase = (size_t)q * a.n_ranges * (size_t)a.cap;
-    for (unsigned e8 = tid; e8 < total; e8 += kRerankThreads) {
-      const unsigned e = e8 >> 3, j = e8 & 7u;
+    auto entry_at = [&](int e) -> size_t {
       int lo = 0, hi = a.n_ranges - 1;   // largest r with s_off[r] <= e
       while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
-        if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
+        if (s_off[mid] <= (unsigned)e) lo = mid; else hi = mid - 1;
       }
-      const size_t at = qbase + (size_t)lo * a.cap + (e - s_off[lo]);
-      const float s = a.cand_v[at * 8 + j];
-      const unsigned ci = a.cand_g[at] + j;   // issued with the score: one memory round trip
-      if (s <= tau && s < INFINITY) {         // +inf = masked / padded row
-        const int pos = atomicAdd(&n_surv, 1);
-        if (pos < kSurvMax) { surv_s[pos] = s; surv_i[pos] = ci; }
+      return qbase + (size_t)lo * a.cap + ((unsigned)e - s_off[lo]);
+    };
+    auto min8 = [](const float4& x, const float4& y) {
+      return fminf(fminf(fminf(x.x, x.y), fminf(x.z, x.w)), fminf(fminf(y.x, y.y), fminf(y.z, y.w)));
+    };
+    unsigned base[2] = {0u, 0u};
+    float4 v[2][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + u * kRerankThreads;
+      if (e < total) {
+        const size_t at = entry_at(e);
+        base[u] = a.cand_g[at];
+        v[u][0] = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
+        v[u][1] = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
       }
     }
-  }
-  __syncthreads();
-  int ns = n_surv;
-  if (ns > kSurvMax) { if (tid == 0) bad = 1; ns = kSurvMax; }
-  __syncthreads();
-  if (!bad) {
-    // 2. A_k = k-th smallest approximate score among the survivors (all of the k smallest
-    //    approximate scores are survivors), then keep s <= A_k + 2 eps.
-    if (tid == 0) s_ak = INFINITY;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = tid + u * kRerankThreads;
+      if (e < total) gmin[e] = min8(v[u][0], v[u][1]);
+    }
+    for (int e = tid + 2 * kRerankThreads; e < total; e += kRerankThreads) {
+      const size_t at = entry_at(e);
+      gmin[e] = min8(reinterpret_cast<const float4*>(a.cand_v)[2 * at],
+                     reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1]);
+    }
     __syncthreads();
-    if (ns >= a.k) {
-      // k-th smallest score by bisection on the order-preserving 32-bit key: the smallest
-      // key K with |{s : key(s) <= K}| >= k.  Keys live in registers, the range starts at
-      // [min key, max key], one barrier per round (double-buffered partial counts).
-      __shared__ int s_count[2][kRerankThreads / 32];
-      __shared__ unsigned s_mm[2][kRerankThreads / 32];
-      constexpr int kPer = kSurvMax / kRerankThreads;
-      unsigned keys[kPer];
-      unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+    // The k smallest group minima belong to k distinct rows, so the k-th smallest of them
+    // bounds A_k (the k-th smallest approximate score) from above: every true top-k row
+    // scores <= that + 2 eps.  Near-duplicate rows share a group, which would otherwise put
+    // all 8 of them among the survivors of every group that passed the GEMM's looser bound.
+    float tau1 = tau;
+    if (total >= a.k) tau1 = fminf(tau, kth_smallest_smem(gmin, total, a.k, scratch, &s_kth) + eps2);
+    __syncthreads();   // gmin is dead: the survivor arrays reuse its memory
+    auto push8 = [&](unsigned b0, const float4& x, const float4& y) {
+      const float sc[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
 #pragma unroll
-      for (int j = 0; j < kPer; ++j) {
-        const int i = tid + j * kRerankThreads;
-        keys[j] = i < ns ? f2ord(surv_s[i]) : 0xFFFFFFFFu;
-        if (i < ns) { kmin = min(kmin, keys[j]); kmax = max(kmax, keys[j]); }
+      for (int j = 0; j < 8; ++j) {
+        if (sc[j] <= tau1 && sc[j] < INFINITY) {   // +inf = masked / padded row
+          const int pos = atomicAdd(&n_surv, 1);
+          if (pos < kSurvMax) { surv_s[pos] = sc[j]; surv_i[pos] = b0 + j; }
+        }
       }
+    };
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+    for (int u = 0; u < 2; ++u)
+      if (tid + u * kRerankThreads < total) push8(base[u], v[u][0], v[u][1]);
+    for (int e = tid + 2 * kRerankThreads; e < total; e += kRerankThreads) {
+      const size_t at = entry_at(e);
+      push8(a.cand_g[at], reinterpret_cast<const float4*>(a.cand_v)[2 * at],
+            reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1]);
+    }
+    __syncthreads();
+    int ns = n_surv;
+    if (ns > kSurvMax) { if (tid == 0) bad = 1; ns = kSurvMax; }
+    __syncthreads();
+    if (!bad) {
+      // stage 2: A_k = k-th smallest approximate score among the survivors (all of the k
+      // smallest approximate scores are survivors), then keep s <= A_k + 2 eps.
+      float tau2 = INFINITY;
+      if (ns >= a.k) tau2 = kth_smallest_smem(surv_s, ns, a.k, scratch, &s_kth) + eps2;
+      for (int i = tid; i < ns; i += kRerankThreads) {
+        if (surv_s[i] <= tau2) {
+          const int pos = atomicAdd(&n_fin, 1);
+          if (pos < kFinalMax) fin_i[pos] = surv_i[i];
+        }
       }
-      if ((tid & 31) == 0) { s_mm[0][tid >> 5] = kmin; s_mm[1][tid >> 5] = kmax; }
       __syncthreads();
-      unsigned lo = 0xFFFFFFFFu, hi = 0u;
-#pragma unroll
-      for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) { lo = min(lo, s_mm[0][w2]); hi = max(hi, s_mm[1][w2]); }
-      int round = 0;
-      while (lo < hi) {
-        const unsigned mid = lo + ((hi - lo) >> 1);
-        int c = 0;
-#pragma unroll
-        for (int j = 0; j < kPer; ++j) c += keys[j] <= mid ? 1 : 0;   // padding keys are 0xFFFFFFFF > mid
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if ((tid & 31) == 0) s_count[round & 1][tid >> 5] = c;
-        __syncthreads();
-        int total = 0;
-#pragma unroll
-        for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) total += s_count[round & 1][w2];
-        if (total >= a.k) hi = mid; else lo = mid + 1;
-        ++round;
-      }
-      if (tid == 0) s_ak = ord2f(lo);
+      if (n_fin > kFinalMax && tid == 0) bad = 1;
+      __syncthreads();
     }
-    __syncthreads();
-    const float tau2 = s_ak + eps2;
-    for (int i = tid; i < ns; i += kRerankThreads) {
-      if (surv_s[i] <= tau2) {
-        const int pos = atomicAdd(&n_fin, 1);
-        if (pos < kFinalMax) fin_i[pos] = surv_i[i];
-      }
-    }
-    __syncthreads();
-    if (n_fin > kFinalMax && tid == 0) bad = 1;
-    __syncthreads();
   }
   if (bad) {
     if (tid == 0) {
@@ -786,29 +871,38 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
     return;
   }
   const int nf = n_fin;
-  // 3. exact distances, reference operation order (nanoflann.hpp:453-487): the per-group
-  //    sums ((d0^2+d1^2)+d2^2)+d3^2 are independent (computed by all threads, coalesced row
-  //    reads); the running sum over groups is a serial chain done by one thread per row.
+  // stage 3: exact distances, reference operation order (nanoflann.hpp:453-487): the
+  // per-group sums ((d0^2+d1^2)+d2^2)+d3^2 are independent -- one warp per row, a lane takes
+  // every 32nd group (coalesced 512 B reads), 4 rows x 4 groups in flight per lane; the
+  // running sum over groups is the serial chain, one thread per row.
   for (int b0 = 0; b0 < nf; b0 += 32) {
     const int nb = min(32, nf - b0);
-    for (int g = tid; g < groups; g += kRerankThreads) {
-      const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * g);
-      for (int c0 = 0; c0 < nb; c0 += 8) {
-        float4 x[8];
+    for (int r0 = warp * 4; r0 < nb; r0 += (kRerankThreads / 32) * 4) {
+      for (int g0 = 0; g0 < groups; g0 += 128) {
+        float4 x[4][4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {   // 8 independent row reads in flight per thread
-          const int c = min(c0 + u, nb - 1);
-          x[u] = __ldg(reinterpret_cast<const float4*>(a.db + (size_t)fin_i[b0 + c] * a.dim) + g);
+        for (int u = 0; u < 4; ++u) {
+          const float4* row = reinterpret_cast<const float4*>(a.db + (size_t)fin_i[b0 + min(r0 + u, nb - 1)] * a.dim);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int g = g0 + lane + 32 * j;
+            x[u][j] = g < groups ? __ldg(row + g) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          if (c0 + u < nb) {
-            const float d0 = __fsub_rn(qq.x, x[u].x), d1 = __fsub_rn(qq.y, x[u].y);
-            const float d2 = __fsub_rn(qq.z, x[u].z), d3 = __fsub_rn(qq.w, x[u].w);
+        for (int u = 0; u < 4; ++u) {
+          if (r0 + u >= nb) continue;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int g = g0 + lane + 32 * j;
+            if (g >= groups) continue;
+            const float4 qq = *reinterpret_cast<const float4*>(qs + 4 * g);
+            const float d0 = __fsub_rn(qq.x, x[u][j].x), d1 = __fsub_rn(qq.y, x[u][j].y);
+            const float d2 = __fsub_rn(qq.z, x[u][j].z), d3 = __fsub_rn(qq.w, x[u][j].w);
             float sg = __fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1));
             sg = __fadd_rn(sg, __fmul_rn(d2, d2));
             sg = __fadd_rn(sg, __fmul_rn(d3, d3));
-            G[(c0 + u) * gstride + g] = sg;
+            G[(r0 + u) * gstride + g] = sg;
           }
         }
       }
@@ -817,19 +911,19 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
     if (tid < nb) {
       float r = 0.f;
       const float* gr = G + tid * gstride;
+#pragma unroll 8
       for (int g = 0; g < groups; ++g) r = __fadd_rn(r, gr[g]);
       fin_d[b0 + tid] = r;
     }
     __syncthreads();
   }
-  // 4. top-k by (d2, idx)
+  // stage 4: top-k by (d2, idx)
   uint64_t* oi = a.out_idx + (size_t)q * a.k;
   float* od = a.out_d2 + (size_t)q * a.k;
-  for (int i = tid; i < a.k; i += kRerankThreads) {
+  for (int i = nf + tid; i < a.k; i += kRerankThreads) {   // fewer finalists than k: empty slots
     oi[i] = 0xFFFFFFFFFFFFFFFFull;
     od[i] = 3.402823466e+38f;
   }
-  __syncthreads();
   for (int i = tid; i < nf; i += kRerankThreads) {
     const uint64_t ki = pack_key(fin_d[i], fin_i[i]);
     int rank = 0;
