@@ -100,10 +100,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+DUP_RUN = 8   # database rows form runs of near-duplicates (consecutive KITTI frames); --dup-run 0: iid rows
+
+
 def make_retrieval_inputs(world: int):
     from gloc3d_b200 import synth
 
-    db = synth.make_descriptors(DB_ROWS, DIM, seed=1234, dup_run=8)
+    db = synth.make_descriptors(DB_ROWS, DIM, seed=1234, dup_run=DUP_RUN)
     nq = Q_PER_GPU * world
     qa = synth.make_queries(db, nq // 2, seed=5678)                    # set A: independent
     qb = synth.make_queries(db, nq - nq // 2, seed=5679, sigma=0.01)   # set B: perturbed copies
@@ -507,7 +510,11 @@ def main():
                          "the result does not depend on it")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dup-run", type=int, default=8,
+                    help="length of the near-duplicate runs in the synthetic database (0 = iid rows)")
     args = ap.parse_args()
+    global DUP_RUN
+    DUP_RUN = args.dup_run
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

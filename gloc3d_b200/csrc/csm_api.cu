@@ -446,6 +446,13 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
     unsigned long long* counters = (unsigned long long*)((char*)st->misc.p + 16);
     const CsmGridDev* dg = (const CsmGridDev*)st->gridtab.p;
     const CsmPairDev* dp = (const CsmPairDev*)st->pairs.p;
+    // tuning aid: GLOC_CSM_TIMING=1 prints the duration of every stage of this sub-batch
+    const bool timing = std::getenv("GLOC_CSM_TIMING") != nullptr;
+    cudaEvent_t tev[5];
+    if (timing) {
+      for (auto& e : tev) cudaEventCreate(&e);
+      cudaEventRecord(tev[0], stream);
+    }
     st->prof.begin(stream);
     cudaError_t ce;
     if (use_bits)
@@ -459,22 +466,35 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
                              use_pm && (size_t)prm.maxc * 4 + 20 * 4096 <= 150 * 1024);
     st->prof.end(stream);
     GLOC_CUDA_TRY(ce);
+    if (timing) cudaEventRecord(tev[1], stream);
     GLOC_CUDA_TRY(launch_csm_seed(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,
                                   prm, (const CsmBounds*)st->bounds.p,
                                   (const unsigned long long*)st->top.p,
                                   (unsigned long long*)st->best.p, stream));
+    if (timing) cudaEventRecord(tev[2], stream);
     GLOC_CUDA_TRY(launch_csm_filter(dp, np, prm, (const CsmBounds*)st->bounds.p,
                                     (const int*)st->coarse.p, (const unsigned long long*)st->best.p,
                                     (unsigned*)st->survivors.p, n_surv, stream));
+    if (timing) cudaEventRecord(tev[3], stream);
     GLOC_CUDA_TRY(launch_csm_refine(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,
                                     prm, (const CsmBounds*)st->bounds.p, (const int*)st->coarse.p,
                                     (const unsigned*)st->survivors.p, n_surv, cursor,
                                     (unsigned long long*)st->best.p, counters, n_ctas, stream));
+    if (timing) cudaEventRecord(tev[4], stream);
     GLOC_CUDA_TRY(cudaMemcpyAsync(hbest.data() + p0, st->best.p, (size_t)np * 8,
                                   cudaMemcpyDeviceToHost, stream));
     unsigned long long hc = 0;
     GLOC_CUDA_TRY(cudaMemcpyAsync(&hc, counters, 8, cudaMemcpyDeviceToHost, stream));
     GLOC_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (timing) {
+      float t[4] = {0, 0, 0, 0};
+      unsigned ns = 0;
+      cudaMemcpy(&ns, n_surv, 4, cudaMemcpyDeviceToHost);
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+      fprintf(stderr, "[csm] pairs=%d coarse(%s)=%.3f ms seed=%.3f filter=%.3f refine=%.3f | survivors=%u "
+                      "expanded=%llu\n", np, use_bits ? "bits" : "u8", t[0], t[1], t[2], t[3], ns, hc);
+      for (auto& e : tev) cudaEventDestroy(e);
+    }
     st->stats.kernel_launches += 4;
     st->stats.refined_nodes += hc;
     st->stats.coarse_candidates += (uint64_t)np * (uint64_t)per_pair;  // upper bound (slots)

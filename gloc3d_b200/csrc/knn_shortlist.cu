@@ -642,7 +642,6 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 
 // ------------------------------------------------------------------ K3: select + exact re-rank
 constexpr int kEntMax = 4096;    // group entries per query handled by K3 (more: exact-scan fallback)
-constexpr int kSurvMax = 2048;   // candidates below the tightened threshold, per query
 constexpr int kFinalMax = 256;   // candidates re-ranked exactly, per query
 constexpr int kRerankThreads = 128;
 constexpr int kMaxLists = 64;    // 2 * n_ranges
@@ -664,89 +663,23 @@ struct RerankArgs {
   unsigned long long* rows_reranked;   // [0] rows re-ranked, [1] overflowed queries (cumulative)
 };
 
-// k-th smallest (k >= 1, k <= n) of the n floats vals[0..n) in shared memory, n <= 8 * threads.
-// Small n: rank by counting on the unique (value, position) key.  Large n: bisection on the
-// order-preserving 32-bit key (smallest K with |{v : key(v) <= K}| >= k), one barrier per
-// round.  Called by all threads of the CTA; `scratch` is 16 words of shared memory.
-__device__ float kth_smallest_smem(const float* vals, int n, int k, unsigned* scratch, float* result) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (n <= 2 * kRerankThreads) {
-    uint64_t key[2];
-    int rank[2] = {0, 0};
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = tid + u * kRerankThreads;
-      key[u] = i < n ? (((uint64_t)f2ord(vals[i]) << 32) | (unsigned)i) : ~0ull;
-    }
-    for (int j = 0; j < n; ++j) {
-      const uint64_t kj = ((uint64_t)f2ord(vals[j]) << 32) | (unsigned)j;
-      rank[0] += kj < key[0] ? 1 : 0;
-      rank[1] += kj < key[1] ? 1 : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int i = tid + u * kRerankThreads;
-      if (i < n && rank[u] == k - 1) *result = vals[i];
-    }
-    __syncthreads();
-    return *result;
-  }
-  unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-  for (int i = tid; i < n; i += kRerankThreads) {
-    const unsigned key = f2ord(vals[i]);
-    kmin = min(kmin, key);
-    kmax = max(kmax, key);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-    kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-  }
-  if (lane == 0) { scratch[warp] = kmin; scratch[4 + warp] = kmax; }
-  __syncthreads();
-  unsigned lo = 0xFFFFFFFFu, hi = 0u;
-#pragma unroll
-  for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) { lo = min(lo, scratch[w2]); hi = max(hi, scratch[4 + w2]); }
-  int round = 0;
-  while (lo < hi) {
-    const unsigned mid = lo + ((hi - lo) >> 1);
-    int c = 0;
-    for (int i = tid; i < n; i += kRerankThreads) c += f2ord(vals[i]) <= mid ? 1 : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) scratch[8 + (round & 1) * 4 + warp] = (unsigned)c;
-    __syncthreads();
-    int total = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) total += (int)scratch[8 + (round & 1) * 4 + w2];
-    if (total >= k) hi = mid; else lo = mid + 1;
-    ++round;
-  }
-  __syncthreads();
-  return ord2f(lo);
-}
-
-// One CTA per query.  The kernel is a chain of dependent global round trips (list sizes ->
-// group entries -> candidate rows), so it is organised to issue every load of a stage at once
-// and to keep its shared-memory footprint small enough for ~10 CTAs per SM.
+// One CTA per query.  Select the rows to re-rank, re-rank them exactly, write the top-k.
+// The selection is a radix select (k-th smallest approximate score) over the scores of the
+// emitted groups, which stay in registers; only the exact re-rank touches the database.
 __global__ void __launch_bounds__(kRerankThreads)
 knn_shortlist_rerank_kernel(RerankArgs a) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
-  float* surv_s = reinterpret_cast<float*>(sm_raw);                       // [kSurvMax]
-  unsigned* surv_i = reinterpret_cast<unsigned*>(surv_s + kSurvMax);      // [kSurvMax]
-  float* gmin = surv_s;   // [kEntMax] group minima: dead before the survivors are written
-  float* G = surv_s;      // [32][dim/4 + 1]: reuses the survivor arrays, dead once the finalists are chosen
   const int groups = a.dim / 4, gstride = groups + 1;
-  const size_t g_bytes = (size_t)32 * gstride * 4, s_bytes = (size_t)kSurvMax * 8;
-  unsigned char* after = sm_raw + (g_bytes > s_bytes ? g_bytes : s_bytes);
-  unsigned* fin_i = reinterpret_cast<unsigned*>(after);                   // [kFinalMax]
+  float* G = reinterpret_cast<float*>(sm_raw);                            // [32][dim/4 + 1]
+  const size_t g_bytes = max((size_t)32 * gstride * 4, (size_t)4 * 256 * 4);
+  unsigned* fin_i = reinterpret_cast<unsigned*>(sm_raw + g_bytes);        // [kFinalMax]
   float* fin_d = reinterpret_cast<float*>(fin_i + kFinalMax);             // [kFinalMax]
   float* qs = fin_d + kFinalMax;                                          // [dim]
-  __shared__ int n_surv, n_fin, bad;
-  __shared__ float s_kth;
-  __shared__ unsigned s_cnt[kMaxLists], s_off[kMaxLists + 1], scratch[16];
+  unsigned* hist = reinterpret_cast<unsigned*>(G);                        // [4][256], dead before G is written
+  __shared__ int n_fin, bad;
+  __shared__ unsigned s_cnt[kMaxLists], s_off[kMaxLists + 1], s_red[3][kRerankThreads / 32], s_sel[2];
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { n_surv = 0; n_fin = 0; bad = 0; }
+  if (tid == 0) { n_fin = 0; bad = 0; }
   // stage 0: everything that only depends on q, issued together
   unsigned my_cnt = 0;
   if (tid < a.n_ranges) my_cnt = a.unit_cnt[(size_t)q * a.n_ranges + tid];
@@ -754,6 +687,7 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   const float eps2 = a.eps2[q];
   for (int i = tid; i < groups; i += kRerankThreads)
     reinterpret_cast<float4*>(qs)[i] = __ldg(reinterpret_cast<const float4*>(a.q + (size_t)q * a.dim) + i);
+  for (int i = tid; i < 4 * 256; i += kRerankThreads) hist[i] = 0u;
   __syncthreads();
   if (tid < a.n_ranges) {
     if (my_cnt > (unsigned)a.cap) bad = 1;
@@ -779,8 +713,8 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   }
   __syncthreads();
   if (!bad) {
-    // stage 1: one thread per group entry (base row + 8 scores); the first two entries of a
-    // thread stay in registers for the second pass
+    // stage 1: one thread per group entry (base row + 8 scores).  The first two entries of a
+    // thread stay in registers; further ones (rare) are re-read from L2 in every pass.
     const int total = (int)s_off[kMaxLists];
     const size_t qbase = (size_t)q * a.n_ranges * (size_t)a.cap;
     auto entry_at = [&](int e) -> size_t {
@@ -791,76 +725,113 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
       }
       return qbase + (size_t)lo * a.cap + ((unsigned)e - s_off[lo]);
     };
-    auto min8 = [](const float4& x, const float4& y) {
-      return fminf(fminf(fminf(x.x, x.y), fminf(x.z, x.w)), fminf(fminf(y.x, y.y), fminf(y.z, y.w)));
-    };
     unsigned base[2] = {0u, 0u};
-    float4 v[2][2];
+    unsigned key[2][8];   // order-preserving keys; 0xFFFFFFFF = not a candidate
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int e = tid + u * kRerankThreads;
+      float4 v0 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), v1 = v0;
       if (e < total) {
         const size_t at = entry_at(e);
         base[u] = a.cand_g[at];
-        v[u][0] = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
-        v[u][1] = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
+        v0 = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
+        v1 = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
       }
-    }
+      const float sc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = tid + u * kRerankThreads;
-      if (e < total) gmin[e] = min8(v[u][0], v[u][1]);
+      for (int j = 0; j < 8; ++j)   // scores above the GEMM's final bound cannot be in the top-k; +inf = masked row
+        key[u][j] = (sc[j] <= tau && sc[j] < INFINITY) ? f2ord(sc[j]) : 0xFFFFFFFFu;
     }
-    for (int e = tid + 2 * kRerankThreads; e < total; e += kRerankThreads) {
-      const size_t at = entry_at(e);
-      gmin[e] = min8(reinterpret_cast<const float4*>(a.cand_v)[2 * at],
-                     reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1]);
-    }
-    __syncthreads();
-    // The k smallest group minima belong to k distinct rows, so the k-th smallest of them
-    // bounds A_k (the k-th smallest approximate score) from above: every true top-k row
-    // scores <= that + 2 eps.  Near-duplicate rows share a group, which would otherwise put
-    // all 8 of them among the survivors of every group that passed the GEMM's looser bound.
-    float tau1 = tau;
-    if (total >= a.k) tau1 = fminf(tau, kth_smallest_smem(gmin, total, a.k, scratch, &s_kth) + eps2);
-    __syncthreads();   // gmin is dead: the survivor arrays reuse its memory
-    auto push8 = [&](unsigned b0, const float4& x, const float4& y) {
-      const float sc[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    // f(key, row) over every candidate score of this thread (f2ord never yields 0xFFFFFFFF
+    // for a finite score)
+    auto for_each = [&](auto&& f) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        if (sc[j] <= tau1 && sc[j] < INFINITY) {   // +inf = masked / padded row
-          const int pos = atomicAdd(&n_surv, 1);
-          if (pos < kSurvMax) { surv_s[pos] = sc[j]; surv_i[pos] = b0 + j; }
-        }
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (key[u][j] != 0xFFFFFFFFu) f(key[u][j], base[u] + j);
+      for (int e = tid + 2 * kRerankThreads; e < total; e += kRerankThreads) {
+        const size_t at = entry_at(e);
+        const unsigned b0 = a.cand_g[at];
+        const float4 v0 = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
+        const float4 v1 = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
+        const float sc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (sc[j] <= tau && sc[j] < INFINITY) f(f2ord(sc[j]), b0 + j);
       }
     };
+    // stage 2: A_k = k-th smallest candidate score (radix select on key - min key, 8 bits per
+    // pass starting at the highest bit in which the candidates differ), then keep the
+    // candidates with s <= A_k + 2 eps.
+    unsigned cnt = 0, kmin = 0xFFFFFFFFu, kmax = 0u;
+    for_each([&](unsigned k32, unsigned) { ++cnt; kmin = min(kmin, k32); kmax = max(kmax, k32); });
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
-      if (tid + u * kRerankThreads < total) push8(base[u], v[u][0], v[u][1]);
-    for (int e = tid + 2 * kRerankThreads; e < total; e += kRerankThreads) {
-      const size_t at = entry_at(e);
-      push8(a.cand_g[at], reinterpret_cast<const float4*>(a.cand_v)[2 * at],
-            reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1]);
+    for (int o = 16; o > 0; o >>= 1) {
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     }
+    if (lane == 0) { s_red[0][warp] = cnt; s_red[1][warp] = kmin; s_red[2][warp] = kmax; }
     __syncthreads();
-    int ns = n_surv;
-    if (ns > kSurvMax) { if (tid == 0) bad = 1; ns = kSurvMax; }
-    __syncthreads();
-    if (!bad) {
-      // stage 2: A_k = k-th smallest approximate score among the survivors (all of the k
-      // smallest approximate scores are survivors), then keep s <= A_k + 2 eps.
-      float tau2 = INFINITY;
-      if (ns >= a.k) tau2 = kth_smallest_smem(surv_s, ns, a.k, scratch, &s_kth) + eps2;
-      for (int i = tid; i < ns; i += kRerankThreads) {
-        if (surv_s[i] <= tau2) {
-          const int pos = atomicAdd(&n_fin, 1);
-          if (pos < kFinalMax) fin_i[pos] = surv_i[i];
+    cnt = 0; kmin = 0xFFFFFFFFu; kmax = 0u;
+#pragma unroll
+    for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) {
+      cnt += s_red[0][w2];
+      kmin = min(kmin, s_red[1][w2]);
+      kmax = max(kmax, s_red[2][w2]);
+    }
+    float tau2 = INFINITY;
+    if (cnt >= (unsigned)a.k) {
+      const unsigned range = kmax - kmin;
+      const int nbits = 32 - __clz(range | 1u);
+      const int passes = (nbits + 7) >> 3;       // 1..4
+      unsigned prefix = 0u, kk = (unsigned)a.k;  // rank (1-based) inside the current prefix class
+      for (int ps = 0; ps < passes; ++ps) {
+        const int shift = 8 * (passes - 1 - ps);
+        unsigned* h = hist + 256 * ps;
+        for_each([&](unsigned k32, unsigned) {
+          const unsigned d = k32 - kmin;
+          if (ps == 0 || (d >> (shift + 8)) == prefix) atomicAdd(&h[(d >> shift) & 255u], 1u);
+        });
+        __syncthreads();
+        if (warp == 0) {   // smallest bin whose cumulative count reaches kk
+          unsigned c[8], sum = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { c[i] = h[lane * 8 + i]; sum += c[i]; }
+          unsigned incl = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+          }
+          const unsigned excl = incl - sum;
+          if (excl < kk && kk <= incl) {   // exactly one lane
+            unsigned run = excl;
+            int bsel = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (run < kk && kk <= run + c[i]) { bsel = i; s_sel[1] = kk - run; }
+              run += c[i];
+            }
+            s_sel[0] = (unsigned)(lane * 8 + bsel);
+          }
         }
+        __syncthreads();
+        prefix = (prefix << 8) | s_sel[0];
+        kk = s_sel[1];
       }
-      __syncthreads();
-      if (n_fin > kFinalMax && tid == 0) bad = 1;
-      __syncthreads();
+      tau2 = ord2f(kmin + prefix) + eps2;
     }
+    for_each([&](unsigned k32, unsigned row) {
+      if (ord2f(k32) <= tau2) {
+        const int pos = atomicAdd(&n_fin, 1);
+        if (pos < kFinalMax) fin_i[pos] = row;
+      }
+    });
+    __syncthreads();
+    if (n_fin > kFinalMax && tid == 0) bad = 1;
+    __syncthreads();
   }
   if (bad) {
     if (tid == 0) {
@@ -1212,7 +1183,7 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     r.overflow_list = (int*)S->ovf_list.p;
     r.overflow_count = (int*)S->ovf_count.p;
     r.rows_reranked = (unsigned long long*)S->rows_ctr.p;
-    const size_t rr_smem = std::max((size_t)kSurvMax * 8, (size_t)32 * (dim / 4 + 1) * 4) +
+    const size_t rr_smem = std::max((size_t)4 * 256 * 4, (size_t)32 * (dim / 4 + 1) * 4) +
                            (size_t)kFinalMax * 8 + (size_t)dim * 4;
     static bool attr2 = false;
     if (!attr2) {
