@@ -475,6 +475,7 @@ csm_coarse_pm_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __r
 
 constexpr int kBitChunk = 4080;     // points per pass: 16 x 255, so 8 high planes cannot overflow
 constexpr int kBitRowSlack = 17;    // zero rows after the last data row (candidate rows read past it)
+constexpr int kBitThreads = 384;    // 192 rotations per CTA, two lanes each
 
 __global__ void csm_build_pmb_kernel(const uint8_t* __restrict__ level, int wide_nx, int wide_ny,
                                      int px, int py, int log2w, int rows,
@@ -510,14 +511,20 @@ __device__ __noinline__ int2 cells_exact(float wx, float wy, double res, double 
   return make_int2(cell_exact(wy, res, max_y), cell_exact(wx, res, max_x));
 }
 
+// Two lanes share one rotation: lane parity h takes candidate rows [8h, 8h + 8) (NP packed
+// words of two rows each), and the two lanes split the discretisation work -- the even lane
+// discretises the even points, the odd lane the odd ones, the (row address, shift, mask) of a
+// point travels to the partner lane by shuffle.  Half the counters per thread: twice the
+// warps per SM for the same shared-memory tile.
 template <int NP>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kBitThreads, 1)
 csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
                        const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
                        CsmBounds* __restrict__ bounds, int* __restrict__ coarse,
                        unsigned long long* __restrict__ top_coarse) {
   extern __shared__ __align__(16) unsigned char csm_smem[];
   const int pi = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int half = tid & 1;
   const CsmPairDev pr = pairs[pi];
   const CsmGridDev g = grids[pr.grid];
   const int log2w = g.pmb_log2w, w = 1 << log2w, wm = w - 1;
@@ -529,7 +536,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
 
   const int P = pr.n_pts;
   const float* sp = pts + 3 * (size_t)pr.pt_begin;
-  const int s = blockIdx.x * blockDim.x + tid;
+  const int s = (blockIdx.x * blockDim.x + tid) >> 1;
   const bool s_ok = s < prm.S;
   const float2 r = rot[s_ok ? s : 0];
   // points after the initial-yaw rotation (fast_..._2d.cpp:278-283), shared by all rotations
@@ -548,7 +555,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     const int n = min(kBitChunk, P - p0);
     stage(p0, n);
 #pragma unroll 4
-    for (int p = 0; p < n; ++p) {
+    for (int p = half; p < n; p += 2) {
       const float2 q = P0[p];
       float x1, y1;
       rot_z(r.x, r.y, q.x, q.y, x1, y1);
@@ -557,6 +564,10 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
       mny = fminf(mny, wy); mxy = fmaxf(mxy, wy);
     }
   }
+  mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, 1));
+  mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, 1));
+  mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, 1));
+  mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, 1));
   CsmBounds b;
   {
     // cell.x = f(wy), cell.y = f(wx), both monotone non-increasing
@@ -568,7 +579,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     b.min_y = max(-prm.n_lin, min(0, -cy_max));
     b.max_y = min(prm.n_lin, max(0, g.ny - 1 - cy_min));
   }
-  if (s_ok) bounds[(size_t)pi * prm.S + s] = b;
+  if (s_ok && half == 0) bounds[(size_t)pi * prm.S + s] = b;
   const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
   const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
 
@@ -578,12 +589,14 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   // |float cell coordinate - exact| <= 2^-24 (|max|/res + 3 |u|) for |u| <= U; 4x safety
   const float U = (float)(max(wide_nx, wide_ny) + 2 * prm.n_lin + 32);
   const float delta = 2.3841858e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
+  const float hi1 = 1.f - delta;
   const int offx = wm + b.min_x + g.pmb_px, offy = wm + b.min_y + g.pmb_py;
   const unsigned span_x = (unsigned)(wide_nx + 2 * prm.n_lin), span_y = (unsigned)(wide_ny + 2 * prm.n_lin);
   const int hx0 = wm + prm.n_lin, hy0 = wm + prm.n_lin;
+  const int row0 = half * 2 * NP;   // first candidate row of this lane
 
-  // the NP packed words (two candidate rows each) a point adds to the counters
-  auto point_words = [&](int p, uint32_t (&v)[NP]) {
+  // (row address, shift / mask description) of one point for this rotation
+  auto point_addr = [&](int p, int& addr, unsigned& meta) {
     const float2 q = P0[p];
     float x1, y1;
     rot_z(r.x, r.y, q.x, q.y, x1, y1);
@@ -592,7 +605,6 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     const float fy = floorf(uy), fx = floorf(ux);
     const float dy = uy - fy, dx = ux - fx;
     int cx = (int)fy, cy = (int)fx;
-    const float hi1 = 1.f - delta;
     if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < 1e7f && fabsf(ux) < 1e7f)) {
       const int2 ce = cells_exact(wx, wy, g.resolution, g.max_x, g.max_y);   // rare: near a rounding boundary
       cx = ce.x;
@@ -605,8 +617,14 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     const int plane = hitable ? (((Y & wm) << log2w) | (X & wm)) : 0;
     const int shl = hitable ? max(0, -ax) : 0, axc = min(max(ax, 0), 63);
     const int nbits = (hitable && ax < 64) ? max(ncx - shl, 0) : 0;
-    const uint32_t m1 = (1u << nbits) - 1u, m2 = m1 | (m1 << 16);
-    const unsigned long long* rowp = bits + plane * rows + ay;
+    addr = plane * rows + ay;
+    meta = (unsigned)axc | ((unsigned)shl << 8) | ((unsigned)nbits << 16);
+  };
+  // the NP packed words (two candidate rows each) a point adds to this lane's counters
+  auto point_words = [&](int addr, unsigned meta, uint32_t (&v)[NP]) {
+    const int axc = meta & 63u, shl = (meta >> 8) & 31u;
+    const uint32_t m1 = (1u << (meta >> 16)) - 1u, m2 = m1 | (m1 << 16);
+    const unsigned long long* rowp = bits + addr + row0;
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
       const uint32_t w0 = (uint32_t)(rowp[2 * j] >> axc), w1 = (uint32_t)(rowp[2 * j + 1] >> axc);
@@ -634,18 +652,15 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
 #pragma unroll
       for (int i = 0; i < 8; ++i) hi[i][j] = 0u;
     }
-    auto pair_words = [&](int p, uint32_t (&ta)[NP]) {   // two points -> carry ta, sum into ones
+    auto pair_words = [&](int p, uint32_t (&ta)[NP]) {   // points p, p+1 -> carry ta, sum into ones
+      int addr = 0;
+      unsigned meta = 0u;   // nbits = 0: contributes nothing
+      if (p + half < n) point_addr(p + half, addr, meta);
+      const int addr_o = __shfl_xor_sync(0xffffffffu, addr, 1);
+      const unsigned meta_o = __shfl_xor_sync(0xffffffffu, meta, 1);
       uint32_t v0[NP], v1[NP];
-      if (p < n) point_words(p, v0);
-      else {
-#pragma unroll
-        for (int j = 0; j < NP; ++j) v0[j] = 0u;
-      }
-      if (p + 1 < n) point_words(p + 1, v1);
-      else {
-#pragma unroll
-        for (int j = 0; j < NP; ++j) v1[j] = 0u;
-      }
+      point_words(addr, meta, v0);
+      point_words(addr_o, meta_o, v1);
       csa(ta, ones, v0, v1);
     };
     auto quad_words = [&](int p, uint32_t (&fa)[NP]) {
@@ -680,9 +695,10 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     if (s_ok) {
       const bool first = p0 == 0, last = p0 + n >= P;
 #pragma unroll
-      for (int iy = 0; iy < 2 * NP; ++iy) {
+      for (int ly = 0; ly < 2 * NP; ++ly) {
+        const int iy = row0 + ly;
         if (iy < ncy) {
-          const int j = iy >> 1, sh0 = (iy & 1) * 16;
+          const int j = ly >> 1, sh0 = (ly & 1) * 16;
           for (int ix = 0; ix < ncx; ++ix) {
             const int bp = sh0 + ix;
             int cnt = (int)((ones[j] >> bp) & 1u) | (int)(((twos[j] >> bp) & 1u) << 1) |
@@ -1006,16 +1022,15 @@ cudaError_t launch_csm_coarse_bits(const CsmGridDev* grids, const CsmPairDev* pa
                                    const float* pts, const float2* rot, CsmParams prm,
                                    CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
                                    size_t smem, int warps, cudaStream_t stream) {
-  const int threads = 32 * warps;
-  dim3 grd((prm.S + threads - 1) / threads, n_pairs);
-  const int np = (prm.max_side + 1) / 2;
+  const int threads = 32 * warps;            // two lanes per rotation
+  dim3 grd((2 * prm.S + threads - 1) / threads, n_pairs);
+  const int np = (prm.max_side + 3) / 4;     // packed words (two rows each) per lane
 #define GLOC_BITS_CASE(N)                                                                       \
   case N:                                                                                       \
     return launch_bits_np<N>(grd, threads, smem, stream, grids, pairs, pts, rot, prm, bounds,   \
                              coarse, top_coarse);
   switch (np) {
     GLOC_BITS_CASE(1) GLOC_BITS_CASE(2) GLOC_BITS_CASE(3) GLOC_BITS_CASE(4)
-    GLOC_BITS_CASE(5) GLOC_BITS_CASE(6) GLOC_BITS_CASE(7) GLOC_BITS_CASE(8)
     default: return cudaErrorInvalidValue;
   }
 #undef GLOC_BITS_CASE

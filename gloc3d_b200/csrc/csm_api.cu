@@ -423,8 +423,8 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
   }
   std::vector<unsigned long long> hbest((size_t)n_pairs);
   const int n_ctas = sm_count(st->device) * 4;
-  int bits_warps = 6;   // rotations per CTA = 32 x warps
-  if (const char* e = std::getenv("GLOC_CSM_BITS_WARPS")) bits_warps = std::min(6, std::max(1, std::atoi(e)));
+  int bits_warps = 12;   // rotations per CTA = 16 x warps (two lanes per rotation)
+  if (const char* e = std::getenv("GLOC_CSM_BITS_WARPS")) bits_warps = std::min(12, std::max(1, std::atoi(e)));
   for (long long p0 = 0; p0 < n_pairs; p0 += sub) {
     const int np = (int)std::min<long long>(sub, n_pairs - p0);
     GLOC_CUDA_TRY(st->pairs.reserve((size_t)np * sizeof(CsmPairDev)));

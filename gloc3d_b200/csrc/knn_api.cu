@@ -1,6 +1,7 @@
 // knn_api.cu -- C ABI of stage 1 (retrieval).  See include/gloc3d.h for the
 // reference interfaces each entry point replaces.
 #include <algorithm>
+#include <cstdlib>
 #include <cfloat>
 #include <cstring>
 #include <mutex>
@@ -76,6 +77,7 @@ struct gloc_knn_index {
   int mode = GLOC_KNN_AUTO;
   cudaStream_t stream = nullptr;  // used by the host-buffer entry points
   DevBuf partial;                 // exact-scan per-range lists
+  DevBuf flag;                    // streaming scan: merge-overflow flag
   DevBuf stage_q, stage_idx, stage_d2;
   ShortlistState* sl = nullptr;   // tensor-shortlist state (bf16 copy, norms, workspaces)
   gloc_knn_stats stats{};
@@ -118,6 +120,19 @@ RangePlan plan_ranges(long long n_search, int nq, int device) {
 
 int exact_query_device(gloc_knn_index* ix, const float* d_q, size_t nq, size_t k,
                        uint64_t* d_idx, float* d_d2, size_t n_search, cudaStream_t stream) {
+  // one to four queries: a single pass over the rows at HBM speed (knn_stream.cu)
+  if (stream_applicable(ix->dim, nq, k) && (reinterpret_cast<uintptr_t>(d_q) & 15) == 0 &&
+      std::getenv("GLOC_KNN_NO_STREAM") == nullptr) {
+    const int grid = stream_grid(ix->device, ix->dim);
+    GLOC_CUDA_TRY(ix->partial.reserve(nq * (size_t)grid * k * sizeof(uint64_t)));
+    GLOC_CUDA_TRY(ix->flag.reserve(16));
+    GLOC_CUDA_TRY(cudaMemsetAsync(ix->flag.p, 0, 4, stream));
+    GLOC_CUDA_TRY(launch_knn_stream(ix->d_db, (long long)n_search, (int)ix->dim, d_q, (int)nq, (int)k,
+                                    grid, (uint64_t*)ix->partial.p, ix->offset, d_idx, d_d2,
+                                    (int*)ix->flag.p, &ix->prof, stream));
+    ix->stats.kernel_launches += 3;
+    return GLOC_OK;
+  }
   const size_t kChunk = 1u << 17;
   for (size_t q0 = 0; q0 < nq; q0 += kChunk) {
     const int cq = (int)std::min(kChunk, nq - q0);
@@ -230,6 +245,7 @@ void gloc_knn_destroy(gloc_knn_index* ix) {
   }
   if (ix->d_db) cudaFree(ix->d_db);
   ix->partial.release();
+  ix->flag.release();
   ix->stage_q.release();
   ix->stage_idx.release();
   ix->stage_d2.release();

@@ -21,4 +21,12 @@ cudaError_t launch_knn_finalize(const uint64_t* partial, int nq, int n_lists, in
 cudaError_t launch_knn_merge_pairs(const uint64_t* idx, const float* d2, int g, int nq, int k,
                                    uint64_t* out_idx, float* out_d2, cudaStream_t stream);
 
+// ---- streaming scan for 1..4 queries per call (knn_stream.cu)
+bool stream_applicable(size_t dim, size_t nq, size_t k);
+int stream_grid(int device, size_t dim);
+cudaError_t launch_knn_stream(const float* db, long long n_rows, int dim, const float* q, int nq,
+                              int k, int grid, uint64_t* partial, uint64_t idx_offset,
+                              uint64_t* out_idx, float* out_d2, int* overflow,
+                              EventProfiler* prof, cudaStream_t stream);
+
 }  // namespace gloc

@@ -257,3 +257,28 @@ def test_million_row_database(oracle):
     sample = np.arange(0, nq, nq // 16)[:16]
     ridx, rd2 = oracle.knn(db, q[sample], k, nthreads=16)
     assert_knn_equal(idx[sample], d2[sample], ridx, rd2)
+
+
+@pytest.mark.parametrize("nq", [1, 2, 3, 4])
+@pytest.mark.parametrize("n,dim,k", [(50_000, 512, 25), (4541, 512, 20), (3001, 128, 32), (777, 64, 1),
+                                     (40, 8, 25)])
+def test_streaming_scan_one_to_four_queries(oracle, nq, n, dim, k):
+    # the reference issues ONE query per call (loop_detector.cpp:42-45): the HBM-bound
+    # streaming kernel answers 1..4 queries; near-duplicate runs + exact duplicates for ties
+    db = synth.make_descriptors(n, dim, seed=n + dim, dup_run=8)
+    db[n // 2] = db[n // 3]                       # one exact duplicate pair
+    q = synth.make_queries(db, nq, seed=nq, sigma=0.01)
+    q[0] = db[n // 3]                             # distance exactly 0, tied between two rows
+    for mode in (g.KNN_AUTO, g.KNN_EXACT_SCAN):
+        idx, d2 = run(db, q, k, mode)
+        assert_knn_equal(idx, d2, *oracle.knn(db, q, k, nthreads=8))
+    # SLAM mode: all but the most recent 30 rows, global index offset
+    if n > 100:
+        ix = g.KnnIndex(dim, 0)
+        ix.set_db(db)
+        ix.set_search_limit(n - 30)
+        ix.set_index_offset(1000)
+        idx, d2 = ix.query(q, k)
+        ix.close()
+        ridx, rd2 = oracle.knn(db[:n - 30], q, k, nthreads=8)
+        assert_knn_equal(idx, d2, ridx + np.uint64(1000), rd2)
