@@ -52,6 +52,12 @@ class CsmStats(C.Structure):
                                           "refined_nodes")]
 
 
+class BevInfo(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("min_ix", C.c_int), ("min_iy", C.c_int),
+                ("ox", C.c_double), ("oy", C.c_double), ("resolution", C.c_double),
+                ("n_occupied", C.c_uint64), ("n_points_in_range", C.c_uint64)]
+
+
 # name -> (restype, argtypes); mirrors include/gloc3d.h one to one
 _vp, _sz, _i, _d, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_double, C.c_float
 _ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
@@ -89,6 +95,14 @@ SIGNATURES = {
     "gloc_csm_get_stats": (_i, [_vp, C.POINTER(CsmStats)]),
     "gloc_csm_set_profiling": (_i, [_vp, _i]),
     "gloc_csm_get_profile": (_i, [_vp, C.POINTER(Profile)]),
+    "gloc_bev_create": (_i, [C.POINTER(_vp), _i, _f, _f]),
+    "gloc_bev_destroy": (None, [_vp]),
+    "gloc_bev_project": (_i, [_vp, _vp, _sz, _i, C.POINTER(BevInfo)]),
+    "gloc_bev_get_image": (_i, [_vp, _vp, _sz]),
+    "gloc_bev_get_cnn_input": (_i, [_vp, _i, _i, _vp]),
+    "gloc_bev_get_occupied_points": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "gloc_bev_kernel_launches": (C.c_uint64, [_vp]),
+    "gloc_csm_add_grid_from_bev": (_i, [_vp, _vp, _ip]),
 }
 
 _lib = None

@@ -796,14 +796,16 @@ csm_seed_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restri
 
 // ------------------------------------------------------------------- K7 filter
 
-// Keep the coarse candidates whose bound can still beat the incumbent.
+// Keep the coarse candidates whose bound can still beat the incumbent: one list per pair
+// (entries = scan * maxc + slot), so that the next stage can work pair by pair.
 __global__ void csm_filter_kernel(const CsmPairDev* __restrict__ pairs, int n_pairs, CsmParams prm,
                                   const CsmBounds* __restrict__ bounds,
                                   const int* __restrict__ coarse,
                                   const unsigned long long* __restrict__ best,
                                   unsigned* __restrict__ survivors,
                                   unsigned* __restrict__ n_survivors) {
-  const size_t total = (size_t)n_pairs * prm.S * prm.maxc;
+  const size_t per_pair = (size_t)prm.S * prm.maxc;
+  const size_t total = (size_t)n_pairs * per_pair;
   for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < total;
        u += (size_t)gridDim.x * blockDim.x) {
     const int slot = (int)(u % prm.maxc);
@@ -816,10 +818,183 @@ __global__ void csm_filter_kernel(const CsmPairDev* __restrict__ pairs, int n_pa
     const int xo = b.min_x + (slot / ncy) * prm.step, yo = b.min_y + (slot % ncy) * prm.step;
     const float sc = score_of(coarse[u], pairs[pi].n_pts, prm);
     if (key_of(sc, rank_of(prm, s, xo, yo)) > best[pi]) {
-      const unsigned pos = atomicAdd(n_survivors, 1u);
-      survivors[pos] = (unsigned)u;
+      const unsigned pos = atomicAdd(n_survivors + pi, 1u);
+      survivors[(size_t)pi * per_pair + pos] = (unsigned)(u - (size_t)pi * per_pair);
     }
   }
+}
+
+// ------------------------------------------------------------------- K7 expand
+
+constexpr int kExpChunk = 2048;   // points staged per pass of the expand kernel
+
+// Binary grids: level -> bit-packed rows (bit x of row y at word y * stride + x / 32).
+__global__ void csm_build_lvb_kernel(const uint8_t* __restrict__ level, int wide_nx, int wide_ny,
+                                     int stride, unsigned* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wide_ny * stride) return;
+  const int y = idx / stride, wx = idx % stride;
+  unsigned bits = 0;
+  for (int i = 0; i < 32; ++i) {
+    const int x = wx * 32 + i;
+    if (x < wide_nx && level[(size_t)y * wide_nx + x]) bits |= 1u << i;
+  }
+  out[idx] = bits;
+}
+
+// Survivors of grids without bit planes go to the depth-first refinement unexpanded.
+__global__ void csm_survivors_to_nodes_kernel(const CsmPairDev* __restrict__ pairs, CsmParams prm,
+                                              const CsmBounds* __restrict__ bounds,
+                                              const int* __restrict__ coarse,
+                                              const unsigned* __restrict__ survivors,
+                                              const unsigned* __restrict__ n_survivors,
+                                              CsmNode* __restrict__ nodes, unsigned* __restrict__ n_nodes,
+                                              unsigned node_cap) {
+  const int pi = blockIdx.y;
+  const unsigned ns = n_survivors[pi];
+  const size_t per_pair = (size_t)prm.S * prm.maxc;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < ns; i += gridDim.x * blockDim.x) {
+    const unsigned v = survivors[(size_t)pi * per_pair + i];
+    const int s = (int)(v / prm.maxc), slot = (int)(v % prm.maxc);
+    const CsmBounds b = bounds[(size_t)pi * prm.S + s];
+    const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+    CsmNode nd;
+    nd.pi = pi; nd.s = s;
+    nd.xo = b.min_x + (slot / ncy) * prm.step;
+    nd.yo = b.min_y + (slot % ncy) * prm.step;
+    nd.d = prm.depth - 1;
+    nd.score = score_of(coarse[(size_t)pi * per_pair + v], pairs[pi].n_pts, prm);
+    const unsigned pos = atomicAdd(n_nodes, 1u);
+    if (pos < node_cap) nodes[pos] = nd;
+  }
+}
+
+// First level below the coarse lattice, where nearly every surviving coarse candidate dies
+// (its four children's bounds fall under the incumbent).  Thread = one survivor, a CTA works
+// on survivors of ONE pair: the pair's points (after the initial-yaw rotation) and the
+// bit-packed next finer level of its (binary) grid are staged in shared memory; every lane
+// rotates the points by its own scan angle, discretises (float fast path with the exact double
+// fallback, see the bit-sliced scorer) and tests its four children's cells.  Children that
+// can still beat the incumbent become nodes for the depth-first refinement; at depth 2 they
+// are leaves.
+__global__ void __launch_bounds__(256)
+csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
+                  const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
+                  const CsmBounds* __restrict__ bounds, const int* __restrict__ coarse,
+                  const unsigned* __restrict__ survivors, const unsigned* __restrict__ n_survivors,
+                  unsigned long long* __restrict__ best, CsmNode* __restrict__ nodes,
+                  unsigned* __restrict__ n_nodes, unsigned node_cap,
+                  unsigned long long* __restrict__ counters) {
+  extern __shared__ __align__(16) unsigned char csm_smem[];
+  const int pi = blockIdx.y, tid = threadIdx.x;
+  const unsigned ns = n_survivors[pi];
+  if ((unsigned)blockIdx.x * 256u >= ns) return;
+  const size_t per_pair = (size_t)prm.S * prm.maxc;
+  const CsmPairDev pr = pairs[pi];
+  const CsmGridDev g = grids[pr.grid];
+  const int P = pr.n_pts;
+  const float* sp = pts + 3 * (size_t)pr.pt_begin;
+  const int d = prm.depth - 2;                   // level of the children
+  const int h = 1 << d, wm1 = h - 1;
+  const int wide_nx = g.nx + wm1, wide_ny = g.ny + wm1, stride = g.lvb_stride;
+  float2* P0 = reinterpret_cast<float2*>(csm_smem);                       // [kExpChunk]
+  // rows 16 k apart (neighbouring coarse candidates of one scan) would share two banks with a
+  // plain row stride: one extra word every 16 rows spreads them over all banks
+  unsigned* bits = reinterpret_cast<unsigned*>(P0 + kExpChunk);          // [wide_ny][stride] (+ row / 16)
+  for (int i = tid; i < wide_ny * stride; i += 256) {
+    const int row = i / stride;
+    bits[i + (row >> 4)] = __ldg(g.lvb + i);
+  }
+  const float mx_f = (float)g.max_x, my_f = (float)g.max_y, ir = (float)(1.0 / g.resolution);
+  const float U = (float)(max(g.nx, g.ny) + 2 * prm.n_lin + 64 + 2 * prm.step);
+  const float delta = 2.3841858e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
+  const float hi1 = 1.f - delta;
+  unsigned long long expanded = 0;
+  const unsigned first_base = (unsigned)blockIdx.x * 256u;
+
+  for (unsigned base = first_base; base < ns; base += gridDim.x * 256u) {
+    const unsigned i = base + tid;
+    bool active = i < ns;
+    int s = 0, xo = 0, yo = 0;
+    CsmBounds b = {0, 0, 0, 0};
+    if (active) {
+      const unsigned v = survivors[(size_t)pi * per_pair + i];
+      s = (int)(v / prm.maxc);
+      const int slot = (int)(v % prm.maxc);
+      b = bounds[(size_t)pi * prm.S + s];
+      const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+      xo = b.min_x + (slot / ncy) * prm.step;
+      yo = b.min_y + (slot % ncy) * prm.step;
+      // the incumbent may have improved since the filter ran
+      const float sc = score_of(coarse[(size_t)pi * per_pair + v], P, prm);
+      active = key_of(sc, rank_of(prm, s, xo, yo)) > ld_best(best + pi);
+    }
+    const float2 r = rot[s];
+    const int ax = xo + wm1, ay = yo + wm1;   // cell -> level frame of child (0, 0)
+    int sum[4] = {0, 0, 0, 0};
+    for (int p0 = 0; p0 < P; p0 += kExpChunk) {
+      const int n = min(kExpChunk, P - p0);
+      __syncthreads();
+      if (base == first_base || P > kExpChunk) {
+        for (int p = tid; p < n; p += 256) {
+          float x0, y0;
+          rot_z(pr.w0, pr.z0, sp[3 * (size_t)(p0 + p)], sp[3 * (size_t)(p0 + p) + 1], x0, y0);
+          P0[p] = make_float2(x0, y0);
+        }
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll 2
+        for (int p = 0; p < n; ++p) {
+          const float2 q = P0[p];
+          float x1, y1;
+          rot_z(r.x, r.y, q.x, q.y, x1, y1);
+          const float wx = __fadd_rn(x1, pr.tx), wy = __fadd_rn(y1, pr.ty);
+          const float uy = (my_f - wy) * ir, ux = (mx_f - wx) * ir;
+          const float fy = floorf(uy), fx = floorf(ux);
+          const float dy = uy - fy, dx = ux - fx;
+          int cx = (int)fy, cy = (int)fx;
+          if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < U && fabsf(ux) < U)) {
+            const int2 ce = cells_exact(wx, wy, g.resolution, g.max_x, g.max_y);
+            cx = ce.x;
+            cy = ce.y;
+          }
+          const int lx = cx + ax, ly = cy + ay;
+          const bool x0ok = (unsigned)lx < (unsigned)wide_nx, x1ok = (unsigned)(lx + h) < (unsigned)wide_nx;
+          const bool y0ok = (unsigned)ly < (unsigned)wide_ny, y1ok = (unsigned)(ly + h) < (unsigned)wide_ny;
+          const unsigned* r0 = bits + ly * stride + (ly >> 4);
+          const unsigned* r1 = bits + (ly + h) * stride + ((ly + h) >> 4);
+          const int w0 = lx >> 5, w1 = (lx + h) >> 5, b0 = lx & 31, b1 = (lx + h) & 31;
+          if (x0ok && y0ok) sum[0] += (r0[w0] >> b0) & 1u;   // child (x, y)
+          if (x0ok && y1ok) sum[1] += (r1[w0] >> b0) & 1u;   // child (x, y + h)
+          if (x1ok && y0ok) sum[2] += (r0[w1] >> b1) & 1u;   // child (x + h, y)
+          if (x1ok && y1ok) sum[3] += (r1[w1] >> b1) & 1u;   // child (x + h, y + h)
+        }
+      }
+    }
+    if (active) {
+      ++expanded;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {   // x outer, y inner (fast_..._2d.cpp:414-429)
+        const int cx = xo + (ch >> 1) * h, cy = yo + (ch & 1) * h;
+        if (cx > b.max_x || cy > b.max_y) continue;
+        const float sc = score_of(255 * sum[ch], P, prm);
+        const unsigned long long key = key_of(sc, rank_of(prm, s, cx, cy));
+        if (!(key > ld_best(best + pi))) continue;
+        if (d == 0) {
+          atomicMax(best + pi, key);
+        } else {
+          const unsigned pos = atomicAdd(n_nodes, 1u);
+          if (pos < node_cap) {
+            CsmNode nd;
+            nd.pi = pi; nd.s = s; nd.xo = cx; nd.yo = cy; nd.d = d; nd.score = sc;
+            nodes[pos] = nd;
+          }
+        }
+      }
+    }
+  }
+  if (expanded) atomicAdd(counters, expanded);
 }
 
 // ------------------------------------------------------------------- K7 refine
@@ -829,54 +1004,65 @@ struct Node {
   float score;
 };
 
-// Persistent warps: each pops a surviving coarse candidate and runs the reference's
-// DFS (children sorted by score, fast_..._2d.cpp:430-436) inside its subtree, pruning
-// against the pair's incumbent shared through global memory.
-__global__ void __launch_bounds__(256)
+constexpr int kRefineThreads = 128;
+
+// Persistent CTAs: each pops a node and runs the reference's DFS (children sorted by score,
+// fast_..._2d.cpp:430-436) inside its subtree, pruning against the pair's incumbent shared
+// through global memory.  The threads of a CTA split the points of every expansion (a node's
+// expansions are sequential, so the chain of dependent lookups per expansion is kept short);
+// they all hold the same stack.
+__global__ void __launch_bounds__(kRefineThreads)
 csm_refine_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
                   const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
-                  const CsmBounds* __restrict__ bounds, const int* __restrict__ coarse,
-                  const unsigned* __restrict__ survivors, const unsigned* __restrict__ n_survivors,
+                  const CsmBounds* __restrict__ bounds, const CsmNode* __restrict__ nodes,
+                  const unsigned* __restrict__ n_nodes, unsigned node_cap,
                   unsigned* __restrict__ cursor, unsigned long long* __restrict__ best,
                   unsigned long long* __restrict__ counters) {
-  const int lane = threadIdx.x & 31;
-  const unsigned total = *n_survivors;
+  __shared__ unsigned s_next;
+  __shared__ int s_sum[2][kRefineThreads / 32][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned total = min(*n_nodes, node_cap);
   unsigned long long expanded = 0;
+  int round = 0;
   Node stack[3 * kCsmMaxDepth + 4];
   for (;;) {
-    unsigned i = 0;
-    if (lane == 0) i = atomicAdd(cursor, 1u);
-    i = __shfl_sync(0xffffffffu, i, 0);
+    __syncthreads();
+    if (tid == 0) s_next = atomicAdd(cursor, 1u);
+    __syncthreads();
+    const unsigned i = s_next;
     if (i >= total) break;
-    const unsigned u = survivors[i];
-    const int slot = (int)(u % prm.maxc);
-    const unsigned ps = u / prm.maxc;
-    const int s = (int)(ps % prm.S), pi = (int)(ps / prm.S);
+    const CsmNode root = nodes[i];
+    const int s = root.s, pi = root.pi;
     const CsmPairDev pr = pairs[pi];
     const CsmGridDev g = grids[pr.grid];
-    const CsmBounds b = bounds[ps];
+    const CsmBounds b = bounds[(size_t)pi * prm.S + s];
     const float2 r = rot[s];
     const int P = pr.n_pts;
     const float* sp = pts + 3 * (size_t)pr.pt_begin;
-    const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
     int top = 0;
-    stack[0].xo = b.min_x + (slot / ncy) * prm.step;
-    stack[0].yo = b.min_y + (slot % ncy) * prm.step;
-    stack[0].d = prm.depth - 1;
-    stack[0].score = score_of(coarse[u], P, prm);
+    stack[0].xo = root.xo;
+    stack[0].yo = root.yo;
+    stack[0].d = root.d;
+    stack[0].score = root.score;
     top = 1;
     while (top > 0) {
       const Node nd = stack[--top];
       const unsigned long long nk = key_of(nd.score, rank_of(prm, s, nd.xo, nd.yo));
-      if (!(nk > ld_best(best + pi))) continue;  // bound cannot beat the incumbent
+      // one thread reads the incumbent so that the whole CTA takes the same decision
+      if (tid == 0) s_next = nk > ld_best(best + pi) ? 1u : 0u;
+      __syncthreads();
+      const bool go = s_next != 0u;
+      __syncthreads();
+      if (!go) continue;                         // bound cannot beat the incumbent
       if (nd.d == 0) {                           // only when depth == 1
-        if (lane == 0) atomicMax(best + pi, nk);
+        if (tid == 0) atomicMax(best + pi, nk);
         continue;
       }
       const int h = 1 << (nd.d - 1);
       const LevelView lv = level_view(g, nd.d - 1);
       int sum[4] = {0, 0, 0, 0};
-      for (int p = lane; p < P; p += 32) {
+#pragma unroll 2
+      for (int p = tid; p < P; p += kRefineThreads) {
         const int2 c = discretize_point(sp + 3 * (size_t)p, pr.w0, pr.z0, r.x, r.y, pr.tx, pr.ty,
                                         g.resolution, g.max_x, g.max_y);
 #pragma unroll
@@ -885,6 +1071,15 @@ csm_refine_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
       }
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) sum[ch] = warp_sum(sum[ch]);
+      if (lane == 0)
+        for (int ch = 0; ch < 4; ++ch) s_sum[round & 1][warp][ch] = sum[ch];
+      __syncthreads();
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        sum[ch] = 0;
+        for (int w2 = 0; w2 < kRefineThreads / 32; ++w2) sum[ch] += s_sum[round & 1][w2][ch];
+      }
+      ++round;
       ++expanded;
       Node kids[4];
       int nk_n = 0;
@@ -901,7 +1096,7 @@ csm_refine_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
         unsigned long long bk = 0;
         for (int c2 = 0; c2 < nk_n; ++c2)
           bk = max(bk, key_of(kids[c2].score, rank_of(prm, s, kids[c2].xo, kids[c2].yo)));
-        if (lane == 0 && bk > ld_best(best + pi)) atomicMax(best + pi, bk);
+        if (tid == 0 && bk > ld_best(best + pi)) atomicMax(best + pi, bk);
       } else {
         // stable insertion sort, descending score; push worst first so best pops first
         for (int a = 1; a < nk_n; ++a) {
@@ -917,7 +1112,7 @@ csm_refine_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
       }
     }
   }
-  if (lane == 0 && expanded) atomicAdd(counters, expanded);
+  if (tid == 0 && expanded) atomicAdd(counters, expanded);
 }
 
 }  // namespace
@@ -1056,15 +1251,51 @@ cudaError_t launch_csm_filter(const CsmPairDev* pairs, int n_pairs, CsmParams pr
   return cudaGetLastError();
 }
 
-cudaError_t launch_csm_refine(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+cudaError_t launch_csm_build_lvb(const uint8_t* level, int wide_nx, int wide_ny, int stride,
+                                 unsigned* out, cudaStream_t stream) {
+  const int n = wide_ny * stride;
+  csm_build_lvb_kernel<<<(n + 255) / 256, 256, 0, stream>>>(level, wide_nx, wide_ny, stride, out);
+  return cudaGetLastError();
+}
+
+size_t csm_expand_smem(int wide_ny, int stride) {
+  return (size_t)kExpChunk * sizeof(float2) + ((size_t)wide_ny * stride + (size_t)(wide_ny >> 4) + 1) * 4;
+}
+
+// bits == true: every grid of the batch carries the bit-packed level depth-2 (lvb), and
+// `smem` is the largest footprint; else the survivors become nodes unexpanded.
+cudaError_t launch_csm_expand(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                               const float* pts, const float2* rot, CsmParams prm,
                               const CsmBounds* bounds, const int* coarse,
                               const unsigned* survivors, const unsigned* n_survivors,
+                              unsigned long long* best, CsmNode* nodes, unsigned* n_nodes,
+                              unsigned node_cap, unsigned long long* counters, int chunks,
+                              bool bits, size_t smem, cudaStream_t stream) {
+  dim3 grd(chunks, n_pairs);
+  if (!bits) {
+    csm_survivors_to_nodes_kernel<<<grd, 256, 0, stream>>>(pairs, prm, bounds, coarse, survivors,
+                                                           n_survivors, nodes, n_nodes, node_cap);
+    return cudaGetLastError();
+  }
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(csm_expand_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  csm_expand_kernel<<<grd, 256, smem, stream>>>(grids, pairs, pts, rot, prm, bounds, coarse, survivors,
+                                                n_survivors, best, nodes, n_nodes, node_cap, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_refine(const CsmGridDev* grids, const CsmPairDev* pairs, const float* pts,
+                              const float2* rot, CsmParams prm, const CsmBounds* bounds,
+                              const CsmNode* nodes, const unsigned* n_nodes, unsigned node_cap,
                               unsigned* cursor, unsigned long long* best,
                               unsigned long long* counters, int n_ctas, cudaStream_t stream) {
-  (void)n_pairs;
-  csm_refine_kernel<<<n_ctas, 256, 0, stream>>>(grids, pairs, pts, rot, prm, bounds, coarse,
-                                                survivors, n_survivors, cursor, best, counters);
+  csm_refine_kernel<<<n_ctas, kRefineThreads, 0, stream>>>(grids, pairs, pts, rot, prm, bounds, nodes,
+                                                           n_nodes, node_cap, cursor, best, counters);
   return cudaGetLastError();
 }
 

@@ -12,6 +12,11 @@
 
 using namespace gloc;
 
+// bev.cu
+const uint8_t* gloc_bev_device_image(const gloc_bev_projector* b, gloc_bev_info* info);
+int gloc_bev_device_of(const gloc_bev_projector* b);
+cudaError_t gloc_bev_launch_level1(const uint8_t* img, size_t n, uint8_t* out, cudaStream_t s);
+
 namespace {
 
 // /root/reference/registration/3d/probability_values.h:64-67, float32 on purpose.
@@ -42,6 +47,8 @@ struct HostGrid {
   unsigned long long* d_pmb = nullptr;
   int pmb_level = -1, pmb_nlin = -1, pmb_rows = 0;
   int binary = -1;   // -1 unknown, 0 some cell is neither 0 nor 255, 1 binary
+  unsigned* d_lvb = nullptr;   // bit-packed level depth-2 (CsmGridDev::lvb)
+  int lvb_level = -1, lvb_stride = 0;
 };
 
 size_t stack_bytes(int nx, int ny, int depth, long long* off) {
@@ -81,7 +88,7 @@ struct gloc_csm_store {
   cudaStream_t stream = nullptr;
   std::vector<HostGrid> grids;
   uint8_t* d_lut = nullptr;  // uint16 cost value -> uint8 width-1 cell
-  Buf pts, pairs, gridtab, rot, bounds, coarse, top, best, survivors, misc, cells16, disc;
+  Buf pts, pairs, gridtab, rot, bounds, coarse, top, best, survivors, nsurv, nodes, misc, cells16, disc;
   gloc_csm_stats stats{};
   EventProfiler prof;
 };
@@ -186,10 +193,11 @@ void gloc_csm_destroy(gloc_csm_store* st) {
     if (gr.d_stack) cudaFree(gr.d_stack);
     if (gr.d_pm) cudaFree(gr.d_pm);
     if (gr.d_pmb) cudaFree(gr.d_pmb);
+    if (gr.d_lvb) cudaFree(gr.d_lvb);
   }
   if (st->d_lut) cudaFree(st->d_lut);
   for (Buf* b : {&st->pts, &st->pairs, &st->gridtab, &st->rot, &st->bounds, &st->coarse, &st->top,
-                 &st->best, &st->survivors, &st->misc, &st->cells16, &st->disc})
+                 &st->best, &st->survivors, &st->nsurv, &st->nodes, &st->misc, &st->cells16, &st->disc})
     b->release();
   delete st;
 }
@@ -236,6 +244,37 @@ int gloc_csm_add_grid_u8(gloc_csm_store* st, const uint8_t* level1, int nx, int 
   HostGrid hg;
   hg.nx = nx; hg.ny = ny; hg.resolution = resolution; hg.max_x = max_x; hg.max_y = max_y;
   hg.d_stack = d_l1; hg.depth = 1; hg.bytes = (size_t)nx * ny;
+  st->grids.push_back(hg);
+  if (grid_id) *grid_id = (int)st->grids.size() - 1;
+  return GLOC_OK;
+}
+
+int gloc_csm_add_grid_from_bev(gloc_csm_store* st, gloc_bev_projector* bev, int* grid_id) {
+  if (!st || !bev) return fail(GLOC_ERR_INVALID, "gloc_csm_add_grid_from_bev: null argument");
+  gloc_bev_info I;
+  const uint8_t* d_img = gloc_bev_device_image(bev, &I);
+  if (!d_img || I.width < 1 || I.height < 1)
+    return fail(GLOC_ERR_NOT_BUILT, "gloc_csm_add_grid_from_bev: the projector holds no image");
+  if (gloc_bev_device_of(bev) != st->device)
+    return fail(GLOC_ERR_INVALID, "gloc_csm_add_grid_from_bev: projector and store live on different devices");
+  DeviceGuard g(st->device);
+  // ProjectToGrid, 3d/submap_3d.cpp:376-388: limits from the voxel bounding box
+  const double max_x = (I.min_ix + I.width - 1) * I.resolution;
+  const double max_y = (I.min_iy + I.height - 1) * I.resolution;
+  uint8_t* d_l1 = nullptr;
+  int rc = add_grid_common(st, I.width, I.height, I.resolution, max_x, max_y, &d_l1);
+  if (rc != GLOC_OK) return rc;
+  const size_t n = (size_t)I.width * I.height;
+  cudaError_t e = gloc_bev_launch_level1(d_img, n, d_l1, st->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d_l1);
+    return fail(GLOC_ERR_CUDA, std::string("gloc_csm_add_grid_from_bev: ") + cudaGetErrorString(e));
+  }
+  st->stats.kernel_launches++;
+  HostGrid hg;
+  hg.nx = I.width; hg.ny = I.height; hg.resolution = I.resolution; hg.max_x = max_x; hg.max_y = max_y;
+  hg.d_stack = d_l1; hg.depth = 1; hg.bytes = n;
   st->grids.push_back(hg);
   if (grid_id) *grid_id = (int)st->grids.size() - 1;
   return GLOC_OK;
@@ -310,7 +349,8 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
   // bit-sliced coarse scorer: binary grids whose coarsest level fits 64 columns per plane
   // row and shared memory, at most 16 lattice candidates per axis
   bool use_bits = std::getenv("GLOC_CSM_NO_BITS") == nullptr && prm.max_side <= 16;
-  size_t bits_smem = 0;
+  size_t bits_smem = 0, exp_smem = 0;
+  bool exp_bits = use_bits && depth >= 2;   // expand stage on bit-packed level depth-2
   std::map<int, int> grid_slot;
   std::vector<CsmGridDev> hg;
   for (int i = 0; i < n_pairs; ++i) {
@@ -349,6 +389,7 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
         d.pm = g.d_pm; d.pm_pad = g.pm_pad; d.pm_pw = g.pm_pw; d.pm_ph = g.pm_ph; d.pm_log2w = level;
       }
       d.pmb = nullptr; d.pmb_rows = 0; d.pmb_px = 0; d.pmb_py = 0; d.pmb_log2w = 0;
+      d.lvb = nullptr; d.lvb_stride = 0;
       if (use_bits && g.binary != 0) {
         const int level = depth - 1, w = 1 << level;
         const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1;
@@ -381,10 +422,32 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
           } else {
             use_bits = false;
           }
+          d.lvb = nullptr; d.lvb_stride = 0;
+          if (g.binary == 1 && depth >= 2) {   // the level below, bit-packed, for the expand stage
+            const int l2 = depth - 2, w2 = 1 << l2;
+            const int wnx = g.nx + w2 - 1, wny = g.ny + w2 - 1, stride = (wnx + 31) / 32 + 1;
+            if (csm_expand_smem(wny, stride) > (size_t)112 * 1024) {
+              exp_bits = false;
+            } else {
+              if (g.lvb_level != l2) {
+                if (g.d_lvb) cudaFree(g.d_lvb);
+                g.d_lvb = nullptr;
+                g.lvb_level = -1;
+                GLOC_CUDA_TRY(cudaMalloc((void**)&g.d_lvb, (size_t)wny * stride * 4));
+                GLOC_CUDA_TRY(launch_csm_build_lvb(g.d_stack + g.off[l2], wnx, wny, stride, g.d_lvb,
+                                                   st->stream));
+                st->stats.kernel_launches++;
+                g.lvb_level = l2; g.lvb_stride = stride;
+              }
+              d.lvb = g.d_lvb; d.lvb_stride = g.lvb_stride;
+              exp_smem = std::max(exp_smem, csm_expand_smem(wny, stride));
+            }
+          }
         }
       } else {
         use_bits = false;
       }
+      if (!use_bits) exp_bits = false;
       it = grid_slot.emplace(gi, (int)hg.size()).first;
       hg.push_back(d);
     }
@@ -422,7 +485,7 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
     init_key = (unsigned long long)u << 32;
   }
   std::vector<unsigned long long> hbest((size_t)n_pairs);
-  const int n_ctas = sm_count(st->device) * 4;
+  const int n_ctas = sm_count(st->device) * 8;   // persistent refinement CTAs (128 threads)
   int bits_warps = 12;   // rotations per CTA = 16 x warps (two lanes per rotation)
   if (const char* e = std::getenv("GLOC_CSM_BITS_WARPS")) bits_warps = std::min(12, std::max(1, std::atoi(e)));
   for (long long p0 = 0; p0 < n_pairs; p0 += sub) {
@@ -433,22 +496,28 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
     GLOC_CUDA_TRY(st->survivors.reserve((size_t)np * per_pair * sizeof(unsigned)));
     GLOC_CUDA_TRY(st->top.reserve((size_t)np * 8));
     GLOC_CUDA_TRY(st->best.reserve((size_t)np * 8));
+    GLOC_CUDA_TRY(st->nsurv.reserve((size_t)np * 4));
+    // nodes handed from the expand stage to the depth-first refinement (24 B each)
+    const unsigned node_cap = (unsigned)std::min<long long>(4ll * np * per_pair, 16ll << 20);
+    GLOC_CUDA_TRY(st->nodes.reserve((size_t)node_cap * sizeof(CsmNode)));
     GLOC_CUDA_TRY(st->misc.reserve(64));
     GLOC_CUDA_TRY(cudaMemcpyAsync(st->pairs.p, hp.data() + p0, (size_t)np * sizeof(CsmPairDev),
                                   cudaMemcpyHostToDevice, stream));
     GLOC_CUDA_TRY(cudaMemsetAsync(st->top.p, 0, (size_t)np * 8, stream));
+    GLOC_CUDA_TRY(cudaMemsetAsync(st->nsurv.p, 0, (size_t)np * 4, stream));
     GLOC_CUDA_TRY(cudaMemsetAsync(st->misc.p, 0, 64, stream));
     std::vector<unsigned long long> init((size_t)np, init_key);
     GLOC_CUDA_TRY(cudaMemcpyAsync(st->best.p, init.data(), (size_t)np * 8, cudaMemcpyHostToDevice,
                                   stream));
-    unsigned* n_surv = (unsigned*)st->misc.p;
-    unsigned* cursor = n_surv + 1;
+    unsigned* n_surv = (unsigned*)st->nsurv.p;
+    unsigned* n_nodes = (unsigned*)st->misc.p;
+    unsigned* cursor = n_nodes + 1;
     unsigned long long* counters = (unsigned long long*)((char*)st->misc.p + 16);
     const CsmGridDev* dg = (const CsmGridDev*)st->gridtab.p;
     const CsmPairDev* dp = (const CsmPairDev*)st->pairs.p;
     // tuning aid: GLOC_CSM_TIMING=1 prints the duration of every stage of this sub-batch
     const bool timing = std::getenv("GLOC_CSM_TIMING") != nullptr;
-    cudaEvent_t tev[5];
+    cudaEvent_t tev[6];
     if (timing) {
       for (auto& e : tev) cudaEventCreate(&e);
       cudaEventRecord(tev[0], stream);
@@ -476,26 +545,47 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
                                     (const int*)st->coarse.p, (const unsigned long long*)st->best.p,
                                     (unsigned*)st->survivors.p, n_surv, stream));
     if (timing) cudaEventRecord(tev[3], stream);
-    GLOC_CUDA_TRY(launch_csm_refine(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,
-                                    prm, (const CsmBounds*)st->bounds.p, (const int*)st->coarse.p,
-                                    (const unsigned*)st->survivors.p, n_surv, cursor,
-                                    (unsigned long long*)st->best.p, counters, n_ctas, stream));
+    if (depth >= 2) {
+      GLOC_CUDA_TRY(launch_csm_expand(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,
+                                      prm, (const CsmBounds*)st->bounds.p, (const int*)st->coarse.p,
+                                      (const unsigned*)st->survivors.p, n_surv,
+                                      (unsigned long long*)st->best.p, (CsmNode*)st->nodes.p, n_nodes,
+                                      node_cap, counters, 64, exp_bits && use_bits, exp_smem, stream));
+      if (timing) cudaEventRecord(tev[5], stream);
+      GLOC_CUDA_TRY(launch_csm_refine(dg, dp, (const float*)st->pts.p, (const float2*)st->rot.p, prm,
+                                      (const CsmBounds*)st->bounds.p, (const CsmNode*)st->nodes.p,
+                                      n_nodes, node_cap, cursor, (unsigned long long*)st->best.p,
+                                      counters, n_ctas, stream));
+    }
     if (timing) cudaEventRecord(tev[4], stream);
     GLOC_CUDA_TRY(cudaMemcpyAsync(hbest.data() + p0, st->best.p, (size_t)np * 8,
                                   cudaMemcpyDeviceToHost, stream));
     unsigned long long hc = 0;
+    unsigned hn = 0;
     GLOC_CUDA_TRY(cudaMemcpyAsync(&hc, counters, 8, cudaMemcpyDeviceToHost, stream));
+    GLOC_CUDA_TRY(cudaMemcpyAsync(&hn, n_nodes, 4, cudaMemcpyDeviceToHost, stream));
     GLOC_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (hn > node_cap)
+      return fail(GLOC_ERR_RANGE, "gloc_csm_match_batch: branch-and-bound node list overflowed "
+                                  "(more than 16M open nodes in one sub-batch); match fewer pairs per call");
     if (timing) {
       float t[4] = {0, 0, 0, 0};
-      unsigned ns = 0;
-      cudaMemcpy(&ns, n_surv, 4, cudaMemcpyDeviceToHost);
+      std::vector<unsigned> hs((size_t)np);
+      cudaMemcpy(hs.data(), n_surv, (size_t)np * 4, cudaMemcpyDeviceToHost);
+      unsigned long long ns = 0;
+      for (unsigned v : hs) ns += v;
       for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
-      fprintf(stderr, "[csm] pairs=%d coarse(%s)=%.3f ms seed=%.3f filter=%.3f refine=%.3f | survivors=%u "
-                      "expanded=%llu\n", np, use_bits ? "bits" : "u8", t[0], t[1], t[2], t[3], ns, hc);
+      float t_exp = 0.f;
+      if (depth >= 2) cudaEventElapsedTime(&t_exp, tev[3], tev[5]);
+      fprintf(stderr, "[csm] pairs=%d coarse(%s)=%.3f ms seed=%.3f filter=%.3f expand+refine=%.3f (expand %.3f) | "
+                      "survivors=%llu nodes=%u expanded=%llu\n", np, use_bits ? "bits" : "u8", t[0], t[1],
+              t[2], t[3], t_exp, ns, hn, hc);
+      unsigned mx = 0;
+      for (unsigned v : hs) mx = std::max(mx, v);
+      fprintf(stderr, "[csm] max survivors in one pair = %u\n", mx);
       for (auto& e : tev) cudaEventDestroy(e);
     }
-    st->stats.kernel_launches += 4;
+    st->stats.kernel_launches += depth >= 2 ? 5 : 3;
     st->stats.refined_nodes += hc;
     st->stats.coarse_candidates += (uint64_t)np * (uint64_t)per_pair;  // upper bound (slots)
   }

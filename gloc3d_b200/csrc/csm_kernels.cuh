@@ -26,6 +26,10 @@ struct CsmGridDev {
   // of the level's own (wide) frame; pmb_rows rows per plane, zero outside the grid.
   const unsigned long long* pmb;
   int pmb_rows, pmb_px, pmb_py, pmb_log2w;
+  // Binary grids only: level depth-2 bit-packed row-major (bit x of row y at word
+  // y * lvb_stride + x / 32), used by the expand stage.
+  const unsigned* lvb;
+  int lvb_stride;
 };
 
 // One (grid, scan) pair.
@@ -50,6 +54,13 @@ struct CsmParams {
 
 struct CsmBounds {
   int min_x, max_x, min_y, max_y;
+};
+
+// A branch-and-bound node: candidate (scan s, offset xo, yo) at tree depth d (its score is
+// the bound of the 2^d x 2^d block of fine offsets it covers).
+struct CsmNode {
+  int pi, s, xo, yo, d;
+  float score;
 };
 
 // K5
@@ -83,16 +94,28 @@ cudaError_t launch_csm_seed(const CsmGridDev* grids, const CsmPairDev* pairs, in
                             const float* pts, const float2* rot, CsmParams prm,
                             const CsmBounds* bounds, const unsigned long long* top_coarse,
                             unsigned long long* best, cudaStream_t stream);
+// survivors: [n_pairs][S * maxc] (entry = scan * maxc + slot), n_survivors: [n_pairs]
 cudaError_t launch_csm_filter(const CsmPairDev* pairs, int n_pairs, CsmParams prm,
                               const CsmBounds* bounds, const int* coarse,
                               const unsigned long long* best, unsigned* survivors,
                               unsigned* n_survivors, cudaStream_t stream);
-cudaError_t launch_csm_refine(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
+// level -> bit-packed rows (binary grids)
+cudaError_t launch_csm_build_lvb(const uint8_t* level, int wide_nx, int wide_ny, int stride,
+                                 unsigned* out, cudaStream_t stream);
+size_t csm_expand_smem(int wide_ny, int stride);
+// the four children of every surviving coarse candidate -> nodes (or leaves at depth 2);
+// bits == false: the survivors themselves become the nodes
+cudaError_t launch_csm_expand(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                               const float* pts, const float2* rot, CsmParams prm,
                               const CsmBounds* bounds, const int* coarse,
                               const unsigned* survivors, const unsigned* n_survivors,
+                              unsigned long long* best, CsmNode* nodes, unsigned* n_nodes,
+                              unsigned node_cap, unsigned long long* counters, int chunks,
+                              bool bits, size_t smem, cudaStream_t stream);
+cudaError_t launch_csm_refine(const CsmGridDev* grids, const CsmPairDev* pairs, const float* pts,
+                              const float2* rot, CsmParams prm, const CsmBounds* bounds,
+                              const CsmNode* nodes, const unsigned* n_nodes, unsigned node_cap,
                               unsigned* cursor, unsigned long long* best,
                               unsigned long long* counters, int n_ctas, cudaStream_t stream);
-
 
 }  // namespace gloc

@@ -54,14 +54,11 @@ constexpr int kStagesB = 3;        // B ring depth
 constexpr int kMaxKBlocks = 8;     // dim <= 512 keeps the whole query tile resident (128 KB)
 constexpr int kABytesPerKB = BM * BK * 2;   // 16 KB
 constexpr int kBBytes = BN * BK * 2;        // 32 KB
-constexpr int kThreads = 352;      // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warps 3-10 epilogue (184 registers/thread)
+constexpr int kThreads = 384;      // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps 4-11 epilogue
 constexpr int kTmemCols = 512;
-constexpr int kWarmChunks = 16;    // 16-column half chunks whose scores all enter the threshold list (per warpgroup)
-constexpr int kXnBytes = BN * 4;    // ||x||^2 of one tile (one slot per accumulator stage)
-// The dynamic shared memory window starts 1024-byte aligned (checked in the kernel: the
-// 128B-swizzled operand tiles need it), so no alignment slack is budgeted.
-constexpr size_t kSmemBytes = (size_t)kMaxKBlocks * kABytesPerKB + (size_t)kStagesB * kBBytes +
-                              2 * kXnBytes + 128 /*barriers*/;
+constexpr int kWarmChunks = 8;     // chunks whose scores all enter the threshold list (per warpgroup)
+constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kMaxKBlocks * kABytesPerKB +
+                              (size_t)kStagesB * kBBytes + 256 /*barriers*/;
 
 // shortlist error-bound constants (see header comment)
 constexpr float kU = 1.f / 2048.f;          // FP16 unit roundoff
@@ -126,14 +123,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
-                                             uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -181,16 +170,6 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
         "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
         "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
         "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-        "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
 }
@@ -340,24 +319,22 @@ struct GemmArgs {
   unsigned* unit_cnt;               // [nq][2*n_ranges]
 };
 
-__global__ void __maxnreg__(184)
+__global__ void __launch_bounds__(kThreads, 1)
 knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
                           const __grid_constant__ CUtensorMap map_db, GemmArgs a) {
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  unsigned char* smem = smem_raw;
-  if ((smem_u32(smem) & 1023u) != 0u) __trap();   // swizzled tiles need 1024-byte alignment
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                                          // n_kb x 16 KB (resident)
   unsigned char* sB = smem + (size_t)kMaxKBlocks * kABytesPerKB;     // kStagesB x 32 KB
-  float* sXn = reinterpret_cast<float*>(sB + (size_t)kStagesB * kBBytes);   // [2][BN] tile row norms
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sXn + 2 * BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kStagesB * kBBytes);
   uint64_t* full_b = bars;                   // [kStagesB]
   uint64_t* empty_b = bars + kStagesB;       // [kStagesB]
   uint64_t* a_full = bars + 2 * kStagesB;    // [1]
   uint64_t* a_empty = a_full + 1;            // [1]
   uint64_t* tm_full = a_empty + 1;           // [2]
   uint64_t* tm_empty = tm_full + 2;          // [2]
-  uint64_t* xn_full = tm_empty + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xn_full + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tm_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = a.n_qtiles * a.n_ranges;
@@ -376,7 +353,6 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     for (int s = 0; s < 2; ++s) {
       mbar_init(tm_full + s, 1);
       mbar_init(tm_empty + s, 8);  // one arrive per epilogue warp
-      mbar_init(xn_full + s, 1);
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -402,21 +378,11 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     t_count = (int)min((long long)a.tiles_per_range, total_tiles - t_begin);
   };
 
-  // Register budget: the kernel is compiled for 168 registers x 384 threads; warps 0-3
-  // (producer, MMA issuer, TMEM allocator, idle) release theirs down to 56 and the two
-  // epilogue warpgroups, which hold a 32-entry sorted list, two 32-column TMEM chunks and the
-  // chunk's scores, grow to 224 (128 x 56 + 256 x 224 = 64512 = 384 x 168).
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 120;");
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
-  }
   if (warp == 0) {
     // ===================================================== TMA producer
     if (lane == 0) {
-      int stage = 0, as = 0;
-      uint32_t phase = 0, uphase = 0, aphase = 0;
-      const int xn_at = min(kStagesB - 1, a.n_kb - 1);   // k-block after which the norms are fetched
+      int stage = 0;
+      uint32_t phase = 0, uphase = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         int qt, rg, t_begin, t_count;
         unit_tiles(u, qt, rg, t_begin, t_count);
@@ -432,15 +398,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             mbar_expect_tx(full_b + stage, kBBytes);
             tma_load_2d(sB + (size_t)stage * kBBytes, &map_db, full_b + stage, kb * BK, t * BN);
             if (++stage == kStagesB) { stage = 0; phase ^= 1; }
-            if (kb == xn_at) {
-              // ||x||^2 of the tile -> the slot of its accumulator stage, free once the
-              // epilogue has handed that stage back (the MMA waits for the same event)
-              mbar_wait(tm_empty + as, aphase ^ 1);
-              mbar_expect_tx(xn_full + as, kXnBytes);
-              bulk_load_1d(sXn + as * BN, a.xn + (size_t)t * BN, kXnBytes, xn_full + as);
-            }
           }
-          if (++as == 2) { as = 0; aphase ^= 1; }
         }
       }
       mbar_wait(a_empty, uphase ^ 1);  // the last unit's commit has landed before the CTA exits
@@ -481,7 +439,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
         tcgen05_commit(a_empty);              // query tile may be overwritten
       }
     }
-  } else if (warp >= 3) {
+  } else if (warp >= 4) {
     // ===================================================== epilogue: selection out of TMEM
     // Thread = one query row.  Fast path per 32-column chunk: scores s = ||x||^2 - 2 dot
     // (32 FFMA) and their minimum (FMNMX tree); a chunk whose minimum is above the threshold
@@ -495,7 +453,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     // threads of a query row keep their own list / candidate list (list index 2*range + wg)
     // and meet in the shared threshold.
     const int ew = warp & 3;                  // this warp's TMEM lane quadrant
-    const int wg = (warp - 3) >> 2;           // 0 or 1
+    const int wg = (warp - 4) >> 2;           // 0 or 1
     const int row = ew * 32 + lane;           // query row inside the tile = TMEM lane
     int as = 0;
     uint32_t aphase = 0;
@@ -569,34 +527,38 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
         unsigned seen = 0xFFFFFFFFu;
         if (q_ok) seen = *reinterpret_cast<volatile unsigned*>(a.thr_ord + q);
         mbar_wait(tm_full + as, aphase);
-        mbar_wait(xn_full + as, aphase);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
-        const float4* xs4 = reinterpret_cast<const float4*>(sXn + as * BN);
+        const float4* xn4 = reinterpret_cast<const float4*>(a.xn + (size_t)t * BN);
         // rows >= n_rows (search limit inside this tile) must neither be short-listed nor
         // tighten the bound; rows >= n_total already carry ||x||^2 = +inf
         const int valid_cols = (int)min((long long)BN, a.n_rows - (long long)t * BN);
-        // one 16-column half chunk h (columns 16 h .. 16 h + 15 of the tile)
-        auto process_half = [&](const uint32_t (&v)[16], const int h) {
-          float sc[16];
+#pragma unroll 1
+        for (int c = wg; c < BN / 32; c += 2) {
+          float4 xr[8];
 #pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 xr = xs4[h * 4 + j4];   // broadcast read of the staged row norms
-            sc[4 * j4 + 0] = fmaf(cm, __uint_as_float(v[4 * j4 + 0]), xr.x);
-            sc[4 * j4 + 1] = fmaf(cm, __uint_as_float(v[4 * j4 + 1]), xr.y);
-            sc[4 * j4 + 2] = fmaf(cm, __uint_as_float(v[4 * j4 + 2]), xr.z);
-            sc[4 * j4 + 3] = fmaf(cm, __uint_as_float(v[4 * j4 + 3]), xr.w);
+          for (int j4 = 0; j4 < 8; ++j4) xr[j4] = __ldg(xn4 + c * 8 + j4);
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          float sc[32];
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            sc[4 * j4 + 0] = fmaf(cm, __uint_as_float(v[4 * j4 + 0]), xr[j4].x);
+            sc[4 * j4 + 1] = fmaf(cm, __uint_as_float(v[4 * j4 + 1]), xr[j4].y);
+            sc[4 * j4 + 2] = fmaf(cm, __uint_as_float(v[4 * j4 + 2]), xr[j4].z);
+            sc[4 * j4 + 3] = fmaf(cm, __uint_as_float(v[4 * j4 + 3]), xr[j4].w);
           }
           if (valid_cols < BN) {  // warp-uniform, last tile of a limited search only
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (h * 16 + j >= valid_cols) sc[j] = INFINITY;
+            for (int j = 0; j < 32; ++j)
+              if (c * 32 + j >= valid_cols) sc[j] = INFINITY;
           }
           const bool warm = warm_left > 0;   // warp-uniform
           if (warm) {
             --warm_left;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < 4; ++g) {
               float r0 = sc[8 * g], r1 = sc[8 * g + 1], r2 = sc[8 * g + 2], r3 = sc[8 * g + 3];
               float r4 = sc[8 * g + 4], r5 = sc[8 * g + 5], r6 = sc[8 * g + 6], r7 = sc[8 * g + 7];
 #pragma unroll 1
@@ -607,9 +569,9 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             }
             thr = fminf(thr, lst[31] + eps2);
           }
-          float mg[2];   // minima of the two 8-column groups
+          float mg[4];   // minima of the four 8-column groups
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int g = 0; g < 4; ++g) {
             mg[g] = fminf(fminf(fminf(sc[8 * g], sc[8 * g + 1]), fminf(sc[8 * g + 2], sc[8 * g + 3])),
                           fminf(fminf(sc[8 * g + 4], sc[8 * g + 5]), fminf(sc[8 * g + 6], sc[8 * g + 7])));
           }
@@ -618,9 +580,9 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
           // base row and all 8 scores (one aligned 32-byte sector); K3 filters the individual
           // scores.  With ~1e3 hits per query some lane of the warp hits in nearly every
           // group, so any per-score or lane-divergent handling here would run all the time.
-          const unsigned col0 = (unsigned)(t * BN + h * 16);
+          const unsigned col0 = (unsigned)(t * BN + c * 32);
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int g = 0; g < 4; ++g) {
             if (mg[g] <= thr) {   // thr = -inf on rows beyond nq
               if (cnt < (unsigned)a.cap) {
                 cand_g[cnt] = col0 + 8 * g;
@@ -634,7 +596,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             // units that maintain their own bound: scores entering the sorted list go through
             // the pending FIFO (visited only where some lane has one: warp-uniform branch)
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
+            for (int g = 0; g < 4; ++g) {
               if (__any_sync(0xffffffffu, mg[g] < lst[31])) {
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
@@ -651,20 +613,6 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
           }
           // flush as soon as some lane's pending buffer is full (warp-uniform, no divergence)
           if (own_list && __any_sync(0xffffffffu, npend >= 8)) flush_pending();
-        };
-        // This warpgroup's 32-column chunks (c = wg, wg+2, wg+4, wg+6) as eight 16-column
-        // halves, with the TMEM load of the next half in flight while the current one is
-        // processed.
-        uint32_t va[16], vb[16];
-        tmem_ld_32x32b_x16(taddr + wg * 32, va);
-#pragma unroll 1
-        for (int c = wg; c < BN / 32; c += 2) {
-          tmem_ld_wait();
-          tmem_ld_32x32b_x16(taddr + c * 32 + 16, vb);
-          process_half(va, 2 * c);
-          tmem_ld_wait();
-          if (c + 2 < BN / 32) tmem_ld_32x32b_x16(taddr + (c + 2) * 32, va);
-          process_half(vb, 2 * c + 1);
         }
         if (own_list && __any_sync(0xffffffffu, npend > 0)) flush_pending();
         // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA

@@ -7,10 +7,18 @@
 
 #include <iostream>
 #include <memory>
+#include <stdexcept>
 #include <vector>
 
 #include "gloc_fast_csm_2d.hpp"
 #include "gloc_inv_key_tree.hpp"
+
+// cv::Mat stand-in for the BEV occupancy image (CV_8UC1: 0 = occupied, 255 = free).
+struct BevImage {
+  int rows = 0, cols = 0;
+  std::vector<uint8_t> data;   // row-major
+  uint8_t at(int r, int c) const { return data[(size_t)r * cols + c]; }
+};
 
 class RpyPCLoopDetectorGpu {
  public:
@@ -23,6 +31,36 @@ class RpyPCLoopDetectorGpu {
   const int NUM_EXCLUDE_RECENT = 30;  // loop_detector.h:77
 
   explicit RpyPCLoopDetectorGpu(int device = 0) : device_(device) {}
+  ~RpyPCLoopDetectorGpu() { gloc_bev_destroy(bev_); }
+  RpyPCLoopDetectorGpu(const RpyPCLoopDetectorGpu&) = delete;
+  RpyPCLoopDetectorGpu& operator=(const RpyPCLoopDetectorGpu&) = delete;
+
+  // get_projected_grid (loop_detector.cpp:122-135): one scan (n points, `stride` floats apart,
+  // x y z first) -> BEV occupancy image; xy_res receives (ox, oy, resolution).
+  BevImage get_projected_grid(const float* points, size_t n, int stride, float xy_res[3]) {
+    ensure_bev();
+    gloc_bev_info info;
+    csm_check(gloc_bev_project(bev_, points, n, stride, &info));
+    BevImage img;
+    img.rows = info.height;
+    img.cols = info.width;
+    img.data.resize((size_t)info.width * info.height);
+    csm_check(gloc_bev_get_image(bev_, img.data.data(), img.data.size()));
+    xy_res[0] = static_cast<float>(info.ox);
+    xy_res[1] = static_cast<float>(info.oy);
+    xy_res[2] = static_cast<float>(info.resolution);
+    return img;
+  }
+  // crop_pad_occupancy (loop_detector.cpp:83-106) of the last projected grid, one channel.
+  BevImage crop_pad_occupancy(size_t width, size_t height) {
+    ensure_bev();
+    BevImage img;
+    img.rows = (int)height;
+    img.cols = (int)width;
+    img.data.resize(width * height);
+    csm_check(gloc_bev_get_cnn_input(bev_, (int)width, (int)height, img.data.data()));
+    return img;
+  }
 
   // add_keyframe (loop_detector.cpp:9-20) with the descriptor and the BEV grid already computed.
   // `cells` must stay alive as long as the detector (the reference keeps cv::Mat copies).
@@ -91,6 +129,12 @@ class RpyPCLoopDetectorGpu {
   float last_score() const { return last_score_; }
 
  private:
+  static void csm_check(int rc) {
+    if (rc != GLOC_OK) throw std::runtime_error(gloc_last_error());
+  }
+  void ensure_bev() {   // high_resolution_ = 0.2, high_resolution_max_range_ = 100 (loop_detector.h:111-116)
+    if (!bev_) csm_check(gloc_bev_create(&bev_, device_, 0.2f, 100.f));
+  }
   void ensure_tree() {
     if (!kdtree_) kdtree_ = std::make_unique<InvKeyTree>(k_dim_, db_features_, 10, device_);
   }
@@ -107,6 +151,7 @@ class RpyPCLoopDetectorGpu {
   std::unique_ptr<InvKeyTree> kdtree_;
   std::vector<Grid2DView> db_grids_;
   Options options_;
+  gloc_bev_projector* bev_ = nullptr;
 };
 
 #endif  // GLOC_LOOP_DETECTOR_HPP_

@@ -127,3 +127,35 @@ def level1_to_cells(level1: np.ndarray) -> np.ndarray:
     v = np.rint((1.0 - lv) * 32766.0).astype(np.int64) + 1
     v = np.clip(v, 1, 32767).astype(np.uint16)
     return np.where(level1 == 0, np.uint16(0), v).astype(np.uint16)
+
+
+def make_lidar_scan(n_walls: int = 40, seed: int = 4444, max_range: float = 90.0,
+                    ground: bool = True) -> np.ndarray:
+    """A KITTI-like [n, 4] float32 scan (x, y, z, intensity): vertical wall segments several
+    voxels tall (they become occupied BEV pixels: >= 2 hit voxels per column), a flat ground
+    disc (one voxel per column: stays free), a few points beyond 100 m (misses) and some
+    exactly on voxel boundaries (rounding half away from zero)."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for _ in range(n_walls):
+        x0, y0 = rng.uniform(-max_range * 0.7, max_range * 0.7, 2)
+        ang = rng.uniform(0, np.pi)
+        length = rng.uniform(3, 25)
+        n = int(length * 12)
+        t = rng.uniform(0, length, n)
+        z = rng.uniform(-1.5, rng.uniform(-1.0, 2.5), n)
+        parts.append(np.stack([x0 + t * np.cos(ang), y0 + t * np.sin(ang), z], axis=1))
+    if ground:
+        r = np.sqrt(rng.uniform(4, (max_range * 0.8) ** 2, 20000))
+        a = rng.uniform(0, 2 * np.pi, 20000)
+        parts.append(np.stack([r * np.cos(a), r * np.sin(a), np.full(20000, -1.73)], axis=1))
+    far = rng.uniform(-1, 1, (200, 3))
+    far = far / np.linalg.norm(far, axis=1, keepdims=True) * rng.uniform(99.5, 130, (200, 1))
+    parts.append(far)
+    # exact half-voxel coordinates (0.1, 0.3, -0.1 ... in float32) and the origin
+    k = np.arange(-20, 21)
+    parts.append(np.stack([(k + 0.5) * 0.2, (k - 0.5) * 0.2, (k % 3) * 0.2], axis=1))
+    parts.append(np.zeros((2, 3)))
+    xyz = np.concatenate(parts).astype(np.float32)
+    inten = rng.uniform(0, 1, (xyz.shape[0], 1)).astype(np.float32)
+    return np.ascontiguousarray(np.concatenate([xyz, inten], axis=1))

@@ -209,6 +209,53 @@ int gloc_csm_get_stats(const gloc_csm_store* store, gloc_csm_stats* stats);
 int gloc_csm_set_profiling(gloc_csm_store* store, int enabled);
 int gloc_csm_get_profile(gloc_csm_store* store, gloc_profile* out);
 
+/* ============================================================ BEV projection
+ * (the producer of both stages' inputs.)  One LiDAR scan ->
+ * the reference's bird's-eye-view occupancy image.  Replaces
+ *   RpyPCLoopDetector::get_projected_grid   loop_detector.cpp:122-135
+ *     = point_cloud_to_range_data           loop_detector.cpp:108-120
+ *     + Submap3D::InsertRangeData           3d/submap_3d.cpp:162-177 (fresh submap, identity pose)
+ *     + ProjectToCvMat                      3d/submap_3d.cpp:238-326
+ *   RpyPCLoopDetector::crop_pad_occupancy   loop_detector.cpp:83-106
+ *   ProjectToGrid                           3d/submap_3d.cpp:328-429 (gloc_csm_add_grid_from_bev)
+ * A pixel is occupied (0; free = 255) iff at least two distinct 0.2 m voxels of
+ * its z column were hit by returns within max_range; the image spans the bounding
+ * box of all hit voxels; (ox, oy) = world coordinates of pixel (0, 0).
+ */
+typedef struct gloc_bev_projector gloc_bev_projector;
+
+typedef struct {
+  int width, height;          /* cv::Mat cols, rows                                   */
+  int min_ix, min_iy;         /* voxel index of pixel (0, 0)                          */
+  double ox, oy, resolution;  /* ProjectToCvMat's out-parameters                      */
+  uint64_t n_occupied;        /* pixels with value 0                                  */
+  uint64_t n_points_in_range; /* returns (range <= max_range)                         */
+} gloc_bev_info;
+
+/* resolution = high_resolution_ (0.2), max_range = high_resolution_max_range_ (100)
+ * in the reference (loop_detector.h:111-116). */
+int gloc_bev_create(gloc_bev_projector** out, int device, float resolution, float max_range);
+void gloc_bev_destroy(gloc_bev_projector* bev);
+/* pts: n_pts points in HOST memory, `stride` floats apart, x y z first (KITTI
+ * .bin scans: stride 4).  The image stays on the device until fetched. */
+int gloc_bev_project(gloc_bev_projector* bev, const float* pts, size_t n_pts, int stride,
+                     gloc_bev_info* info);
+/* The image of the last projection, height*width bytes, row-major (host). */
+int gloc_bev_get_image(gloc_bev_projector* bev, uint8_t* img, size_t capacity);
+/* crop_pad_occupancy: centre crop / 255-pad to width x height (768 x 768 in the
+ * reference, loop_detector.cpp:144), one channel. */
+int gloc_bev_get_cnn_input(gloc_bev_projector* bev, int width, int height, uint8_t* out);
+/* Occupied pixels as GridToVirtualPointCloud produces them from ProjectToGrid's
+ * grid (fast_..._2d.cpp:78-95): (ox + i*res, oy + j*res, 0), i outer.  pts may be
+ * NULL to query the count. */
+int gloc_bev_get_occupied_points(gloc_bev_projector* bev, float* pts, size_t capacity,
+                                 size_t* n_out);
+uint64_t gloc_bev_kernel_launches(const gloc_bev_projector* bev);
+/* Adds the last projection to a scan-match store as ProjectToGrid builds it:
+ * num_x_cells = width, num_y_cells = height, max = (max_ix, max_iy) * resolution,
+ * occupied -> cost 0.1 (level-1 value 255), free -> cost 0.9 (0); device to device. */
+int gloc_csm_add_grid_from_bev(gloc_csm_store* store, gloc_bev_projector* bev, int* grid_id);
+
 #ifdef __cplusplus
 }
 #endif

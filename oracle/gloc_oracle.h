@@ -165,6 +165,19 @@ void gloc_oracle_csm_match_batch_mt(const uint8_t* const* grids, int nx, int ny,
                                     float min_score, int mode, int nthreads,
                                     gloc_oracle_match_result* out);
 
+/* ------------------------------------------------------------- BEV projection */
+
+/* One scan -> the reference's BEV image (0 = occupied, 255 = free): see bev_oracle.c for
+ * the path restated (loop_detector.cpp:108-135, 3d/submap_3d.cpp:238-326,
+ * 3d/range_data_inserter_3d.cpp:57-77, 3d/hybrid_grid.h:429-434).  PARITY UNPINNED. */
+int gloc_oracle_bev_project(const float* pts, size_t n, int stride, float resolution,
+                            float max_range, uint8_t* img, size_t img_capacity, int* w, int* h,
+                            int* min_ix, int* min_iy, double* ox, double* oy,
+                            size_t* n_hit_voxels, size_t* n_occupied);
+/* RpyPCLoopDetector::crop_pad_occupancy (loop_detector.cpp:83-106), one channel. */
+void gloc_oracle_crop_pad(const uint8_t* src, int sw, int sh, int width, int height,
+                          uint8_t* dst);
+
 #ifdef __cplusplus
 }
 #endif

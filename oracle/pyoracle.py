@@ -102,6 +102,13 @@ def lib():
             C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
             C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_int,
             C.c_int, C.c_int, C.c_double, C.c_float, C.c_int, C.c_int, C.POINTER(MatchResult)]
+        L.gloc_oracle_bev_project.restype = C.c_int
+        L.gloc_oracle_bev_project.argtypes = [
+            C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
+            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+            C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_size_t),
+            C.POINTER(C.c_size_t)]
+        L.gloc_oracle_crop_pad.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -299,3 +306,30 @@ def csm_match_batch(grids, resolution, max_x, max_y, depth, pts_list, inits, n_l
                                          init.ctypes.data_as(C.POINTER(C.c_double)), n, n_lin,
                                          n_ang, ang_step, min_score, mode, nthreads, out)
     return list(out)
+
+
+def bev_project(pts: np.ndarray, resolution: float = 0.2, max_range: float = 100.0):
+    """pts: [n, 3 or 4] float32.  Returns (img uint8 [h, w] with 0 = occupied / 255 = free,
+    (ox, oy, resolution), (min_ix, min_iy), n_hit_voxels, n_occupied) as the reference's
+    get_projected_grid (loop_detector.cpp:122-135) does for one scan."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    n, stride = pts.shape
+    w, h, mx, my = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    ox, oy = C.c_double(), C.c_double()
+    nv, no = C.c_size_t(), C.c_size_t()
+    args = (C.byref(w), C.byref(h), C.byref(mx), C.byref(my), C.byref(ox), C.byref(oy),
+            C.byref(nv), C.byref(no))
+    lib().gloc_oracle_bev_project(pts.ctypes.data, n, stride, resolution, max_range, None, 0, *args)
+    img = np.empty((h.value, w.value), np.uint8)
+    lib().gloc_oracle_bev_project(pts.ctypes.data, n, stride, resolution, max_range,
+                                  img.ctypes.data, img.size, *args)
+    res = float(np.float32(resolution))
+    return img, (ox.value, oy.value, res), (mx.value, my.value), nv.value, no.value
+
+
+def crop_pad(img: np.ndarray, width: int = 768, height: int = 768) -> np.ndarray:
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty((height, width), np.uint8)
+    lib().gloc_oracle_crop_pad(img.ctypes.data, img.shape[1], img.shape[0], width, height,
+                               out.ctypes.data)
+    return out

@@ -99,6 +99,35 @@ int main() {
   det.add_keyframe(near, grid);   // the newest keyframe revisits keyframe 123
   size_t qi = 0, li = 0;
   EXPECT(det.detect(qi, li) && qi == 400 && li == 123);
+
+  // ---- BEV projection through the loop detector's own interface vs the oracle
+  {
+    std::vector<float> scan;
+    std::uniform_real_distribution<float> u(-60.f, 60.f), uz(-1.5f, 2.f);
+    for (int w = 0; w < 30; ++w) {
+      const float x0 = u(rng), y0 = u(rng), dx = u(rng) / 60.f, dy = u(rng) / 60.f;
+      for (int t = 0; t < 200; ++t) {
+        scan.push_back(x0 + dx * t * 0.1f);
+        scan.push_back(y0 + dy * t * 0.1f);
+        scan.push_back(uz(rng));
+        scan.push_back(0.5f);
+      }
+    }
+    float xy_res[3];
+    const BevImage img = det.get_projected_grid(scan.data(), scan.size() / 4, 4, xy_res);
+    int w = 0, h = 0, mix = 0, miy = 0;
+    double ox = 0, oy = 0;
+    size_t nv = 0, no = 0;
+    gloc_oracle_bev_project(scan.data(), scan.size() / 4, 4, 0.2f, 100.f, nullptr, 0, &w, &h, &mix, &miy, &ox, &oy, &nv, &no);
+    std::vector<uint8_t> ref((size_t)w * h);
+    gloc_oracle_bev_project(scan.data(), scan.size() / 4, 4, 0.2f, 100.f, ref.data(), ref.size(), &w, &h, &mix, &miy, &ox, &oy, &nv, &no);
+    EXPECT(img.rows == h && img.cols == w && img.data == ref && no > 100);
+    EXPECT(xy_res[0] == (float)ox && xy_res[1] == (float)oy && xy_res[2] == 0.2f);
+    const BevImage cnn = det.crop_pad_occupancy(768, 768);
+    std::vector<uint8_t> cref((size_t)768 * 768);
+    gloc_oracle_crop_pad(ref.data(), w, h, 768, 768, cref.data());
+    EXPECT(cnn.data == cref);
+  }
   std::printf("PASS host mirrors\n");
   return 0;
 }

@@ -48,7 +48,18 @@ def csm_case(name, nx, ny, seed, yaw, dx, dy, n_lin, n_ang, step, depth, min_sco
     print(name, r.as_tuple())
 
 
+def bev_case(name, every=4):
+    """Every `every`-th point of the reference's only real scan (s2s_libtorch/000000.bin, a
+    KITTI frame) and the BEV image the oracle computes for it (needs /root/reference)."""
+    pts = np.fromfile("/root/reference/s2s_libtorch/000000.bin", np.float32).reshape(-1, 4)[::every].copy()
+    img, (ox, oy, res), (mx, my), nv, no = po.bev_project(pts)
+    np.savez_compressed(os.path.join(OUT, name), pts=pts, occupied_bits=np.packbits(img == 0),
+                        shape=np.array(img.shape), min_and_count=np.array([mx, my, no]))
+    print(name, pts.shape, img.shape, no)
+
+
 if __name__ == "__main__":
+    bev_case("bev_kitti_subsample.npz")
     knn_case("knn_d512_k20.npz", 160, 512, 6, 20, 11)                      # reference k (loop_detector.h:98)
     knn_case("knn_d512_k25_dups.npz", 160, 512, 6, 25, 21, dup_run=8, sigma=0.002)
     knn_case("knn_d30_tail.npz", 200, 30, 5, 7, 31)                        # dim % 4 != 0 tail path
