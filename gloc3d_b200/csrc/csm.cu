@@ -886,9 +886,10 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
                   unsigned* __restrict__ n_nodes, unsigned node_cap,
                   unsigned long long* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char csm_smem[];
-  const int pi = blockIdx.y, tid = threadIdx.x;
+  __shared__ int s_sum[32][4];
+  const int pi = blockIdx.y, tid = threadIdx.x, lane = tid & 31, slice = tid >> 5;
   const unsigned ns = n_survivors[pi];
-  if ((unsigned)blockIdx.x * 256u >= ns) return;
+  if ((unsigned)blockIdx.x * 32u >= ns) return;
   const size_t per_pair = (size_t)prm.S * prm.maxc;
   const CsmPairDev pr = pairs[pi];
   const CsmGridDev g = grids[pr.grid];
@@ -910,10 +911,13 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
   const float delta = 2.3841858e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
   const float hi1 = 1.f - delta;
   unsigned long long expanded = 0;
-  const unsigned first_base = (unsigned)blockIdx.x * 256u;
+  const unsigned first_base = (unsigned)blockIdx.x * 32u;
 
-  for (unsigned base = first_base; base < ns; base += gridDim.x * 256u) {
-    const unsigned i = base + tid;
+  // 32 survivors per pass (one per lane); the 8 warps split the points of every pass, so that
+  // the serial chain of one thread stays short (the kernel's latency is what matters: there
+  // are only a few hundred survivors per pair)
+  for (unsigned base = first_base; base < ns; base += gridDim.x * 32u) {
+    const unsigned i = base + lane;
     bool active = i < ns;
     int s = 0, xo = 0, yo = 0;
     CsmBounds b = {0, 0, 0, 0};
@@ -932,6 +936,7 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
     const float2 r = rot[s];
     const int ax = xo + wm1, ay = yo + wm1;   // cell -> level frame of child (0, 0)
     int sum[4] = {0, 0, 0, 0};
+    if (tid < 128) s_sum[tid >> 2][tid & 3] = 0;
     for (int p0 = 0; p0 < P; p0 += kExpChunk) {
       const int n = min(kExpChunk, P - p0);
       __syncthreads();
@@ -944,41 +949,65 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
       }
       __syncthreads();
       if (active) {
-#pragma unroll 2
-        for (int p = 0; p < n; ++p) {
-          const float2 q = P0[p];
-          float x1, y1;
-          rot_z(r.x, r.y, q.x, q.y, x1, y1);
-          const float wx = __fadd_rn(x1, pr.tx), wy = __fadd_rn(y1, pr.ty);
-          const float uy = (my_f - wy) * ir, ux = (mx_f - wx) * ir;
-          const float fy = floorf(uy), fx = floorf(ux);
-          const float dy = uy - fy, dx = ux - fx;
-          int cx = (int)fy, cy = (int)fx;
-          if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < U && fabsf(ux) < U)) {
-            const int2 ce = cells_exact(wx, wy, g.resolution, g.max_x, g.max_y);
-            cx = ce.x;
-            cy = ce.y;
+        // four points per step: all float discretisations first (independent chains, no
+        // branch between them), one rarely taken exact fallback, then the cell tests
+        for (int p = 4 * slice; p < n; p += 32) {
+          int cxs[4], cys[4];
+          float wxs[4], wys[4];
+          unsigned need = 0u;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 q = P0[min(p + u, n - 1)];
+            float x1, y1;
+            rot_z(r.x, r.y, q.x, q.y, x1, y1);
+            wxs[u] = __fadd_rn(x1, pr.tx);
+            wys[u] = __fadd_rn(y1, pr.ty);
+            const float uy = (my_f - wys[u]) * ir, ux = (mx_f - wxs[u]) * ir;
+            const float fy = floorf(uy), fx = floorf(ux);
+            const float dy = uy - fy, dx = ux - fx;
+            cxs[u] = (int)fy;
+            cys[u] = (int)fx;
+            if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < U && fabsf(ux) < U))
+              need |= 1u << u;
           }
-          const int lx = cx + ax, ly = cy + ay;
-          const bool x0ok = (unsigned)lx < (unsigned)wide_nx, x1ok = (unsigned)(lx + h) < (unsigned)wide_nx;
-          const bool y0ok = (unsigned)ly < (unsigned)wide_ny, y1ok = (unsigned)(ly + h) < (unsigned)wide_ny;
-          const unsigned* r0 = bits + ly * stride + (ly >> 4);
-          const unsigned* r1 = bits + (ly + h) * stride + ((ly + h) >> 4);
-          const int w0 = lx >> 5, w1 = (lx + h) >> 5, b0 = lx & 31, b1 = (lx + h) & 31;
-          if (x0ok && y0ok) sum[0] += (r0[w0] >> b0) & 1u;   // child (x, y)
-          if (x0ok && y1ok) sum[1] += (r1[w0] >> b0) & 1u;   // child (x, y + h)
-          if (x1ok && y0ok) sum[2] += (r0[w1] >> b1) & 1u;   // child (x + h, y)
-          if (x1ok && y1ok) sum[3] += (r1[w1] >> b1) & 1u;   // child (x + h, y + h)
+          if (need) {   // rare: near a rounding boundary
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (need & (1u << u)) {
+                const int2 ce = cells_exact(wxs[u], wys[u], g.resolution, g.max_x, g.max_y);
+                cxs[u] = ce.x;
+                cys[u] = ce.y;
+              }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int lx = cxs[u] + ax, ly = cys[u] + ay;
+            const bool in = p + u < n;
+            const bool x0ok = in && (unsigned)lx < (unsigned)wide_nx, x1ok = in && (unsigned)(lx + h) < (unsigned)wide_nx;
+            const bool y0ok = (unsigned)ly < (unsigned)wide_ny, y1ok = (unsigned)(ly + h) < (unsigned)wide_ny;
+            const unsigned* r0 = bits + ly * stride + (ly >> 4);
+            const unsigned* r1 = bits + (ly + h) * stride + ((ly + h) >> 4);
+            const int w0 = lx >> 5, w1 = (lx + h) >> 5, b0 = lx & 31, b1 = (lx + h) & 31;
+            if (x0ok && y0ok) sum[0] += (r0[w0] >> b0) & 1u;   // child (x, y)
+            if (x0ok && y1ok) sum[1] += (r1[w0] >> b0) & 1u;   // child (x, y + h)
+            if (x1ok && y0ok) sum[2] += (r0[w1] >> b1) & 1u;   // child (x + h, y)
+            if (x1ok && y1ok) sum[3] += (r1[w1] >> b1) & 1u;   // child (x + h, y + h)
+          }
         }
       }
     }
     if (active) {
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) atomicAdd(&s_sum[lane][ch], sum[ch]);
+    }
+    __syncthreads();
+    if (active && slice == 0) {
       ++expanded;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {   // x outer, y inner (fast_..._2d.cpp:414-429)
         const int cx = xo + (ch >> 1) * h, cy = yo + (ch & 1) * h;
         if (cx > b.max_x || cy > b.max_y) continue;
-        const float sc = score_of(255 * sum[ch], P, prm);
+        const float sc = score_of(255 * s_sum[lane][ch], P, prm);
         const unsigned long long key = key_of(sc, rank_of(prm, s, cx, cy));
         if (!(key > ld_best(best + pi))) continue;
         if (d == 0) {
@@ -993,11 +1022,10 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
         }
       }
     }
+    __syncthreads();   // s_sum is reset by the next pass
   }
   if (expanded) atomicAdd(counters, expanded);
 }
-
-// ------------------------------------------------------------------- K7 refine
 
 struct Node {
   int xo, yo, d;

@@ -550,7 +550,7 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
                                       prm, (const CsmBounds*)st->bounds.p, (const int*)st->coarse.p,
                                       (const unsigned*)st->survivors.p, n_surv,
                                       (unsigned long long*)st->best.p, (CsmNode*)st->nodes.p, n_nodes,
-                                      node_cap, counters, 64, exp_bits && use_bits, exp_smem, stream));
+                                      node_cap, counters, 128, exp_bits && use_bits, exp_smem, stream));
       if (timing) cudaEventRecord(tev[5], stream);
       GLOC_CUDA_TRY(launch_csm_refine(dg, dp, (const float*)st->pts.p, (const float2*)st->rot.p, prm,
                                       (const CsmBounds*)st->bounds.p, (const CsmNode*)st->nodes.p,
