@@ -595,30 +595,51 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   const int hx0 = wm + prm.n_lin, hy0 = wm + prm.n_lin;
   const int row0 = half * 2 * NP;   // first candidate row of this lane
 
-  // (row address, shift / mask description) of one point for this rotation
-  auto point_addr = [&](int p, int& addr, unsigned& meta) {
-    const float2 q = P0[p];
-    float x1, y1;
-    rot_z(r.x, r.y, q.x, q.y, x1, y1);
-    const float wx = __fadd_rn(x1, pr.tx), wy = __fadd_rn(y1, pr.ty);
-    const float uy = (my_f - wy) * ir, ux = (mx_f - wx) * ir;
-    const float fy = floorf(uy), fx = floorf(ux);
-    const float dy = uy - fy, dx = ux - fx;
-    int cx = (int)fy, cy = (int)fx;
-    if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < 1e7f && fabsf(ux) < 1e7f)) {
-      const int2 ce = cells_exact(wx, wy, g.resolution, g.max_x, g.max_y);   // rare: near a rounding boundary
-      cx = ce.x;
-      cy = ce.y;
+  // (row address, shift / mask description) of this lane's four points of an 8-point group
+  // (points p + 2 i + half): all float discretisations first -- four independent chains with
+  // no branch between them --, then one rarely taken exact fallback, then the addressing.
+  auto point_addr4 = [&](int p, int n, int (&addr)[4], unsigned (&meta)[4]) {
+    float wxs[4], wys[4];
+    int cxs[4], cys[4];
+    unsigned need = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 q = P0[min(p + 2 * i + half, n - 1)];
+      float x1, y1;
+      rot_z(r.x, r.y, q.x, q.y, x1, y1);
+      wxs[i] = __fadd_rn(x1, pr.tx);
+      wys[i] = __fadd_rn(y1, pr.ty);
+      const float uy = (my_f - wys[i]) * ir, ux = (mx_f - wxs[i]) * ir;
+      const float fy = floorf(uy), fx = floorf(ux);
+      const float dy = uy - fy, dx = ux - fx;
+      cxs[i] = (int)fy;
+      cys[i] = (int)fx;
+      if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < 1e7f && fabsf(ux) < 1e7f))
+        need |= 1u << i;
     }
-    // can the point land on the grid for some offset of the window at all?
-    const bool hitable = (unsigned)(cx + hx0) < span_x && (unsigned)(cy + hy0) < span_y && s_ok;
-    const int X = cx + offx, Y = cy + offy;           // Y >= 0 for hitable points
-    const int ax = X >> log2w, ay = hitable ? (Y >> log2w) : 0;
-    const int plane = hitable ? (((Y & wm) << log2w) | (X & wm)) : 0;
-    const int shl = hitable ? max(0, -ax) : 0, axc = min(max(ax, 0), 63);
-    const int nbits = (hitable && ax < 64) ? max(ncx - shl, 0) : 0;
-    addr = plane * rows + ay;
-    meta = (unsigned)axc | ((unsigned)shl << 8) | ((unsigned)nbits << 16);
+    if (need) {   // rare: near a rounding boundary
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (need & (1u << i)) {
+          const int2 ce = cells_exact(wxs[i], wys[i], g.resolution, g.max_x, g.max_y);
+          cxs[i] = ce.x;
+          cys[i] = ce.y;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cx = cxs[i], cy = cys[i];
+      // can the point land on the grid for some offset of the window at all?
+      const bool hitable = (unsigned)(cx + hx0) < span_x && (unsigned)(cy + hy0) < span_y && s_ok &&
+                           p + 2 * i + half < n;
+      const int X = cx + offx, Y = cy + offy;           // Y >= 0 for hitable points
+      const int ax = X >> log2w, ay = hitable ? (Y >> log2w) : 0;
+      const int plane = hitable ? (((Y & wm) << log2w) | (X & wm)) : 0;
+      const int shl = hitable ? max(0, -ax) : 0, axc = min(max(ax, 0), 63);
+      const int nbits = (hitable && ax < 64) ? max(ncx - shl, 0) : 0;
+      addr[i] = plane * rows + ay;
+      meta[i] = (unsigned)axc | ((unsigned)shl << 8) | ((unsigned)nbits << 16);
+    }
   };
   // the NP packed words (two candidate rows each) a point adds to this lane's counters
   auto point_words = [&](int addr, unsigned meta, uint32_t (&v)[NP]) {
@@ -652,10 +673,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
 #pragma unroll
       for (int i = 0; i < 8; ++i) hi[i][j] = 0u;
     }
-    auto pair_words = [&](int p, uint32_t (&ta)[NP]) {   // points p, p+1 -> carry ta, sum into ones
-      int addr = 0;
-      unsigned meta = 0u;   // nbits = 0: contributes nothing
-      if (p + half < n) point_addr(p + half, addr, meta);
+    auto pair_words = [&](int addr, unsigned meta, uint32_t (&ta)[NP]) {   // two points -> carry ta, sum into ones
       const int addr_o = __shfl_xor_sync(0xffffffffu, addr, 1);
       const unsigned meta_o = __shfl_xor_sync(0xffffffffu, meta, 1);
       uint32_t v0[NP], v1[NP];
@@ -663,16 +681,23 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
       point_words(addr_o, meta_o, v1);
       csa(ta, ones, v0, v1);
     };
-    auto quad_words = [&](int p, uint32_t (&fa)[NP]) {
-      uint32_t ta[NP], tb[NP];
-      pair_words(p, ta);
-      pair_words(p + 2, tb);
-      csa(fa, twos, ta, tb);
-    };
-    auto oct_words = [&](int p, uint32_t (&ea)[NP]) {
+    auto oct_words = [&](int p, uint32_t (&ea)[NP]) {   // 8 points -> carry ea
+      int addr[4];
+      unsigned meta[4];
+      point_addr4(p, n, addr, meta);
       uint32_t fa[NP], fb[NP];
-      quad_words(p, fa);
-      quad_words(p + 4, fb);
+      {
+        uint32_t ta[NP], tb[NP];
+        pair_words(addr[0], meta[0], ta);
+        pair_words(addr[1], meta[1], tb);
+        csa(fa, twos, ta, tb);
+      }
+      {
+        uint32_t ta[NP], tb[NP];
+        pair_words(addr[2], meta[2], ta);
+        pair_words(addr[3], meta[3], tb);
+        csa(fb, twos, ta, tb);
+      }
       csa(ea, fours, fa, fb);
     };
 #pragma unroll 1
