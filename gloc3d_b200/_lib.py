@@ -103,6 +103,7 @@ SIGNATURES = {
     "gloc_bev_get_occupied_points": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "gloc_bev_kernel_launches": (C.c_uint64, [_vp]),
     "gloc_csm_add_grid_from_bev": (_i, [_vp, _vp, _ip]),
+    "gloc_csm_add_grid_from_bev_aligned": (_i, [_vp, _vp, _ip]),
 }
 
 _lib = None

@@ -70,6 +70,18 @@ class BevProjector:
                                       (i.min_iy + i.height - 1) * i.resolution, i.width, i.height))
         return gid.value
 
+    def add_to_store_aligned(self, store) -> int:
+        """The same occupancy as a MapLimits-consistent map grid (gloc_csm_add_grid_from_bev_aligned):
+        a world point looks up the pixel of its own voxel, so rigid alignment is possible."""
+        from .scan_matching import MapLimits
+
+        gid = C.c_int()
+        check(_lib.lib().gloc_csm_add_grid_from_bev_aligned(store._h, self._h, C.byref(gid)))
+        i = self.info
+        store.limits.append(MapLimits(i.resolution, (i.min_ix + i.width - 1 + 0.5) * i.resolution,
+                                      (i.min_iy + i.height - 1 + 0.5) * i.resolution, i.height, i.width))
+        return gid.value
+
     def kernel_launches(self) -> int:
         return int(_lib.lib().gloc_bev_kernel_launches(self._h))
 

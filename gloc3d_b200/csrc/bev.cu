@@ -130,6 +130,15 @@ __global__ void bev_level1_kernel(const uint8_t* __restrict__ img, size_t n, uin
   if (i < n) out[i] = img[i] == 0 ? 255 : 0;
 }
 
+// MapLimits-consistent layout (see gloc_csm_add_grid_from_bev_aligned): cell (cx, cy) holds
+// pixel (ix, iy) = (W - 1 - cy, H - 1 - cx); flat index H * cy + cx (num_x_cells = H).
+__global__ void bev_level1_aligned_kernel(const uint8_t* __restrict__ img, int W, int H,
+                                          uint8_t* __restrict__ out) {
+  const int cx = blockIdx.x * blockDim.x + threadIdx.x, cy = blockIdx.y;
+  if (cx >= H || cy >= W) return;
+  out[(size_t)H * cy + cx] = img[(size_t)(H - 1 - cx) * W + (W - 1 - cy)] == 0 ? 255 : 0;
+}
+
 // GridToVirtualPointCloud (2d/fast_correlative_scan_matcher_2d.cpp:78-95): i outer, j inner
 __global__ void bev_points_kernel(const uint8_t* __restrict__ img, int w, int h, double ox, double oy,
                                   double res, const int* __restrict__ col_prefix,
@@ -167,6 +176,13 @@ int gloc_bev_device_of(const gloc_bev_projector* b) { return b ? b->device : -1;
 cudaError_t gloc_bev_launch_level1(const uint8_t* img, size_t n, uint8_t* out, cudaStream_t s) {
   if (n == 0) return cudaSuccess;
   bev_level1_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(img, n, out);
+  return cudaGetLastError();
+}
+
+cudaError_t gloc_bev_launch_level1_aligned(const uint8_t* img, int W, int H, uint8_t* out,
+                                           cudaStream_t s) {
+  dim3 grd((H + 127) / 128, W);
+  bev_level1_aligned_kernel<<<grd, 128, 0, s>>>(img, W, H, out);
   return cudaGetLastError();
 }
 

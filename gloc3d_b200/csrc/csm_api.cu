@@ -16,6 +16,7 @@ using namespace gloc;
 const uint8_t* gloc_bev_device_image(const gloc_bev_projector* b, gloc_bev_info* info);
 int gloc_bev_device_of(const gloc_bev_projector* b);
 cudaError_t gloc_bev_launch_level1(const uint8_t* img, size_t n, uint8_t* out, cudaStream_t s);
+cudaError_t gloc_bev_launch_level1_aligned(const uint8_t* img, int W, int H, uint8_t* out, cudaStream_t s);
 
 namespace {
 
@@ -275,6 +276,38 @@ int gloc_csm_add_grid_from_bev(gloc_csm_store* st, gloc_bev_projector* bev, int*
   HostGrid hg;
   hg.nx = I.width; hg.ny = I.height; hg.resolution = I.resolution; hg.max_x = max_x; hg.max_y = max_y;
   hg.d_stack = d_l1; hg.depth = 1; hg.bytes = n;
+  st->grids.push_back(hg);
+  if (grid_id) *grid_id = (int)st->grids.size() - 1;
+  return GLOC_OK;
+}
+
+int gloc_csm_add_grid_from_bev_aligned(gloc_csm_store* st, gloc_bev_projector* bev, int* grid_id) {
+  if (!st || !bev) return fail(GLOC_ERR_INVALID, "gloc_csm_add_grid_from_bev_aligned: null argument");
+  gloc_bev_info I;
+  const uint8_t* d_img = gloc_bev_device_image(bev, &I);
+  if (!d_img || I.width < 1 || I.height < 1)
+    return fail(GLOC_ERR_NOT_BUILT, "gloc_csm_add_grid_from_bev_aligned: the projector holds no image");
+  if (gloc_bev_device_of(bev) != st->device)
+    return fail(GLOC_ERR_INVALID, "gloc_csm_add_grid_from_bev_aligned: projector and store live on different devices");
+  DeviceGuard g(st->device);
+  // cell x runs along world -y and cell y along world -x (2d/map_limits.h:69-76): the grid has
+  // height x width cells and max() half a cell beyond the last voxel centre
+  const int nx = I.height, ny = I.width;
+  const double max_x = (I.min_ix + I.width - 1 + 0.5) * I.resolution;
+  const double max_y = (I.min_iy + I.height - 1 + 0.5) * I.resolution;
+  uint8_t* d_l1 = nullptr;
+  int rc = add_grid_common(st, nx, ny, I.resolution, max_x, max_y, &d_l1);
+  if (rc != GLOC_OK) return rc;
+  cudaError_t e = gloc_bev_launch_level1_aligned(d_img, I.width, I.height, d_l1, st->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);
+  if (e != cudaSuccess) {
+    cudaFree(d_l1);
+    return fail(GLOC_ERR_CUDA, std::string("gloc_csm_add_grid_from_bev_aligned: ") + cudaGetErrorString(e));
+  }
+  st->stats.kernel_launches++;
+  HostGrid hg;
+  hg.nx = nx; hg.ny = ny; hg.resolution = I.resolution; hg.max_x = max_x; hg.max_y = max_y;
+  hg.d_stack = d_l1; hg.depth = 1; hg.bytes = (size_t)nx * ny;
   st->grids.push_back(hg);
   if (grid_id) *grid_id = (int)st->grids.size() - 1;
   return GLOC_OK;

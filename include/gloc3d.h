@@ -255,6 +255,14 @@ uint64_t gloc_bev_kernel_launches(const gloc_bev_projector* bev);
  * num_x_cells = width, num_y_cells = height, max = (max_ix, max_iy) * resolution,
  * occupied -> cost 0.1 (level-1 value 255), free -> cost 0.9 (0); device to device. */
 int gloc_csm_add_grid_from_bev(gloc_csm_store* store, gloc_bev_projector* bev, int* grid_id);
+/* Same occupancy, laid out so that MapLimits::GetCellIndex (2d/map_limits.h:69-76) of a world
+ * point lands on the pixel of its own voxel: num_x_cells = height, num_y_cells = width, cell
+ * (cx, cy) = pixel (ix, iy) = (width-1-cy, height-1-cx), max = (max_ix + 0.5, max_iy + 0.5) *
+ * resolution.  ProjectToGrid stores pixel (ix, iy) at cell (ix, iy) while the matcher looks
+ * points up through GetCellIndex, which swaps and flips the axes -- a lookup then hits the
+ * mirror image and no rigid transform can align two such grids.  This entry
+ * point is the consistent construction the driver uses for the north-star verifier. */
+int gloc_csm_add_grid_from_bev_aligned(gloc_csm_store* store, gloc_bev_projector* bev, int* grid_id);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,465 @@
+// global_localization -- the reference's evaluation driver on top of libgloc3d.so.
+//
+//   global_localization VALSET GT_POSE MODEL [any 4th argument]
+//
+// Same command line, same input formats, same log lines and the same two result files as
+// /root/reference/registration/global_localization.cpp (main :577-600): VALSET and GT_POSE
+// exactly as dataset/kitti_i2i.py:76-122 writes them, scans as raw float32 x y z i.  The hot
+// path runs on the GPU through the C ABI (include/gloc3d.h):
+//   BEV projection         gloc_bev_*                (get_projected_grid, loop_detector.cpp:122-135)
+//   retrieval, k = 20      gloc_knn_*                (InvKeyTree::query, loop_detector.cpp:34-45)
+//   verification           gloc_csm_match_batch      (the slot of loop_detector_.match, :519-524)
+// What is NOT part of the query path stays outside:
+//   * MODEL: the reference loads a TorchScript CNN here (loop_detector.cpp:157-163).  This
+//     build takes the descriptors from a table instead: MODEL is a raw float32 file with
+//     (db_num + q_num) x 512 values in valset order (what the CNN forward would produce).
+//   * the 4th argument (ground alignment, PCL) is accepted and ignored with a log line.
+// Own code: a small logger that prints glog-style lines, a reader for each format.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../include/gloc3d.h"
+
+namespace {
+
+// ---- glog-style lines: "I1018 12:34:56.789012 global_localization.cpp:123] message"
+struct LogLine {
+  std::ostringstream os;
+  LogLine(char sev, int line) {
+    using namespace std::chrono;
+    const auto now = system_clock::now();
+    const std::time_t t = system_clock::to_time_t(now);
+    const long us = (long)(duration_cast<microseconds>(now.time_since_epoch()).count() % 1000000);
+    std::tm tm{};
+    localtime_r(&t, &tm);
+    char buf[64];
+    std::snprintf(buf, sizeof buf, "%c%02d%02d %02d:%02d:%02d.%06ld global_localization.cpp:%d] ", sev,
+                  tm.tm_mon + 1, tm.tm_mday, tm.tm_hour, tm.tm_min, tm.tm_sec, us, line);
+    os << buf;
+  }
+  ~LogLine() { std::cerr << os.str() << std::endl; }
+};
+#define LOG_INFO LogLine('I', __LINE__).os
+#define LOG_ERROR LogLine('E', __LINE__).os
+
+struct TicToc {  // registration/tic_toc.h: wall-clock milliseconds
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  double toc() const {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+
+void check(int rc, const char* what) {
+  if (rc != GLOC_OK) {
+    LOG_ERROR << what << ": " << gloc_last_error();
+    std::exit(2);
+  }
+}
+
+std::vector<std::string> split(const std::string& s, const std::string& sep) {  // global_localization.cpp:40-62
+  std::vector<std::string> res;
+  if (s.empty()) return res;
+  size_t start = 0;
+  for (;;) {
+    const size_t at = s.find(sep, start);
+    if (at == std::string::npos) {
+      if (start < s.size()) res.push_back(s.substr(start));
+      break;
+    }
+    if (at > start) res.push_back(s.substr(start, at - start));
+    start = at + sep.size();
+  }
+  return res;
+}
+
+struct Mat4 {
+  float m[4][4];
+  static Mat4 identity() {
+    Mat4 r{};
+    for (int i = 0; i < 4; ++i) r.m[i][i] = 1.f;
+    return r;
+  }
+};
+Mat4 mul(const Mat4& a, const Mat4& b) {
+  Mat4 r{};
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      float s = 0.f;
+      for (int k = 0; k < 4; ++k) s += a.m[i][k] * b.m[k][j];
+      r.m[i][j] = s;
+    }
+  return r;
+}
+Mat4 rigid_inverse(const Mat4& a) {  // [R t; 0 1]^-1 = [R^T -R^T t; 0 1]
+  Mat4 r = Mat4::identity();
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
+  for (int i = 0; i < 3; ++i)
+    r.m[i][3] = -(r.m[i][0] * a.m[0][3] + r.m[i][1] * a.m[1][3] + r.m[i][2] * a.m[2][3]);
+  return r;
+}
+// Eigen::Quaternionf(w, x, y, z).toRotationMatrix()
+Mat4 pose_from(float qw, float qx, float qy, float qz, float x, float y, float z) {
+  Mat4 p = Mat4::identity();
+  const float tx = 2.f * qx, ty = 2.f * qy, tz = 2.f * qz;
+  const float twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  const float txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  const float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  p.m[0][0] = 1.f - (tyy + tzz); p.m[0][1] = txy - twz;         p.m[0][2] = txz + twy;
+  p.m[1][0] = txy + twz;         p.m[1][1] = 1.f - (txx + tzz); p.m[1][2] = tyz - twx;
+  p.m[2][0] = txz - twy;         p.m[2][1] = tyz + twx;         p.m[2][2] = 1.f - (txx + tyy);
+  p.m[0][3] = x; p.m[1][3] = y; p.m[2][3] = z;
+  return p;
+}
+
+// ReadValset, global_localization.cpp:64-122
+bool ReadValset(const std::string& filename, std::vector<std::string>& db_files,
+                std::vector<std::string>& q_files, std::vector<std::vector<size_t>>& pos_idx) {
+  std::ifstream ifs(filename);
+  db_files.clear();
+  q_files.clear();
+  pos_idx.clear();
+  if (!ifs.is_open()) {
+    std::cout << "failed to open file " << filename << "\n";
+    return false;
+  }
+  std::string line;
+  std::getline(ifs, line);
+  std::vector<std::string> sub = split(line, " ");
+  if (sub.size() < 2) return false;
+  const int db_num = std::atoi(sub[0].c_str()), q_num = std::atoi(sub[1].c_str());
+  for (int i = 0; i < db_num; ++i) {
+    std::getline(ifs, line);
+    db_files.push_back(line);
+  }
+  for (int i = 0; i < q_num; ++i) {
+    std::getline(ifs, line);
+    q_files.push_back(line);
+  }
+  for (int i = 0; i < q_num; ++i) {
+    if (!std::getline(ifs, line)) break;
+    if (line.empty()) break;
+    sub = split(line, ":");
+    if (sub.size() == 1) {
+      pos_idx.push_back({});
+      continue;
+    }
+    const std::string pos_str = sub[1];
+    if (pos_str.empty()) {
+      pos_idx.push_back({});
+      continue;
+    }
+    sub = split(pos_str, " ");
+    std::vector<size_t> tmp;
+    for (const auto& t : sub) tmp.push_back((size_t)std::atoi(t.c_str()));
+    pos_idx.push_back(tmp);
+  }
+  LOG_INFO << "db_num and db_files: " << db_num << ", " << db_files.size();
+  LOG_INFO << "q_num and q_files: " << q_num << ", " << q_files.size();
+  LOG_INFO << "q_num and q_pos_index: " << q_num << ", " << pos_idx.size();
+  return true;
+}
+
+// ReadValsetPose, global_localization.cpp:124-156: "qx qy qz qw x y z" per line
+bool ReadValsetPose(const std::string& filename, std::vector<Mat4>& poses) {
+  std::ifstream ifs(filename);
+  poses.clear();
+  if (!ifs.is_open()) {
+    LOG_ERROR << "failed to open file " << filename;
+    return false;
+  }
+  std::string line;
+  while (std::getline(ifs, line)) {
+    const std::vector<std::string> sub = split(line, " ");
+    if (sub.size() != 7) {
+      LOG_ERROR << "Check failed: substrs.size()==7";
+      std::exit(1);
+    }
+    poses.push_back(pose_from((float)std::atof(sub[3].c_str()), (float)std::atof(sub[0].c_str()),
+                              (float)std::atof(sub[1].c_str()), (float)std::atof(sub[2].c_str()),
+                              (float)std::atof(sub[4].c_str()), (float)std::atof(sub[5].c_str()),
+                              (float)std::atof(sub[6].c_str())));
+  }
+  LOG_INFO << "Read poses with size: " << poses.size();
+  return true;
+}
+
+// read_lidar_data, global_localization.cpp:160-182: raw float32 x y z i
+std::vector<float> read_lidar_data(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  std::vector<float> buf;
+  if (!f) return buf;
+  f.seekg(0, std::ios::end);
+  const size_t n = (size_t)f.tellg() / sizeof(float);
+  f.seekg(0, std::ios::beg);
+  buf.resize(n / 4 * 4);
+  f.read(reinterpret_cast<char*>(buf.data()), (std::streamsize)(buf.size() * sizeof(float)));
+  return buf;
+}
+
+void caculate_mean_std(const std::vector<double>& v, double& mean, double& stddev) {
+  mean = 0.;
+  stddev = 0.;
+  if (v.empty()) return;
+  for (double x : v) mean += x;
+  mean /= (double)v.size();
+  for (double x : v) stddev += (x - mean) * (x - mean);
+  stddev = std::sqrt(stddev / (double)v.size());
+}
+
+class GlocEvaluator {
+ public:
+  bool align_ground_ = false;
+
+  bool load_valset(const std::string& q_db_file, const std::string& pose_file) {
+    return ReadValset(q_db_file, db_files_, q_files_, gt_q_pos_idx_) && ReadValsetPose(pose_file, poses_db_q_);
+  }
+
+  // construct_db, global_localization.cpp:419-449
+  void construct_db(const std::string& model_file_path) {
+    load_descriptors(model_file_path);
+    LOG_INFO << "LOAD descriptor table (stand-in for the libtorch model) from: " << model_file_path;
+    check(gloc_bev_create(&bev_, device_, 0.2f, 100.f), "gloc_bev_create");
+    check(gloc_csm_create(&store_, device_), "gloc_csm_create");
+    check(gloc_knn_create(&index_, kDim, device_), "gloc_knn_create");
+    if (align_ground_) LOG_INFO << "ground alignment is outside the query path (SURVEY.md 2): ignored";
+    int i = 0;
+    double t_align = 0., t_detect = 0.;
+    for (const auto& filename : db_files_) {
+      ++i;
+      const std::vector<float> kf = read_lidar_data(filename);
+      TicToc tb;
+      gloc_bev_info info;
+      check(gloc_bev_project(bev_, kf.data(), kf.size() / 4, 4, &info), "gloc_bev_project");
+      int gid = -1;
+      check(gloc_csm_add_grid_from_bev_aligned(store_, bev_, &gid), "gloc_csm_add_grid_from_bev_aligned");
+      db_grid_ids_.push_back(gid);
+      if (i > 2) t_detect += tb.toc();
+    }
+    check(gloc_knn_set_db(index_, feats_.data(), db_files_.size()), "gloc_knn_set_db");
+    LOG_INFO << "time cost for align to ground: " << t_align / double(i) << "ms.";
+    LOG_INFO << "time cost for feature extraction: " << t_detect / double(i - 2) << "ms.";
+  }
+
+  void locate_all_query() {
+    if (queried_idx_.empty()) detect_all_query();
+    located_db_.clear();
+    located_pose_.clear();
+    global_registraion_all();
+  }
+
+  // detect_all_query, global_localization.cpp:482-509 + RpyPCLoopDetector::detect, loop_detector.cpp:22-46
+  void detect_all_query() {
+    double t_sum = 0.;
+    const size_t n_db = db_files_.size();
+    for (size_t qi = 0; qi < q_files_.size(); ++qi) {
+      const std::vector<float> q_pc = read_lidar_data(q_files_[qi]);
+      TicToc t;
+      std::vector<size_t> loop_indices;
+      gloc_bev_info info;
+      check(gloc_bev_project(bev_, q_pc.data(), q_pc.size() / 4, 4, &info), "gloc_bev_project");
+      size_t n_occ = 0;
+      check(gloc_bev_get_occupied_points(bev_, nullptr, 0, &n_occ), "gloc_bev_get_occupied_points");
+      std::vector<float> pts(n_occ * 3);
+      if (n_occ) check(gloc_bev_get_occupied_points(bev_, pts.data(), n_occ, &n_occ), "gloc_bev_get_occupied_points");
+      if (n_db <= kNumExcludeRecent + kTopK) {  // loop_detector.cpp:27-30
+        std::cout << "Not enough keyframes in database." << std::endl;
+      } else {
+        std::vector<uint64_t> idx(kTopK);
+        std::vector<float> d2(kTopK);
+        check(gloc_knn_query(index_, feats_.data() + (n_db + qi) * kDim, 1, kTopK, idx.data(), d2.data()),
+              "gloc_knn_query");
+        loop_indices.assign(idx.begin(), idx.end());
+      }
+      t_sum += t.toc();
+      q_scans_.push_back(pts);
+      queried_idx_.push_back(loop_indices);
+    }
+    LOG_INFO << "Each query cost: " << t_sum / q_files_.size() << "ms.";
+  }
+
+  // recognition_recalls, global_localization.cpp:221-268
+  void recognition_recalls() {
+    const std::vector<int> k_values = {1, 5, 10, 20};
+    std::vector<float> k_recalls = {0.f, 0.f, 0.f, 0.f};
+    int valid_query_num = 0;
+    for (size_t i = 0; i < q_files_.size(); ++i) {
+      if (i >= gt_q_pos_idx_.size() || gt_q_pos_idx_[i].empty()) continue;
+      valid_query_num++;
+      if (queried_idx_[i].empty()) {
+        failed_detect_indices_.push_back((int)i);
+        continue;
+      }
+      const std::vector<size_t>& cand = queried_idx_[i];
+      bool detected = false;
+      for (size_t k = 0; k < k_values.size(); ++k) {
+        for (int j = 0; j < k_values[k] && j < (int)cand.size(); ++j) {
+          if (std::find(gt_q_pos_idx_[i].begin(), gt_q_pos_idx_[i].end(), cand[j]) != gt_q_pos_idx_[i].end()) {
+            k_recalls[k] += 1;
+            detected = true;
+            break;
+          }
+        }
+      }
+      if (!detected) failed_detect_indices_.push_back((int)i);
+    }
+    if (valid_query_num > 0) {
+      for (size_t i = 0; i < k_recalls.size(); ++i) {
+        k_recalls[i] /= valid_query_num;
+        LOG_INFO << "Recall @ " << k_values[i] << ": " << k_recalls[i];
+      }
+    }
+    write_indices("failed_detect_indices.txt", failed_detect_indices_);
+  }
+
+  // registration_recalls, global_localization.cpp:270-335
+  void registration_recalls() {
+    const int all_tests = (int)located_db_.size();
+    int succeed_tests = 0;
+    std::vector<double> rot_err, pos_err;
+    const float rad2deg = 180. / M_PI;
+    const size_t num_db = db_files_.size();
+    for (size_t i = 0; i < located_db_.size(); ++i) {
+      const size_t db_idx = located_db_[i];
+      if (db_idx >= db_files_.size()) {
+        failed_registration_indices_.push_back((int)i);
+        continue;
+      }
+      const Mat4 q2db = mul(rigid_inverse(poses_db_q_[db_idx]), poses_db_q_[i + num_db]);
+      const Mat4& loc = located_pose_[i];
+      float trace = 0.f;  // trace(gt_rot^T * R_restored)
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) trace += q2db.m[b][a] * loc.m[b][a];
+      float offset_trace = 0.5f * (trace - 1.f);
+      offset_trace = offset_trace < -0.999999f ? -0.999999f : offset_trace;
+      offset_trace = offset_trace > 0.999999f ? 0.999999f : offset_trace;
+      float err_rot = std::fabs(std::acos(offset_trace));
+      const float ex = q2db.m[0][3] - loc.m[0][3], ey = q2db.m[1][3] - loc.m[1][3], ez = q2db.m[2][3] - loc.m[2][3];
+      const float err_pos = std::sqrt(ex * ex + ey * ey + ez * ez);
+      err_rot = err_rot * rad2deg;
+      if (std::fabs(err_rot - 180.f) < 5.f) err_rot = std::fabs(err_rot - 180.f);
+      if (err_pos < 1.0f && err_rot < 5.f) {
+        succeed_tests++;
+        rot_err.push_back(err_rot);
+        pos_err.push_back(err_pos);
+      }
+    }
+    double mean_rot, std_rot, mean_pos, std_pos;
+    caculate_mean_std(pos_err, mean_pos, std_pos);
+    caculate_mean_std(rot_err, mean_rot, std_rot);
+    LOG_INFO << succeed_tests << ", " << all_tests;
+    LOG_INFO << "Success rate: " << static_cast<float>(succeed_tests) / static_cast<float>(all_tests);
+    LOG_INFO << "Rot error: " << mean_rot << ", " << std_rot;
+    LOG_INFO << "Pos error: " << mean_pos << ", " << std_pos;
+    write_indices("failed_registration_indices.txt", failed_registration_indices_);
+    LOG_INFO << "Average 2D match costs " << time_sum_match_ / times_call_match_ << "ms.";
+  }
+
+  ~GlocEvaluator() {
+    gloc_knn_destroy(index_);
+    gloc_csm_destroy(store_);
+    gloc_bev_destroy(bev_);
+  }
+
+ private:
+  static constexpr size_t kDim = 512, kTopK = 20, kNumExcludeRecent = 30;  // loop_detector.h:97-100
+
+  void load_descriptors(const std::string& path) {
+    const size_t rows = db_files_.size() + q_files_.size();
+    std::ifstream f(path, std::ios::binary);
+    feats_.assign(rows * kDim, 0.f);
+    if (!f || !f.read(reinterpret_cast<char*>(feats_.data()), (std::streamsize)(feats_.size() * sizeof(float)))) {
+      LOG_ERROR << "MODEL must hold (db_num + q_num) x 512 float32 descriptors in valset order: " << path;
+      std::exit(1);
+    }
+  }
+
+  void write_indices(const std::string& name, const std::vector<int>& v) {
+    std::ofstream ofs(name, std::ios::out);
+    if (!ofs) LOG_ERROR << "Failed open " << name;
+    for (int idx : v) ofs << idx << " ";
+    ofs << "\n";
+  }
+
+  // global_registraion_all / global_registraion, global_localization.cpp:342-356, :511-574: the
+  // candidates of a query are verified in retrieval order and the first match wins -- here
+  // all of them go to the GPU in one batch and the first success in that order is taken.
+  void global_registraion_all() {
+    const char* ms = std::getenv("GLOC_MATCH_MIN_SCORE");
+    const float min_score = ms ? (float)std::atof(ms) : 0.35f;
+    located_db_.assign(q_files_.size(), db_files_.size() + 1);
+    located_pose_.assign(q_files_.size(), Mat4::identity());
+    for (size_t qi = 0; qi < q_files_.size(); ++qi) {
+      const std::vector<size_t>& cand = queried_idx_[qi];
+      const int n = (int)std::min(kTopK, cand.size());
+      if (n == 0 || q_scans_[qi].empty()) continue;
+      std::vector<int> gids(n), sids(n, 0);
+      std::vector<double> init(3 * (size_t)n, 0.);
+      for (int i = 0; i < n; ++i) gids[i] = db_grid_ids_[cand[i]];
+      const int64_t offs[2] = {0, (int64_t)(q_scans_[qi].size() / 3)};
+      std::vector<gloc_csm_result> res(n);
+      TicToc t;
+      check(gloc_csm_match_batch(store_, q_scans_[qi].data(), offs, 1, gids.data(), sids.data(), init.data(), n,
+                                 /*n_lin*/ 100, /*n_ang*/ 180, 2. * M_PI / 360., /*depth*/ 5, min_score, res.data()),
+            "gloc_csm_match_batch");
+      time_sum_match_ += t.toc();
+      times_call_match_ += n;
+      for (int i = 0; i < n; ++i) {
+        if (!res[i].found) continue;
+        // RollPitchYaw(0, 0, yaw) and (dx, dy, 0): global_localization.cpp:556-569
+        const float yaw = (float)res[i].pose_yaw;
+        Mat4 p = Mat4::identity();
+        p.m[0][0] = std::cos(yaw); p.m[0][1] = -std::sin(yaw);
+        p.m[1][0] = std::sin(yaw); p.m[1][1] = std::cos(yaw);
+        p.m[0][3] = (float)res[i].pose_x;
+        p.m[1][3] = (float)res[i].pose_y;
+        located_db_[qi] = cand[i];
+        located_pose_[qi] = p;
+        break;
+      }
+    }
+  }
+
+  int device_ = 0;
+  std::vector<std::string> db_files_, q_files_;
+  std::vector<std::vector<size_t>> gt_q_pos_idx_;
+  std::vector<Mat4> poses_db_q_;
+  std::vector<float> feats_;                    // (db_num + q_num) x 512
+  std::vector<int> db_grid_ids_;
+  std::vector<std::vector<float>> q_scans_;     // occupied-pixel points of every query BEV
+  std::vector<std::vector<size_t>> queried_idx_;
+  std::vector<size_t> located_db_;
+  std::vector<Mat4> located_pose_;
+  std::vector<int> failed_detect_indices_, failed_registration_indices_;
+  double time_sum_match_ = 0., times_call_match_ = 0.;
+  gloc_bev_projector* bev_ = nullptr;
+  gloc_csm_store* store_ = nullptr;
+  gloc_knn_index* index_ = nullptr;
+};
+
+}  // namespace
+
+int main(int argc, char* argv[]) {
+  if (argc < 4) {
+    std::cerr << "usage: global_localization VALSET GT_POSE MODEL [align_ground]\n";
+    return 1;
+  }
+  GlocEvaluator gloc;
+  gloc.align_ground_ = argc == 5;
+  if (!gloc.load_valset(argv[1], argv[2])) return 1;
+  gloc.construct_db(argv[3]);
+  gloc.locate_all_query();
+  gloc.recognition_recalls();
+  gloc.registration_recalls();
+  return 0;
+}
