@@ -76,6 +76,8 @@ struct gloc_knn_index {
   uint64_t offset = 0;
   int mode = GLOC_KNN_AUTO;
   cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+  cudaStream_t copy_stream = nullptr;   // host<->device copies of large batches overlap the search
+  cudaEvent_t ev_in[8] = {}, ev_out[8] = {};
   DevBuf partial;                 // exact-scan per-range lists
   DevBuf flag;                    // streaming scan: merge-overflow flag
   DevBuf stage_q, stage_idx, stage_d2;
@@ -228,6 +230,11 @@ int gloc_knn_create(gloc_knn_index** out, size_t dim, int device) {
   ix->device = device;
   ix->dim = dim;
   e = cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) {
+    e = cudaEventCreateWithFlags(&ix->ev_in[i], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ix->ev_out[i], cudaEventDisableTiming);
+  }
   if (e != cudaSuccess) {
     delete ix;
     return fail(GLOC_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
@@ -242,6 +249,14 @@ void gloc_knn_destroy(gloc_knn_index* ix) {
   if (ix->stream) {
     cudaStreamSynchronize(ix->stream);
     cudaStreamDestroy(ix->stream);
+  }
+  if (ix->copy_stream) {
+    cudaStreamSynchronize(ix->copy_stream);
+    cudaStreamDestroy(ix->copy_stream);
+  }
+  for (int i = 0; i < 8; ++i) {
+    if (ix->ev_in[i]) cudaEventDestroy(ix->ev_in[i]);
+    if (ix->ev_out[i]) cudaEventDestroy(ix->ev_out[i]);
   }
   if (ix->d_db) cudaFree(ix->d_db);
   ix->partial.release();
@@ -397,16 +412,41 @@ int gloc_knn_query(gloc_knn_index* ix, const float* q, size_t nq, size_t k, uint
   GLOC_CUDA_TRY(ix->stage_q.reserve(nq * ix->dim * sizeof(float)));
   GLOC_CUDA_TRY(ix->stage_idx.reserve(nq * k * sizeof(uint64_t)));
   GLOC_CUDA_TRY(ix->stage_d2.reserve(nq * k * sizeof(float)));
-  GLOC_CUDA_TRY(cudaMemcpyAsync(ix->stage_q.p, q, nq * ix->dim * sizeof(float),
-                                cudaMemcpyHostToDevice, ix->stream));
-  int rc = gloc_knn_query_device(ix, (const float*)ix->stage_q.p, nq, k,
-                                 (uint64_t*)ix->stage_idx.p, (float*)ix->stage_d2.p, ix->stream);
-  if (rc != GLOC_OK) return rc;
-  GLOC_CUDA_TRY(cudaMemcpyAsync(out_idx, ix->stage_idx.p, nq * k * sizeof(uint64_t),
-                                cudaMemcpyDeviceToHost, ix->stream));
-  GLOC_CUDA_TRY(cudaMemcpyAsync(out_d2, ix->stage_d2.p, nq * k * sizeof(float),
-                                cudaMemcpyDeviceToHost, ix->stream));
-  GLOC_CUDA_TRY(cudaStreamSynchronize(ix->stream));
+  // Large batches are cut into up to 8 chunks: the upload of chunk i+1 and the download of
+  // chunk i-1 (copy stream) overlap the search of chunk i (compute stream).  The results do
+  // not depend on the chunking.
+  const size_t kMinChunk = 4096;
+  size_t n_chunks = std::min<size_t>(8, nq / kMinChunk);
+  if (n_chunks < 2) n_chunks = 1;
+  const size_t per = ((nq + n_chunks - 1) / n_chunks + 127) / 128 * 128;
+  const float* dq = (const float*)ix->stage_q.p;
+  uint64_t* di = (uint64_t*)ix->stage_idx.p;
+  float* dd = (float*)ix->stage_d2.p;
+  cudaStream_t cs = n_chunks > 1 ? ix->copy_stream : ix->stream;
+  size_t c = 0;
+  for (size_t q0 = 0; q0 < nq; q0 += per, ++c) {
+    const size_t n = std::min(per, nq - q0);
+    GLOC_CUDA_TRY(cudaMemcpyAsync((void*)(dq + q0 * ix->dim), q + q0 * ix->dim, n * ix->dim * sizeof(float),
+                                  cudaMemcpyHostToDevice, cs));
+    if (n_chunks > 1) GLOC_CUDA_TRY(cudaEventRecord(ix->ev_in[c], cs));
+  }
+  c = 0;
+  for (size_t q0 = 0; q0 < nq; q0 += per, ++c) {
+    const size_t n = std::min(per, nq - q0);
+    if (n_chunks > 1) GLOC_CUDA_TRY(cudaStreamWaitEvent(ix->stream, ix->ev_in[c], 0));
+    int rc = gloc_knn_query_device(ix, dq + q0 * ix->dim, n, k, di + q0 * k, dd + q0 * k, ix->stream);
+    if (rc != GLOC_OK) return rc;
+    if (n_chunks > 1) {
+      GLOC_CUDA_TRY(cudaEventRecord(ix->ev_out[c], ix->stream));
+      GLOC_CUDA_TRY(cudaStreamWaitEvent(cs, ix->ev_out[c], 0));
+    }
+    GLOC_CUDA_TRY(cudaMemcpyAsync(out_idx + q0 * k, di + q0 * k, n * k * sizeof(uint64_t),
+                                  cudaMemcpyDeviceToHost, cs));
+    GLOC_CUDA_TRY(cudaMemcpyAsync(out_d2 + q0 * k, dd + q0 * k, n * k * sizeof(float),
+                                  cudaMemcpyDeviceToHost, cs));
+  }
+  GLOC_CUDA_TRY(cudaStreamSynchronize(cs));
+  if (n_chunks > 1) GLOC_CUDA_TRY(cudaStreamSynchronize(ix->stream));
   return GLOC_OK;
 }
 
