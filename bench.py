@@ -61,7 +61,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (20 ms period; the
+    timed regions here last tens of milliseconds, so the sampler keeps running while a
+    trailing burst of the same steps keeps the GPU under the same load -- see `hold`)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -72,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -179,11 +181,17 @@ def run_retrieval(args, rank, world, local_rank):
             out = sr.query(q_dev, K_NN)
         e1.record()
         barrier()
-        clk = clocks.stop() if rank == 0 else None
-        ms_total = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX)
         dom_ms, dom_n = sr.index.profile()
         sr.index.set_profiling(False)
         st = sr.index.stats()
+        if rank == 0:   # keep the same load up until the sampler has seen it for >= 0.25 s
+            t_hold = time.perf_counter()
+            while time.perf_counter() - t_hold < 0.25:
+                sr.query(q_dev, K_NN)
+                torch.cuda.synchronize(dev)
+        clk = clocks.stop() if rank == 0 else None
+        barrier()
+        ms_total = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX)
         own = (st.kernel_launches - launches0) + (steps if sr.world_size > 1 else 0)   # + K4 merge
         launches = int(reduce_ranks(float(own), dist.ReduceOp.SUM))
         ms_per_step = ms_total / steps
@@ -392,15 +400,21 @@ def run_stream(args, rank, world, local_rank):
         out = step(i)
     e1.record()
     barrier()
+    dom_ms, dom_n = ix.profile()
+    ix.set_profiling(False)
+    st = ix.stats()
+    if rank == 0:   # keep the same load up until the sampler has seen it for >= 0.25 s
+        t_hold = time.perf_counter()
+        while time.perf_counter() - t_hold < 0.25:
+            step(0)
+            torch.cuda.synchronize(dev)
     clk = clocks.stop() if rank == 0 else None
+    barrier()
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    dom_ms, dom_n = ix.profile()
-    ix.set_profiling(False)
-    st = ix.stats()
     launches = (st.kernel_launches - l0) * world
     ms = ms_total / args.steps
 
@@ -574,13 +588,19 @@ def run_verify(args, rank, world, local_rank):
         out = step()
     dt = (time.perf_counter() - t0) * 1e3
     barrier()
+    dom_ms, dom_n = st.profile()
+    st.set_profiling(False)
+    launches = st.stats().kernel_launches - l0
+    if rank == 0:   # keep the same load up until the sampler has seen it for >= 0.25 s
+        t_hold = time.perf_counter()
+        while time.perf_counter() - t_hold < 0.25:
+            step()
     clk = clocks.stop() if rank == 0 else None
+    barrier()
     if world > 1:
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    dom_ms, dom_n = st.profile()
-    launches = st.stats().kernel_launches - l0
     if rank != 0:
         return None
     ms = dt / args.steps
