@@ -122,17 +122,21 @@ RangePlan plan_ranges(long long n_search, int nq, int device) {
 
 int exact_query_device(gloc_knn_index* ix, const float* d_q, size_t nq, size_t k,
                        uint64_t* d_idx, float* d_d2, size_t n_search, cudaStream_t stream) {
-  // one to four queries: a single pass over the rows at HBM speed (knn_stream.cu)
-  if (stream_applicable(ix->dim, nq, k) && (reinterpret_cast<uintptr_t>(d_q) & 15) == 0 &&
-      std::getenv("GLOC_KNN_NO_STREAM") == nullptr) {
+  // up to 16 queries: passes over the rows at HBM speed, four queries per pass (knn_stream.cu);
+  // beyond that the register-tiled exact scan amortises the row reads better
+  if (nq <= 16 && stream_applicable(ix->dim, std::min<size_t>(nq, 4), k) &&
+      (reinterpret_cast<uintptr_t>(d_q) & 15) == 0 && std::getenv("GLOC_KNN_NO_STREAM") == nullptr) {
     const int grid = stream_grid(ix->device, ix->dim);
-    GLOC_CUDA_TRY(ix->partial.reserve(nq * (size_t)grid * k * sizeof(uint64_t)));
+    GLOC_CUDA_TRY(ix->partial.reserve(4 * (size_t)grid * k * sizeof(uint64_t)));
     GLOC_CUDA_TRY(ix->flag.reserve(16));
-    GLOC_CUDA_TRY(cudaMemsetAsync(ix->flag.p, 0, 4, stream));
-    GLOC_CUDA_TRY(launch_knn_stream(ix->d_db, (long long)n_search, (int)ix->dim, d_q, (int)nq, (int)k,
-                                    grid, (uint64_t*)ix->partial.p, ix->offset, d_idx, d_d2,
-                                    (int*)ix->flag.p, &ix->prof, stream));
-    ix->stats.kernel_launches += 3;
+    for (size_t q0 = 0; q0 < nq; q0 += 4) {
+      const int cq = (int)std::min<size_t>(4, nq - q0);
+      GLOC_CUDA_TRY(cudaMemsetAsync(ix->flag.p, 0, 4, stream));
+      GLOC_CUDA_TRY(launch_knn_stream(ix->d_db, (long long)n_search, (int)ix->dim, d_q + q0 * ix->dim, cq,
+                                      (int)k, grid, (uint64_t*)ix->partial.p, ix->offset, d_idx + q0 * k,
+                                      d_d2 + q0 * k, (int*)ix->flag.p, &ix->prof, stream));
+      ix->stats.kernel_launches += 3;
+    }
     return GLOC_OK;
   }
   const size_t kChunk = 1u << 17;

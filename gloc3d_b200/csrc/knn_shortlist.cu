@@ -642,6 +642,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 
 // ------------------------------------------------------------------ K3: select + exact re-rank
 constexpr int kEntMax = 4096;    // group entries per query handled by K3 (more: exact-scan fallback)
+constexpr int kCandMax = 2048;   // scores under the GEMM's final bound, per query
 constexpr int kFinalMax = 256;   // candidates re-ranked exactly, per query
 constexpr int kRerankThreads = 128;
 constexpr int kMaxLists = 64;    // 2 * n_ranges
@@ -671,15 +672,17 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int groups = a.dim / 4, gstride = groups + 1;
   float* G = reinterpret_cast<float*>(sm_raw);                            // [32][dim/4 + 1]
-  const size_t g_bytes = max((size_t)32 * gstride * 4, (size_t)4 * 256 * 4);
-  unsigned* fin_i = reinterpret_cast<unsigned*>(sm_raw + g_bytes);        // [kFinalMax]
+  unsigned* ckey = reinterpret_cast<unsigned*>(sm_raw);                   // [kCandMax] candidate keys  } dead before
+  unsigned* crow = ckey + kCandMax;                                       // [kCandMax] candidate rows  } G is written
+  const size_t g_bytes = max((size_t)32 * gstride * 4, (size_t)kCandMax * 8);
+  unsigned* hist = reinterpret_cast<unsigned*>(sm_raw + g_bytes);         // [4][256]
+  unsigned* fin_i = hist + 4 * 256;                                       // [kFinalMax]
   float* fin_d = reinterpret_cast<float*>(fin_i + kFinalMax);             // [kFinalMax]
   float* qs = fin_d + kFinalMax;                                          // [dim]
-  unsigned* hist = reinterpret_cast<unsigned*>(G);                        // [4][256], dead before G is written
-  __shared__ int n_fin, bad;
+  __shared__ int n_fin, n_cand, bad;
   __shared__ unsigned s_cnt[kMaxLists], s_off[kMaxLists + 1], s_red[3][kRerankThreads / 32], s_sel[2];
   const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) { n_fin = 0; bad = 0; }
+  if (tid == 0) { n_fin = 0; n_cand = 0; bad = 0; }
   // stage 0: everything that only depends on q, issued together
   unsigned my_cnt = 0;
   if (tid < a.n_ranges) my_cnt = a.unit_cnt[(size_t)q * a.n_ranges + tid];
@@ -713,8 +716,9 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
   }
   __syncthreads();
   if (!bad) {
-    // stage 1: one thread per group entry (base row + 8 scores).  The first two entries of a
-    // thread stay in registers; further ones (rare) are re-read from L2 in every pass.
+    // stage 1: one thread per group entry (base row + 8 scores): the scores under the GEMM's
+    // final bound (the only ones that can be in the top-k; typically a small fraction of what
+    // was emitted under the looser running bounds) are compacted into shared memory
     const int total = (int)s_off[kMaxLists];
     const size_t qbase = (size_t)q * a.n_ranges * (size_t)a.cap;
     auto entry_at = [&](int e) -> size_t {
@@ -725,110 +729,108 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
       }
       return qbase + (size_t)lo * a.cap + ((unsigned)e - s_off[lo]);
     };
-    unsigned base[2] = {0u, 0u};
-    unsigned key[2][8];   // order-preserving keys; 0xFFFFFFFF = not a candidate
+    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+    for (int e0 = tid; e0 < total; e0 += 2 * kRerankThreads) {   // two entries in flight per thread
+      unsigned base[2] = {0u, 0u};
+      float4 v[2][2];
+      bool ok[2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int e = tid + u * kRerankThreads;
-      float4 v0 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY), v1 = v0;
-      if (e < total) {
-        const size_t at = entry_at(e);
-        base[u] = a.cand_g[at];
-        v0 = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
-        v1 = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
+      for (int u = 0; u < 2; ++u) {
+        const int e = e0 + u * kRerankThreads;
+        ok[u] = e < total;
+        if (ok[u]) {
+          const size_t at = entry_at(e);
+          base[u] = a.cand_g[at];
+          v[u][0] = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
+          v[u][1] = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
+        }
       }
-      const float sc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j)   // scores above the GEMM's final bound cannot be in the top-k; +inf = masked row
-        key[u][j] = (sc[j] <= tau && sc[j] < INFINITY) ? f2ord(sc[j]) : 0xFFFFFFFFu;
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        const float sc[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w,
+                             v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (sc[j] <= tau && sc[j] < INFINITY) {   // +inf = masked / padded row
+            const int pos = atomicAdd(&n_cand, 1);
+            const unsigned k32 = f2ord(sc[j]);
+            if (pos < kCandMax) { ckey[pos] = k32; crow[pos] = base[u] + j; }
+            kmin = min(kmin, k32);
+            kmax = max(kmax, k32);
+          }
+        }
+      }
     }
-    // f(key, row) over every candidate score of this thread (f2ord never yields 0xFFFFFFFF
-    // for a finite score)
-    auto for_each = [&](auto&& f) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (key[u][j] != 0xFFFFFFFFu) f(key[u][j], base[u] + j);
-      for (int e = tid + 2 * kRerankThreads; e < total; e += kRerankThreads) {
-        const size_t at = entry_at(e);
-        const unsigned b0 = a.cand_g[at];
-        const float4 v0 = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
-        const float4 v1 = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
-        const float sc[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (sc[j] <= tau && sc[j] < INFINITY) f(f2ord(sc[j]), b0 + j);
-      }
-    };
-    // stage 2: A_k = k-th smallest candidate score (radix select on key - min key, 8 bits per
-    // pass starting at the highest bit in which the candidates differ), then keep the
-    // candidates with s <= A_k + 2 eps.
-    unsigned cnt = 0, kmin = 0xFFFFFFFFu, kmax = 0u;
-    for_each([&](unsigned k32, unsigned) { ++cnt; kmin = min(kmin, k32); kmax = max(kmax, k32); });
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
       kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
       kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
     }
-    if (lane == 0) { s_red[0][warp] = cnt; s_red[1][warp] = kmin; s_red[2][warp] = kmax; }
+    if (lane == 0) { s_red[1][warp] = kmin; s_red[2][warp] = kmax; }
     __syncthreads();
-    cnt = 0; kmin = 0xFFFFFFFFu; kmax = 0u;
+    const int cnt = n_cand;
+    if (cnt > kCandMax) {
+      if (tid == 0) bad = 1;
+    } else {
+      kmin = 0xFFFFFFFFu; kmax = 0u;
 #pragma unroll
-    for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) {
-      cnt += s_red[0][w2];
-      kmin = min(kmin, s_red[1][w2]);
-      kmax = max(kmax, s_red[2][w2]);
-    }
-    float tau2 = INFINITY;
-    if (cnt >= (unsigned)a.k) {
-      const unsigned range = kmax - kmin;
-      const int nbits = 32 - __clz(range | 1u);
-      const int passes = (nbits + 7) >> 3;       // 1..4
-      unsigned prefix = 0u, kk = (unsigned)a.k;  // rank (1-based) inside the current prefix class
-      for (int ps = 0; ps < passes; ++ps) {
-        const int shift = 8 * (passes - 1 - ps);
-        unsigned* h = hist + 256 * ps;
-        for_each([&](unsigned k32, unsigned) {
-          const unsigned d = k32 - kmin;
-          if (ps == 0 || (d >> (shift + 8)) == prefix) atomicAdd(&h[(d >> shift) & 255u], 1u);
-        });
-        __syncthreads();
-        if (warp == 0) {   // smallest bin whose cumulative count reaches kk
-          unsigned c[8], sum = 0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { c[i] = h[lane * 8 + i]; sum += c[i]; }
-          unsigned incl = sum;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+      for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) {
+        kmin = min(kmin, s_red[1][w2]);
+        kmax = max(kmax, s_red[2][w2]);
+      }
+      // stage 2: A_k = k-th smallest candidate score (radix select on key - min key, 8 bits per
+      // pass starting at the highest bit in which the candidates differ), then keep the
+      // candidates with s <= A_k + 2 eps.
+      float tau2 = INFINITY;
+      if (cnt >= a.k) {
+        const unsigned range = kmax - kmin;
+        const int nbits = 32 - __clz(range | 1u);
+        const int passes = (nbits + 7) >> 3;       // 1..4
+        unsigned prefix = 0u, kk = (unsigned)a.k;  // rank (1-based) inside the current prefix class
+        for (int ps = 0; ps < passes; ++ps) {
+          const int shift = 8 * (passes - 1 - ps);
+          unsigned* h = hist + 256 * ps;
+          for (int i = tid; i < cnt; i += kRerankThreads) {
+            const unsigned d = ckey[i] - kmin;
+            if (ps == 0 || (d >> (shift + 8)) == prefix) atomicAdd(&h[(d >> shift) & 255u], 1u);
           }
-          const unsigned excl = incl - sum;
-          if (excl < kk && kk <= incl) {   // exactly one lane
-            unsigned run = excl;
-            int bsel = 0;
+          __syncthreads();
+          if (warp == 0) {   // smallest bin whose cumulative count reaches kk
+            unsigned c[8], sum = 0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              if (run < kk && kk <= run + c[i]) { bsel = i; s_sel[1] = kk - run; }
-              run += c[i];
+            for (int i = 0; i < 8; ++i) { c[i] = h[lane * 8 + i]; sum += c[i]; }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += y;
             }
-            s_sel[0] = (unsigned)(lane * 8 + bsel);
+            const unsigned excl = incl - sum;
+            if (excl < kk && kk <= incl) {   // exactly one lane
+              unsigned run = excl;
+              int bsel = 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (run < kk && kk <= run + c[i]) { bsel = i; s_sel[1] = kk - run; }
+                run += c[i];
+              }
+              s_sel[0] = (unsigned)(lane * 8 + bsel);
+            }
           }
+          __syncthreads();
+          prefix = (prefix << 8) | s_sel[0];
+          kk = s_sel[1];
         }
-        __syncthreads();
-        prefix = (prefix << 8) | s_sel[0];
-        kk = s_sel[1];
+        tau2 = ord2f(kmin + prefix) + eps2;
       }
-      tau2 = ord2f(kmin + prefix) + eps2;
+      for (int i = tid; i < cnt; i += kRerankThreads) {
+        if (ord2f(ckey[i]) <= tau2) {
+          const int pos = atomicAdd(&n_fin, 1);
+          if (pos < kFinalMax) fin_i[pos] = crow[i];
+        }
+      }
     }
-    for_each([&](unsigned k32, unsigned row) {
-      if (ord2f(k32) <= tau2) {
-        const int pos = atomicAdd(&n_fin, 1);
-        if (pos < kFinalMax) fin_i[pos] = row;
-      }
-    });
     __syncthreads();
     if (n_fin > kFinalMax && tid == 0) bad = 1;
     __syncthreads();
@@ -1183,7 +1185,7 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     r.overflow_list = (int*)S->ovf_list.p;
     r.overflow_count = (int*)S->ovf_count.p;
     r.rows_reranked = (unsigned long long*)S->rows_ctr.p;
-    const size_t rr_smem = std::max((size_t)4 * 256 * 4, (size_t)32 * (dim / 4 + 1) * 4) +
+    const size_t rr_smem = std::max((size_t)kCandMax * 8, (size_t)32 * (dim / 4 + 1) * 4) + (size_t)4 * 256 * 4 +
                            (size_t)kFinalMax * 8 + (size_t)dim * 4;
     static bool attr2 = false;
     if (!attr2) {

@@ -25,6 +25,7 @@ namespace {
 constexpr int kStreamWarps = 4;      // warps per CTA
 constexpr int kStreamMaxJ = 4;       // float4 groups per lane: dim <= 512
 constexpr int kStreamCandMax = 2048; // keys gathered by the final merge
+constexpr int kStreamHeadCache = 2048;   // list heads cached in shared memory by the final merge
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
   float4 v;
@@ -174,12 +175,16 @@ knn_stream_merge_kernel(const uint64_t* __restrict__ partial, int n_lists, int k
   const uint64_t* P = partial + (size_t)q * n_lists * k;
   if (tid == 0) n_cand = 0;
   // k-th smallest head distance (bit pattern order == value order for d2 >= 0): bisection
+  // over the heads cached in shared memory (0xFFFFFFFF = empty list)
+  __shared__ unsigned s_hd[kStreamHeadCache];
+  const bool cached = n_lists <= kStreamHeadCache;
   unsigned lo = 0xFFFFFFFFu, hi = 0u;
   int heads = 0;
   for (int l = tid; l < n_lists; l += 256) {
     const uint64_t h = P[(size_t)l * k];
+    const unsigned d = h != kEmptyKey ? (unsigned)(h >> 32) : 0xFFFFFFFFu;
+    if (cached) s_hd[l] = d;
     if (h != kEmptyKey) {
-      const unsigned d = (unsigned)(h >> 32);
       lo = min(lo, d);
       hi = max(hi, d);
       ++heads;
@@ -202,9 +207,13 @@ knn_stream_merge_kernel(const uint64_t* __restrict__ partial, int n_lists, int k
     while (lo < hi) {
       const unsigned mid = lo + ((hi - lo) >> 1);
       int c = 0;
-      for (int l = tid; l < n_lists; l += 256) {
-        const uint64_t h = P[(size_t)l * k];
-        c += (h != kEmptyKey && (unsigned)(h >> 32) <= mid) ? 1 : 0;
+      if (cached) {
+        for (int l = tid; l < n_lists; l += 256) c += s_hd[l] <= mid ? 1 : 0;   // mid < 0xFFFFFFFF
+      } else {
+        for (int l = tid; l < n_lists; l += 256) {
+          const uint64_t h = P[(size_t)l * k];
+          c += (h != kEmptyKey && (unsigned)(h >> 32) <= mid) ? 1 : 0;
+        }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);

@@ -259,12 +259,13 @@ def test_million_row_database(oracle):
     assert_knn_equal(idx[sample], d2[sample], ridx, rd2)
 
 
-@pytest.mark.parametrize("nq", [1, 2, 3, 4])
+@pytest.mark.parametrize("nq", [1, 2, 3, 4, 5, 8, 13, 16])
 @pytest.mark.parametrize("n,dim,k", [(50_000, 512, 25), (4541, 512, 20), (3001, 128, 32), (777, 64, 1),
                                      (40, 8, 25)])
-def test_streaming_scan_one_to_four_queries(oracle, nq, n, dim, k):
+def test_streaming_scan_small_batches(oracle, nq, n, dim, k):
     # the reference issues ONE query per call (loop_detector.cpp:42-45): the HBM-bound
-    # streaming kernel answers 1..4 queries; near-duplicate runs + exact duplicates for ties
+    # streaming kernel answers up to 4 queries per pass, up to 16 per call; near-duplicate
+    # runs + exact duplicates for ties
     db = synth.make_descriptors(n, dim, seed=n + dim, dup_run=8)
     db[n // 2] = db[n // 3]                       # one exact duplicate pair
     q = synth.make_queries(db, nq, seed=nq, sigma=0.01)
