@@ -729,101 +729,121 @@ knn_shortlist_rerank_kernel(RerankArgs a) {
       }
       return qbase + (size_t)lo * a.cap + ((unsigned)e - s_off[lo]);
     };
-    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
-    for (int e0 = tid; e0 < total; e0 += 2 * kRerankThreads) {   // two entries in flight per thread
-      unsigned base[2] = {0u, 0u};
-      float4 v[2][2];
-      bool ok[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int e = e0 + u * kRerankThreads;
-        ok[u] = e < total;
-        if (ok[u]) {
-          const size_t at = entry_at(e);
-          base[u] = a.cand_g[at];
-          v[u][0] = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
-          v[u][1] = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
+    // k-th smallest of the cnt keys in ckey (radix select on key - kmin, 8 bits per pass
+    // starting at the highest bit in which the keys differ).  `hist` must be zero on entry.
+    auto radix_kth = [&](int cnt, unsigned kmin, unsigned kmax) -> unsigned {
+      const unsigned range = kmax - kmin;
+      const int nbits = 32 - __clz(range | 1u);
+      const int passes = (nbits + 7) >> 3;       // 1..4
+      unsigned prefix = 0u, kk = (unsigned)a.k;  // rank (1-based) inside the current prefix class
+      for (int ps = 0; ps < passes; ++ps) {
+        const int shift = 8 * (passes - 1 - ps);
+        unsigned* h = hist + 256 * ps;
+        for (int i = tid; i < cnt; i += kRerankThreads) {
+          const unsigned d = ckey[i] - kmin;
+          if (ps == 0 || (d >> (shift + 8)) == prefix) atomicAdd(&h[(d >> shift) & 255u], 1u);
         }
+        __syncthreads();
+        if (warp == 0) {   // smallest bin whose cumulative count reaches kk
+          unsigned c[8], sum = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { c[i] = h[lane * 8 + i]; sum += c[i]; }
+          unsigned incl = sum;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+          }
+          const unsigned excl = incl - sum;
+          if (excl < kk && kk <= incl) {   // exactly one lane
+            unsigned run = excl;
+            int bsel = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (run < kk && kk <= run + c[i]) { bsel = i; s_sel[1] = kk - run; }
+              run += c[i];
+            }
+            s_sel[0] = (unsigned)(lane * 8 + bsel);
+          }
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | s_sel[0];
+        kk = s_sel[1];
       }
+      return kmin + prefix;
+    };
+    float tau_cur = tau;
+    int cnt = 0;
+    unsigned kmin = 0xFFFFFFFFu, kmax = 0u;
+    for (int attempt = 0;; ++attempt) {
+      kmin = 0xFFFFFFFFu;
+      kmax = 0u;
+      for (int e0 = tid; e0 < total; e0 += 2 * kRerankThreads) {   // two entries in flight per thread
+        unsigned base[2] = {0u, 0u};
+        float4 v[2][2];
+        bool ok[2];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (!ok[u]) continue;
-        const float sc[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w,
-                             v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+        for (int u = 0; u < 2; ++u) {
+          const int e = e0 + u * kRerankThreads;
+          ok[u] = e < total;
+          if (ok[u]) {
+            const size_t at = entry_at(e);
+            base[u] = a.cand_g[at];
+            v[u][0] = reinterpret_cast<const float4*>(a.cand_v)[2 * at];
+            v[u][1] = reinterpret_cast<const float4*>(a.cand_v)[2 * at + 1];
+          }
+        }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (sc[j] <= tau && sc[j] < INFINITY) {   // +inf = masked / padded row
-            const int pos = atomicAdd(&n_cand, 1);
-            const unsigned k32 = f2ord(sc[j]);
-            if (pos < kCandMax) { ckey[pos] = k32; crow[pos] = base[u] + j; }
-            kmin = min(kmin, k32);
-            kmax = max(kmax, k32);
+        for (int u = 0; u < 2; ++u) {
+          if (!ok[u]) continue;
+          const float sc[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w,
+                               v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (sc[j] <= tau_cur && sc[j] < INFINITY) {   // +inf = masked / padded row
+              const int pos = atomicAdd(&n_cand, 1);
+              if (pos < kCandMax) {
+                const unsigned k32 = f2ord(sc[j]);
+                ckey[pos] = k32;
+                crow[pos] = base[u] + j;
+                kmin = min(kmin, k32);
+                kmax = max(kmax, k32);
+              }
+            }
           }
         }
       }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
-      kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
-    }
-    if (lane == 0) { s_red[1][warp] = kmin; s_red[2][warp] = kmax; }
-    __syncthreads();
-    const int cnt = n_cand;
-    if (cnt > kCandMax) {
-      if (tid == 0) bad = 1;
-    } else {
+      for (int o = 16; o > 0; o >>= 1) {
+        kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+      }
+      if (lane == 0) { s_red[1][warp] = kmin; s_red[2][warp] = kmax; }
+      __syncthreads();
+      cnt = n_cand;
       kmin = 0xFFFFFFFFu; kmax = 0u;
 #pragma unroll
       for (int w2 = 0; w2 < kRerankThreads / 32; ++w2) {
         kmin = min(kmin, s_red[1][w2]);
         kmax = max(kmax, s_red[2][w2]);
       }
-      // stage 2: A_k = k-th smallest candidate score (radix select on key - min key, 8 bits per
-      // pass starting at the highest bit in which the candidates differ), then keep the
-      // candidates with s <= A_k + 2 eps.
+      if (cnt <= kCandMax || attempt == 1) break;
+      // More candidates than fit (near-duplicate rows pass the bound together): the k-th
+      // smallest of the kCandMax stored ones -- k distinct rows -- bounds A_k from above, so
+      // collect again under that tighter bound.
+      tau_cur = fminf(tau_cur, ord2f(radix_kth(kCandMax, kmin, kmax)) + eps2);
+      __syncthreads();
+      for (int i = tid; i < 4 * 256; i += kRerankThreads) hist[i] = 0u;
+      if (tid == 0) n_cand = 0;
+      __syncthreads();
+    }
+    if (cnt > kCandMax) {
+      if (tid == 0) bad = 1;
+    } else {
+      // stage 2: A_k = k-th smallest candidate score, then keep the candidates with
+      // s <= A_k + 2 eps.
       float tau2 = INFINITY;
-      if (cnt >= a.k) {
-        const unsigned range = kmax - kmin;
-        const int nbits = 32 - __clz(range | 1u);
-        const int passes = (nbits + 7) >> 3;       // 1..4
-        unsigned prefix = 0u, kk = (unsigned)a.k;  // rank (1-based) inside the current prefix class
-        for (int ps = 0; ps < passes; ++ps) {
-          const int shift = 8 * (passes - 1 - ps);
-          unsigned* h = hist + 256 * ps;
-          for (int i = tid; i < cnt; i += kRerankThreads) {
-            const unsigned d = ckey[i] - kmin;
-            if (ps == 0 || (d >> (shift + 8)) == prefix) atomicAdd(&h[(d >> shift) & 255u], 1u);
-          }
-          __syncthreads();
-          if (warp == 0) {   // smallest bin whose cumulative count reaches kk
-            unsigned c[8], sum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { c[i] = h[lane * 8 + i]; sum += c[i]; }
-            unsigned incl = sum;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
-              if (lane >= o) incl += y;
-            }
-            const unsigned excl = incl - sum;
-            if (excl < kk && kk <= incl) {   // exactly one lane
-              unsigned run = excl;
-              int bsel = 0;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (run < kk && kk <= run + c[i]) { bsel = i; s_sel[1] = kk - run; }
-                run += c[i];
-              }
-              s_sel[0] = (unsigned)(lane * 8 + bsel);
-            }
-          }
-          __syncthreads();
-          prefix = (prefix << 8) | s_sel[0];
-          kk = s_sel[1];
-        }
-        tau2 = ord2f(kmin + prefix) + eps2;
-      }
+      if (cnt >= a.k) tau2 = ord2f(radix_kth(cnt, kmin, kmax)) + eps2;
       for (int i = tid; i < cnt; i += kRerankThreads) {
         if (ord2f(ckey[i]) <= tau2) {
           const int pos = atomicAdd(&n_fin, 1);

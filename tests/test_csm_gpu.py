@@ -194,3 +194,23 @@ def test_errors():
     r = st.match_batch([scan], [gid], [0], [(0, 0, 0)], 5, 5, 0.1, 3, 0.3)[0]    # empty map: no match
     assert not r.found
     st.close()
+
+
+def test_kitti_fixture_shape_off_centre_limits(oracle):
+    # the shape of the reference's only real BEV (781 x 504) with limits that do not
+    # centre the grid, full +-100-cell window: different plane widths / heights in x and y,
+    # border points on one side only, and an initial pose away from the origin
+    res = 0.2
+    step = 2 * np.pi / 360
+    grid = synth.make_bev_grid(781, 504, seed=77, n_segments=50, n_blobs=30)
+    mx0, my0 = synth.centered_limits(781, 504, res)
+    mx, my = mx0 + 13.4, my0 - 7.8
+    scan = synth.planted_scan(grid, res, mx, my, yaw=-2.6, dx=9.0, dy=4.2, dropout=0.25, jitter_cells=0.5, seed=9)
+    st = g.CsmStore(0)
+    gid = st.add_grid_u8(grid, res, mx, my)
+    init = (1.3, -0.7, 0.2)
+    r = st.match_batch([scan], [gid], [0], [init], 100, 180, step, 5, 0.3)[0]
+    o = oracle.csm_match(grid, res, mx, my, 5, scan, init, 100, 180, step, 0.3, 0)
+    same(r, o)
+    assert r.found and abs(r.pose_x - 9.0) <= 0.31 and abs(r.pose_y - 4.2) <= 0.31
+    st.close()
