@@ -648,7 +648,10 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     const unsigned long long* rowp = bits + addr + row0;
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
-      const uint32_t w0 = (uint32_t)(rowp[2 * j] >> axc), w1 = (uint32_t)(rowp[2 * j + 1] >> axc);
+      // candidate rows beyond the lattice are never read back: skip their loads (fewer
+      // shared-memory wavefronts: this kernel is LSU-bound)
+      const uint32_t w0 = row0 + 2 * j < prm.max_side ? (uint32_t)(rowp[2 * j] >> axc) : 0u;
+      const uint32_t w1 = row0 + 2 * j + 1 < prm.max_side ? (uint32_t)(rowp[2 * j + 1] >> axc) : 0u;
       v[j] = (__byte_perm(w0, w1, 0x5410) & m2) << shl;
     }
   };
