@@ -108,6 +108,14 @@ class ClockSampler:
 DUP_RUN = 8   # database rows form runs of near-duplicates (consecutive KITTI frames); --dup-run 0: iid rows
 
 
+def hold_steps(ms_per_step: float) -> int:
+    """Extra steps that keep the measured load up for ~0.25 s after the timed region so that
+    the 20 ms clock sampler sees it.  A pure function of a value that is identical on every
+    rank (the max-reduced step time): all ranks run the SAME number of steps, which matters
+    when a step contains a collective."""
+    return int(min(4000, max(1, round(250.0 / max(ms_per_step, 0.05)))))
+
+
 def make_retrieval_inputs(world: int):
     from gloc3d_b200 import synth
 
@@ -184,14 +192,11 @@ def run_retrieval(args, rank, world, local_rank):
         dom_ms, dom_n = sr.index.profile()
         sr.index.set_profiling(False)
         st = sr.index.stats()
-        if rank == 0:   # keep the same load up until the sampler has seen it for >= 0.25 s
-            t_hold = time.perf_counter()
-            while time.perf_counter() - t_hold < 0.25:
-                sr.query(q_dev, K_NN)
-                torch.cuda.synchronize(dev)
-        clk = clocks.stop() if rank == 0 else None
-        barrier()
         ms_total = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX)
+        for _ in range(hold_steps(ms_total / steps)):   # every rank: the same count (see hold_steps)
+            sr.query(q_dev, K_NN)
+        barrier()
+        clk = clocks.stop() if rank == 0 else None
         own = (st.kernel_launches - launches0) + (steps if sr.world_size > 1 else 0)   # + K4 merge
         launches = int(reduce_ranks(float(own), dist.ReduceOp.SUM))
         ms_per_step = ms_total / steps
@@ -403,18 +408,15 @@ def run_stream(args, rank, world, local_rank):
     dom_ms, dom_n = ix.profile()
     ix.set_profiling(False)
     st = ix.stats()
-    if rank == 0:   # keep the same load up until the sampler has seen it for >= 0.25 s
-        t_hold = time.perf_counter()
-        while time.perf_counter() - t_hold < 0.25:
-            step(0)
-            torch.cuda.synchronize(dev)
-    clk = clocks.stop() if rank == 0 else None
-    barrier()
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+    for _ in range(hold_steps(ms_total / args.steps)):   # every rank: the same count (see hold_steps)
+        step(0)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
     launches = (st.kernel_launches - l0) * world
     ms = ms_total / args.steps
 
@@ -591,16 +593,14 @@ def run_verify(args, rank, world, local_rank):
     dom_ms, dom_n = st.profile()
     st.set_profiling(False)
     launches = st.stats().kernel_launches - l0
-    if rank == 0:   # keep the same load up until the sampler has seen it for >= 0.25 s
-        t_hold = time.perf_counter()
-        while time.perf_counter() - t_hold < 0.25:
-            step()
-    clk = clocks.stop() if rank == 0 else None
-    barrier()
     if world > 1:
         t = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
+    for _ in range(hold_steps(dt / args.steps)):   # every rank: the same count (see hold_steps)
+        step()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
     if rank != 0:
         return None
     ms = dt / args.steps

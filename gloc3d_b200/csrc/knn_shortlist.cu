@@ -7,9 +7,10 @@
 // Q x N distance matrix never touches HBM: the approximate score
 //     s(q, x) = ||x||^2 - 2 <fp16(q), fp16(x)>        (D_apx = ||q||^2 + s)
 // lives only in tensor memory; each epilogue thread owns one query row, keeps a running
-// upper bound of the k-th smallest score and appends the few rows below it to that query's
-// candidate list.  K3 re-computes the survivors' distances exactly (bit-exact with
-// L2_Adaptor::evalMetric, nanoflann.hpp:453-487) and selects the top-k by (d2, idx).
+// upper bound of the k-th smallest score and appends the 8-row groups that hold a score
+// below it to that query's candidate list.  K3 selects among the listed scores, re-computes
+// the survivors' distances exactly (bit-exact with L2_Adaptor::evalMetric,
+// nanoflann.hpp:453-487) and picks the top-k by (d2, idx).
 //
 // Operand precision: FP16 (11-bit significand, u = 2^-11; same tensor rate as BF16, 8x
 // tighter) after an exact power-of-two scaling (one scale for the database, one per query
@@ -22,9 +23,10 @@
 //                              + 2^-16 (||q|| + Xmax)^2 + tiny           FP32 norms / FFMA / reference rounding
 // with Xmax = max ||x||, DXmax = max ||dx||.  Every true top-k row therefore has
 // D_apx <= A_k + 2 eps, A_k = k-th smallest D_apx.  A thread's threshold is B + 2 eps with
-// B >= A_k at all times (B = 32nd smallest minimum of disjoint 32-row chunks, k <= 32), hence
-// the candidate list is a superset of the true top-k.  Lists that overflow their capacity are
-// detected and those queries are re-run through the exact scan on the GPU -- never on a CPU.
+// B >= A_k at all times (B = 32nd smallest score among 32 distinct rows already seen,
+// k <= 32), hence the emitted groups contain every true top-k row.  Lists that overflow their
+// capacity are detected and those queries are re-run through the exact scan on the GPU --
+// never on a CPU.
 //
 // sm_100a only: tcgen05.mma (kind::f16, M=128, N=256, K=16, cta_group::1), accumulators in
 // TMEM (2 x 256 columns, double buffered against the epilogue), operands staged by TMA
@@ -441,13 +443,13 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     }
   } else if (warp >= 4) {
     // ===================================================== epilogue: selection out of TMEM
-    // Thread = one query row.  Fast path per 32-column chunk: scores s = ||x||^2 - 2 dot
-    // (32 FFMA) and their minimum (FMNMX tree); a chunk whose minimum is above the threshold
-    // is done.  Otherwise (rare) every score under the threshold is appended to the candidate
-    // list AND inserted into the thread's sorted list of the 32 smallest scores seen, whose
-    // largest entry B = lst[31] bounds the 32nd (hence k-th, k <= 32) smallest score of the
-    // whole database from above; the threshold is B + 2 eps, shared between the units of a
-    // query through global memory.  Every score <= B passes the test, so the list is exact.
+    // Thread = one query row.  Per 32-column chunk: scores s = ||x||^2 - 2 dot (32 FFMA) and
+    // the minima of its four 8-column groups (FMNMX3 tree); a group whose minimum is under the
+    // thread's threshold is appended, whole, to the candidate list (predicated stores, no
+    // divergence).  Units that start without any bound also keep a sorted list of the 32
+    // smallest scores seen, whose largest entry B = lst[31] bounds the 32nd (hence k-th,
+    // k <= 32) smallest score of the whole database from above; the threshold is B + 2 eps,
+    // shared between the units of a query through global memory.
     // Two warpgroups (warps 4-7 and 8-11) share every tile: group wg takes the chunks with
     // c % 2 == wg, so each scheduler has two epilogue warps to hide TMEM/L1 latency.  Both
     // threads of a query row keep their own list / candidate list (list index 2*range + wg)
