@@ -71,3 +71,47 @@ def test_sharded_query_gloo(tmp_path, world):
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert open(tmp_path / f"rank{r}.txt").read() == "ok"
+
+
+def test_bench_steps_are_rank_uniform():
+    """bench.py: a step may contain a collective (row-sharded protocol: all-gather of the local
+    top-k), so no step may run under a rank-dependent condition -- a rank-0-only loop of steps
+    dead-locks every N > 1 run.  Static check of the control flow."""
+    import ast
+    import os
+
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    tree = ast.parse(src)
+
+    def mentions_rank(node):
+        return any(isinstance(n, ast.Name) and n.id == "rank" for n in ast.walk(node))
+
+    def step_calls(node):
+        out = []
+        for n in ast.walk(node):
+            if isinstance(n, ast.Call):
+                f = n.func
+                name = f.attr if isinstance(f, ast.Attribute) else getattr(f, "id", "")
+                if name in ("query", "query_host", "query_device", "query_ptr", "step", "e2e_step", "match_batch",
+                            "all_reduce", "all_gather", "all_gather_into_tensor", "barrier", "measure"):
+                    out.append(name)
+        return out
+
+    bad = []
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.If, ast.While)) and mentions_rank(node.test):
+            for stmt in node.body:
+                bad += step_calls(stmt)
+    assert not bad, f"steps / collectives under a rank-dependent condition: {bad}"
+
+
+def test_hold_steps_is_a_pure_function():
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location(
+        "bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.hold_steps(1.0) == 250 and bench.hold_steps(5.2) == 48 and bench.hold_steps(1e-9) == 4000
+    assert bench.hold_steps(1e9) == 1
