@@ -55,6 +55,17 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count(int device);
 
+// Per-device one-time setup (cudaFuncSetAttribute applies to the current device only): true the
+// first time it is called on the current device for the given mask, false afterwards.
+inline bool first_use_on_current_device(unsigned long long& mask) {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;   // unknown: just do the setup
+  const unsigned long long bit = 1ull << d;
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
+
 // Times one kernel class with CUDA events recorded on the launching stream (the bench's
 // roofline line needs the dominant kernel's average launch duration, measured live).
 struct EventProfiler {

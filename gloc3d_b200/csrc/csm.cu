@@ -1215,12 +1215,11 @@ cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, 
   dim3 grd(prm.S, n_pairs);
   if (phase_major) {
     const size_t smem = (size_t)kPointChunk * (8 + 4 + 8) + (size_t)prm.maxc * 4;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_mask = 0;
+    if (first_use_on_current_device(attr_mask)) {
       cudaError_t e = cudaFuncSetAttribute(csm_coarse_pm_kernel,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       if (e != cudaSuccess) return e;
-      attr = true;
     }
     csm_coarse_pm_kernel<<<grd, kPmThreads, smem, stream>>>(grids, pairs, pts, rot, prm, bounds,
                                                             coarse, top_coarse);
@@ -1254,12 +1253,11 @@ cudaError_t launch_bits_np(dim3 grd, int threads, size_t smem, cudaStream_t stre
                            const CsmGridDev* grids, const CsmPairDev* pairs, const float* pts,
                            const float2* rot, CsmParams prm, CsmBounds* bounds, int* coarse,
                            unsigned long long* top_coarse) {
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (first_use_on_current_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(csm_coarse_bits_kernel<NP>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   csm_coarse_bits_kernel<NP><<<grd, threads, smem, stream>>>(grids, pairs, pts, rot, prm, bounds,
                                                              coarse, top_coarse);
@@ -1333,12 +1331,11 @@ cudaError_t launch_csm_expand(const CsmGridDev* grids, const CsmPairDev* pairs, 
                                                            n_survivors, nodes, n_nodes, node_cap);
     return cudaGetLastError();
   }
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr_mask = 0;
+  if (first_use_on_current_device(attr_mask)) {
     cudaError_t e = cudaFuncSetAttribute(csm_expand_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    attr = true;
   }
   csm_expand_kernel<<<grd, 256, smem, stream>>>(grids, pairs, pts, rot, prm, bounds, coarse, survivors,
                                                 n_survivors, best, nodes, n_nodes, node_cap, counters);

@@ -1172,12 +1172,11 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     g.cand_g = (unsigned*)S->cand_g.p;
     g.cand_v = (float4*)S->cand_v.p;
     g.unit_cnt = (unsigned*)S->unit_cnt.p;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_mask = 0;
+    if (first_use_on_current_device(attr_mask)) {
       GLOC_CUDA_TRY(cudaFuncSetAttribute(knn_shortlist_gemm_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemBytes));
-      attr_set = true;
     }
     const int n_units = n_qtiles * plan.n_ranges;
     const int grid = std::min(n_units, sms);
@@ -1209,11 +1208,10 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     r.rows_reranked = (unsigned long long*)S->rows_ctr.p;
     const size_t rr_smem = std::max((size_t)kCandMax * 8, (size_t)32 * (dim / 4 + 1) * 4) + (size_t)4 * 256 * 4 +
                            (size_t)kFinalMax * 8 + (size_t)dim * 4;
-    static bool attr2 = false;
-    if (!attr2) {
+    static unsigned long long attr2_mask = 0;
+    if (first_use_on_current_device(attr2_mask)) {
       GLOC_CUDA_TRY(cudaFuncSetAttribute(knn_shortlist_rerank_kernel,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      attr2 = true;
     }
     knn_shortlist_rerank_kernel<<<nq, kRerankThreads, rr_smem, st>>>(r);
     GLOC_CUDA_TRY(cudaGetLastError());

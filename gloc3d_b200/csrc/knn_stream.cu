@@ -281,12 +281,11 @@ cudaError_t launch_knn_stream(const float* db, long long n_rows, int dim, const 
   cudaError_t e = cudaSuccess;
 #define GLOC_STREAM(QN)                                                                       \
   do {                                                                                        \
-    static bool attr = false;                                                                 \
-    if (!attr) {                                                                              \
+    static unsigned long long attr_mask = 0;                                                  \
+    if (first_use_on_current_device(attr_mask)) {                                             \
       e = cudaFuncSetAttribute(knn_stream_kernel<QN>,                                         \
                                cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);      \
       if (e != cudaSuccess) return e;                                                         \
-      attr = true;                                                                            \
     }                                                                                         \
     if (prof) prof->begin(stream);                                                            \
     knn_stream_kernel<QN><<<grid, kStreamWarps * 32, smem, stream>>>(db, n_rows, dim, q, nq,  \
