@@ -82,6 +82,29 @@ def test_driver_compiles_and_reads_formats(tmp_path):
     assert r.returncode == 1 and "failed to open file" in r.stdout
 
 
+def test_driver_reads_a_whole_drive_without_gpu(tmp_path):
+    # valset (dataset/kitti_i2i.py:76-104), poses (:108-120), raw scans, descriptor table
+    build()
+    tmp = str(tmp_path)
+    valset, poses, model, files, feats, db_pose, q_pose = make_drive(tmp, n_db=12, n_q=3)
+    n_pos = sum(1 for x, y, _ in q_pose for dx, dy, _ in db_pose if (dx - x) ** 2 + (dy - y) ** 2 < 16.0)
+    n_pts = sum(os.path.getsize(f) // 16 for f in files)
+    env = dict(os.environ, GLOC_DRIVER_PARSE_ONLY="1")
+    r = subprocess.run([BIN, valset, poses, model], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert (f"inputs: 12 db scans, 3 query scans, 15 poses, {n_pos} positives, 15 descriptors, {n_pts} points, "
+            "0 unreadable scans") in r.stderr
+    assert "db_num and db_files: 12, 12" in r.stderr and "Read poses with size: 15" in r.stderr
+    # a truncated descriptor table is an error, as is a missing scan
+    open(model, "wb").write(feats[:5].tobytes())
+    r = subprocess.run([BIN, valset, poses, model], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "MODEL must hold (db_num + q_num) x 512 float32" in r.stderr
+    feats.tofile(model)
+    os.remove(files[2])
+    r = subprocess.run([BIN, valset, poses, model], capture_output=True, text=True, env=env)
+    assert r.returncode == 1 and "1 unreadable scans" in r.stderr
+
+
 @pytest.mark.gpu
 def test_driver_matches_python_pipeline(tmp_path):
     import gloc3d_b200 as g

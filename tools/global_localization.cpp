@@ -225,6 +225,26 @@ class GlocEvaluator {
     return ReadValset(q_db_file, db_files_, q_files_, gt_q_pos_idx_) && ReadValsetPose(pose_file, poses_db_q_);
   }
 
+  // GLOC_DRIVER_PARSE_ONLY=1: read every input the run would read (valset, poses, descriptor
+  // table, every scan file) and report what was found, without touching the GPU.
+  bool check_inputs(const std::string& model_file_path) {
+    load_descriptors(model_file_path);
+    size_t n_pts = 0, missing = 0;
+    std::vector<std::string> all = db_files_;
+    all.insert(all.end(), q_files_.begin(), q_files_.end());
+    for (const auto& f : all) {
+      const std::vector<float> pc = read_lidar_data(f);
+      if (pc.empty()) ++missing;
+      n_pts += pc.size() / 4;
+    }
+    size_t n_pos = 0;
+    for (const auto& v : gt_q_pos_idx_) n_pos += v.size();
+    LOG_INFO << "inputs: " << db_files_.size() << " db scans, " << q_files_.size() << " query scans, "
+             << poses_db_q_.size() << " poses, " << n_pos << " positives, " << feats_.size() / kDim
+             << " descriptors, " << n_pts << " points, " << missing << " unreadable scans";
+    return missing == 0 && poses_db_q_.size() == all.size();
+  }
+
   // construct_db, global_localization.cpp:419-449
   void construct_db(const std::string& model_file_path) {
     load_descriptors(model_file_path);
@@ -457,6 +477,7 @@ int main(int argc, char* argv[]) {
   GlocEvaluator gloc;
   gloc.align_ground_ = argc == 5;
   if (!gloc.load_valset(argv[1], argv[2])) return 1;
+  if (std::getenv("GLOC_DRIVER_PARSE_ONLY")) return gloc.check_inputs(argv[3]) ? 0 : 1;   // no GPU needed
   gloc.construct_db(argv[3]);
   gloc.locate_all_query();
   gloc.recognition_recalls();
