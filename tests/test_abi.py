@@ -60,6 +60,9 @@ def test_compute_fails_loudly_without_gpu():
     assert e.value.code == _lib.GLOC_ERR_CUDA
     with pytest.raises(g.GlocError):
         g.InvKeyTree(512, np.zeros((4, 512), np.float32))
+    with pytest.raises(g.GlocError) as e:
+        g.BevProjector(0)
+    assert e.value.code == _lib.GLOC_ERR_CUDA and "no CPU fallback" in str(e.value)
 
 
 def test_argument_validation_without_gpu():
@@ -70,6 +73,14 @@ def test_argument_validation_without_gpu():
     assert lib.gloc_knn_size(None) == 0
     assert lib.gloc_knn_query(None, None, 1, 1, None, None) == _lib.GLOC_ERR_INVALID
     assert lib.gloc_csm_num_grids(None) == 0
+    assert lib.gloc_bev_create(None, 0, 0.2, 100.0) == _lib.GLOC_ERR_INVALID
+    assert lib.gloc_bev_create(C.byref(h), 0, 0.0, 100.0) == _lib.GLOC_ERR_RANGE       # resolution > 0
+    assert lib.gloc_bev_create(C.byref(h), 0, 0.001, 100.0) == _lib.GLOC_ERR_RANGE     # dense arrays bounded
+    assert lib.gloc_bev_project(None, None, 0, 4, None) == _lib.GLOC_ERR_INVALID
+    assert lib.gloc_bev_get_image(None, None, 0) == _lib.GLOC_ERR_NOT_BUILT
+    assert lib.gloc_bev_kernel_launches(None) == 0
+    assert lib.gloc_csm_add_grid_from_bev(None, None, None) == _lib.GLOC_ERR_INVALID
+    assert lib.gloc_csm_add_grid_from_bev_aligned(None, None, None) == _lib.GLOC_ERR_INVALID
     # host-side helpers of the boundary work without a device
     pts = np.array([[3, 4, 0], [-60, 45, 1]], np.float32)
     nl, na, st = g.search_parameters(3.0, 3.0, pts, 0.2)
