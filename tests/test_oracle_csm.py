@@ -147,3 +147,96 @@ def test_csm_golden_regression(oracle, golden_dir):
         assert np.array_equal(c[0], z["cells_first"]) and np.array_equal(c[-1], z["cells_last"])
         for w in (2, 4, 16):
             assert np.array_equal(oracle.precomp_from_level1(z["grid"], w), z[f"level{w}"])
+
+
+def _numpy_matcher(level1, res, max_x, max_y, pts, init, n_lin, n_ang, step, min_score):
+    """A second, independently written restatement of MatchWithSearchParameters (numpy, brute
+    force) from SURVEY.md Appendix B: Eigen's quaternion rotation in float32, GetCellIndex in
+    double with lround, ShrinkToFit, integer sums, float32 score, ties to the smallest
+    (scan, x, y).  Used to cross-check oracle/csm_oracle.c, whose parity with the reference is
+    otherwise unpinned (registration/2d does not compile here)."""
+    f32 = np.float32
+    ny, nx = level1.shape
+    P = pts.shape[0]
+
+    def rot(p, theta):          # Quaternionf(AngleAxisf(theta, Z)) * p, fast_..._2d.cpp:278-283
+        th = f32(theta)
+        w, z = f32(np.cos(f32(0.5) * th, dtype=f32)), f32(np.sin(f32(0.5) * th, dtype=f32))
+        x, y = p[:, 0].astype(f32), p[:, 1].astype(f32)
+        ux, uy = -(z * y), z * x
+        ux, uy = ux + ux, uy + uy
+        return np.stack([(x + w * ux) + (-(z * uy)), (y + w * uy) + (z * ux)], axis=1).astype(f32)
+
+    def lround(v):              # half away from zero (port.h:41-43)
+        return np.where(v >= 0, np.floor(v + 0.5), np.ceil(v - 0.5)).astype(np.int64)
+
+    p0 = rot(pts, init[2])
+    min_s, max_s = f32(1) - (f32(1) - f32(0.1)), f32(1) - (f32(1) - (f32(1) - f32(0.1)))
+    coef = (max_s - min_s) / f32(255)
+    best = None
+    theta = -n_ang * step       # accumulated in double, correlative_..._2d.cpp:99-107
+    for s in range(2 * n_ang + 1):
+        sc = rot(p0, theta)
+        theta += step
+        wx, wy = sc[:, 0] + f32(init[0]), sc[:, 1] + f32(init[1])
+        cx = lround((max_y - wy.astype(np.float64)) / res - 0.5)      # map_limits.h:69-76
+        cy = lround((max_x - wx.astype(np.float64)) / res - 0.5)
+        lo_x, hi_x = max(-n_lin, min(0, int((-cx).min()))), min(n_lin, max(0, int((nx - 1 - cx).max())))
+        lo_y, hi_y = max(-n_lin, min(0, int((-cy).min()))), min(n_lin, max(0, int((ny - 1 - cy).max())))
+        for xo in range(lo_x, hi_x + 1):
+            X = cx + xo
+            okx = (X >= 0) & (X < nx)
+            for yo in range(lo_y, hi_y + 1):
+                Y = cy + yo
+                ok = okx & (Y >= 0) & (Y < ny)
+                total = int(level1[Y[ok], X[ok]].astype(np.int64).sum())
+                score = f32(min_s + f32(f32(total) / f32(P)) * coef)
+                if best is None or score > best[0]:
+                    best = (score, s, xo, yo)
+    if best is None or not best[0] > f32(min_score):
+        return None
+    return best
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_agrees_with_an_independent_numpy_restatement(oracle, seed):
+    rng = np.random.default_rng(40 + seed)
+    nx, ny = int(rng.integers(40, 70)), int(rng.integers(40, 70))
+    res = 0.2
+    g = synth.make_bev_grid(nx, ny, seed=300 + seed, n_segments=8, n_blobs=5, graded=bool(seed % 2))
+    mx, my = synth.centered_limits(nx, ny, res)
+    mx, my = mx + 0.37, my - 1.13                       # limits that do not centre the grid
+    scan = synth.planted_scan(g, res, mx, my, yaw=rng.uniform(-0.3, 0.3), dx=rng.uniform(-0.8, 0.8),
+                              dy=rng.uniform(-0.8, 0.8), dropout=0.3, jitter_cells=0.5, seed=seed)[:120]
+    init = (0.05, -0.03, 0.02)
+    n_lin, n_ang, step = 6, 4, np.pi / 70
+    ref = _numpy_matcher(g, res, mx, my, scan, init, n_lin, n_ang, step, 0.12)
+    for mode in (0, 1):
+        o = oracle.csm_match(g, res, mx, my, 3, scan, init, n_lin, n_ang, step, 0.12, mode)
+        assert ref is not None and o.found
+        assert np.float32(o.score) == ref[0]
+        if mode == 1:   # the exhaustive scan resolves ties to the smallest (scan, x, y), like the restatement
+            assert (o.scan_index, o.x_offset, o.y_offset) == ref[1:]
+    # the discretisation on its own (GenerateRotatedScans + DiscretizeScans), cell for cell
+    c = oracle.discretize(scan, init, n_ang, step, res, mx, my)
+    assert c.shape == (2 * n_ang + 1, scan.shape[0], 2)
+    f32 = np.float32
+
+    def rot(p, theta):
+        th = f32(theta)
+        w, z = f32(np.cos(f32(0.5) * th, dtype=f32)), f32(np.sin(f32(0.5) * th, dtype=f32))
+        x, y = p[:, 0].astype(f32), p[:, 1].astype(f32)
+        ux, uy = -(z * y), z * x
+        ux, uy = ux + ux, uy + uy
+        return np.stack([(x + w * ux) + (-(z * uy)), (y + w * uy) + (z * ux)], axis=1).astype(f32)
+
+    p0, theta = rot(scan, init[2]), -n_ang * step
+    for s_i in range(2 * n_ang + 1):
+        sc = rot(p0, theta)
+        theta += step
+        wx, wy = sc[:, 0] + f32(init[0]), sc[:, 1] + f32(init[1])
+        vx = (my - wy.astype(np.float64)) / res - 0.5
+        vy = (mx - wx.astype(np.float64)) / res - 0.5
+        cx = np.where(vx >= 0, np.floor(vx + 0.5), np.ceil(vx - 0.5)).astype(np.int64)
+        cy = np.where(vy >= 0, np.floor(vy + 0.5), np.ceil(vy - 0.5)).astype(np.int64)
+        assert np.array_equal(c[s_i, :, 0], cx) and np.array_equal(c[s_i, :, 1], cy)
