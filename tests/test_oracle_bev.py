@@ -77,3 +77,26 @@ def test_reference_scan_matches_survey():
     pts = np.fromfile(f, np.float32).reshape(-1, 4)
     img, geo, mn, nv, no = po.bev_project(pts)
     assert img.shape == (504, 781) and no == 4698
+
+
+def test_oracle_agrees_with_an_independent_numpy_restatement(oracle):
+    # a second restatement of get_projected_grid, written from the sources' description
+    #  with numpy set operations instead of a sort
+    f32 = np.float32
+    for seed in (21, 22):
+        scan = synth.make_lidar_scan(seed=seed, n_walls=25)
+        xyz = scan[:, :3].astype(f32)
+        rng = np.sqrt((xyz[:, 0] * xyz[:, 0] + xyz[:, 1] * xyz[:, 1]) + xyz[:, 2] * xyz[:, 2], dtype=f32)
+        hits = xyz[rng <= f32(100.0)]
+        q = hits / f32(0.2)                                                       # float division
+        vox = np.where(q >= 0, np.floor(q + f32(0.5)), np.ceil(q - f32(0.5))).astype(np.int64)   # lround
+        vox = np.unique(vox, axis=0)                                              # distinct hit voxels
+        cols, counts = np.unique(vox[:, :2], axis=0, return_counts=True)
+        mnx, mny = vox[:, 0].min(), vox[:, 1].min()
+        w, h = vox[:, 0].max() - mnx + 1, vox[:, 1].max() - mny + 1
+        img = np.full((h, w), 255, np.uint8)
+        occ = cols[counts >= 2]                                                   # 2 x 0.55 > 0.9
+        img[occ[:, 1] - mny, occ[:, 0] - mnx] = 0
+        o_img, (ox, oy, res), (mx, my), nv, no = oracle.bev_project(scan)
+        assert np.array_equal(o_img, img) and (mx, my) == (mnx, mny) and nv == len(vox) and no == len(occ)
+        assert ox == mnx * float(f32(0.2)) and oy == mny * float(f32(0.2))
