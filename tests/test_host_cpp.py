@@ -25,6 +25,21 @@ def test_host_mirrors_compile_and_link():
     assert os.path.exists(BIN)
 
 
+def test_host_only_logic_without_gpu():
+    """Guards, SearchParameters, GridToVirtualPointCloud, option defaults: no device needed."""
+    from oracle import pyoracle
+
+    pyoracle.build()
+    exe = os.path.join(ROOT, "tests", "cpp", "_host_cpu_test")
+    cmd = ["g++", "-O2", "-std=c++14", "-ffp-contract=off", os.path.join(ROOT, "tests", "cpp", "host_cpu_test.cpp"),
+           "-o", exe, f"-L{ROOT}/gloc3d_b200", f"-L{ROOT}/oracle", "-lgloc3d", "-lgloc_oracle",
+           f"-Wl,-rpath,{ROOT}/gloc3d_b200", f"-Wl,-rpath,{ROOT}/oracle", "-lpthread"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "PASS host cpu" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.gpu
 def test_host_mirrors_match_oracle():
     build()
