@@ -105,6 +105,36 @@ def test_driver_reads_a_whole_drive_without_gpu(tmp_path):
     assert r.returncode == 1 and "1 unreadable scans" in r.stderr
 
 
+def test_driver_levels_scans_without_gpu(tmp_path):
+    """4th argument = ground alignment (global_localization.cpp:431-440, :495-499): in parse-only
+    mode the driver runs the host half of it -- every scan through the ground estimator."""
+    from test_ground_host import make_scene
+
+    build()
+    tmp = str(tmp_path)
+    heights = (1.73, 1.80, 1.65, 1.73)
+    files = []
+    for i, h in enumerate(heights):
+        pts, _ = make_scene(40 + i, 0.02 * (i - 1), -0.015 * i, h, n_ground=15000, n_wall=6000)
+        f = os.path.join(tmp, f"{i:06d}.bin")
+        pts.tofile(f)
+        files.append(f)
+    with open(os.path.join(tmp, "valset.txt"), "w") as f:
+        f.write("3 1\n" + "".join(p + "\n" for p in files) + "0:0 1\n")
+    with open(os.path.join(tmp, "poses.txt"), "w") as f:
+        f.write("0 0 0 1 0 0 0\n" * 4)
+    np.zeros((4, 512), np.float32).tofile(os.path.join(tmp, "descriptors.bin"))
+    env = dict(os.environ, GLOC_DRIVER_PARSE_ONLY="1")
+    args = [BIN, os.path.join(tmp, "valset.txt"), os.path.join(tmp, "poses.txt"), os.path.join(tmp, "descriptors.bin")]
+    r = subprocess.run(args + ["align"], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    m = re.search(r"ground alignment: (\d+) of (\d+) scans levelled, mean sensor height ([0-9.]+) m", r.stderr)
+    assert m and (int(m.group(1)), int(m.group(2))) == (4, 4), r.stderr
+    assert abs(float(m.group(3)) - np.mean(heights)) < 0.05
+    r = subprocess.run(args, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "ground alignment" not in r.stderr
+
+
 @pytest.mark.gpu
 def test_driver_matches_python_pipeline(tmp_path):
     import gloc3d_b200 as g

@@ -13,7 +13,11 @@
 //   * MODEL: the reference loads a TorchScript CNN here (loop_detector.cpp:157-163).  This
 //     build takes the descriptors from a table instead: MODEL is a raw float32 file with
 //     (db_num + q_num) x 512 values in valset order (what the CNN forward would produce).
-//   * the 4th argument (ground alignment, PCL) is accepted and ignored with a log line.
+//   * the 4th argument switches ground alignment on like the reference's (:419-449, :482-509,
+//     :524-569): every scan is levelled on the host by gloc::GroundEstimator before the BEV
+//     projection and the located pose is composed from the 2-D match and the two ground
+//     transforms (gloc3d_b200/host/gloc_ground.hpp -- the reference does this on the CPU with
+//     PCL; the plane fit there is a RANSAC whose samples cannot be reproduced without PCL).
 // Own code: a small logger that prints glog-style lines, a reader for each format.
 #include <algorithm>
 #include <chrono>
@@ -28,6 +32,7 @@
 #include <string>
 #include <vector>
 
+#include "../gloc3d_b200/host/gloc_ground.hpp"
 #include "../include/gloc3d.h"
 
 namespace {
@@ -82,45 +87,10 @@ std::vector<std::string> split(const std::string& s, const std::string& sep) {  
   return res;
 }
 
-struct Mat4 {
-  float m[4][4];
-  static Mat4 identity() {
-    Mat4 r{};
-    for (int i = 0; i < 4; ++i) r.m[i][i] = 1.f;
-    return r;
-  }
-};
-Mat4 mul(const Mat4& a, const Mat4& b) {
-  Mat4 r{};
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) {
-      float s = 0.f;
-      for (int k = 0; k < 4; ++k) s += a.m[i][k] * b.m[k][j];
-      r.m[i][j] = s;
-    }
-  return r;
-}
-Mat4 rigid_inverse(const Mat4& a) {  // [R t; 0 1]^-1 = [R^T -R^T t; 0 1]
-  Mat4 r = Mat4::identity();
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i];
-  for (int i = 0; i < 3; ++i)
-    r.m[i][3] = -(r.m[i][0] * a.m[0][3] + r.m[i][1] * a.m[1][3] + r.m[i][2] * a.m[2][3]);
-  return r;
-}
-// Eigen::Quaternionf(w, x, y, z).toRotationMatrix()
-Mat4 pose_from(float qw, float qx, float qy, float qz, float x, float y, float z) {
-  Mat4 p = Mat4::identity();
-  const float tx = 2.f * qx, ty = 2.f * qy, tz = 2.f * qz;
-  const float twx = tx * qw, twy = ty * qw, twz = tz * qw;
-  const float txx = tx * qx, txy = ty * qx, txz = tz * qx;
-  const float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-  p.m[0][0] = 1.f - (tyy + tzz); p.m[0][1] = txy - twz;         p.m[0][2] = txz + twy;
-  p.m[1][0] = txy + twz;         p.m[1][1] = 1.f - (txx + tzz); p.m[1][2] = tyz - twx;
-  p.m[2][0] = txz - twy;         p.m[2][1] = tyz + twx;         p.m[2][2] = 1.f - (txx + tyy);
-  p.m[0][3] = x; p.m[1][3] = y; p.m[2][3] = z;
-  return p;
-}
+using Mat4 = gloc::Mat4f;
+using gloc::mul;
+using gloc::pose_from;
+using gloc::rigid_inverse;
 
 // ReadValset, global_localization.cpp:64-122
 bool ReadValset(const std::string& filename, std::vector<std::string>& db_files,
@@ -226,17 +196,30 @@ class GlocEvaluator {
   }
 
   // GLOC_DRIVER_PARSE_ONLY=1: read every input the run would read (valset, poses, descriptor
-  // table, every scan file) and report what was found, without touching the GPU.
+  // table, every scan file; with the 4th argument also level every scan) and report what was
+  // found, without touching the GPU.
   bool check_inputs(const std::string& model_file_path) {
     load_descriptors(model_file_path);
     size_t n_pts = 0, missing = 0;
     std::vector<std::string> all = db_files_;
     all.insert(all.end(), q_files_.begin(), q_files_.end());
+    size_t levelled = 0;
+    double height = 0.;
     for (const auto& f : all) {
-      const std::vector<float> pc = read_lidar_data(f);
+      std::vector<float> pc = read_lidar_data(f);
       if (pc.empty()) ++missing;
       n_pts += pc.size() / 4;
+      if (align_ground_ && !pc.empty()) {   // the host half of the aligned run: level every scan
+        const Mat4 T = align_to_ground(&pc);
+        if (T.m[2][3] > 0.f) {
+          ++levelled;
+          height += T.m[2][3];
+        }
+      }
     }
+    if (align_ground_)
+      LOG_INFO << "ground alignment: " << levelled << " of " << all.size() << " scans levelled, mean sensor height "
+               << (levelled ? height / (double)levelled : 0.) << " m";
     size_t n_pos = 0;
     for (const auto& v : gt_q_pos_idx_) n_pos += v.size();
     LOG_INFO << "inputs: " << db_files_.size() << " db scans, " << q_files_.size() << " query scans, "
@@ -252,12 +235,16 @@ class GlocEvaluator {
     check(gloc_bev_create(&bev_, device_, 0.2f, 100.f), "gloc_bev_create");
     check(gloc_csm_create(&store_, device_), "gloc_csm_create");
     check(gloc_knn_create(&index_, kDim, device_), "gloc_knn_create");
-    if (align_ground_) LOG_INFO << "ground alignment is outside the query path (SURVEY.md 2): ignored";
     int i = 0;
     double t_align = 0., t_detect = 0.;
     for (const auto& filename : db_files_) {
       ++i;
-      const std::vector<float> kf = read_lidar_data(filename);
+      std::vector<float> kf = read_lidar_data(filename);
+      if (align_ground_) {
+        TicToc ta;
+        db_rpz_estimates_.push_back(align_to_ground(&kf));
+        t_align += ta.toc();
+      }
       TicToc tb;
       gloc_bev_info info;
       check(gloc_bev_project(bev_, kf.data(), kf.size() / 4, 4, &info), "gloc_bev_project");
@@ -283,7 +270,8 @@ class GlocEvaluator {
     double t_sum = 0.;
     const size_t n_db = db_files_.size();
     for (size_t qi = 0; qi < q_files_.size(); ++qi) {
-      const std::vector<float> q_pc = read_lidar_data(q_files_[qi]);
+      std::vector<float> q_pc = read_lidar_data(q_files_[qi]);
+      if (align_ground_) q_rpz_estimates_.push_back(align_to_ground(&q_pc));
       TicToc t;
       std::vector<size_t> loop_indices;
       gloc_bev_info info;
@@ -347,7 +335,6 @@ class GlocEvaluator {
     const int all_tests = (int)located_db_.size();
     int succeed_tests = 0;
     std::vector<double> rot_err, pos_err;
-    const float rad2deg = 180. / M_PI;
     const size_t num_db = db_files_.size();
     for (size_t i = 0; i < located_db_.size(); ++i) {
       const size_t db_idx = located_db_[i];
@@ -355,19 +342,8 @@ class GlocEvaluator {
         failed_registration_indices_.push_back((int)i);
         continue;
       }
-      const Mat4 q2db = mul(rigid_inverse(poses_db_q_[db_idx]), poses_db_q_[i + num_db]);
-      const Mat4& loc = located_pose_[i];
-      float trace = 0.f;  // trace(gt_rot^T * R_restored)
-      for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) trace += q2db.m[b][a] * loc.m[b][a];
-      float offset_trace = 0.5f * (trace - 1.f);
-      offset_trace = offset_trace < -0.999999f ? -0.999999f : offset_trace;
-      offset_trace = offset_trace > 0.999999f ? 0.999999f : offset_trace;
-      float err_rot = std::fabs(std::acos(offset_trace));
-      const float ex = q2db.m[0][3] - loc.m[0][3], ey = q2db.m[1][3] - loc.m[1][3], ez = q2db.m[2][3] - loc.m[2][3];
-      const float err_pos = std::sqrt(ex * ex + ey * ey + ez * ez);
-      err_rot = err_rot * rad2deg;
-      if (std::fabs(err_rot - 180.f) < 5.f) err_rot = std::fabs(err_rot - 180.f);
+      float err_rot, err_pos;
+      gloc::RegistrationError(poses_db_q_[db_idx], poses_db_q_[i + num_db], located_pose_[i], &err_rot, &err_pos);
       if (err_pos < 1.0f && err_rot < 5.f) {
         succeed_tests++;
         rot_err.push_back(err_rot);
@@ -404,6 +380,20 @@ class GlocEvaluator {
     }
   }
 
+  // EsitmateGroundAndTransform on one scan, in place; returns T_l2g.  A scan without a usable
+  // ground keeps its points and gets the identity (the reference hands an EMPTY cloud to the
+  // projection in that case, which has no defined result).
+  Mat4 align_to_ground(std::vector<float>* scan) {
+    std::vector<float> levelled;
+    const Mat4 T = ground_estimator_.EsitmateGroundAndTransform(scan->data(), scan->size() / 4, 4, &levelled);
+    if (levelled.empty()) {
+      LogLine('W', __LINE__).os << "No valid ground found!";
+      return Mat4::identity();
+    }
+    scan->swap(levelled);
+    return T;
+  }
+
   void write_indices(const std::string& name, const std::vector<int>& v) {
     std::ofstream ofs(name, std::ios::out);
     if (!ofs) LOG_ERROR << "Failed open " << name;
@@ -436,13 +426,10 @@ class GlocEvaluator {
       times_call_match_ += n;
       for (int i = 0; i < n; ++i) {
         if (!res[i].found) continue;
-        // RollPitchYaw(0, 0, yaw) and (dx, dy, 0): global_localization.cpp:556-569
-        const float yaw = (float)res[i].pose_yaw;
-        Mat4 p = Mat4::identity();
-        p.m[0][0] = std::cos(yaw); p.m[0][1] = -std::sin(yaw);
-        p.m[1][0] = std::sin(yaw); p.m[1][1] = std::cos(yaw);
-        p.m[0][3] = (float)res[i].pose_x;
-        p.m[1][3] = (float)res[i].pose_y;
+        // global_localization.cpp:524-569
+        const float xy_yaw[3] = {(float)res[i].pose_x, (float)res[i].pose_y, (float)res[i].pose_yaw};
+        const Mat4 p = align_ground_ ? gloc::ComposeLocatedPose(true, xy_yaw, q_rpz_estimates_[qi], db_rpz_estimates_[cand[i]])
+                                     : gloc::ComposeLocatedPose(false, xy_yaw, Mat4::identity(), Mat4::identity());
         located_db_[qi] = cand[i];
         located_pose_[qi] = p;
         break;
@@ -460,6 +447,8 @@ class GlocEvaluator {
   std::vector<std::vector<size_t>> queried_idx_;
   std::vector<size_t> located_db_;
   std::vector<Mat4> located_pose_;
+  gloc::GroundEstimator ground_estimator_;
+  std::vector<Mat4> db_rpz_estimates_, q_rpz_estimates_;
   std::vector<int> failed_detect_indices_, failed_registration_indices_;
   double time_sum_match_ = 0., times_call_match_ = 0.;
   gloc_bev_projector* bev_ = nullptr;
