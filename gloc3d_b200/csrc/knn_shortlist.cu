@@ -61,6 +61,14 @@ constexpr int kTmemCols = 512;
 constexpr int kWarmChunks = 8;     // chunks whose scores all enter the threshold list (per warpgroup)
 constexpr size_t kSmemBytes = 1024 /*align slack*/ + (size_t)kMaxKBlocks * kABytesPerKB +
                               (size_t)kStagesB * kBBytes + 256 /*barriers*/;
+// CTA-pair variant (experimental, GLOC_KNN_PAIR=1): two CTAs of a cluster run one
+// tcgen05.mma.cta_group::2 of M = 256 (each CTA its own 128-query tile) x N = 256; each CTA
+// stages only its half of the database tile (128 rows, 16 KB per k-block), so the L2 -> SM
+// traffic of the database halves and the same shared memory holds a ring twice as deep.
+constexpr int kStagesBPair = 6;
+constexpr int kBBytesPair = (BN / 2) * BK * 2;   // 16 KB
+static_assert(kStagesBPair * kBBytesPair == kStagesB * kBBytes, "both variants use the same shared memory");
+static_assert(2 * kStagesBPair + 6 <= 32, "barrier block is 256 bytes");
 
 // shortlist error-bound constants (see header comment)
 constexpr float kU = 1.f / 2048.f;          // FP16 unit roundoff
@@ -125,6 +133,52 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+// ---- cluster / CTA-pair flavours (cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load of a CTA pair: data into this CTA's shared memory, bytes counted on the barrier at
+// `bar_cluster_addr` (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map,
+                                                 uint32_t bar_cluster_addr, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in both CTAs of the pair
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -161,6 +215,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // cute::UMMA::InstrDescriptor for kind::f16: c_format F32 [4,6)=1, a/b_format F16 [7,10),
 // [10,13)=0, a/b K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29).
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kInstrDescPair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -321,18 +376,24 @@ struct GemmArgs {
   unsigned* unit_cnt;               // [nq][2*n_ranges]
 };
 
+// kPair = false: one CTA per SM, cta_group::1 (the shipped path).  kPair = true: clusters of two
+// CTAs, cta_group::2 (see kStagesBPair); a.n_qtiles then counts PAIRS of query tiles and map_db
+// has a 128-row box.
+template <bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
                           const __grid_constant__ CUtensorMap map_db, GemmArgs a) {
+  constexpr int kStages = kPair ? kStagesBPair : kStagesB;
+  constexpr int kStageBytes = kPair ? kBBytesPair : kBBytes;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char* sA = smem;                                          // n_kb x 16 KB (resident)
-  unsigned char* sB = smem + (size_t)kMaxKBlocks * kABytesPerKB;     // kStagesB x 32 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kStagesB * kBBytes);
-  uint64_t* full_b = bars;                   // [kStagesB]
-  uint64_t* empty_b = bars + kStagesB;       // [kStagesB]
-  uint64_t* a_full = bars + 2 * kStagesB;    // [1]
+  unsigned char* sB = smem + (size_t)kMaxKBlocks * kABytesPerKB;     // kStages x kStageBytes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)kStages * kStageBytes);
+  uint64_t* full_b = bars;                   // [kStages]
+  uint64_t* empty_b = bars + kStages;        // [kStages]
+  uint64_t* a_full = bars + 2 * kStages;     // [1]
   uint64_t* a_empty = a_full + 1;            // [1]
   uint64_t* tm_full = a_empty + 1;           // [2]
   uint64_t* tm_empty = tm_full + 2;          // [2]
@@ -340,13 +401,19 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_units = a.n_qtiles * a.n_ranges;
+  // persistent worker = CTA (or CTA pair); in a pair only rank 0 ("leader") issues MMAs and owns
+  // the barriers the operands and the accumulator hand-back are counted on
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
+#define GLOC_WORKER (kPair ? (blockIdx.x >> 1) : blockIdx.x)
+#define GLOC_N_WORKERS (kPair ? (gridDim.x >> 1) : gridDim.x)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_db) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStagesB; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(full_b + s, 1);
       mbar_init(empty_b + s, 1);
     }
@@ -354,26 +421,36 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(tm_full + s, 1);
-      mbar_init(tm_empty + s, 8);  // one arrive per epilogue warp
+      mbar_init(tm_empty + s, kPair ? 16 : 8);  // one arrive per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
     fence_proxy_async();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32(tmem_slot)),
-                 "n"(kTmemCols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (kPair) {   // the same warp of both CTAs
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                       smem_u32(tmem_slot)),
+                   "n"(kTmemCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised, too
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   // Tiles a unit runs -- every role computes the same schedule.
   auto unit_tiles = [&](int u, int& qt, int& rg, int& t_begin, int& t_count) {
     qt = u % a.n_qtiles;
+    if constexpr (kPair) qt = 2 * qt + (int)cta_rank;   // this CTA's query tile of the pair
     rg = u / a.n_qtiles;
     t_begin = rg * a.tiles_per_range;
     const long long total_tiles = (a.n_rows + BN - 1) / BN;
@@ -385,21 +462,31 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0, uphase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      // pair: both CTAs load their own halves; every byte is counted on the leader's barriers,
+      // which the leader arms for both (the empty barriers are per CTA: multicast commits)
+      const uint32_t a_full_ld = kPair ? map_to_cta(smem_u32(a_full), 0) : 0u;
+      for (int u = GLOC_WORKER; u < n_units; u += GLOC_N_WORKERS) {
         int qt, rg, t_begin, t_count;
         unit_tiles(u, qt, rg, t_begin, t_count);
         mbar_wait(a_empty, uphase ^ 1);  // previous unit's MMAs no longer read the query tile
-        mbar_expect_tx(a_full, (uint32_t)(a.n_kb * kABytesPerKB));
-        for (int kb = 0; kb < a.n_kb; ++kb)
-          tma_load_2d(sA + (size_t)kb * kABytesPerKB, &map_q, a_full, kb * BK, qt * BM);
+        if (leader) mbar_expect_tx(a_full, (uint32_t)(a.n_kb * kABytesPerKB) * (kPair ? 2u : 1u));
+        for (int kb = 0; kb < a.n_kb; ++kb) {
+          if constexpr (kPair) tma_load_2d_pair(sA + (size_t)kb * kABytesPerKB, &map_q, a_full_ld, kb * BK, qt * BM);
+          else tma_load_2d(sA + (size_t)kb * kABytesPerKB, &map_q, a_full, kb * BK, qt * BM);
+        }
         uphase ^= 1;
         for (int it = 0; it < t_count; ++it) {
           const int t = t_begin + it;
           for (int kb = 0; kb < a.n_kb; ++kb) {
             mbar_wait(empty_b + stage, phase ^ 1);
-            mbar_expect_tx(full_b + stage, kBBytes);
-            tma_load_2d(sB + (size_t)stage * kBBytes, &map_db, full_b + stage, kb * BK, t * BN);
-            if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+            if (leader) mbar_expect_tx(full_b + stage, kBBytes);   // 32 KB = both halves of a pair
+            if constexpr (kPair)
+              tma_load_2d_pair(sB + (size_t)stage * kStageBytes, &map_db,
+                               map_to_cta(smem_u32(full_b + stage), 0), kb * BK,
+                               t * BN + (int)cta_rank * (BN / 2));
+            else
+              tma_load_2d(sB + (size_t)stage * kStageBytes, &map_db, full_b + stage, kb * BK, t * BN);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -407,12 +494,12 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer (one thread)
-    if (lane == 0) {
+    if (lane == 0 && leader) {
       int stage = 0, as = 0;
       uint32_t phase = 0, aphase = 0, uphase = 0;
       const uint64_t a_desc0 = make_sw128_desc(smem_u32(sA));
       const uint64_t b_desc0 = make_sw128_desc(smem_u32(sB));
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int u = GLOC_WORKER; u < n_units; u += GLOC_N_WORKERS) {
         int qt, rg, t_begin, t_count;
         unit_tiles(u, qt, rg, t_begin, t_count);
         mbar_wait(a_full, uphase);
@@ -426,19 +513,26 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
             tcgen05_fence_after();
             // descriptors differ only in the 14-bit start-address field (units of 16 B)
             const uint64_t ad = a_desc0 + (uint64_t)(kb * (kABytesPerKB >> 4));
-            const uint64_t bd = b_desc0 + (uint64_t)(stage * (kBBytes >> 4));
+            const uint64_t bd = b_desc0 + (uint64_t)(stage * (kStageBytes >> 4));
 #pragma unroll
             for (int k4 = 0; k4 < BK / UK; ++k4) {
-              umma_f16(d_tmem, ad + (uint64_t)(k4 * (UK * 2 >> 4)), bd + (uint64_t)(k4 * (UK * 2 >> 4)),
-                       kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
+              if constexpr (kPair)
+                umma_f16_pair(d_tmem, ad + (uint64_t)(k4 * (UK * 2 >> 4)), bd + (uint64_t)(k4 * (UK * 2 >> 4)),
+                              kInstrDescPair, (kb | k4) != 0 ? 1u : 0u);
+              else
+                umma_f16(d_tmem, ad + (uint64_t)(k4 * (UK * 2 >> 4)), bd + (uint64_t)(k4 * (UK * 2 >> 4)),
+                         kInstrDesc, (kb | k4) != 0 ? 1u : 0u);
             }
-            tcgen05_commit(empty_b + stage);  // B slot reusable once these MMAs retire
-            if (++stage == kStagesB) { stage = 0; phase ^= 1; }
+            // B slot reusable once these MMAs retire (pair: in both CTAs)
+            if constexpr (kPair) tcgen05_commit_pair(empty_b + stage); else tcgen05_commit(empty_b + stage);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(tm_full + as);       // accumulator ready for the epilogue
+          // accumulator ready for the epilogue (pair: each CTA's own 128 lanes)
+          if constexpr (kPair) tcgen05_commit_pair(tm_full + as); else tcgen05_commit(tm_full + as);
           if (++as == 2) { as = 0; aphase ^= 1; }
         }
-        tcgen05_commit(a_empty);              // query tile may be overwritten
+        // query tile may be overwritten
+        if constexpr (kPair) tcgen05_commit_pair(a_empty); else tcgen05_commit(a_empty);
       }
     }
   } else if (warp >= 4) {
@@ -461,7 +555,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
     uint32_t aphase = 0;
     const float xmax = sqrtf(__uint_as_float(*a.max_norm2_bits)) * kInfl;
     const float dxmax = sqrtf(__uint_as_float(*a.max_dx2_bits)) * kInfl;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int u = GLOC_WORKER; u < n_units; u += GLOC_N_WORKERS) {
       int qt, rg, t_begin, t_count;
       unit_tiles(u, qt, rg, t_begin, t_count);
       const int q = qt * BM + row;
@@ -620,7 +714,11 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
         // all of this warp's TMEM reads of the stage are complete: hand it back to the MMA
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tm_empty + as);
+        if constexpr (kPair) {   // the leader's MMA thread waits for the epilogues of both CTAs
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(smem_u32(tm_empty + as), 0));
+        } else {
+          if (lane == 0) mbar_arrive(tm_empty + as);
+        }
         if (++as == 2) { as = 0; aphase ^= 1; }
         if (q_ok) {  // publish / pick up the bound shared by all units of this query
           const unsigned mine = f2ord(thr);
@@ -633,14 +731,22 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // neither CTA leaves while its peer can still reach it
+  else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "n"(kTmemCols)
-                 : "memory");
+    if constexpr (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "n"(kTmemCols)
+                   : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                   "n"(kTmemCols)
+                   : "memory");
   }
 }
+#undef GLOC_WORKER
+#undef GLOC_N_WORKERS
 
 // ------------------------------------------------------------------ K3: select + exact re-rank
 constexpr int kEntMax = 4096;    // group entries per query handled by K3 (more: exact-scan fallback)
@@ -1027,9 +1133,9 @@ struct Plan {
   int n_ranges, tiles_per_range, r_big, cap;
 };
 
-Plan make_plan(long long n_rows, int nq, int sms) {
+// n_qtiles: query tiles (or pairs of them) a unit covers; sms: persistent workers
+Plan make_plan_units(long long n_rows, int n_qtiles, int sms) {
   const long long tiles = (n_rows + BN - 1) / BN;
-  const int n_qtiles = (nq + BM - 1) / BM;
   const long long max_r = std::max<long long>(1, std::min<long long>(16, tiles / 8));
   double best = -1;
   long long best_r = 1;
@@ -1046,6 +1152,46 @@ Plan make_plan(long long n_rows, int nq, int sms) {
   p.r_big = std::min<int>(p.n_ranges, (sms + n_qtiles - 1) / n_qtiles);
   p.cap = 512;
   return p;
+}
+Plan make_plan(long long n_rows, int nq, int sms) {
+  return make_plan_units(n_rows, (nq + BM - 1) / BM, sms);
+}
+
+// GLOC_KNN_PAIR=1 (experimental): CTA-pair GEMM.  Returns the number of resident CTA pairs, 0
+// when the variant is off or cannot be launched.
+int pair_workers() {
+  static int cached = -1;
+  static int cached_dev = -1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cached >= 0 && cached_dev == dev) return cached;
+  cached_dev = dev;
+  cached = 0;
+  const char* e = getenv("GLOC_KNN_PAIR");
+  if (!e || atoi(e) == 0) return 0;
+  if (cudaFuncSetAttribute(knn_shortlist_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)kSmemBytes) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * sm_count(dev));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, knn_shortlist_gemm_kernel<true>, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  cached = n;
+  return cached;
 }
 
 }  // namespace
@@ -1099,22 +1245,26 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     S->prepared_src = A.d_db;
   }
 
+  const int pairs = pair_workers();   // 0: the shipped one-CTA-per-SM kernel
   CUtensorMap map_db;
-  if (!make_map(&map_db, S->db_h.p, A.n_rows, (uint64_t)dim, BN))
+  if (!make_map(&map_db, S->db_h.p, A.n_rows, (uint64_t)dim, pairs ? BN / 2 : BN))
     return fail(GLOC_ERR_CUDA, "cuTensorMapEncodeTiled(db) failed");
 
   // queries per pass: bounded so that the candidate workspace (2 lists per unit, 36 B per
   // group slot) stays under ~16 GB
   size_t kChunk = 65536;
   {
-    const Plan p0 = make_plan((long long)A.n_rows, (int)std::min<size_t>(A.nq, kChunk), sms);
+    const int nq0 = (int)std::min<size_t>(A.nq, kChunk);
+    const Plan p0 = pairs ? make_plan_units((long long)A.n_rows, ((nq0 + BM - 1) / BM + 1) / 2, pairs)
+                          : make_plan((long long)A.n_rows, nq0, sms);
     const size_t per_query = (size_t)p0.n_ranges * 2 * p0.cap * 36;
     kChunk = std::max<size_t>(BM, std::min<size_t>(kChunk, ((size_t)16 << 30) / per_query / BM * BM));
   }
   for (size_t q0 = 0; q0 < A.nq; q0 += kChunk) {
     const int nq = (int)std::min(kChunk, A.nq - q0);
-    const Plan plan = make_plan((long long)A.n_rows, nq, sms);
     const int n_qtiles = (nq + BM - 1) / BM;
+    const Plan plan = pairs ? make_plan_units((long long)A.n_rows, (n_qtiles + 1) / 2, pairs)
+                            : make_plan((long long)A.n_rows, nq, sms);
     const size_t lists = (size_t)nq * plan.n_ranges * 2;  // two epilogue warpgroups per unit
     GLOC_CUDA_TRY(S->q_h.reserve((size_t)n_qtiles * BM * dim * 2));
     GLOC_CUDA_TRY(S->qn.reserve((size_t)nq * 4));
@@ -1152,7 +1302,7 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     // K2
     GemmArgs g;
     g.nq = nq;
-    g.n_qtiles = n_qtiles;
+    g.n_qtiles = pairs ? (n_qtiles + 1) / 2 : n_qtiles;   // units per range
     g.n_ranges = plan.n_ranges;
     g.tiles_per_range = plan.tiles_per_range;
     g.n_kb = dim / BK;
@@ -1174,16 +1324,35 @@ int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launc
     g.unit_cnt = (unsigned*)S->unit_cnt.p;
     static unsigned long long attr_mask = 0;
     if (first_use_on_current_device(attr_mask)) {
-      GLOC_CUDA_TRY(cudaFuncSetAttribute(knn_shortlist_gemm_kernel,
+      GLOC_CUDA_TRY(cudaFuncSetAttribute(knn_shortlist_gemm_kernel<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemBytes));
     }
-    const int n_units = n_qtiles * plan.n_ranges;
-    const int grid = std::min(n_units, sms);
-    if (A.prof) A.prof->begin(st);
-    knn_shortlist_gemm_kernel<<<grid, kThreads, kSmemBytes, st>>>(map_q, map_db, g);
-    cudaError_t ge = cudaGetLastError();
-    if (A.prof) A.prof->end(st);
+    const int n_units = g.n_qtiles * plan.n_ranges;
+    cudaError_t ge;
+    if (pairs) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2 * (unsigned)std::min(n_units, pairs));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = kSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      if (A.prof) A.prof->begin(st);
+      ge = cudaLaunchKernelEx(&cfg, knn_shortlist_gemm_kernel<true>, map_q, map_db, g);
+      if (A.prof) A.prof->end(st);
+    } else {
+      const int grid = std::min(n_units, sms);
+      if (A.prof) A.prof->begin(st);
+      knn_shortlist_gemm_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(map_q, map_db, g);
+      ge = cudaGetLastError();
+      if (A.prof) A.prof->end(st);
+    }
     GLOC_CUDA_TRY(ge);
 
     // K3
