@@ -31,6 +31,7 @@ C ABI / public API with HOST (pinned) buffers, H2D + D2H inside the timed region
 from __future__ import annotations
 
 import argparse
+import datetime
 import json
 import os
 import statistics
@@ -737,7 +738,9 @@ def main():
         return 2
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # a rank that dies must not hold the others (and the GPU box) for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=300))
     try:
         fn = {"retrieval": run_retrieval, "verify": run_verify, "stream": run_stream}[args.workload]
         line = fn(args, rank, world, local_rank)
