@@ -52,6 +52,11 @@ class CsmStats(C.Structure):
                                           "refined_nodes")]
 
 
+class GridInfo(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("resolution", C.c_double),
+                ("max_x", C.c_double), ("max_y", C.c_double)]
+
+
 class BevInfo(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("min_ix", C.c_int), ("min_iy", C.c_int),
                 ("ox", C.c_double), ("oy", C.c_double), ("resolution", C.c_double),
@@ -104,6 +109,13 @@ SIGNATURES = {
     "gloc_bev_kernel_launches": (C.c_uint64, [_vp]),
     "gloc_csm_add_grid_from_bev": (_i, [_vp, _vp, _ip]),
     "gloc_csm_add_grid_from_bev_aligned": (_i, [_vp, _vp, _ip]),
+    "gloc_csm_get_grid_info": (_i, [_vp, _i, C.POINTER(GridInfo)]),
+    "gloc_grid_file_write": (_i, [C.c_char_p, C.POINTER(GridInfo), C.POINTER(_vp), _sz]),
+    "gloc_grid_file_open": (_i, [C.c_char_p, C.POINTER(_vp), C.POINTER(_sz)]),
+    "gloc_grid_file_next": (_i, [_vp, C.POINTER(GridInfo), _vp, _sz]),
+    "gloc_grid_file_close": (None, [_vp]),
+    "gloc_csm_save_grids": (_i, [_vp, C.c_char_p]),
+    "gloc_csm_load_grids": (_i, [_vp, C.c_char_p, _ip, _ip]),
 }
 
 _lib = None

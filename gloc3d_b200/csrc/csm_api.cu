@@ -315,6 +315,19 @@ int gloc_csm_add_grid_from_bev_aligned(gloc_csm_store* st, gloc_bev_projector* b
 
 int gloc_csm_num_grids(const gloc_csm_store* st) { return st ? (int)st->grids.size() : 0; }
 
+int gloc_csm_get_grid_info(const gloc_csm_store* st, int grid_id, gloc_grid_info* out) {
+  if (!st || !out) return fail(GLOC_ERR_INVALID, "gloc_csm_get_grid_info: null argument");
+  if (grid_id < 0 || grid_id >= (int)st->grids.size())
+    return fail(GLOC_ERR_INVALID, "gloc_csm_get_grid_info: bad grid id");
+  const HostGrid& hg = st->grids[grid_id];
+  out->nx = hg.nx;
+  out->ny = hg.ny;
+  out->resolution = hg.resolution;
+  out->max_x = hg.max_x;
+  out->max_y = hg.max_y;
+  return GLOC_OK;
+}
+
 int gloc_csm_get_precomputation_grid(gloc_csm_store* st, int grid_id, int width, uint8_t* out) {
   if (!st || !out) return fail(GLOC_ERR_INVALID, "gloc_csm_get_precomputation_grid: null argument");
   if (grid_id < 0 || grid_id >= (int)st->grids.size())

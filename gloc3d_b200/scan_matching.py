@@ -87,6 +87,24 @@ class CsmStore:
     def __len__(self) -> int:
         return int(_lib.lib().gloc_csm_num_grids(self._h))
 
+    def grid_info(self, grid_id: int) -> MapLimits:
+        info = _lib.GridInfo()
+        check(_lib.lib().gloc_csm_get_grid_info(self._h, grid_id, C.byref(info)))
+        return MapLimits(info.resolution, info.max_x, info.max_y, info.nx, info.ny)
+
+    def save_grids(self, path: str) -> None:
+        """Every grid of the store -> a grid store file (gloc_csm_save_grids)."""
+        check(_lib.lib().gloc_csm_save_grids(self._h, path.encode()))
+
+    def load_grids(self, path: str) -> list[int]:
+        """Appends the grids of a grid store file; returns their ids (gloc_csm_load_grids)."""
+        first, n = C.c_int(), C.c_int()
+        check(_lib.lib().gloc_csm_load_grids(self._h, path.encode(), C.byref(first), C.byref(n)))
+        ids = list(range(first.value, first.value + n.value))
+        for gid in ids:
+            self.limits.append(self.grid_info(gid))
+        return ids
+
     def precomputation_grid(self, grid_id: int, width: int) -> np.ndarray:
         lim = self.limits[grid_id]
         out = np.empty((lim.num_y_cells + width - 1, lim.num_x_cells + width - 1), np.uint8)

@@ -264,6 +264,42 @@ int gloc_csm_add_grid_from_bev(gloc_csm_store* store, gloc_bev_projector* bev, i
  * point is the consistent construction the driver uses for the north-star verifier. */
 int gloc_csm_add_grid_from_bev_aligned(gloc_csm_store* store, gloc_bev_projector* bev, int* grid_id);
 
+/* ============================================================ grid store file
+ * (a map's BEV grids on disk, so that a database is projected once.)
+ * The reference keeps its grids in memory only (db_grids_, loop_detector.h:36-39) and
+ * re-projects every scan at start-up (global_localization.cpp:419-449); this is the
+ * file that replaces that pass.  Little-endian:
+ *   header   "GLOCGRD1" | u32 version = 1 | u32 0 | u64 n_grids
+ *   per grid i32 nx | i32 ny | f64 resolution | f64 max_x | f64 max_y | u32 encoding | u32 0 |
+ *            u64 payload_bytes | payload
+ *   encoding 1  bit-packed binary grid: bit (i & 7) of byte (i >> 3) is set iff level-1 cell
+ *               i = nx*y + x is 255 (occupied), clear iff it is 0; ceil(nx*ny / 8) bytes
+ *   encoding 0  the uint8 level-1 grid as it is, nx*ny bytes (grids with other values)
+ * The file functions run on the host only (no device needed). */
+typedef struct {
+  int32_t nx, ny;              /* MapLimits cell counts                                */
+  double resolution, max_x, max_y;
+} gloc_grid_info;
+
+typedef struct gloc_grid_file gloc_grid_file;
+
+/* MapLimits of a grid of the store (host metadata). */
+int gloc_csm_get_grid_info(const gloc_csm_store* store, int grid_id, gloc_grid_info* out);
+/* Writes n grids; level1[i] is the nx*ny uint8 width-1 precomputation grid of grid i
+ * (what gloc_csm_add_grid_u8 takes / gloc_csm_get_precomputation_grid(width = 1) returns). */
+int gloc_grid_file_write(const char* path, const gloc_grid_info* infos,
+                         const uint8_t* const* level1, size_t n);
+int gloc_grid_file_open(const char* path, gloc_grid_file** out, size_t* n_grids);
+/* Reads the next grid: info always; the cells into level1 when capacity >= nx*ny, otherwise
+ * the record is NOT consumed (call again with a large enough buffer).  GLOC_ERR_RANGE after
+ * the last grid. */
+int gloc_grid_file_next(gloc_grid_file* f, gloc_grid_info* info, uint8_t* level1, size_t capacity);
+void gloc_grid_file_close(gloc_grid_file* f);
+/* Every grid of the store -> file; file -> grids appended to the store (ids first_grid_id ..
+ * first_grid_id + n_grids - 1, in file order). */
+int gloc_csm_save_grids(gloc_csm_store* store, const char* path);
+int gloc_csm_load_grids(gloc_csm_store* store, const char* path, int* first_grid_id, int* n_grids);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,6 +18,7 @@
 //     projection and the located pose is composed from the 2-D match and the two ground
 //     transforms (gloc3d_b200/host/gloc_ground.hpp -- the reference does this on the CPU with
 //     PCL; the plane fit there is a RANSAC whose samples cannot be reproduced without PCL).
+//   * GLOC_GRID_STORE=<file> keeps the database's BEV grids in a grid store file between runs.
 // Own code: a small logger that prints glog-style lines, a reader for each format.
 #include <algorithm>
 #include <chrono>
@@ -237,6 +238,26 @@ class GlocEvaluator {
     check(gloc_knn_create(&index_, kDim, device_), "gloc_knn_create");
     int i = 0;
     double t_align = 0., t_detect = 0.;
+    // GLOC_GRID_STORE=<file>: the database's BEV grids on disk (grid store file, include/gloc3d.h):
+    // loaded when the file holds one grid per database scan, written after the projection pass
+    // otherwise.  Not used with ground alignment (the per-scan ground transforms are not in it).
+    const char* grid_store = align_ground_ ? nullptr : std::getenv("GLOC_GRID_STORE");
+    if (grid_store) {
+      gloc_grid_file* gf = nullptr;
+      size_t n_stored = 0;
+      if (gloc_grid_file_open(grid_store, &gf, &n_stored) == GLOC_OK) {
+        gloc_grid_file_close(gf);
+        if (n_stored == db_files_.size()) {
+          int first = 0, n = 0;
+          check(gloc_csm_load_grids(store_, grid_store, &first, &n), "gloc_csm_load_grids");
+          for (int k = 0; k < n; ++k) db_grid_ids_.push_back(first + k);
+          check(gloc_knn_set_db(index_, feats_.data(), db_files_.size()), "gloc_knn_set_db");
+          LOG_INFO << "loaded " << n << " database grids from " << grid_store;
+          return;
+        }
+        LOG_INFO << grid_store << " holds " << n_stored << " grids for " << db_files_.size() << " scans: rebuilding";
+      }
+    }
     for (const auto& filename : db_files_) {
       ++i;
       std::vector<float> kf = read_lidar_data(filename);
@@ -254,6 +275,10 @@ class GlocEvaluator {
       if (i > 2) t_detect += tb.toc();
     }
     check(gloc_knn_set_db(index_, feats_.data(), db_files_.size()), "gloc_knn_set_db");
+    if (grid_store) {
+      check(gloc_csm_save_grids(store_, grid_store), "gloc_csm_save_grids");
+      LOG_INFO << "wrote " << db_grid_ids_.size() << " database grids to " << grid_store;
+    }
     LOG_INFO << "time cost for align to ground: " << t_align / double(i) << "ms.";
     LOG_INFO << "time cost for feature extraction: " << t_detect / double(i - 2) << "ms.";
   }
