@@ -6,6 +6,7 @@ container (needs /root/reference for the nanoflann build under oracle/_ref):
 knn_*.npz   outputs of the REFERENCE ITSELF (its nanoflann + adaptor compiled unmodified
             from /root/reference/registration, oracle/nanoflann_ref.cpp) on seeded inputs;
             inputs are stored too so the fixtures do not depend on numpy's RNG stream.
+vlad_*.npz  outputs of the REFERENCE ITSELF (model/netvlad_fc.py, torch CPU) on hashed weights.
 csm_*.npz   outputs of the stage-2 restatement (oracle/csm_oracle.c); the reference's
             registration/2d cannot be built here, so these pin the restatement against
             regressions only (parity unpinned, see oracle/gloc_oracle.h).
@@ -58,6 +59,29 @@ def bev_case(name, every=4):
     print(name, pts.shape, img.shape, no)
 
 
+def vlad_case(name, K, C, H, W, B, seed):
+    """Outputs of the REFERENCE's own NetVLAD_fc module (model/netvlad_fc.py imported from
+    /root/reference, torch CPU float32) for hashed weights and features (oracle/vlad_oracle.py:
+    integer-hash generators, so only the outputs need storing)."""
+    import torch
+
+    sys.path.insert(0, "/root/reference/model")
+    import netvlad_fc
+    from oracle import vlad_oracle as vo
+
+    conv_w, cent, hid = vo.hashed_weights(K, C, C, seed)
+    x = vo.hashed_features(B, C, H * W, seed + 10).reshape(B, C, H, W)
+    m = netvlad_fc.NetVLAD(num_clusters=K, dim=C)
+    with torch.no_grad():
+        m.conv.weight.copy_(torch.from_numpy(conv_w)[:, :, None, None])
+        m.centroids.copy_(torch.from_numpy(cent))
+        m.hidden1_weights.copy_(torch.from_numpy(hid))
+        out = m(torch.from_numpy(x)).numpy()
+    np.savez_compressed(os.path.join(OUT, name), K=K, C=C, H=H, W=W, B=B, seed=seed, out=out,
+                        probe=np.array([conv_w[0, 0], cent[-1, -1], hid[-1, -1], x[-1, -1, -1, -1]]))
+    print(name, out.shape, float(np.abs(out).max()))
+
+
 if __name__ == "__main__":
     bev_case("bev_kitti_subsample.npz")
     knn_case("knn_d512_k20.npz", 160, 512, 6, 20, 11)                      # reference k (loop_detector.h:98)
@@ -65,3 +89,5 @@ if __name__ == "__main__":
     knn_case("knn_d30_tail.npz", 200, 30, 5, 7, 31)                        # dim % 4 != 0 tail path
     csm_case("csm_binary.npz", 150, 110, 41, 0.35, 1.2, -0.8, 14, 24, np.pi / 90, 4, 0.3)
     csm_case("csm_graded.npz", 120, 140, 51, -0.6, -1.0, 0.6, 10, 20, np.pi / 60, 3, 0.2, graded=True)
+    vlad_case("vlad_small.npz", 8, 32, 6, 5, 3, 61)
+    vlad_case("vlad_full.npz", 64, 512, 48, 48, 2, 71)                     # the reference's sizes (768^2 input)
