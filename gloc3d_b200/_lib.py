@@ -116,6 +116,11 @@ SIGNATURES = {
     "gloc_grid_file_close": (None, [_vp]),
     "gloc_csm_save_grids": (_i, [_vp, C.c_char_p]),
     "gloc_csm_load_grids": (_i, [_vp, C.c_char_p, _ip, _ip]),
+    "gloc_vlad_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "gloc_vlad_destroy": (None, [_vp]),
+    "gloc_vlad_forward_device": (_i, [_vp, _vp, _i, _i, _vp]),
+    "gloc_vlad_forward": (_i, [_vp, _vp, _i, _i, _vp]),
+    "gloc_vlad_kernel_launches": (C.c_uint64, [_vp]),
 }
 
 _lib = None

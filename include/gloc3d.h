@@ -264,6 +264,32 @@ int gloc_csm_add_grid_from_bev(gloc_csm_store* store, gloc_bev_projector* bev, i
  * point is the consistent construction the driver uses for the north-star verifier. */
 int gloc_csm_add_grid_from_bev_aligned(gloc_csm_store* store, gloc_bev_projector* bev, int* grid_id);
 
+/* ============================================================ descriptor head
+ * (last step of descriptor extraction.)  The NetVLAD_fc pooling layer
+ * that turns the encoder's feature map into the 512-d place descriptor stage 1 searches:
+ *   NetVLAD.forward   model/netvlad_fc.py:73-109 (vladv2 = False, gating off), as traced into
+ *   the TorchScript module of RpyPCLoopDetector::get_place_feature (loop_detector.cpp:137-172)
+ * Batched, device to device: descriptors can go straight into gloc_knn_query_device /
+ * gloc_knn_set_db_device.  FP32; matches the reference module within 1e-5 of the largest
+ * output component (summation order differs).  The VGG16 encoder is NOT part of this library.
+ *   conv_w    [clusters][dim]            1x1 conv weight (netvlad_fc.py:34)
+ *   conv_b    [clusters] or NULL         its bias (NULL for vladv2 = False)
+ *   centroids [clusters][dim]            (:35)
+ *   hidden_w  [clusters*dim][out_dim]    hidden1_weights (:37-38; out_dim = dim in the reference)
+ * Limits: dim % 32 == 0, clusters <= 64, clusters * dim <= 51200. */
+typedef struct gloc_vlad_head gloc_vlad_head;
+int gloc_vlad_create(gloc_vlad_head** out, int device, int dim, int clusters, int out_dim,
+                     const float* conv_w, const float* conv_b, const float* centroids,
+                     const float* hidden_w);
+void gloc_vlad_destroy(gloc_vlad_head* head);
+/* feat: [batch][dim][n_loc] float32 (the encoder's NCHW output with H*W = n_loc), out:
+ * [batch][out_dim]; both in DEVICE memory of the head's device. */
+int gloc_vlad_forward_device(gloc_vlad_head* head, const float* d_feat, int batch, int n_loc,
+                             float* d_out);
+/* The same with HOST buffers (copies inside). */
+int gloc_vlad_forward(gloc_vlad_head* head, const float* feat, int batch, int n_loc, float* out);
+uint64_t gloc_vlad_kernel_launches(const gloc_vlad_head* head);
+
 /* ============================================================ grid store file
  * (a map's BEV grids on disk, so that a database is projected once.)
  * The reference keeps its grids in memory only (db_grids_, loop_detector.h:36-39) and
