@@ -244,15 +244,6 @@ using gloc::fail;
 
 namespace {
 
-struct DeviceScope {   // current device for the duration of a call
-  int prev = 0;
-  explicit DeviceScope(int dev) {
-    cudaGetDevice(&prev);
-    cudaSetDevice(dev);
-  }
-  ~DeviceScope() { cudaSetDevice(prev); }
-};
-
 int forward_device(gloc_vlad_head* h, const float* d_feat, int B, int S, float* d_out) {
   using namespace gloc;
   const int C = h->C, K = h->K, D = h->D, I = K * C;
@@ -311,7 +302,7 @@ int gloc_vlad_create(gloc_vlad_head** out, int device, int dim, int clusters, in
   int major = 0;
   GLOC_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
   if (major != 10) return fail(GLOC_ERR_CUDA, "gloc_vlad_create: device is not sm_100 (kernels are sm_100a only)");
-  DeviceScope scope(device);
+  gloc::DeviceGuard scope(device);
   gloc_vlad_head* h = new gloc_vlad_head;
   h->device = device;
   h->C = dim;
@@ -339,7 +330,7 @@ int gloc_vlad_create(gloc_vlad_head** out, int device, int dim, int clusters, in
 
 void gloc_vlad_destroy(gloc_vlad_head* h) {
   if (!h) return;
-  DeviceScope scope(h->device);
+  gloc::DeviceGuard scope(h->device);
   for (float* p : {h->d_w, h->d_b, h->d_cent, h->d_hidden})
     if (p) cudaFree(p);
   for (gloc::DevBuf* b : {&h->a, &h->inv, &h->V, &h->partial, &h->feat, &h->out}) b->release();
@@ -351,7 +342,7 @@ int gloc_vlad_forward_device(gloc_vlad_head* h, const float* d_feat, int batch, 
   if (!h || !d_feat || !d_out) return fail(GLOC_ERR_INVALID, "gloc_vlad_forward_device: null argument");
   if (batch < 0 || n_loc < 1) return fail(GLOC_ERR_INVALID, "gloc_vlad_forward_device: batch >= 0 and n_loc >= 1 required");
   if (batch == 0) return GLOC_OK;
-  DeviceScope scope(h->device);
+  gloc::DeviceGuard scope(h->device);
   const int rc = forward_device(h, d_feat, batch, n_loc, d_out);
   if (rc != GLOC_OK) return rc;
   GLOC_CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -362,7 +353,7 @@ int gloc_vlad_forward(gloc_vlad_head* h, const float* feat, int batch, int n_loc
   if (!h || !feat || !out) return fail(GLOC_ERR_INVALID, "gloc_vlad_forward: null argument");
   if (batch < 0 || n_loc < 1) return fail(GLOC_ERR_INVALID, "gloc_vlad_forward: batch >= 0 and n_loc >= 1 required");
   if (batch == 0) return GLOC_OK;
-  DeviceScope scope(h->device);
+  gloc::DeviceGuard scope(h->device);
   const size_t n_in = (size_t)batch * h->C * n_loc, n_out = (size_t)batch * h->D;
   GLOC_CUDA_TRY(h->feat.reserve(n_in));
   GLOC_CUDA_TRY(h->out.reserve(n_out));
