@@ -47,6 +47,7 @@ namespace gloc {
 
 namespace {
 
+// [emu-a-begin] (tests/cpp/gemm_emu_test.cpp compiles the marked regions for the host)
 // ------------------------------------------------------------------ tile shape
 constexpr int BM = 128;            // queries per tile = TMEM lanes = UMMA M
 constexpr int BN = 256;            // DB rows per tile = UMMA N = TMEM columns per stage
@@ -85,6 +86,7 @@ __device__ __forceinline__ float ord2f(unsigned o) {
   return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
 }
 
+// [emu-a-end]
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -200,6 +202,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// [emu-b-begin]
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row atoms 1024 B apart (SBO).
 // cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1
 // [46,48), layout_type SWIZZLE_128B=2 [61,64).
@@ -216,6 +219,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // [10,13)=0, a/b K-major [15],[16]=0, N>>3 [17,23), M>>4 [24,29).
 constexpr uint32_t kInstrDesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 constexpr uint32_t kInstrDescPair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+// [emu-b-end]
 
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -357,6 +361,7 @@ __global__ void knn_query_prep_kernel(const float* __restrict__ src, int n, int 
   }
 }
 
+// [emu-c-begin]
 // ------------------------------------------------------------------ K2: GEMM shortlist
 struct GemmArgs {
   int nq, n_qtiles, n_ranges, tiles_per_range, n_kb, k, cap, r_big;
@@ -747,6 +752,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 }
 #undef GLOC_WORKER
 #undef GLOC_N_WORKERS
+// [emu-c-end]
 
 // ------------------------------------------------------------------ K3: select + exact re-rank
 constexpr int kEntMax = 4096;    // group entries per query handled by K3 (more: exact-scan fallback)
