@@ -238,6 +238,7 @@ __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// [emu-k1-begin]
 // ------------------------------------------------------------------ K1: norms + FP16 copy
 // power of two that maps max|v| into [2^13, 2^14): far from FP16 overflow (65504) and
 // underflow (2^-14) for every element that matters
@@ -361,6 +362,7 @@ __global__ void knn_query_prep_kernel(const float* __restrict__ src, int n, int 
   }
 }
 
+// [emu-k1-end]
 // [emu-c-begin]
 // ------------------------------------------------------------------ K2: GEMM shortlist
 struct GemmArgs {
@@ -754,6 +756,7 @@ knn_shortlist_gemm_kernel(const __grid_constant__ CUtensorMap map_q,
 #undef GLOC_N_WORKERS
 // [emu-c-end]
 
+// [emu-k3-begin]
 // ------------------------------------------------------------------ K3: select + exact re-rank
 constexpr int kEntMax = 4096;    // group entries per query handled by K3 (more: exact-scan fallback)
 constexpr int kCandMax = 2048;   // scores under the GEMM's final bound, per query
@@ -1048,6 +1051,7 @@ __global__ void knn_fill_u32_kernel(unsigned* p, size_t n, unsigned v) {
   if (i < n) p[i] = v;
 }
 
+// [emu-k3-end]
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,

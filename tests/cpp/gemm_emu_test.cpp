@@ -326,8 +326,90 @@ static inline unsigned atomicMin(unsigned* p, unsigned v) {
   return cur;
 }
 
+// ---- what the K1 / K3 kernels need on top
+template <typename T>
+static inline T emu_shfl(T v, int src_lane) {   // every lane of the warp calls; src_lane per caller
+  static_assert(sizeof(T) == 4, "32-bit shuffles");
+  emu::Cta& c = emu::g_cta[emu::t_rank];
+  const int warp = emu::t_tid >> 5, lane = emu::t_tid & 31;
+  uint32_t bits;
+  std::memcpy(&bits, &v, 4);
+  c.warp_x[warp][lane] = bits;
+  c.warp_bar[warp]->arrive_and_wait();
+  const uint32_t got = (src_lane >= 0 && src_lane < 32) ? c.warp_x[warp][src_lane] : bits;
+  c.warp_bar[warp]->arrive_and_wait();
+  T out;
+  std::memcpy(&out, &got, 4);
+  return out;
+}
+template <typename T>
+static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, (emu::t_tid & 31) ^ m); }
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int d) {
+  const int lane = emu::t_tid & 31;
+  return emu_shfl(v, lane - d >= 0 ? lane - d : lane);
+}
+template <typename T>
+static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, src & 31); }
+template <typename T, typename U>
+static inline T atomicAdd(T* p, U v) {
+  return std::atomic_ref<T>(*p).fetch_add((T)v);
+}
+static inline unsigned atomicMax(unsigned* p, unsigned v) {
+  std::atomic_ref<unsigned> r(*p);
+  unsigned cur = r.load();
+  while (v > cur && !r.compare_exchange_weak(cur, v)) {
+  }
+  return cur;
+}
+static inline float __fadd_rn(float a, float b) { return a + b; }   // built with -ffp-contract=off
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline float __int_as_float(int i) {
+  float f;
+  std::memcpy(&f, &i, 4);
+  return f;
+}
+#define __align__(n) alignas(n)
+struct float2 {
+  float x, y;
+};
+struct __half {
+  uint16_t bits;
+};
+struct __half2 {
+  __half x, y;
+};
+static inline uint16_t float_to_half_rn(float f) {   // IEEE round to nearest even, like cvt.rn.f16.f32
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t a = u & 0x7FFFFFFFu;
+  if (a >= 0x7F800000u) return (uint16_t)(sign | 0x7C00u | (a > 0x7F800000u ? 0x200u : 0));
+  if (a >= 0x477FF000u) return (uint16_t)(sign | 0x7C00u);            // rounds to infinity
+  if (a < 0x33000001u) return (uint16_t)sign;                           // below half of the smallest subnormal
+  int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7FFFFFu) | 0x800000u;
+  int shift = e >= -14 ? 13 : 13 + (-14 - e);                           // subnormal halves lose more bits
+  uint32_t half_m = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_m & 1))) ++half_m;
+  uint32_t h = e >= -14 ? (((uint32_t)(e + 15) << 10) + (half_m - 0x400u)) : half_m;   // carries propagate
+  return (uint16_t)(sign | h);
+}
+static inline __half2 __floats2half2_rn(float a, float b) {
+  return __half2{__half{float_to_half_rn(a)}, __half{float_to_half_rn(b)}};
+}
+static inline float2 __half22float2(__half2 h) {
+  return float2{emu::half_to_float(h.x.bits), emu::half_to_float(h.y.bits)};
+}
+
 namespace gloc {
 namespace {
+
+constexpr uint64_t kEmptyKey = 0xFFFFFFFFFFFFFFFFull;   // csrc/common.cuh
+inline uint64_t pack_key(float d2, uint32_t idx) { return ((uint64_t)__float_as_uint(d2) << 32) | idx; }
 
 // ---- the kernel's PTX wrappers, emulated (same names and signatures as in knn_shortlist.cu)
 inline uint32_t smem_u32(const void* p) { return emu::addr_of(p); }
@@ -411,7 +493,9 @@ thread_local unsigned char* t_smem_raw = nullptr;
 
 #include "_gemm_a.inc"
 #include "_gemm_b.inc"
+#include "_gemm_k1.inc"
 #include "_gemm_c.inc"
+#include "_gemm_k3.inc"
 
 }  // namespace
 }  // namespace gloc
@@ -474,14 +558,157 @@ static void run_grid(int n_workers, const CUtensorMap& map_q, const CUtensorMap&
   }
 }
 
+// ordinary kernels (K1, K3): blocks one after the other, block_threads OS threads each
+template <typename F>
+static void launch_blocks(unsigned grid_x, unsigned block_threads, size_t dyn_smem, F body) {
+  emu::g_n_cta = 1;
+  emu::g_grid.x = grid_x;
+  emu::g_blockdim.x = block_threads;
+  emu::Cta& c = emu::g_cta[0];
+  if (!c.smem) c.smem = static_cast<unsigned char*>(std::aligned_alloc(1024, emu::kSmemBuf));
+  if (dyn_smem + 16 > emu::kSmemBuf) std::abort();
+  for (unsigned bx = 0; bx < grid_x; ++bx) {
+    c.block_bar.reset(new std::barrier<>(block_threads));
+    c.warp_bar.clear();
+    for (unsigned w = 0; w < (block_threads + 31) / 32; ++w)
+      c.warp_bar.emplace_back(new std::barrier<>(std::min(32u, block_threads - 32 * w)));
+    c.warp_x.assign((block_threads + 31) / 32, std::vector<uint32_t>(32, 0));
+    std::vector<std::thread> ts;
+    for (unsigned t = 0; t < block_threads; ++t)
+      ts.emplace_back([&, t] {
+        emu::t_rank = 0;
+        emu::t_tid = (int)t;
+        emu::t_thread.x = t;
+        emu::t_block.x = bx;
+        t_smem_raw = c.smem + 16;
+        body();
+        c.block_bar->arrive_and_drop();                  // early returns must not block the others
+        c.warp_bar[t >> 5]->arrive_and_drop();
+      });
+    for (auto& th : ts) th.join();
+  }
+}
+
+// mode 1: the whole shortlist path from float32 rows -- K1 (stats, FP16 copy, query prep), K2, K3 --
+// with the launch geometry of shortlist_query(); writes the top-k and the overflow count.
+static int run_full(FILE* f, const std::vector<int32_t>& h, const char* out_path) {
+  const int nq = h[0], n_rows = h[1], n_pad = h[2], dim = h[3], k = h[4], cap = h[5], n_ranges = h[6],
+            tiles_per_range = h[7], pair = h[8], workers = h[9];
+  const std::vector<float> q = read_vec<float>(f, (size_t)nq * dim), db = read_vec<float>(f, (size_t)n_rows * dim);
+  std::fclose(f);
+  // K1, database
+  std::vector<uint16_t> db_h((size_t)n_pad * dim, 0xCDCD), q_h((size_t)nq * dim, 0xCDCD);
+  std::vector<float> xn((size_t)n_pad, NAN), qn((size_t)nq), qe((size_t)nq), qinv((size_t)nq);
+  std::vector<unsigned> stats(4, 0u);
+  const int wpb = 8;
+  launch_blocks((unsigned)((n_rows + wpb - 1) / wpb), wpb * 32, 0, [&] {
+    knn_db_stats_kernel(db.data(), n_rows, dim, xn.data(), stats.data(), stats.data() + 1);
+  });
+  const float scale_x = pow2_scale_for(__uint_as_float(stats[1]));
+  launch_blocks((unsigned)((n_pad + wpb - 1) / wpb), wpb * 32, 0, [&] {
+    knn_db_convert_kernel(db.data(), n_rows, n_pad, dim, scale_x, reinterpret_cast<__half*>(db_h.data()), xn.data(),
+                          stats.data() + 2);
+  });
+  // K1, queries
+  launch_blocks((unsigned)((nq + wpb - 1) / wpb), wpb * 32, 0, [&] {
+    knn_query_prep_kernel(q.data(), nq, dim, reinterpret_cast<__half*>(q_h.data()), qn.data(), qe.data(), qinv.data());
+  });
+  // K2
+  const int n_qtiles = (nq + BM - 1) / BM;
+  const size_t lists = (size_t)nq * n_ranges * 2;
+  std::vector<unsigned> thr((size_t)nq, 0xFF800000u), cand_g(lists * cap, 0xFFFFFFFFu), unit_cnt(lists, 0xFFFFFFFFu);
+  std::vector<float> eps2((size_t)nq, -1.f);
+  std::vector<float4> cand_v(lists * cap * 2, float4{NAN, NAN, NAN, NAN});
+  GemmArgs g;
+  g.nq = nq;
+  g.n_qtiles = pair ? (n_qtiles + 1) / 2 : n_qtiles;
+  g.n_ranges = n_ranges;
+  g.tiles_per_range = tiles_per_range;
+  g.n_kb = dim / BK;
+  g.k = k;
+  g.cap = cap;
+  g.r_big = 1;
+  g.n_rows = n_rows;
+  g.xn = xn.data();
+  g.qn = qn.data();
+  g.qe = qe.data();
+  g.qinv = qinv.data();
+  g.inv_sx = 1.f / scale_x;
+  g.max_norm2_bits = stats.data();
+  g.max_dx2_bits = stats.data() + 2;
+  g.thr_ord = thr.data();
+  g.eps2 = eps2.data();
+  g.cand_g = cand_g.data();
+  g.cand_v = cand_v.data();
+  g.unit_cnt = unit_cnt.data();
+  const CUtensorMap map_q{q_h.data(), (uint64_t)nq, (uint64_t)dim, (uint32_t)BM};
+  const CUtensorMap map_db{db_h.data(), (uint64_t)n_rows, (uint64_t)dim, (uint32_t)(pair ? BN / 2 : BN)};
+  const int n_workers = std::min(g.n_qtiles * n_ranges, workers);
+  if (pair) run_grid<true>(n_workers, map_q, map_db, g);
+  else run_grid<false>(n_workers, map_q, map_db, g);
+  emu::g_engine.finish();
+  // K3
+  std::vector<uint64_t> out_idx((size_t)nq * k, 0);
+  std::vector<float> out_d2((size_t)nq * k, NAN);
+  std::vector<int> ovf_list((size_t)nq, -1), ovf_count(1, 0);
+  std::vector<unsigned long long> rows_ctr(2, 0);
+  RerankArgs r;
+  r.db = db.data();
+  r.q = q.data();
+  r.nq = nq;
+  r.dim = dim;
+  r.k = k;
+  r.n_ranges = n_ranges * 2;
+  r.cap = cap;
+  r.cand_g = cand_g.data();
+  r.cand_v = reinterpret_cast<const float*>(cand_v.data());
+  r.unit_cnt = unit_cnt.data();
+  r.thr_ord = thr.data();
+  r.eps2 = eps2.data();
+  r.offset = 0;
+  r.out_idx = out_idx.data();
+  r.out_d2 = out_d2.data();
+  r.overflow_list = ovf_list.data();
+  r.overflow_count = ovf_count.data();
+  r.rows_reranked = rows_ctr.data();
+  const size_t rr_smem = std::max((size_t)kCandMax * 8, (size_t)32 * (dim / 4 + 1) * 4) + (size_t)4 * 256 * 4 +
+                         (size_t)kFinalMax * 8 + (size_t)dim * 4;
+  launch_blocks((unsigned)nq, kRerankThreads, rr_smem, [&] { knn_shortlist_rerank_kernel(r); });
+  FILE* o = std::fopen(out_path, "wb");
+  if (!o) return 2;
+  std::fwrite(out_idx.data(), 8, out_idx.size(), o);
+  std::fwrite(out_d2.data(), 4, out_d2.size(), o);
+  std::fwrite(ovf_count.data(), 4, 1, o);
+  std::fwrite(rows_ctr.data(), 8, 2, o);
+  std::fclose(o);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc != 3) return 2;
   FILE* f = std::fopen(argv[1], "rb");
   if (!f) return 2;
   // header: nq, n_rows, n_pad, dim, k, cap, n_ranges, tiles_per_range, pair, workers
-  const std::vector<int32_t> h = read_vec<int32_t>(f, 10);
+  const std::vector<int32_t> h = read_vec<int32_t>(f, 11);
   const int nq = h[0], n_rows = h[1], n_pad = h[2], dim = h[3], k = h[4], cap = h[5], n_ranges = h[6],
-            tiles_per_range = h[7], pair = h[8], workers = h[9];
+            tiles_per_range = h[7], pair = h[8], workers = h[9], mode = h[10];
+  if (mode == 1) {
+    std::thread([] {   // the same watchdog, detached
+      uint64_t last = emu::g_progress.load();
+      for (int idle = 0;; ) {
+        std::this_thread::sleep_for(std::chrono::seconds(1));
+        const uint64_t now = emu::g_progress.load();
+        idle = now == last ? idle + 1 : 0;
+        last = now;
+        if (idle >= 120) {
+          std::fprintf(stderr, "emu: DEADLOCK -- no barrier progress for 120 s\n");
+          std::_Exit(3);
+        }
+      }
+    }).detach();
+    if (const char* e = std::getenv("GLOC_EMU_ASYNC")) emu::g_engine.start((unsigned)std::atoi(e));
+    return run_full(f, h, argv[2]);
+  }
   const float inv_sx = read_vec<float>(f, 1)[0];
   const std::vector<unsigned> stats = read_vec<unsigned>(f, 3);          // max ||x||^2, -, max ||dx||^2 (float bits)
   const std::vector<uint16_t> q_h = read_vec<uint16_t>(f, (size_t)nq * dim);

@@ -23,7 +23,7 @@ BM, BN = 128, 256
 @pytest.fixture(scope="module")
 def exe():
     src = open(os.path.join(ROOT, "gloc3d_b200", "csrc", "knn_shortlist.cu")).read()
-    for tag in "abc":
+    for tag in ("a", "b", "c", "k1", "k3"):
         m = re.search(r"// \[emu-%s-begin\].*?\n(.*?)// \[emu-%s-end\]" % (tag, tag), src, re.S)
         assert m, f"marker emu-{tag} missing"
         text = m.group(1)
@@ -34,8 +34,13 @@ def exe():
                 return "*tmem_slot = 0;" if "tcgen05.alloc" in mm.group(0) else "(void)0;"
             text, n = re.subn(r"asm volatile\(.*?\);", asm_sub, text, flags=re.S)
             assert n == 8 and "asm" not in text, n
+        if tag == "k3":
+            text = text.replace("extern __shared__ __align__(16) unsigned char sm_raw[];",
+                                "unsigned char* sm_raw = t_smem_raw;")
+            assert "extern" not in text
         open(os.path.join(CPP, f"_gemm_{tag}.inc"), "w").write(text)
-    r = subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", os.path.join(CPP, "gemm_emu_test.cpp"), "-o", EXE],
+    r = subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-ffp-contract=off",
+                        os.path.join(CPP, "gemm_emu_test.cpp"), "-o", EXE],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-6000:]
     return EXE
@@ -73,7 +78,7 @@ def prepare(nq, n_rows, dim, seed, dup=False):
 def run(exe, tmp_path, P, nq, n_rows, dim, k, cap, n_ranges, tiles_per_range, pair, workers, async_seed=None):
     inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     with open(inp, "wb") as f:
-        f.write(np.array([nq, n_rows, P["n_pad"], dim, k, cap, n_ranges, tiles_per_range, int(pair), workers],
+        f.write(np.array([nq, n_rows, P["n_pad"], dim, k, cap, n_ranges, tiles_per_range, int(pair), workers, 0],
                          np.int32).tobytes())
         f.write(np.array([P["inv_sx"]], np.float32).tobytes())
         f.write(P["stats"].tobytes())
@@ -149,3 +154,32 @@ def test_emulated_gemm_epilogue(exe, tmp_path, case, pair, async_seed):
               async_seed=async_seed)
     n = check(P, out, nq, n_rows, dim, k, cap, n_ranges, tpr)
     assert n > nq          # something was emitted for every query
+
+
+@pytest.mark.parametrize("pair", [False, True])
+def test_emulated_shortlist_path_is_bit_exact(exe, tmp_path, pair):
+    """K1 -> K2 -> K3, all from the kernels' own source, against the nanoflann-order oracle:
+    indices and distances bit for bit, no query falls back."""
+    from oracle import pyoracle as po
+
+    nq, n_rows, dim, k, n_ranges, tpr = 200, 1000, 128, 25, 2, 2
+    P = prepare(nq, n_rows, dim, seed=99, dup=True)
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        f.write(np.array([nq, n_rows, P["n_pad"], dim, k, 512, n_ranges, tpr, int(pair), 1 if pair else 2, 1],
+                         np.int32).tobytes())
+        f.write(np.ascontiguousarray(P["q"]).tobytes())
+        f.write(np.ascontiguousarray(P["db"]).tobytes())
+    env = dict(os.environ, GLOC_EMU_ASYNC="5")
+    r = subprocess.run([exe, inp, outp], capture_output=True, text=True, timeout=2400, env=env)
+    assert r.returncode == 0, r.stderr[-4000:]
+    raw = open(outp, "rb").read()
+    idx = np.frombuffer(raw, np.uint64, nq * k).reshape(nq, k)
+    d2 = np.frombuffer(raw, np.float32, nq * k, offset=nq * k * 8).reshape(nq, k)
+    n_ovf = np.frombuffer(raw, np.int32, 1, offset=nq * k * 12)[0]
+    rows = np.frombuffer(raw, np.uint64, 2, offset=nq * k * 12 + 4)
+    ref_idx, ref_d2 = po.knn(P["db"], P["q"], k, nthreads=4)
+    assert n_ovf == 0
+    assert np.array_equal(idx, ref_idx.astype(np.uint64))
+    assert np.array_equal(d2.view(np.uint32), ref_d2.view(np.uint32))
+    assert k * nq <= rows[0] <= 12 * k * nq          # the shortlist is short
