@@ -121,6 +121,12 @@ SIGNATURES = {
     "gloc_vlad_forward_device": (_i, [_vp, _vp, _i, _i, _vp]),
     "gloc_vlad_forward": (_i, [_vp, _vp, _i, _i, _vp]),
     "gloc_vlad_kernel_launches": (C.c_uint64, [_vp]),
+    "gloc_enc_create": (_i, [C.POINTER(_vp), _i, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
+    "gloc_enc_destroy": (None, [_vp]),
+    "gloc_enc_feature_shape": (_i, [_vp, _ip, _ip]),
+    "gloc_enc_forward_device": (_i, [_vp, _vp, _i, _vp]),
+    "gloc_enc_forward": (_i, [_vp, _vp, _i, _vp]),
+    "gloc_enc_kernel_launches": (C.c_uint64, [_vp]),
 }
 
 _lib = None

@@ -1,4 +1,6 @@
-"""NetVLAD_fc pooling head on the GPU (C ABI: gloc_vlad_*; reference: model/netvlad_fc.py:73-109
+"""Descriptor extraction on the GPU: the VGG16 encoder (C ABI: gloc_enc_*; reference:
+main.py:531-536 as run by RpyPCLoopDetector::get_place_feature, loop_detector.cpp:137-172) and the
+NetVLAD_fc pooling head on the GPU (C ABI: gloc_vlad_*; reference: model/netvlad_fc.py:73-109
 as run by RpyPCLoopDetector::get_place_feature, loop_detector.cpp:137-172): encoder feature maps
 in, 512-d place descriptors out, batched; the device entry point feeds KnnIndex.query_device /
 set_db_device without a host round trip.  The VGG16 encoder is not part of this package."""
@@ -56,6 +58,61 @@ class NetVladHead:
     def close(self) -> None:
         if self._h:
             _lib.lib().gloc_vlad_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+VGG16_COUT = (64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512)
+
+
+class Encoder:
+    """VGG16 features[:-2] on uint8 BEV images [B, H, W] -> feature maps [B, 512, H/16 * W/16]."""
+
+    def __init__(self, conv_w, conv_b, height: int = 768, width: int = 768, device: int = 0):
+        """conv_w: 13 arrays [Cout, Cin, 3, 3] float32 (torchvision layout), conv_b: 13 arrays [Cout]."""
+        if len(conv_w) != 13 or len(conv_b) != 13:
+            raise ValueError("13 convolution layers expected")
+        cin = 3
+        ws, bs = [], []
+        for w, b, cout in zip(conv_w, conv_b, VGG16_COUT):
+            w = np.ascontiguousarray(w, np.float32)
+            b = np.ascontiguousarray(b, np.float32)
+            if w.shape != (cout, cin, 3, 3) or b.shape != (cout,):
+                raise ValueError(f"layer with {cout} outputs: weight {w.shape}, bias {b.shape}")
+            ws.append(w)
+            bs.append(b)
+            cin = cout
+        self._keep = (ws, bs)
+        wp = (C.c_void_p * 13)(*[w.ctypes.data for w in ws])
+        bp = (C.c_void_p * 13)(*[b.ctypes.data for b in bs])
+        self.height, self.width, self.device = height, width, device
+        self._h = C.c_void_p()
+        check(_lib.lib().gloc_enc_create(C.byref(self._h), device, height, width, wp, bp))
+        self.channels, self.n_loc = 512, (height // 16) * (width // 16)
+
+    def forward(self, images: np.ndarray) -> np.ndarray:
+        images = np.ascontiguousarray(images, np.uint8)
+        if images.ndim != 3 or images.shape[1:] != (self.height, self.width):
+            raise ValueError(f"images must be [B, {self.height}, {self.width}] uint8")
+        out = np.empty((images.shape[0], self.channels, self.n_loc), np.float32)
+        check(_lib.lib().gloc_enc_forward(self._h, images.ctypes.data, images.shape[0], out.ctypes.data))
+        return out
+
+    def forward_device(self, images_ptr: int, batch: int, feat_ptr: int) -> None:
+        check(_lib.lib().gloc_enc_forward_device(self._h, C.c_void_p(images_ptr), batch, C.c_void_p(feat_ptr)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(_lib.lib().gloc_enc_kernel_launches(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            _lib.lib().gloc_enc_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -290,6 +290,28 @@ int gloc_vlad_forward_device(gloc_vlad_head* head, const float* d_feat, int batc
 int gloc_vlad_forward(gloc_vlad_head* head, const float* feat, int batch, int n_loc, float* out);
 uint64_t gloc_vlad_kernel_launches(const gloc_vlad_head* head);
 
+/* ============================================================ descriptor encoder
+ * (first step of descriptor extraction.)  VGG16 features[:-2] as the
+ * reference assembles it (main.py:531-536: 13 3x3 convolutions + ReLU, the first four 2x2
+ * max-pools, last ReLU and pool dropped) on the BEV occupancy image that
+ * RpyPCLoopDetector::get_place_feature feeds it (loop_detector.cpp:137-172: 768 x 768, three
+ * identical channels, 1/255).  Batched, device to device; output [batch][512][H/16 * W/16]
+ * float32 is what gloc_vlad_forward_device takes.  Tensor-core implicit GEMM (tcgen05, FP16
+ * operands, FP32 accumulation -- the significand of the TF32 path the reference's cuDNN uses).
+ *   conv_w[l]  [Cout][Cin][3][3] float32, l = 0..12 (torchvision's layout; Cin = 3 for l = 0)
+ *   conv_b[l]  [Cout]
+ * images: uint8 [batch][height][width] (one plane: the three channels are identical; the plane
+ * gloc_bev_get_cnn_input returns).  height % 128 == 0, width % 256 == 0. */
+typedef struct gloc_encoder gloc_encoder;
+int gloc_enc_create(gloc_encoder** out, int device, int height, int width,
+                    const float* const* conv_w, const float* const* conv_b);
+void gloc_enc_destroy(gloc_encoder* enc);
+int gloc_enc_feature_shape(const gloc_encoder* enc, int* channels, int* n_loc);
+int gloc_enc_forward_device(gloc_encoder* enc, const uint8_t* d_images, int batch, float* d_feat);
+/* The same with HOST buffers (copies inside). */
+int gloc_enc_forward(gloc_encoder* enc, const uint8_t* images, int batch, float* feat);
+uint64_t gloc_enc_kernel_launches(const gloc_encoder* enc);
+
 /* ============================================================ grid store file
  * (a map's BEV grids on disk, so that a database is projected once.)
  * The reference keeps its grids in memory only (db_grids_, loop_detector.h:36-39) and

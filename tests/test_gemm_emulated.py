@@ -39,7 +39,7 @@ def exe():
                                 "unsigned char* sm_raw = t_smem_raw;")
             assert "extern" not in text
         open(os.path.join(CPP, f"_gemm_{tag}.inc"), "w").write(text)
-    r = subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-ffp-contract=off",
+    r = subprocess.run(["g++", "-O2", "-std=c++20", "-pthread", "-ffp-contract=off", "-fno-strict-aliasing",
                         os.path.join(CPP, "gemm_emu_test.cpp"), "-o", EXE],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-6000:]

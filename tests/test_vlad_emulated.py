@@ -25,7 +25,7 @@ def exe():
     text = m.group(1).replace("extern __shared__", "extern")
     assert "__shared__" in text and "__syncthreads" in text
     open(os.path.join(CPP, "_vlad_kernels.inc"), "w").write(text)
-    r = subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off",
+    r = subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-ffp-contract=off", "-fno-strict-aliasing",
                         os.path.join(CPP, "vlad_emu_test.cpp"), "-o", EXE], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     return EXE
