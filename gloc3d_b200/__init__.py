@@ -9,7 +9,7 @@ no CPU fallback anywhere in this package.
 from . import _lib  # noqa: F401
 from ._lib import GlocError, KNN_AUTO, KNN_EXACT_SCAN, KNN_SHORTLIST  # noqa: F401
 from .bev import BevProjector  # noqa: F401
-from .descriptor import Encoder, NetVladHead  # noqa: F401
+from .descriptor import DescriptorExtractor, Encoder, NetVladHead  # noqa: F401
 from .grid_store import StoredGrid, read_grid_file, write_grid_file  # noqa: F401
 from .retrieval import InvKeyTree, KnnIndex, merge_topk_device  # noqa: F401
 from .scan_matching import (CsmStore, FastCorrelativeScanMatcher2D,  # noqa: F401
@@ -19,4 +19,4 @@ from .scan_matching import (CsmStore, FastCorrelativeScanMatcher2D,  # noqa: F40
 __all__ = ["GlocError", "BevProjector", "InvKeyTree", "KnnIndex", "merge_topk_device", "CsmStore",
            "FastCorrelativeScanMatcher2D", "FastCorrelativeScanMatcherOptions2D", "MapLimits",
            "ProbabilityGrid", "Rigid2d", "grid_to_virtual_point_cloud", "search_parameters",
-           "KNN_AUTO", "KNN_EXACT_SCAN", "KNN_SHORTLIST", "StoredGrid", "read_grid_file", "write_grid_file", "NetVladHead", "Encoder"]
+           "KNN_AUTO", "KNN_EXACT_SCAN", "KNN_SHORTLIST", "StoredGrid", "read_grid_file", "write_grid_file", "NetVladHead", "Encoder", "DescriptorExtractor"]

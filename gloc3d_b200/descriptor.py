@@ -120,3 +120,51 @@ class Encoder:
             self.close()
         except Exception:
             pass
+
+
+class DescriptorExtractor:
+    """BEV image plane(s) -> place descriptors: encoder + NetVLAD_fc head, device-resident in
+    between (torch only provides the device buffers)."""
+
+    def __init__(self, conv_w, conv_b, vlad_conv_w, centroids, hidden_w, vlad_conv_b=None,
+                 height: int = 768, width: int = 768, device: int = 0):
+        self.device = device
+        self.enc = Encoder(conv_w, conv_b, height=height, width=width, device=device)
+        self.head = NetVladHead(vlad_conv_w, centroids, hidden_w, conv_b=vlad_conv_b, device=device)
+        self.out_dim = self.head.out_dim
+        self._feat = None
+
+    @classmethod
+    def from_file(cls, path: str, **kw):
+        from .weights import load_weights
+
+        conv_w, conv_b, vw, vb, cent, hid = load_weights(path)
+        return cls(conv_w, conv_b, vw, cent, hid, vlad_conv_b=vb, **kw)
+
+    def describe_device(self, images_ptr: int, batch: int, desc_ptr: int) -> None:
+        """uint8 planes [batch][H][W] (device) -> descriptors [batch][D] float32 (device)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        if self._feat is None or self._feat.shape[0] < batch:
+            self._feat = torch.empty((batch, self.enc.channels, self.enc.n_loc), dtype=torch.float32, device=dev)
+            torch.cuda.synchronize(dev)
+        self.enc.forward_device(images_ptr, batch, self._feat.data_ptr())
+        self.head.forward_device(self._feat.data_ptr(), batch, self.enc.n_loc, desc_ptr)
+
+    def describe(self, images: np.ndarray) -> np.ndarray:
+        """uint8 planes [B, H, W] (host) -> descriptors [B, D] float32 (host)."""
+        import torch
+
+        dev = torch.device("cuda", self.device)
+        images = np.ascontiguousarray(images, np.uint8)
+        d_img = torch.from_numpy(images).to(dev)
+        d_desc = torch.empty((images.shape[0], self.out_dim), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize(dev)
+        self.describe_device(d_img.data_ptr(), images.shape[0], d_desc.data_ptr())
+        return d_desc.cpu().numpy()
+
+    def close(self) -> None:
+        self.enc.close()
+        self.head.close()
+        self._feat = None

@@ -159,3 +159,49 @@ def make_lidar_scan(n_walls: int = 40, seed: int = 4444, max_range: float = 90.0
     xyz = np.concatenate(parts).astype(np.float32)
     inten = rng.uniform(0, 1, (xyz.shape[0], 1)).astype(np.float32)
     return np.ascontiguousarray(np.concatenate([xyz, inten], axis=1))
+
+
+# ------------------------------------------------------------------ descriptor network
+VGG16_COUT = (64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512)
+
+
+def hash_uniform(shape, seed):
+    """Deterministic pseudo-random float32 values in [-1, 1) from integer arithmetic only (a
+    splitmix64 finaliser of the element index): identical on every platform and numpy version,
+    so fixtures need not store large weight tensors."""
+    n = int(np.prod(shape))
+    off = np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
+    with np.errstate(over="ignore"):
+        z = np.arange(n, dtype=np.uint64) + off
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u24 = (z >> np.uint64(40)).astype(np.float32)          # 24 random bits: exact in float32
+    return (u24 / np.float32(1 << 23) - np.float32(1.0)).reshape(shape)
+
+
+def hashed_vlad_weights(K, C, D, seed):
+    """conv_w [K, C] ~ U(-1, 1)/sqrt(C) (the Conv2d default init range, netvlad_fc.py:34),
+    centroids [K, C] ~ U(0, 1) (:35), hidden_w [K*C, D] ~ U(-1, 1) sqrt(3/C) (same variance as
+    the reference's randn/sqrt(dim), :37-38)."""
+    conv_w = hash_uniform((K, C), seed) / np.float32(np.sqrt(C))
+    centroids = (hash_uniform((K, C), seed + 1) + np.float32(1.0)) * np.float32(0.5)
+    hidden_w = hash_uniform((K * C, D), seed + 2) * np.float32(np.sqrt(3.0 / C))
+    return conv_w.astype(np.float32), centroids.astype(np.float32), hidden_w.astype(np.float32)
+
+
+def hashed_features(B, C, S, seed):
+    """A feature map [B, C, S] with conv5_3-like statistics (no ReLU: both signs)."""
+    return (hash_uniform((B, C, S), seed) * np.float32(3.0)).astype(np.float32)
+
+
+def hashed_vgg_weights(seed, gain=1.0):
+    """13 (weight [Cout, Cin, 3, 3], bias [Cout]) pairs from the integer-hash generator of
+    above (platform independent), He-scaled so that activations keep their magnitude."""
+    ws, bs, cin = [], [], 3
+    for l, cout in enumerate(VGG16_COUT):
+        std = gain * np.sqrt(2.0 / (9 * cin))
+        ws.append((hash_uniform((cout, cin, 3, 3), seed + 2 * l) * np.float32(std * np.sqrt(3.0))).astype(np.float32))
+        bs.append((hash_uniform((cout,), seed + 2 * l + 1) * np.float32(0.05)).astype(np.float32))
+        cin = cout
+    return ws, bs

@@ -15,18 +15,7 @@ VGG16_COUT = (64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512)
 POOL_AFTER = (1, 3, 6, 9)          # 0-based convolution indices followed by a 2x2 max-pool
 
 
-def hashed_vgg_weights(seed, gain=1.0):
-    """13 (weight [Cout, Cin, 3, 3], bias [Cout]) pairs from the integer-hash generator of
-    vlad_oracle (platform independent), He-scaled so that activations keep their magnitude."""
-    from .vlad_oracle import _hash_uniform
-
-    ws, bs, cin = [], [], 3
-    for l, cout in enumerate(VGG16_COUT):
-        std = gain * np.sqrt(2.0 / (9 * cin))
-        ws.append((_hash_uniform((cout, cin, 3, 3), seed + 2 * l) * np.float32(std * np.sqrt(3.0))).astype(np.float32))
-        bs.append((_hash_uniform((cout,), seed + 2 * l + 1) * np.float32(0.05)).astype(np.float32))
-        cin = cout
-    return ws, bs
+from gloc3d_b200.synth import hashed_vgg_weights  # noqa: E402,F401
 
 
 def vgg16_features(images_u8, conv_w, conv_b):

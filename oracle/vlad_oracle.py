@@ -48,31 +48,6 @@ def netvlad_fc(x, conv_w, centroids, hidden_w, conv_b=None):
     return out
 
 
-def _hash_uniform(shape, seed):
-    """Deterministic pseudo-random float32 values in [-1, 1) from integer arithmetic only (a
-    splitmix64 finaliser of the element index): identical on every platform and numpy version,
-    so fixtures need not store large weight tensors."""
-    n = int(np.prod(shape))
-    off = np.uint64((int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF)
-    with np.errstate(over="ignore"):
-        z = np.arange(n, dtype=np.uint64) + off
-        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-        z = z ^ (z >> np.uint64(31))
-    u24 = (z >> np.uint64(40)).astype(np.float32)          # 24 random bits: exact in float32
-    return (u24 / np.float32(1 << 23) - np.float32(1.0)).reshape(shape)
-
-
-def hashed_weights(K, C, D, seed):
-    """conv_w [K, C] ~ U(-1, 1)/sqrt(C) (the Conv2d default init range, netvlad_fc.py:34),
-    centroids [K, C] ~ U(0, 1) (:35), hidden_w [K*C, D] ~ U(-1, 1) sqrt(3/C) (same variance as
-    the reference's randn/sqrt(dim), :37-38)."""
-    conv_w = _hash_uniform((K, C), seed) / np.float32(np.sqrt(C))
-    centroids = (_hash_uniform((K, C), seed + 1) + np.float32(1.0)) * np.float32(0.5)
-    hidden_w = _hash_uniform((K * C, D), seed + 2) * np.float32(np.sqrt(3.0 / C))
-    return conv_w.astype(np.float32), centroids.astype(np.float32), hidden_w.astype(np.float32)
-
-
-def hashed_features(B, C, S, seed):
-    """A feature map [B, C, S] with conv5_3-like statistics (no ReLU: both signs)."""
-    return (_hash_uniform((B, C, S), seed) * np.float32(3.0)).astype(np.float32)
+# synthetic weights / features: the integer-hash generators live with the other synthetic inputs
+from gloc3d_b200.synth import hash_uniform as _hash_uniform  # noqa: E402,F401
+from gloc3d_b200.synth import hashed_features, hashed_vlad_weights as hashed_weights  # noqa: E402,F401

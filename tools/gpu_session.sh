@@ -56,7 +56,8 @@ for stage in "${STAGES[@]}"; do
       run bench_retrieval 900 python bench.py
       run bench_verify 900 python bench.py --workload verify
       run bench_stream 900 python bench.py --workload stream
-      for w in retrieval verify stream; do last_json "$OUT/bench_$w.log" > "$OUT/bench_$w.json"; done
+      run bench_describe 900 python bench.py --workload describe --steps 5 --warmup 3
+      for w in retrieval verify stream describe; do last_json "$OUT/bench_$w.log" > "$OUT/bench_$w.json"; done
       ;;
     launches)
       for w in retrieval verify stream; do
