@@ -196,6 +196,16 @@ extern "C" {
 int gloc_version(void) { return 100; }
 const char* gloc_last_error(void) { return g_last_error.c_str(); }
 
+int gloc_knn_pair_workers(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  gloc::DeviceGuard g(device);
+  return gloc::shortlist_pair_workers();
+}
+
 int gloc_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {

@@ -1206,6 +1206,8 @@ int pair_workers() {
 
 }  // namespace
 
+int shortlist_pair_workers() { return pair_workers(); }
+
 int shortlist_query(ShortlistState** sp, const ShortlistArgs& A, uint64_t* launches,
                     uint64_t* fallback, uint64_t* rows_reranked) {
   if (!*sp) *sp = new ShortlistState;

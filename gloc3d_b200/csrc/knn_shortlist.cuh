@@ -39,4 +39,8 @@ int shortlist_query(ShortlistState** s, const ShortlistArgs& a, uint64_t* launch
 // whose shortlist overflowed (re-run by the exact scan).
 int shortlist_counters(ShortlistState* s, uint64_t* rows_reranked, uint64_t* overflowed);
 
+// Resident CTA pairs the experimental cta_group::2 GEMM would run with on the current device;
+// 0 unless GLOC_KNN_PAIR=1 is set and the variant can be launched.
+int shortlist_pair_workers();
+
 }  // namespace gloc

@@ -107,6 +107,11 @@ int gloc_knn_get_profile(gloc_knn_index* index, gloc_profile* out);
  * copies happen inside the call. */
 int gloc_knn_query(gloc_knn_index* index, const float* queries, size_t nq, size_t k,
                    uint64_t* out_idx, float* out_d2);
+/* Experimental: GLOC_KNN_PAIR=1 in the environment selects the CTA-pair (cta_group::2) form of
+ * the shortlist GEMM.  Returns the number of resident CTA pairs it would
+ * run with on `device`, 0 when the variable is unset or the variant cannot be launched. */
+int gloc_knn_pair_workers(int device);
+
 /* Same with queries and outputs in DEVICE memory; work is enqueued on `stream`
  * (a cudaStream_t, NULL = the legacy default stream) and not synchronised. */
 int gloc_knn_query_device(gloc_knn_index* index, const float* d_queries, size_t nq,

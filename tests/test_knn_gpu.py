@@ -283,3 +283,16 @@ def test_streaming_scan_small_batches(oracle, nq, n, dim, k):
         ix.close()
         ridx, rd2 = oracle.knn(db[:n - 30], q, k, nthreads=8)
         assert_knn_equal(idx, d2, ridx + np.uint64(1000), rd2)
+
+
+@pytest.mark.gpu
+def test_pair_variant_is_active_when_requested():
+    """With GLOC_KNN_PAIR=1 (tests/test_zz_first_gpu_run.py, tools/gpu_session.sh) this whole file
+    exercises the CTA-pair GEMM: make sure it really is the kernel that runs."""
+    import os
+
+    from gloc3d_b200 import _lib
+
+    if not os.environ.get("GLOC_KNN_PAIR"):
+        pytest.skip("GLOC_KNN_PAIR not set: the shipped one-CTA-per-SM kernel is under test")
+    assert _lib.lib().gloc_knn_pair_workers(0) >= 60
