@@ -170,8 +170,8 @@ int main(int argc, char** argv) {
       const uint64_t now = emu::g_progress.load();
       idle = now == last ? idle + 1 : 0;
       last = now;
-      if (idle >= 30 && !emu::g_done.load()) {
-        std::fprintf(stderr, "emu: DEADLOCK -- no barrier progress for 30 s.  Waiting threads:\n");
+      if (idle >= 90 && !emu::g_done.load()) {
+        std::fprintf(stderr, "emu: DEADLOCK -- no barrier progress for 90 s.  Waiting threads:\n");
         for (int t = 0; t < emu::kMaxThreads; ++t)
           if (emu::g_waiting[0][t].parity.load() >= 0)
             std::fprintf(stderr, "  thread %3d (warp %2d): barrier %08x parity %d\n", t, t >> 5,

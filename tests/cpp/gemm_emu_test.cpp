@@ -364,7 +364,7 @@ int main(int argc, char** argv) {
   const int n_units = g.n_qtiles * n_ranges;
   const int n_workers = std::min(n_units, workers);
 
-  std::thread watchdog([] {   // no barrier traffic for 20 s: report who waits on what, give up
+  std::thread watchdog([] {   // no barrier traffic for 60 s: report who waits on what, give up
     uint64_t last = emu::g_progress.load();
     int idle = 0;
     while (!emu::g_done.load()) {
@@ -372,8 +372,8 @@ int main(int argc, char** argv) {
       const uint64_t now = emu::g_progress.load();
       idle = now == last ? idle + 1 : 0;
       last = now;
-      if (idle >= 40) {
-        std::fprintf(stderr, "emu: DEADLOCK -- no barrier progress for 20 s.  Waiting threads:\n");
+      if (idle >= 120) {
+        std::fprintf(stderr, "emu: DEADLOCK -- no barrier progress for 60 s.  Waiting threads:\n");
         for (int r = 0; r < 2; ++r)
           for (int t = 0; t < emu::kMaxThreads; ++t)
             if (emu::g_waiting[r][t].parity.load() >= 0)
