@@ -128,6 +128,7 @@ SIGNATURES = {
     "gloc_enc_forward": (_i, [_vp, _vp, _i, _vp]),
     "gloc_enc_kernel_launches": (C.c_uint64, [_vp]),
     "gloc_knn_pair_workers": (_i, [_i]),
+    "gloc_desc_extract": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
 }
 
 _lib = None

@@ -352,7 +352,8 @@ struct gloc_encoder {
   size_t act_elems = 0;
   uint8_t* d_img = nullptr;
   float* d_feat = nullptr;
-  size_t img_bytes = 0, feat_elems = 0;
+  float* d_desc = nullptr;
+  size_t img_bytes = 0, feat_elems = 0, desc_elems = 0;
   cudaStream_t stream = nullptr;
   uint64_t launches = 0;
   int sms = 0;
@@ -507,6 +508,7 @@ void gloc_enc_destroy(gloc_encoder* e) {
     if (e->d_act[i]) cudaFree(e->d_act[i]);
   if (e->d_img) cudaFree(e->d_img);
   if (e->d_feat) cudaFree(e->d_feat);
+  if (e->d_desc) cudaFree(e->d_desc);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -529,11 +531,8 @@ int gloc_enc_forward_device(gloc_encoder* e, const uint8_t* d_images, int batch,
   return GLOC_OK;
 }
 
-int gloc_enc_forward(gloc_encoder* e, const uint8_t* images, int batch, float* feat) {
-  if (!e || !images || !feat) return fail(GLOC_ERR_INVALID, "gloc_enc_forward: null argument");
-  if (batch < 0) return fail(GLOC_ERR_INVALID, "gloc_enc_forward: negative batch");
-  if (batch == 0) return GLOC_OK;
-  gloc::DeviceGuard scope(e->device);
+// host planes -> device, encoder -> e->d_feat (both buffers grown on demand); asynchronous on e->stream
+static int stage_and_encode(gloc_encoder* e, const uint8_t* images, int batch) {
   const size_t in_bytes = (size_t)batch * e->H * e->W, out_elems = (size_t)batch * 512 * (e->H / 16) * (e->W / 16);
   if (in_bytes > e->img_bytes) {
     if (e->d_img) cudaFree(e->d_img);
@@ -550,7 +549,39 @@ int gloc_enc_forward(gloc_encoder* e, const uint8_t* images, int batch, float* f
     e->feat_elems = out_elems;
   }
   GLOC_CUDA_TRY(cudaMemcpyAsync(e->d_img, images, in_bytes, cudaMemcpyHostToDevice, e->stream));
-  const int rc = forward_device(e, e->d_img, batch, e->d_feat);
+  return forward_device(e, e->d_img, batch, e->d_feat);
+}
+
+int gloc_desc_extract(gloc_encoder* e, gloc_vlad_head* head, int out_dim, const uint8_t* images, int batch,
+                      float* desc) {
+  if (!e || !head || !images || !desc) return fail(GLOC_ERR_INVALID, "gloc_desc_extract: null argument");
+  if (batch < 0 || out_dim < 1) return fail(GLOC_ERR_INVALID, "gloc_desc_extract: bad batch / out_dim");
+  if (batch == 0) return GLOC_OK;
+  gloc::DeviceGuard scope(e->device);
+  int rc = stage_and_encode(e, images, batch);
+  if (rc != GLOC_OK) return rc;
+  const size_t n_desc = (size_t)batch * out_dim;
+  if (n_desc > e->desc_elems) {
+    if (e->d_desc) cudaFree(e->d_desc);
+    e->d_desc = nullptr;
+    e->desc_elems = 0;
+    GLOC_CUDA_TRY(cudaMalloc(&e->d_desc, n_desc * 4));
+    e->desc_elems = n_desc;
+  }
+  GLOC_CUDA_TRY(cudaStreamSynchronize(e->stream));   // the head runs on its own stream
+  rc = gloc_vlad_forward_device(head, e->d_feat, batch, (e->H / 16) * (e->W / 16), e->d_desc);   // synchronous
+  if (rc != GLOC_OK) return rc;
+  GLOC_CUDA_TRY(cudaMemcpy(desc, e->d_desc, n_desc * 4, cudaMemcpyDeviceToHost));
+  return GLOC_OK;
+}
+
+int gloc_enc_forward(gloc_encoder* e, const uint8_t* images, int batch, float* feat) {
+  if (!e || !images || !feat) return fail(GLOC_ERR_INVALID, "gloc_enc_forward: null argument");
+  if (batch < 0) return fail(GLOC_ERR_INVALID, "gloc_enc_forward: negative batch");
+  if (batch == 0) return GLOC_OK;
+  gloc::DeviceGuard scope(e->device);
+  const size_t out_elems = (size_t)batch * 512 * (e->H / 16) * (e->W / 16);
+  const int rc = stage_and_encode(e, images, batch);
   if (rc != GLOC_OK) return rc;
   GLOC_CUDA_TRY(cudaMemcpyAsync(feat, e->d_feat, out_elems * 4, cudaMemcpyDeviceToHost, e->stream));
   GLOC_CUDA_TRY(cudaStreamSynchronize(e->stream));

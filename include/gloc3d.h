@@ -317,6 +317,11 @@ int gloc_enc_forward_device(gloc_encoder* enc, const uint8_t* d_images, int batc
 int gloc_enc_forward(gloc_encoder* enc, const uint8_t* images, int batch, float* feat);
 uint64_t gloc_enc_kernel_launches(const gloc_encoder* enc);
 
+/* Host convenience over both halves: uint8 planes [batch][H][W] (host) -> descriptors
+ * [batch][out_dim] (host); the feature maps stay on the device.  out_dim is the head's. */
+int gloc_desc_extract(gloc_encoder* enc, gloc_vlad_head* head, int out_dim, const uint8_t* images,
+                      int batch, float* desc);
+
 /* ============================================================ grid store file
  * (a map's BEV grids on disk, so that a database is projected once.)
  * The reference keeps its grids in memory only (db_grids_, loop_detector.h:36-39) and

@@ -135,6 +135,30 @@ def test_driver_levels_scans_without_gpu(tmp_path):
     assert r.returncode == 0 and "ground alignment" not in r.stderr
 
 
+def test_driver_accepts_the_network_weights_as_model(tmp_path):
+    """MODEL = the weight container tools/export_weights.py writes (gloc3d_b200/weights.py): the
+    driver reads and validates it on the host (parse-only mode; the forward needs the GPU)."""
+    from gloc3d_b200 import synth, weights
+
+    build()
+    tmp = str(tmp_path)
+    valset, poses, _, files, feats, db_pose, q_pose = make_drive(tmp, n_db=4, n_q=1)
+    ws, bs = synth.hashed_vgg_weights(1)
+    cw, cent, hid = synth.hashed_vlad_weights(64, 512, 512, 2)
+    model = os.path.join(tmp, "model.glocw")
+    weights.save_weights(model, ws, bs, cw, cent, hid)
+    env = dict(os.environ, GLOC_DRIVER_PARSE_ONLY="1")
+    r = subprocess.run([BIN, valset, poses, model], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "MODEL: 13 convolutions + NetVLAD_fc (64 clusters, 512-d)" in r.stderr
+    assert "positives, network, " in r.stderr
+    # a container with a wrong layer shape is refused
+    ws[3] = ws[3][:, :64]
+    weights.save_weights(model, ws, bs, cw, cent, hid)
+    r = subprocess.run([BIN, valset, poses, model], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 1 and "layer 3 missing or of the wrong shape" in r.stderr
+
+
 @pytest.mark.gpu
 def test_driver_matches_python_pipeline(tmp_path):
     import gloc3d_b200 as g

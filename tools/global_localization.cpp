@@ -10,9 +10,14 @@
 //   retrieval, k = 20      gloc_knn_*                (InvKeyTree::query, loop_detector.cpp:34-45)
 //   verification           gloc_csm_match_batch      (the slot of loop_detector_.match, :519-524)
 // What is NOT part of the query path stays outside:
-//   * MODEL: the reference loads a TorchScript CNN here (loop_detector.cpp:157-163).  This
-//     build takes the descriptors from a table instead: MODEL is a raw float32 file with
-//     (db_num + q_num) x 512 values in valset order (what the CNN forward would produce).
+//   * MODEL: the reference loads a TorchScript CNN here (loop_detector.cpp:157-163), which needs
+//     libtorch.  Two forms are accepted instead:
+//       - the network's weights in the plain container tools/export_weights.py writes from that
+//         TorchScript file ("GLOCW001": 13 VGG16 convolutions + NetVLAD_fc): descriptors are then
+//         computed like get_place_feature does (loop_detector.cpp:137-172) -- BEV image, crop/pad
+//         to 768 x 768, encoder, pooling head -- through gloc_desc_extract;
+//       - a raw float32 table with (db_num + q_num) x 512 descriptors in valset order (what that
+//         forward would produce), for runs without a network.
 //   * the 4th argument switches ground alignment on like the reference's (:419-449, :482-509,
 //     :524-569): every scan is levelled on the host by gloc::GroundEstimator before the BEV
 //     projection and the located pose is composed from the 2-D match and the two ground
@@ -29,6 +34,7 @@
 #include <ctime>
 #include <fstream>
 #include <iostream>
+#include <map>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -224,8 +230,8 @@ class GlocEvaluator {
     size_t n_pos = 0;
     for (const auto& v : gt_q_pos_idx_) n_pos += v.size();
     LOG_INFO << "inputs: " << db_files_.size() << " db scans, " << q_files_.size() << " query scans, "
-             << poses_db_q_.size() << " poses, " << n_pos << " positives, " << feats_.size() / kDim
-             << " descriptors, " << n_pts << " points, " << missing << " unreadable scans";
+             << poses_db_q_.size() << " poses, " << n_pos << " positives, "
+             << (have_network_ ? std::string("network") : std::to_string(feats_.size() / kDim) + " descriptors") << ", " << n_pts << " points, " << missing << " unreadable scans";
     return missing == 0 && poses_db_q_.size() == all.size();
   }
 
@@ -236,12 +242,14 @@ class GlocEvaluator {
     check(gloc_bev_create(&bev_, device_, 0.2f, 100.f), "gloc_bev_create");
     check(gloc_csm_create(&store_, device_), "gloc_csm_create");
     check(gloc_knn_create(&index_, kDim, device_), "gloc_knn_create");
+    if (have_network_) create_network();
     int i = 0;
     double t_align = 0., t_detect = 0.;
     // GLOC_GRID_STORE=<file>: the database's BEV grids on disk (grid store file, include/gloc3d.h):
     // loaded when the file holds one grid per database scan, written after the projection pass
     // otherwise.  Not used with ground alignment (the per-scan ground transforms are not in it).
-    const char* grid_store = align_ground_ ? nullptr : std::getenv("GLOC_GRID_STORE");
+    // (a grid store holds no descriptors: with a network every database scan is projected anyway)
+    const char* grid_store = (align_ground_ || have_network_) ? nullptr : std::getenv("GLOC_GRID_STORE");
     if (grid_store) {
       gloc_grid_file* gf = nullptr;
       size_t n_stored = 0;
@@ -272,8 +280,13 @@ class GlocEvaluator {
       int gid = -1;
       check(gloc_csm_add_grid_from_bev_aligned(store_, bev_, &gid), "gloc_csm_add_grid_from_bev_aligned");
       db_grid_ids_.push_back(gid);
+      if (have_network_) {
+        push_plane();
+        if (i % kCnnBatch == 0) flush_planes((size_t)(i - kCnnBatch));
+      }
       if (i > 2) t_detect += tb.toc();
     }
+    if (have_network_) flush_planes(db_files_.size() - planes_.size() / ((size_t)kCnnSide * kCnnSide));
     check(gloc_knn_set_db(index_, feats_.data(), db_files_.size()), "gloc_knn_set_db");
     if (grid_store) {
       check(gloc_csm_save_grids(store_, grid_store), "gloc_csm_save_grids");
@@ -305,6 +318,10 @@ class GlocEvaluator {
       check(gloc_bev_get_occupied_points(bev_, nullptr, 0, &n_occ), "gloc_bev_get_occupied_points");
       std::vector<float> pts(n_occ * 3);
       if (n_occ) check(gloc_bev_get_occupied_points(bev_, pts.data(), n_occ, &n_occ), "gloc_bev_get_occupied_points");
+      if (have_network_) {                      // the query's own descriptor, one frame like the reference
+        push_plane();
+        flush_planes(n_db + qi);
+      }
       if (n_db <= kNumExcludeRecent + kTopK) {  // loop_detector.cpp:27-30
         std::cout << "Not enough keyframes in database." << std::endl;
       } else {
@@ -388,14 +405,111 @@ class GlocEvaluator {
 
   ~GlocEvaluator() {
     gloc_knn_destroy(index_);
+    gloc_enc_destroy(enc_);
+    gloc_vlad_destroy(head_);
     gloc_csm_destroy(store_);
     gloc_bev_destroy(bev_);
   }
 
  private:
   static constexpr size_t kDim = 512, kTopK = 20, kNumExcludeRecent = 30;  // loop_detector.h:97-100
+  static constexpr int kCnnSide = 768, kCnnBatch = 16;                     // loop_detector.cpp:144-145
+
+  // "GLOCW001" container (gloc3d_b200/weights.py): name -> (shape, float32 data)
+  struct Array {
+    std::vector<uint64_t> shape;
+    std::vector<float> data;
+  };
+  static bool read_weight_file(const std::string& path, std::map<std::string, Array>* out) {
+    std::ifstream f(path, std::ios::binary);
+    char magic[8];
+    if (!f || !f.read(magic, 8) || std::memcmp(magic, "GLOCW001", 8) != 0) return false;
+    uint32_t n = 0;
+    f.read(reinterpret_cast<char*>(&n), 4);
+    for (uint32_t i = 0; i < n && f; ++i) {
+      uint16_t ln = 0;
+      f.read(reinterpret_cast<char*>(&ln), 2);
+      std::string name(ln, '\0');
+      f.read(&name[0], ln);
+      uint32_t nd = 0;
+      f.read(reinterpret_cast<char*>(&nd), 4);
+      if (nd > 8) return false;
+      Array a;
+      a.shape.resize(nd);
+      f.read(reinterpret_cast<char*>(a.shape.data()), 8 * nd);
+      uint64_t cnt = 1;
+      for (uint64_t d : a.shape) cnt *= d;
+      if (cnt > (1ull << 32)) return false;
+      a.data.resize(cnt);
+      f.read(reinterpret_cast<char*>(a.data.data()), (std::streamsize)(4 * cnt));
+      if (!f) return false;
+      (*out)[name] = std::move(a);
+    }
+    return (bool)f;
+  }
+
+  // MODEL = weight container: keep the arrays; returns false when MODEL is something else
+  bool load_network(const std::string& path) {
+    std::map<std::string, Array> w;
+    if (!read_weight_file(path, &w)) return false;
+    static const uint64_t cout[13] = {64, 64, 128, 128, 256, 256, 256, 512, 512, 512, 512, 512, 512};
+    uint64_t cin = 3;
+    for (int l = 0; l < 13; ++l) {
+      const auto wi = w.find("enc." + std::to_string(l) + ".weight"), bi = w.find("enc." + std::to_string(l) + ".bias");
+      if (wi == w.end() || bi == w.end() || wi->second.shape != std::vector<uint64_t>{cout[l], cin, 3, 3} ||
+          bi->second.shape != std::vector<uint64_t>{cout[l]}) {
+        LOG_ERROR << "MODEL: layer " << l << " missing or of the wrong shape";
+        std::exit(1);
+      }
+      cin = cout[l];
+    }
+    const auto cw = w.find("vlad.conv.weight"), ce = w.find("vlad.centroids"), hi = w.find("vlad.hidden");
+    if (cw == w.end() || ce == w.end() || hi == w.end() || cw->second.shape.size() != 2 || cw->second.shape[1] != 512 ||
+        ce->second.shape != cw->second.shape || hi->second.shape.size() != 2 ||
+        hi->second.shape[0] != cw->second.shape[0] * 512 || hi->second.shape[1] != kDim) {
+      LOG_ERROR << "MODEL: NetVLAD_fc arrays missing or of the wrong shape";
+      std::exit(1);
+    }
+    net_ = std::move(w);
+    have_network_ = true;
+    LOG_INFO << "MODEL: 13 convolutions + NetVLAD_fc (" << net_["vlad.conv.weight"].shape[0] << " clusters, "
+             << net_["vlad.hidden"].shape[1] << "-d) from " << path;
+    return true;
+  }
+
+  void create_network() {   // needs the GPU
+    const float* cw[13];
+    const float* cb[13];
+    for (int l = 0; l < 13; ++l) {
+      cw[l] = net_["enc." + std::to_string(l) + ".weight"].data.data();
+      cb[l] = net_["enc." + std::to_string(l) + ".bias"].data.data();
+    }
+    check(gloc_enc_create(&enc_, device_, kCnnSide, kCnnSide, cw, cb), "gloc_enc_create");
+    const auto bias = net_.find("vlad.conv.bias");
+    check(gloc_vlad_create(&head_, device_, 512, (int)net_["vlad.conv.weight"].shape[0], (int)kDim,
+                           net_["vlad.conv.weight"].data.data(), bias == net_.end() ? nullptr : bias->second.data.data(),
+                           net_["vlad.centroids"].data.data(), net_["vlad.hidden"].data.data()),
+          "gloc_vlad_create");
+    feats_.assign((db_files_.size() + q_files_.size()) * kDim, 0.f);
+  }
+
+  // get_place_feature (loop_detector.cpp:137-172) for the planes collected so far: rows first .. of feats_
+  void flush_planes(size_t first_row) {
+    const int n = (int)(planes_.size() / ((size_t)kCnnSide * kCnnSide));
+    if (n == 0) return;
+    check(gloc_desc_extract(enc_, head_, (int)kDim, planes_.data(), n, feats_.data() + first_row * kDim),
+          "gloc_desc_extract");
+    planes_.clear();
+  }
+  // the projector's current image, cropped / padded to the CNN input, appended to the batch
+  void push_plane() {
+    const size_t at = planes_.size();
+    planes_.resize(at + (size_t)kCnnSide * kCnnSide);
+    check(gloc_bev_get_cnn_input(bev_, kCnnSide, kCnnSide, planes_.data() + at), "gloc_bev_get_cnn_input");
+  }
 
   void load_descriptors(const std::string& path) {
+    if (load_network(path)) return;
     const size_t rows = db_files_.size() + q_files_.size();
     std::ifstream f(path, std::ios::binary);
     feats_.assign(rows * kDim, 0.f);
@@ -479,6 +593,11 @@ class GlocEvaluator {
   gloc_bev_projector* bev_ = nullptr;
   gloc_csm_store* store_ = nullptr;
   gloc_knn_index* index_ = nullptr;
+  bool have_network_ = false;
+  std::map<std::string, Array> net_;
+  gloc_encoder* enc_ = nullptr;
+  gloc_vlad_head* head_ = nullptr;
+  std::vector<uint8_t> planes_;                 // CNN inputs waiting for the next batch
 };
 
 }  // namespace
