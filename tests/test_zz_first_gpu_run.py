@@ -34,7 +34,7 @@ def test_first_run_vlad_head_and_grid_store():
 @pytest.mark.gpu
 @pytest.mark.xfail(reason="tcgen05 encoder: not yet run on a GPU", strict=False)
 def test_first_run_encoder():
-    run_group(["tests/test_encoder_gpu.py"], {}, 900)
+    run_group(["tests/test_encoder_gpu.py", "tests/test_driver_network_gpu.py"], {}, 1200)
 
 
 @pytest.mark.gpu

@@ -42,7 +42,7 @@ for stage in "${STAGES[@]}"; do
       run tests 1500 python -m pytest tests -x -q -m gpu
       ;;
     unverified)
-      GLOC_TEST_UNVERIFIED=1 run unverified 900 python -m pytest tests/test_vlad_gpu.py tests/test_encoder_gpu.py tests/test_grid_store.py -q -m gpu
+      GLOC_TEST_UNVERIFIED=1 run unverified 900 python -m pytest tests/test_vlad_gpu.py tests/test_encoder_gpu.py tests/test_driver_network_gpu.py tests/test_grid_store.py -q -m gpu
       ;;
     pair)
       # a protocol bug in the pair kernel traps after ~2 s (bounded mbarrier waits) instead of hanging
