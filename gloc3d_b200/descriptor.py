@@ -3,7 +3,7 @@ main.py:531-536 as run by RpyPCLoopDetector::get_place_feature, loop_detector.cp
 NetVLAD_fc pooling head on the GPU (C ABI: gloc_vlad_*; reference: model/netvlad_fc.py:73-109
 as run by RpyPCLoopDetector::get_place_feature, loop_detector.cpp:137-172): encoder feature maps
 in, 512-d place descriptors out, batched; the device entry point feeds KnnIndex.query_device /
-set_db_device without a host round trip.  The VGG16 encoder is not part of this package."""
+set_db_device without a host round trip."""
 from __future__ import annotations
 
 import ctypes as C

@@ -1,7 +1,8 @@
 // gloc_loop_detector.hpp -- the hot-path half of RpyPCLoopDetector
 // (/root/reference/registration/loop_detector.{h,cpp}) on top of the GPU path: same member
-// names, constants and guards for detect()/match(); descriptors and BEV grids are handed in
-// (the CNN forward and the BEV projection are outside the north-star path).
+// names, constants and guards for detect()/match(); descriptors are handed in (the network
+// runs through gloc_enc_* / gloc_vlad_*, see tools/global_localization.cpp), BEV grids are
+// handed in or come from get_projected_grid() (gloc_bev_*).
 #ifndef GLOC_LOOP_DETECTOR_HPP_
 #define GLOC_LOOP_DETECTOR_HPP_
 
