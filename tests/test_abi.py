@@ -87,3 +87,18 @@ def test_argument_validation_without_gpu():
     assert nl == 15 and na == int(np.ceil(3.0 / st))
     with pytest.raises(AssertionError):
         g.InvKeyTree(512, np.zeros((0, 512), np.float32))
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/gloc3d.h compiles as C99 and links against the library."""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text('#include "gloc3d.h"\n'
+                   'int main(void) { gloc_grid_info i; i.nx = 0; return (gloc_version() < 0) + i.nx; }\n')
+    exe = tmp_path / "abi"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{ROOT}/include", str(src),
+                        f"-L{ROOT}/gloc3d_b200", "-lgloc3d", f"-Wl,-rpath,{ROOT}/gloc3d_b200", "-o", str(exe)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert subprocess.run([str(exe)]).returncode == 0
