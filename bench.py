@@ -615,6 +615,18 @@ def run_verify(args, rank, world, local_rank):
     side = (2 * VER["n_lin"]) // (1 << (VER["depth"] - 1)) + 1
     lookups = (2 * VER["n_ang"] + 1) * side * side * P * len(mine)      # coarse level, per launch
     peaks = load_peaks()
+    # the scorer's binding unit: random 8-byte shared-memory loads, one per (rotation, point, candidate
+    # row); ceiling measured live by the library's micro-benchmark
+    lsu = None
+    try:
+        import ctypes
+
+        from gloc3d_b200 import _lib
+        peak = ctypes.c_double()
+        if _lib.lib().gloc_bench_smem_gather(local_rank, ctypes.byref(peak)) == 0 and peak.value > 0:
+            lsu = {"peak_random_lds64_per_s": peak.value}
+    except Exception as e:   # the ceiling is an annotation: never fail the bench over it
+        lsu = {"error": str(e)}
     hbm_bytes = len(set(gi)) * VER["nx"] * VER["ny"] + sum(s.shape[0] for s in scans) * 12 + len(mine) * 24
     avg_ms = dom_ms / max(dom_n, 1)
     line = {
@@ -638,9 +650,13 @@ def run_verify(args, rank, world, local_rank):
                      "traffic": verify_traffic(), "kernel_ms": avg_ms,
                      "note": "compulsory HBM bytes are tiny; the binding limit is the shared-memory gather "
                              "rate of the LSU (ncu: l1tex throughput 78 %)",
-                     "gather_lookups_per_s": lookups / (avg_ms * 1e-3) if avg_ms else None},
+                     "gather_lookups_per_s": lookups / (avg_ms * 1e-3) if avg_ms else None,
+                     "lsu_gather": lsu},
         "stats": {"found": int(found), "pairs": len(mine)},
     }
+    if lsu and "peak_random_lds64_per_s" in lsu and avg_ms:
+        lsu["achieved_lds64_per_s"] = lookups / side / (avg_ms * 1e-3)   # one load serves a row of `side` candidates
+        lsu["frac"] = lsu["achieved_lds64_per_s"] / lsu["peak_random_lds64_per_s"]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_verify(maps, mx, my, scans, pairs, args.cpu_budget)
     st.close()

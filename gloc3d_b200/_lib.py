@@ -129,6 +129,7 @@ SIGNATURES = {
     "gloc_enc_kernel_launches": (C.c_uint64, [_vp]),
     "gloc_knn_pair_workers": (_i, [_i]),
     "gloc_desc_extract": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "gloc_bench_smem_gather": (_i, [_i, C.POINTER(C.c_double)]),
 }
 
 _lib = None

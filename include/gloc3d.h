@@ -358,6 +358,12 @@ void gloc_grid_file_close(gloc_grid_file* f);
 int gloc_csm_save_grids(gloc_csm_store* store, const char* path);
 int gloc_csm_load_grids(gloc_csm_store* store, const char* path, int* first_grid_id, int* n_grids);
 
+/* ============================================================ measured ceilings
+ * Chip-wide rate of random 8-byte shared-memory loads (LDS.64 with the bank conflicts random
+ * addresses bring): the unit the stage-2 coarse scorer is bound by (SURVEY.md 8d asks for its
+ * gather rate against a measured ceiling).  Takes a few milliseconds of GPU time. */
+int gloc_bench_smem_gather(int device, double* loads_per_s);
+
 #ifdef __cplusplus
 }
 #endif

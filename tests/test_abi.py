@@ -102,3 +102,14 @@ def test_header_is_plain_c(tmp_path):
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_microbench_validates_arguments_and_needs_a_gpu():
+    import ctypes as C
+
+    L = _lib.lib()
+    assert L.gloc_bench_smem_gather(0, None) == _lib.GLOC_ERR_INVALID
+    v = C.c_double(-1.0)
+    rc = L.gloc_bench_smem_gather(0, C.byref(v))
+    if L.gloc_device_count() == 0:
+        assert rc == _lib.GLOC_ERR_CUDA and v.value == 0.0
