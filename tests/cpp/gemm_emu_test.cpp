@@ -172,7 +172,9 @@ static void run_grid(int n_workers, const CUtensorMap& map_q, const CUtensorMap&
   }
 }
 
-// ordinary kernels (K1, K3): blocks one after the other, block_threads OS threads each
+// ordinary kernels (K1, K3): blocks one after the other on ONE team of block_threads OS threads
+// (a barrier between blocks rebuilds the per-block barriers; spawning a team per block is what
+// made this slow)
 template <typename F>
 static void launch_blocks(unsigned grid_x, unsigned block_threads, size_t dyn_smem, F body) {
   emu::g_n_cta = 1;
@@ -181,26 +183,32 @@ static void launch_blocks(unsigned grid_x, unsigned block_threads, size_t dyn_sm
   emu::Cta& c = emu::g_cta[0];
   if (!c.smem) c.smem = static_cast<unsigned char*>(std::aligned_alloc(1024, emu::kSmemBuf));
   if (dyn_smem + 16 > emu::kSmemBuf) std::abort();
-  for (unsigned bx = 0; bx < grid_x; ++bx) {
+  const unsigned n_warps = (block_threads + 31) / 32;
+  auto rebuild = [&c, block_threads, n_warps]() noexcept {
     c.block_bar.reset(new std::barrier<>(block_threads));
     c.warp_bar.clear();
-    for (unsigned w = 0; w < (block_threads + 31) / 32; ++w)
+    for (unsigned w = 0; w < n_warps; ++w)
       c.warp_bar.emplace_back(new std::barrier<>(std::min(32u, block_threads - 32 * w)));
-    c.warp_x.assign((block_threads + 31) / 32, std::vector<uint32_t>(32, 0));
-    std::vector<std::thread> ts;
-    for (unsigned t = 0; t < block_threads; ++t)
-      ts.emplace_back([&, t] {
-        emu::t_rank = 0;
-        emu::t_tid = (int)t;
-        emu::t_thread.x = t;
+  };
+  rebuild();
+  c.warp_x.assign(n_warps, std::vector<uint32_t>(32, 0));
+  std::barrier between_blocks(block_threads, rebuild);
+  std::vector<std::thread> ts;
+  for (unsigned t = 0; t < block_threads; ++t)
+    ts.emplace_back([&, t] {
+      emu::t_rank = 0;
+      emu::t_tid = (int)t;
+      emu::t_thread.x = t;
+      t_smem_raw = c.smem + 16;
+      for (unsigned bx = 0; bx < grid_x; ++bx) {
         emu::t_block.x = bx;
-        t_smem_raw = c.smem + 16;
         body();
         c.block_bar->arrive_and_drop();                  // early returns must not block the others
         c.warp_bar[t >> 5]->arrive_and_drop();
-      });
-    for (auto& th : ts) th.join();
-  }
+        between_blocks.arrive_and_wait();
+      }
+    });
+  for (auto& th : ts) th.join();
 }
 
 // mode 1: the whole shortlist path from float32 rows -- K1 (stats, FP16 copy, query prep), K2, K3 --
