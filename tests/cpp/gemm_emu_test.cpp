@@ -302,6 +302,7 @@ static int run_full(FILE* f, const std::vector<int32_t>& h, const char* out_path
   std::fwrite(out_d2.data(), 4, out_d2.size(), o);
   std::fwrite(ovf_count.data(), 4, 1, o);
   std::fwrite(rows_ctr.data(), 8, 2, o);
+  std::fwrite(ovf_list.data(), 4, ovf_list.size(), o);
   std::fclose(o);
   return 0;
 }

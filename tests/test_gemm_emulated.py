@@ -193,3 +193,33 @@ def test_emulated_shortlist_path_is_bit_exact(exe, tmp_path, pair, case):
     assert np.array_equal(idx, ref_idx.astype(np.uint64))
     assert np.array_equal(d2.view(np.uint32), ref_d2.view(np.uint32))
     assert k * nq <= rows[0] <= max(12 * k, 40) * nq          # the shortlist is short
+
+
+def test_emulated_shortlist_flags_what_it_cannot_answer(exe, tmp_path):
+    """Thousands of identical rows pass every bound together: K3 must hand those queries to the
+    exact scan (overflow list) instead of answering from a truncated shortlist, and still answer
+    the other queries exactly."""
+    from oracle import pyoracle as po
+
+    nq, n_rows, dim, k, n_ranges, tpr = 128, 3072, 64, 10, 1, 12
+    P = prepare(nq, n_rows, dim, seed=5)
+    P["db"][:2600] = P["db"][0]                        # 2600 copies of one row
+    P["q"][:40] = P["db"][0] + np.float32(1e-3)        # 40 queries right next to them
+    inp, outp = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(inp, "wb") as f:
+        f.write(np.array([nq, n_rows, P["n_pad"], dim, k, 512, n_ranges, tpr, 0, 1, 1], np.int32).tobytes())
+        f.write(np.ascontiguousarray(P["q"]).tobytes())
+        f.write(np.ascontiguousarray(P["db"]).tobytes())
+    r = subprocess.run([exe, inp, outp], capture_output=True, text=True, timeout=2400)
+    assert r.returncode == 0, r.stderr[-4000:]
+    raw = open(outp, "rb").read()
+    idx = np.frombuffer(raw, np.uint64, nq * k).reshape(nq, k)
+    d2 = np.frombuffer(raw, np.float32, nq * k, offset=nq * k * 8).reshape(nq, k)
+    n_ovf = int(np.frombuffer(raw, np.int32, 1, offset=nq * k * 12)[0])
+    ovf = set(np.frombuffer(raw, np.int32, nq, offset=nq * k * 12 + 4 + 16)[:n_ovf].tolist())
+    assert set(range(40)) <= ovf, "the tie-heavy queries must be flagged"
+    ref_idx, ref_d2 = po.knn(P["db"], P["q"], k, nthreads=4)
+    ok = [q for q in range(nq) if q not in ovf]
+    assert len(ok) >= 40
+    assert np.array_equal(idx[ok], ref_idx[ok].astype(np.uint64))
+    assert np.array_equal(d2[ok].view(np.uint32), ref_d2[ok].view(np.uint32))
