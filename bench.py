@@ -261,6 +261,8 @@ def run_retrieval(args, rank, world, local_rank):
                    "db_rows": DB_ROWS, "queries_per_step": nq_job, "k": K_NN, "dim": DIM,
                    "sharding": shard_txt[r["sharding"]] if world > 1 else "none",
                    "strategy": {1: "exact_scan", 2: "tensor_shortlist"}.get(last_mode, str(last_mode)),
+                   "gemm_variant": "cta_pair (GLOC_KNN_PAIR)" if os.environ.get("GLOC_KNN_PAIR", "0") not in ("", "0")
+                                   else "one CTA per SM",
                    "l2": "inputs larger than L2 (DB + query batch > 126 MB per rank); no flush"},
         "e2e": {"value": r["e2e_value"], "unit": UNIT, "ms_per_step": r["e2e_ms"],
                 "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
