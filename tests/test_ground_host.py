@@ -290,3 +290,19 @@ def test_no_ground_returns_identity_and_an_empty_cloud(exe):
     assert out[0].split()[0] == "0"
     assert np.allclose(np.array([float(v) for v in out[2].split()]).reshape(4, 4), np.eye(4))
     assert int(out[3]) == 0
+
+
+KITTI_SCAN = "/root/reference/s2s_libtorch/000000.bin"
+
+
+@pytest.mark.skipif(not os.path.exists(KITTI_SCAN), reason="the reference's one real scan (build container only)")
+def test_ground_of_the_references_kitti_scan(exe):
+    """KITTI's Velodyne sits 1.73 m above the road: the estimator has to find that ground."""
+    pts = np.fromfile(KITTI_SCAN, np.float32).reshape(-1, 4)
+    out = run(exe, "ground", len(pts), pts).strip().splitlines()
+    ok, n_near, n_ground = (int(v) for v in out[0].split())
+    coeff = np.array([float(v) for v in out[1].split()])
+    assert ok == 1 and n_ground > 10000
+    n = coeff[:3] * np.sign(coeff[2])
+    assert abs(abs(coeff[3]) - 1.73) < 0.15
+    assert np.degrees(np.arccos(n[2] / np.linalg.norm(n))) < 5.0
