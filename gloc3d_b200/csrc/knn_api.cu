@@ -170,6 +170,7 @@ int grow_db(gloc_knn_index* ix, size_t need_rows) {
   if (e != cudaSuccess) return fail(GLOC_ERR_NOMEM, std::string("cudaMalloc(db): ") + cudaGetErrorString(e));
   if (ix->n > 0) {
     e = cudaMemcpy(nd, ix->d_db, ix->n * ix->dim * sizeof(float), cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);   // asynchronous to the host otherwise
     if (e != cudaSuccess) {
       cudaFree(nd);
       return fail(GLOC_ERR_CUDA, std::string("cudaMemcpy(db grow): ") + cudaGetErrorString(e));
@@ -186,6 +187,9 @@ int put_rows(gloc_knn_index* ix, const float* rows, size_t n, size_t at, cudaMem
   int rc = grow_db(ix, at + n);
   if (rc != GLOC_OK) return rc;
   GLOC_CUDA_TRY(cudaMemcpy(ix->d_db + at * ix->dim, rows, n * ix->dim * sizeof(float), kind));
+  // device-to-device and small pageable copies return before the data has landed, and the
+  // searches run on non-blocking streams that do not order against the legacy stream
+  GLOC_CUDA_TRY(cudaStreamSynchronize(0));
   return GLOC_OK;
 }
 
@@ -386,7 +390,7 @@ int gloc_knn_query_device(gloc_knn_index* ix, const float* d_q, size_t nq, size_
   int rc;
   if (mode == GLOC_KNN_SHORTLIST) {
     if (!shortlist_supported(ix->dim, k))
-      return fail(GLOC_ERR_RANGE, "gloc_knn_query: GLOC_KNN_SHORTLIST needs dim % 64 == 0, dim <= 2048, k <= 128");
+      return fail(GLOC_ERR_RANGE, "gloc_knn_query: GLOC_KNN_SHORTLIST needs dim % 64 == 0, dim <= 512, k <= 32 (GLOC_KNN_AUTO takes the exact scan otherwise)");
     ShortlistArgs a;
     a.device = ix->device;
     a.d_db = ix->d_db;

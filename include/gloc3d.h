@@ -55,7 +55,9 @@ typedef struct gloc_knn_index gloc_knn_index;
 #define GLOC_KNN_EXACT_SCAN 1 /* FP32 exact scan of every row (K3 as a full scan)    */
 #define GLOC_KNN_SHORTLIST 2 /* FP16 tcgen05 GEMM shortlist (K1+K2) + FP32 re-rank  */
                              /* (K3); queries whose shortlist overflows are re-run  */
-                             /* through the exact scan on the GPU                   */
+                             /* through the exact scan on the GPU.  Limits: dim % 64 */
+                             /* == 0, dim <= 512, k <= 32 (GLOC_ERR_RANGE beyond;    */
+                             /* GLOC_KNN_AUTO takes the exact scan there, k <= 128)  */
 
 typedef struct {
   uint64_t queries;            /* queries answered since creation                   */

@@ -11,12 +11,9 @@ import gloc3d_b200 as g
 from gloc3d_b200 import synth, weights
 from test_driver import BIN, build, make_drive
 
-unverified = pytest.mark.skipif(not os.environ.get("GLOC_TEST_UNVERIFIED"),
-                                reason="not yet run on a GPU; enable with GLOC_TEST_UNVERIFIED=1, then drop this guard")
 
 
 @pytest.mark.gpu
-@unverified
 def test_driver_computes_its_descriptors(tmp_path):
     build()
     tmp = str(tmp_path)

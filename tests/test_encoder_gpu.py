@@ -1,7 +1,7 @@
 """VGG16 encoder on the GPU (gloc_enc_*) against the oracle (pinned to torchvision's feature
 stack as the reference cuts it), and the whole descriptor path image -> encoder -> NetVLAD_fc
-head -> retrieval on the device.  Written without a GPU at hand; the kernel source is checked on
-the host by tests/test_encoder_emulated.py.  Opt-in (GLOC_TEST_UNVERIFIED=1) until run once."""
+head -> retrieval on the device.  First passed on a B200 in round 1's driver run; the kernel source is also
+checked on the host by tests/test_encoder_emulated.py."""
 import ctypes as C
 import os
 
@@ -13,8 +13,6 @@ from gloc3d_b200 import _lib
 from oracle import encoder_oracle as eo
 from oracle import vlad_oracle as vo
 
-unverified = pytest.mark.skipif(not os.environ.get("GLOC_TEST_UNVERIFIED"),
-                                reason="not yet run on a GPU; enable with GLOC_TEST_UNVERIFIED=1, then drop this guard")
 
 
 def test_create_validates_arguments_and_fails_loudly_without_gpu():
@@ -53,7 +51,6 @@ def bev_like(B, H, W, seed):
 
 
 @pytest.mark.gpu
-@unverified
 @pytest.mark.parametrize("H,W,B", [(128, 256, 3), (256, 256, 1)])
 def test_encoder_against_oracle(H, W, B):
     ws, bs = eo.hashed_vgg_weights(11)
@@ -69,7 +66,6 @@ def test_encoder_against_oracle(H, W, B):
 
 
 @pytest.mark.gpu
-@unverified
 def test_descriptor_path_on_the_device():
     import torch
 

@@ -137,8 +137,6 @@ def test_store_level_entry_points_validate_arguments_without_gpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("GLOC_TEST_UNVERIFIED"),
-                    reason="written without a GPU at hand; enable with GLOC_TEST_UNVERIFIED=1, then drop this guard")
 def test_store_round_trip_through_the_device(tmp_path):
     grids = make_grids(11)
     st = g.CsmStore(0)

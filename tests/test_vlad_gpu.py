@@ -1,7 +1,6 @@
 """NetVLAD_fc head on the GPU (gloc_vlad_*) against the oracle, which is pinned to the
-reference's own module (tests/golden/vlad_*.npz).  The kernels were written without a GPU at
-hand; their source is already checked on the host by tests/test_vlad_emulated.py.  The GPU tests
-are opt-in (GLOC_TEST_UNVERIFIED=1) until they have run once on a B200."""
+reference's own module (tests/golden/vlad_*.npz).  The kernel source is also checked on the host by
+tests/test_vlad_emulated.py."""
 import os
 
 import numpy as np
@@ -12,8 +11,6 @@ from gloc3d_b200 import _lib
 from oracle import vlad_oracle as vo
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-unverified = pytest.mark.skipif(not os.environ.get("GLOC_TEST_UNVERIFIED"),
-                                reason="not yet run on a GPU; enable with GLOC_TEST_UNVERIFIED=1, then drop this guard")
 
 
 def test_create_fails_loudly_without_gpu_and_validates_arguments():
@@ -36,7 +33,6 @@ def test_create_fails_loudly_without_gpu_and_validates_arguments():
 
 
 @pytest.mark.gpu
-@unverified
 @pytest.mark.parametrize("name", ["vlad_small.npz", "vlad_full.npz"])
 def test_reference_goldens(name):
     z = np.load(os.path.join(GOLD, name))
@@ -51,7 +47,6 @@ def test_reference_goldens(name):
 
 
 @pytest.mark.gpu
-@unverified
 @pytest.mark.parametrize("B,C,S,K,D,bias", [(9, 64, 70, 64, 130, True), (2, 96, 129, 5, 17, False),
                                             (33, 512, 2304, 64, 512, False)])
 def test_against_oracle_and_batch_independence(B, C, S, K, D, bias):
@@ -68,7 +63,6 @@ def test_against_oracle_and_batch_independence(B, C, S, K, D, bias):
 
 
 @pytest.mark.gpu
-@unverified
 def test_descriptors_feed_retrieval_on_the_device():
     import torch
 

@@ -9,7 +9,6 @@
 #   tests      pytest -m gpu (the parity suite through the C ABI)
 #   pair       the retrieval parity tests and the default bench with the CTA-pair GEMM
 #              (GLOC_KNN_PAIR=1) next to the shipped kernel
-#   unverified GPU tests written without a GPU at hand (NetVLAD head, encoder, grid store round trip)
 #   bench      the three workloads of bench.py, one JSON line each
 #   launches   ncu launch lists (gpu__time_duration) of the three workloads
 #   full       one ncu --set full capture of each dominant kernel (+ tools/ncu_summary.py tables)
@@ -19,7 +18,7 @@ cd "$(dirname "$0")/.."
 OUT=gpurun_out/session
 mkdir -p "$OUT"
 STAGES=("$@")
-[ ${#STAGES[@]} -eq 0 ] && STAGES=(smoke tests unverified pair bench launches full)
+[ ${#STAGES[@]} -eq 0 ] && STAGES=(smoke tests pair bench launches full)
 
 run() {   # run <name> <timeout_s> <command...>: stdout+stderr to $OUT/<name>.log, status to status.txt
   local name=$1 limit=$2
@@ -40,9 +39,6 @@ for stage in "${STAGES[@]}"; do
       ;;
     tests)
       run tests 1500 python -m pytest tests -x -q -m gpu
-      ;;
-    unverified)
-      GLOC_TEST_UNVERIFIED=1 run unverified 900 python -m pytest tests/test_vlad_gpu.py tests/test_encoder_gpu.py tests/test_driver_network_gpu.py tests/test_grid_store.py -q -m gpu
       ;;
     pair)
       # a protocol bug in the pair kernel traps after ~2 s (bounded mbarrier waits) instead of hanging
