@@ -711,6 +711,325 @@ def run_reference_verify(args):
             "gpu_launches": 0}
 
 
+
+# ------------------------------------------------------------------- localize
+# The metric itself (BASELINE.json): retrieval + pose verification as ONE measured path,
+# global_localization.cpp:482-574 (detect_all_query -> global_registraion -> match per candidate).
+LOC = dict(rows=1_000_000, grids=8192, base_grids=1024, q_per_gpu=64, nx=800, ny=800, res=0.2,
+           n_lin=100, n_ang=180, step=2 * np.pi / 360, depth=5, min_score=0.3, k=K_NN, batches=24)
+
+
+class LocWorld:
+    """1M-descriptor database (runs of 8 near-duplicate rows = consecutive frames), 8192 distinct
+    800 x 800 BEV grids (1024 seeded wall/blob layouts x the 8 dihedral variants), row r taken at
+    place r % 8192.  A query revisits the place of a random row: its descriptor is that row plus
+    N(0, 0.01^2) noise, its scan is the place's grid seen from a planted pose (yaw in [-pi, pi),
+    |dx|, |dy| <= 18 m, 20 % dropout, +-1 cell jitter)."""
+
+    def __init__(self, rows=None, grids=None):
+        from gloc3d_b200 import synth
+
+        self.synth = synth
+        self.rows = rows or LOC["rows"]
+        self.n_grids = grids or LOC["grids"]
+        self.n_base = max(1, self.n_grids // 8)
+        self.mx, self.my = synth.centered_limits(LOC["nx"], LOC["ny"], LOC["res"])
+        self.db = synth.make_descriptors_mt(self.rows, DIM, seed=1234, dup_run=8)
+        self.base = [synth.make_bev_grid(LOC["nx"], LOC["ny"], seed=2222 + i) for i in range(self.n_base)]
+
+    def grid(self, gid: int) -> np.ndarray:
+        b, v = gid % self.n_base, gid // self.n_base
+        g = self.base[b]
+        if v & 1:
+            g = g[::-1, :]
+        if v & 2:
+            g = g[:, ::-1]
+        if v & 4:
+            g = g.T
+        return np.ascontiguousarray(g)
+
+    def grid_of_row(self) -> np.ndarray:
+        return (np.arange(self.rows, dtype=np.int64) % self.n_grids).astype(np.int32)
+
+    def batch(self, b: int, nq: int):
+        """Query batch b: (descriptors [nq, 512], scans list, rows)."""
+        rng = np.random.default_rng([5678, b])
+        rows = rng.integers(0, self.rows, nq)
+        q = (self.db[rows] + rng.standard_normal((nq, DIM)).astype(np.float32) * np.float32(0.01)).astype(np.float32)
+        scans = []
+        for i, r in enumerate(rows):
+            yaw, dx, dy = rng.uniform(-np.pi, np.pi), rng.uniform(-18, 18), rng.uniform(-18, 18)
+            scans.append(self.synth.planted_scan(self.grid(int(r) % self.n_grids), LOC["res"], self.mx, self.my,
+                                                 yaw, dx, dy, dropout=0.2, jitter_cells=1.0, seed=3333 + 1000 * b + i))
+        return q, scans, rows
+
+
+def loc_config(W, nq_job, sharding):
+    return {"workload": f"configs[0]+[2] at configs[3] scale: {W.rows} x 512-d f32 descriptor DB, top-25 exact L2 retrieval "
+                        "+ scan-match verification of all 25 candidates per query (361 yaw bins, +-100 cells "
+                        "@0.2 m, branch and bound, 800x800 BEV grids, min_score 0.3) -> located frame + pose",
+            "db_rows": W.rows, "distinct_grids": W.n_grids, "queries_per_step": nq_job, "k": LOC["k"],
+            "candidates_verified_per_query": LOC["k"], "dim": DIM, "sharding": sharding,
+            "grid_store": "bit-packed width-1 grids only; coarser levels rebuilt on the device per batch",
+            "l2": "every step is a new query batch whose ~1600 candidate grids (82 KB each) and 2 GB database "
+                  "exceed L2; no flush"}
+
+
+def run_localize(args, rank, world, local_rank):
+    import ctypes
+
+    import torch
+    import torch.distributed as dist
+
+    import gloc3d_b200 as g
+    from gloc3d_b200 import _lib
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    W = LocWorld(args.loc_rows, args.loc_grids)
+    nq = args.loc_queries
+    ix = g.KnnIndex(DIM, local_rank)
+    ix.set_db(W.db)
+    st = g.CsmStore(local_rank)
+    t0 = time.perf_counter()
+    for gid in range(W.n_grids):
+        st.add_grid_u8(W.grid(gid), LOC["res"], W.mx, W.my)
+    t_add = time.perf_counter() - t0
+    loc = g.Localizer(ix, st)
+    loc.set_row_grids(W.grid_of_row())
+    prm = loc.params(LOC["k"], LOC["n_lin"], LOC["n_ang"], LOC["step"], args.verify_depth or LOC["depth"],
+                     LOC["min_score"], g.LOC_FIRST_MATCH if args.loc_policy == "first" else g.LOC_VERIFY_ALL)
+    n_batches = min(LOC["batches"], args.steps + args.warmup)
+    batches = []
+    for b in range(n_batches):                      # every rank works on its own query batches
+        q, scans, rows = W.batch(b * world + rank, nq)
+        pts, offs = g.Localizer.pack_scans(scans)
+        batches.append(dict(q=q, pts=pts, offs=offs, rows=rows, scans=scans,
+                            q_dev=torch.from_numpy(q).to(dev), pts_dev=torch.from_numpy(pts).to(dev),
+                            q_pin=torch.from_numpy(q).pin_memory(), pts_pin=torch.from_numpy(pts).pin_memory()))
+    oi = torch.empty((nq, LOC["k"]), dtype=torch.int64).pin_memory()
+    od = torch.empty((nq, LOC["k"]), dtype=torch.float32).pin_memory()
+    res = (_lib.LocResult * nq)()
+    cand = (_lib.CsmResult * (nq * LOC["k"]))()
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def reduce_ranks(x, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def step(i, host=False, keep=False):
+        B = batches[i % n_batches]
+        if host:
+            loc.localize_ptr(B["q_pin"].data_ptr(), nq, B["pts_pin"].data_ptr(), B["offs"], prm, oi.data_ptr(),
+                             od.data_ptr(), res, cand if keep else None)
+        else:
+            loc.localize_ptr(B["q_dev"].data_ptr(), nq, B["pts_dev"].data_ptr(), B["offs"], prm, oi.data_ptr(),
+                             od.data_ptr(), res, cand if keep else None, device=True)
+
+    # ---- device-resident timing (value): CUDA events on the library's stream + host clock around it
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    loc.set_profiling(True)
+    st.set_profiling(True)
+    ix.set_profiling(True)
+    l0 = st.stats().kernel_launches + ix.stats().kernel_launches + loc.stats().kernel_launches
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    torch.cuda.synchronize(dev)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    total_ms, retr_ms, calls = loc.profile()
+    coarse_ms, coarse_n = st.profile()
+    gemm_ms, gemm_n = ix.profile()
+    loc.set_profiling(False)
+    st.set_profiling(False)
+    ix.set_profiling(False)
+    launches = st.stats().kernel_launches + ix.stats().kernel_launches + loc.stats().kernel_launches - l0
+    ms_total = reduce_ranks(wall_ms, dist.ReduceOp.MAX)        # host clock >= device events (conservative)
+    dev_ms = reduce_ranks(total_ms, dist.ReduceOp.MAX)
+    for i in range(hold_steps(ms_total / args.steps)):
+        step(i)
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    # ---- end to end with host (pinned) buffers: H2D of descriptors + scans, D2H of the results
+    for i in range(2):
+        step(i, host=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i, host=True, keep=(i == args.steps - 1))
+    torch.cuda.synchronize(dev)
+    e2e_ms = reduce_ranks((time.perf_counter() - t0) * 1e3, dist.ReduceOp.MAX) / args.steps
+    barrier()
+    last = batches[(args.warmup + args.steps - 1) % n_batches]
+    got_idx = oi.numpy().copy().view(np.uint64)
+    got_res = [(r.located, r.candidate, r.db_index) for r in res]
+    got_cand = [c.as_tuple() for c in cand]
+    launches = int(reduce_ranks(float(launches), dist.ReduceOp.SUM))
+    grid_bytes, ws_bytes = st.store_bytes()
+    if rank != 0:
+        return None
+    nq_job = nq * world
+    ms = ms_total / args.steps
+    located = sum(r[0] for r in got_res)
+    # did the query find its own place?  (rows r and r' share a place iff r % grids == r' % grids)
+    right_place = sum(1 for r, row in zip(got_res, last["rows"]) if r[0] and int(r[2]) % W.n_grids == int(row) % W.n_grids)
+    P = float(np.mean([s.shape[0] for b in batches for s in b["scans"]]))
+    side = (2 * LOC["n_lin"]) // (1 << (LOC["depth"] - 1)) + 1
+    S = 2 * LOC["n_ang"] + 1
+    pairs_per_launch = nq * LOC["k"] * args.steps / max(coarse_n, 1)
+    lds_per_launch = S * side * P * pairs_per_launch            # one LDS.64 per (rotation, point, candidate row)
+    avg_coarse = coarse_ms / max(coarse_n, 1)
+    lsu = {}
+    try:
+        peak = ctypes.c_double()
+        if _lib.lib().gloc_bench_smem_gather(local_rank, ctypes.byref(peak)) == 0 and peak.value > 0:
+            lsu = {"peak_random_lds64_per_s": peak.value}
+    except Exception as e:   # the ceiling is an annotation: never fail the bench over it
+        lsu = {"error": str(e)}
+    ach = lds_per_launch / (avg_coarse * 1e-3) if avg_coarse else None
+    hbm_bytes = pairs_per_launch * (LOC["nx"] * LOC["ny"] / 8 + 12 * P + 24)
+    roof = {"bound": "lsu", "kernel": "csm_coarse_bits_kernel",
+            "achieved": ach / 1e9 if ach else None,
+            "peak": lsu.get("peak_random_lds64_per_s", 0) / 1e9 or None, "unit": "G LDS.64/s",
+            "frac": (ach / lsu["peak_random_lds64_per_s"]) if ach and lsu.get("peak_random_lds64_per_s") else None,
+            "traffic": verify_traffic(),
+            "peak_source": "measured live: gloc_bench_smem_gather (random 8-byte shared-memory loads, chip-wide)",
+            "kernel_ms": avg_coarse, "kernel_launches_timed": coarse_n,
+            "algorithmic_lookups_per_launch": lds_per_launch * side,
+            "algorithmic_lds64_per_launch": lds_per_launch,
+            "hbm": {"algorithmic_bytes_per_launch": hbm_bytes,
+                    "achieved_gbs": hbm_bytes / (avg_coarse * 1e-3) / 1e9 if avg_coarse else None,
+                    "frac_of_peak": hbm_bytes / (avg_coarse * 1e-3) / 1e9 / peaks["hbm_gbs"] if avg_coarse else None},
+            "stages_ms_per_step": {"device_total": dev_ms / args.steps, "retrieval": retr_ms / args.steps,
+                                   "verification": (total_ms - retr_ms) / args.steps,
+                                   "coarse_scorer": coarse_ms / args.steps},
+            "retrieval_gemm": {"bound": "tensor", "kernel": "knn_shortlist_gemm_kernel",
+                               "kernel_ms": gemm_ms / max(gemm_n, 1), "launches": gemm_n,
+                               "achieved_tflops": (2.0 * nq * W.rows * DIM * args.steps / max(gemm_n, 1)) /
+                                                  (gemm_ms / max(gemm_n, 1) * 1e-3) / 1e12 if gemm_ms else None,
+                               "peak_tflops": peaks["bf16_tflops"],
+                               "note": "64 queries fill half of one 128-row query tile: this launch is latency-, "
+                                       "not tensor-bound; see --workload retrieval for the GEMM at batch size"}}
+    line = {
+        "metric": METRIC, "value": nq_job / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp16 tensor shortlist + f32 exact re-rank; u8/bit sums -> f32 score", "data": "synthetic",
+        "config": loc_config(W, nq_job, "none" if world == 1 else
+                             f"{world} replicas: database + grids replicated, every rank its own {nq} queries"),
+        "e2e": {"value": nq_job / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(last["q"].nbytes + last["pts"].nbytes) * world,
+                "d2h_bytes_per_step": int(nq * LOC["k"] * 12 + nq * LOC["k"] * 8) * world},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof,
+        "timing": "value: host clock around K synchronous C-ABI calls between device synchronisations "
+                  f"(device events on the library's stream: {dev_ms / args.steps:.3f} ms/step)",
+        "stats": {"policy": args.loc_policy, "located": int(located), "located_at_the_right_place": int(right_place),
+                  "queries_last_step": nq, "grid_store_bytes": grid_bytes, "grid_store_workspace_bytes": ws_bytes,
+                  "grids_added_s": t_add},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_localize(W, last, got_idx, got_cand, args.cpu_budget, check=True)[0]
+    loc.close()
+    st.close()
+    ix.close()
+    return line
+
+
+def cpu_baseline_localize(W, B, gpu_idx, gpu_cand, budget_s, check, tree=None):
+    """The reference's CPU path on all host threads, bounded sample of one query batch: nanoflann
+    (compiled from /root/reference) against the full 1M-row database for n_r queries, the
+    branch-and-bound restatement of registration/2d for n_v of their (query, candidate) pairs.  A
+    query costs one retrieval + 25 verifications, all cores busy in both stages:
+    q/s = 1 / (t_retrieval / n_r + 25 * t_verify / n_v).  With check=True the sample's indices and
+    poses are asserted equal to the GPU's."""
+    from oracle import pyoracle as po
+
+    cores = os.cpu_count() or 1
+    k = LOC["k"]
+    build_s = 0.0
+    if tree is None and po.have_ref():
+        t0 = time.perf_counter()
+        tree = po.RefTree(W.db, 10)
+        build_s = time.perf_counter() - t0
+    kind = "reference" if tree is not None else "port"
+    n_r = min(B["q"].shape[0], cores)
+    t0 = time.perf_counter()
+    if tree is not None:
+        ref_idx, ref_d2 = tree.query(B["q"][:n_r], k, nthreads=cores)
+    else:
+        ref_idx, ref_d2 = po.knn(W.db, B["q"][:n_r], k, nthreads=cores)
+    t_r = time.perf_counter() - t0
+    # verification sample: the first candidates of the first queries (the planted place is usually among them)
+    n_v = int(max(cores, min(n_r * k, (budget_s / 0.7) * cores)))
+    n_v = min(n_r * k, n_v // cores * cores)
+    per_q = max(1, n_v // n_r)
+    sel = [(qi, c) for qi in range(n_r) for c in range(per_q)][:n_v]
+    grids = [W.grid(int(ref_idx[qi, c]) % W.n_grids) for qi, c in sel]
+    t0 = time.perf_counter()
+    out = po.csm_match_batch(grids, LOC["res"], W.mx, W.my, LOC["depth"], [B["scans"][qi] for qi, _ in sel],
+                             [(0, 0, 0)] * len(sel), LOC["n_lin"], LOC["n_ang"], LOC["step"], LOC["min_score"], 0, cores)
+    t_v = time.perf_counter() - t0
+    checked = None
+    if check:
+        # nanoflann's order among exactly equal distances is traversal order; ours is (d2, idx)
+        exact = po.knn(W.db, B["q"][:n_r], k, nthreads=cores)[0] if tree is not None else ref_idx
+        assert np.array_equal(gpu_idx[:n_r], exact), "retrieval indices differ from the oracle"
+        assert np.array_equal(np.sort(ref_idx, 1), np.sort(exact, 1)), "nanoflann and the brute-force oracle disagree"
+        for (qi, c), o in zip(sel, out):
+            r = gpu_cand[qi * k + c]
+            assert r[0] == o.found, f"found flag differs at query {qi} candidate {c}"
+            if o.found:
+                assert r[2:5] == (o.scan_index, o.x_offset, o.y_offset) and np.float32(r[1]) == np.float32(o.score) \
+                    and r[5:8] == (o.pose_x, o.pose_y, o.pose_yaw), f"pose differs at query {qi} candidate {c}"
+        checked = {"queries": n_r, "pairs": len(sel), "matched_pairs": int(sum(o.found for o in out))}
+    v = 1.0 / (t_r / n_r + k * t_v / len(sel))
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": kind + " (retrieval) + port (verification)",
+            "sample": f"{n_r} queries of the step against the full {W.rows}-row DB through nanoflann (KD-tree, leaf 10, "
+                      f"built once in {build_s:.1f} s, not counted): {t_r:.2f} s; {len(sel)} of their (query, candidate) "
+                      f"pairs through oracle/csm_oracle.c: {t_v:.2f} s; {cores} threads in both stages; "
+                      f"q/s = 1 / (t_r/{n_r} + {k} * t_v/{len(sel)})",
+            "retrieval_qps": n_r / t_r, "verification_pairs_per_s": len(sel) / t_v,
+            "parity_checked_against_gpu": checked}, tree
+
+
+def run_reference_localize(args):
+    W = LocWorld(args.loc_rows, args.loc_grids)
+    B = dict(zip(("q", "scans", "rows"), W.batch(0, min(args.loc_queries, os.cpu_count() or 1))))
+    total = args.steps + args.warmup
+    cb, tree = cpu_baseline_localize(W, B, None, None, 0.0, check=False)       # builds the tree once
+    vals = []
+    t0 = time.perf_counter()
+    for i in range(total):
+        cb, tree = cpu_baseline_localize(W, B, None, None, 0.0, check=False, tree=tree)
+        if i >= args.warmup:
+            vals.append(cb["value"])
+        if i == args.warmup - 1:
+            t0 = time.perf_counter()
+    ms = (time.perf_counter() - t0) * 1e3 / max(args.steps, 1)
+    v = float(len(vals) / sum(1.0 / x for x in vals))           # total queries / total time over the steps
+    cb["value"] = v
+    return {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 (nanoflann) + u8 sums -> f32 score", "data": "synthetic",
+            "config": loc_config(W, args.loc_queries, "none"),
+            "cpu_baseline": cb, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
 # ------------------------------------------------------------------- describe
 DESC_HW = 768          # the reference's CNN input (loop_detector.cpp:144-147)
 DESC_BATCH = 16        # frames per step and GPU
@@ -885,7 +1204,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="retrieval", choices=["retrieval", "verify", "stream", "describe"])
+    ap.add_argument("--workload", default="localize", choices=["localize", "retrieval", "verify", "stream", "describe"])
+    ap.add_argument("--loc-queries", type=int, default=LOC["q_per_gpu"], help="queries per GPU per step (localize)")
+    ap.add_argument("--loc-rows", type=int, default=LOC["rows"], help="database rows (localize)")
+    ap.add_argument("--loc-grids", type=int, default=LOC["grids"], help="distinct map grids (localize; multiple of 8)")
+    ap.add_argument("--loc-policy", default="all", choices=["all", "first"],
+                    help="all: verify every one of the 25 candidates (headline); first: the reference's order "
+                         "of evaluation, stop at the first candidate that matches")
     ap.add_argument("--stream-queries", type=int, default=1, help="queries per call of the stream workload (1..4)")
     ap.add_argument("--mode", default="auto", choices=["auto", "exact", "shortlist"])
     ap.add_argument("--sharding", default="queries", choices=["queries", "db"],
@@ -911,8 +1236,9 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        line = {"retrieval": run_reference_retrieval, "verify": run_reference_verify,
-                "stream": run_reference_stream, "describe": run_reference_describe}[args.workload](args)
+        line = {"localize": run_reference_localize, "retrieval": run_reference_retrieval,
+                "verify": run_reference_verify, "stream": run_reference_stream,
+                "describe": run_reference_describe}[args.workload](args)
         print(json.dumps(line), flush=True)
         return 0
 
@@ -928,8 +1254,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
                                 timeout=datetime.timedelta(seconds=300))
     try:
-        fn = {"retrieval": run_retrieval, "verify": run_verify, "stream": run_stream,
-              "describe": run_describe}[args.workload]
+        fn = {"localize": run_localize, "retrieval": run_retrieval, "verify": run_verify,
+              "stream": run_stream, "describe": run_describe}[args.workload]
         line = fn(args, rank, world, local_rank)
         if rank == 0:
             print(json.dumps(line), flush=True)

@@ -20,6 +20,7 @@ GLOC_ERR_RANGE = 4
 GLOC_ERR_NOMEM = 5
 
 KNN_AUTO, KNN_EXACT_SCAN, KNN_SHORTLIST = 0, 1, 2
+LOC_VERIFY_ALL, LOC_FIRST_MATCH = 0, 1
 
 
 class GlocError(RuntimeError):
@@ -57,6 +58,24 @@ class GridInfo(C.Structure):
                 ("max_x", C.c_double), ("max_y", C.c_double)]
 
 
+class LocParams(C.Structure):
+    _fields_ = [("k", C.c_int), ("n_lin", C.c_int), ("n_ang", C.c_int), ("ang_step", C.c_double),
+                ("depth", C.c_int), ("min_score", C.c_float), ("policy", C.c_int)]
+
+
+class LocResult(C.Structure):
+    _fields_ = [("located", C.c_int), ("candidate", C.c_int), ("best_candidate", C.c_int),
+                ("n_verified", C.c_int), ("db_index", C.c_uint64), ("match", CsmResult)]
+
+
+class LocStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("queries", "pairs_verified", "waves", "kernel_launches")]
+
+
+class LocProfile(C.Structure):
+    _fields_ = [("total_ms", C.c_double), ("retrieval_ms", C.c_double), ("calls", C.c_uint64)]
+
+
 class BevInfo(C.Structure):
     _fields_ = [("width", C.c_int), ("height", C.c_int), ("min_ix", C.c_int), ("min_iy", C.c_int),
                 ("ox", C.c_double), ("oy", C.c_double), ("resolution", C.c_double),
@@ -91,6 +110,15 @@ SIGNATURES = {
     "gloc_csm_add_grid_cells": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ip]),
     "gloc_csm_add_grid_u8": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ip]),
     "gloc_csm_num_grids": (_i, [_vp]),
+    "gloc_csm_store_bytes": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "gloc_loc_create": (_i, [C.POINTER(_vp), _vp, _vp]),
+    "gloc_loc_destroy": (None, [_vp]),
+    "gloc_loc_set_row_grids": (_i, [_vp, _vp, _sz]),
+    "gloc_loc_localize": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(LocParams), _vp, _vp, _vp, _vp]),
+    "gloc_loc_localize_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(LocParams), _vp, _vp, _vp, _vp]),
+    "gloc_loc_get_stats": (_i, [_vp, C.POINTER(LocStats)]),
+    "gloc_loc_set_profiling": (_i, [_vp, _i]),
+    "gloc_loc_get_profile": (_i, [_vp, C.POINTER(LocProfile)]),
     "gloc_csm_get_precomputation_grid": (_i, [_vp, _i, _i, _vp]),
     "gloc_csm_match_batch": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _d, _i, _f,
                                   C.POINTER(CsmResult)]),

@@ -27,6 +27,7 @@ namespace {
 constexpr int kPointChunk = 4096;  // discretised points cached in shared memory per pass
 constexpr int kCoarseThreads = 256;
 constexpr int kCandPerThread = 4;
+constexpr int kBitRowSlack = 17;    // zero plane rows after the last data row (candidate rows read past it)
 
 // Eigen Quaternionf(AngleAxisf(theta, UnitZ)) * v  with vec = (0, 0, z):
 //   uv = vec x v; uv += uv; v' = v + w*uv + vec x uv      (see oracle/csm_oracle.c)
@@ -59,24 +60,29 @@ __device__ __forceinline__ int2 discretize_point(const float* __restrict__ p, fl
 }
 
 struct LevelView {
-  const uint8_t* cells;
+  const uint8_t* cells;     // uint8 level (binary == 0)
+  const unsigned* bits;     // bit-packed level (binary == 1)
+  int stride;               // words per bit-packed row
   int wide_nx, wide_ny, wm1;
 };
 
 __device__ __forceinline__ LevelView level_view(const CsmGridDev& g, int level) {
   LevelView v;
   const int w = 1 << level;
-  v.cells = g.stack + g.off[level];
+  v.cells = g.binary ? nullptr : g.stack + g.off[level];
+  v.bits = g.binary ? g.lvl[level] : nullptr;
+  v.stride = g.lvs[level];
   v.wide_nx = g.nx + w - 1;
   v.wide_ny = g.ny + w - 1;
   v.wm1 = w - 1;
   return v;
 }
 
-// PrecomputationGrid2D::GetValue, fast_..._2d.h:68-83
+// PrecomputationGrid2D::GetValue, fast_..._2d.h:68-83 (a binary grid holds 0 / 255 only)
 __device__ __forceinline__ int level_val(const LevelView& v, int x, int y) {
   const unsigned lx = (unsigned)(x + v.wm1), ly = (unsigned)(y + v.wm1);
   if (lx >= (unsigned)v.wide_nx || ly >= (unsigned)v.wide_ny) return 0;
+  if (v.bits) return (int)((__ldg(v.bits + (size_t)ly * v.stride + (lx >> 5)) >> (lx & 31)) & 1u) * 255;
   return __ldg(v.cells + (size_t)ly * v.wide_nx + lx);
 }
 
@@ -114,28 +120,199 @@ __global__ void csm_level1_from_cells_kernel(const uint16_t* __restrict__ cells,
   if (i < n) out[i] = lut[cells[i]];
 }
 
+// ---- store encodings
+
+// uint8 width-1 grid -> bit-packed rows (bit x of row y at word y * stride + x / 32, stride =
+// (nx + 31) / 32 + 1, zero beyond nx); *not_binary is set when a cell is neither 0 nor 255.
+__global__ void csm_pack_bits_kernel(const uint8_t* __restrict__ level1, int nx, int ny, int stride,
+                                     unsigned* __restrict__ out, int* __restrict__ not_binary) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= ny * stride) return;
+  const int y = idx / stride, wx = idx % stride;
+  unsigned bits = 0;
+  bool odd = false;
+  for (int i = 0; i < 32; ++i) {
+    const int x = wx * 32 + i;
+    if (x < nx) {
+      const unsigned v = level1[(size_t)y * nx + x];
+      if (v) bits |= 1u << i;
+      odd |= (v != 0u && v != 255u);
+    }
+  }
+  out[idx] = bits;
+  if (odd) atomicOr(not_binary, 1);
+}
+
+__global__ void csm_unpack_bits_kernel(const unsigned* __restrict__ bits, int nx, int ny, int stride,
+                                       uint8_t* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nx * ny) return;
+  const int y = (int)(i / nx), x = (int)(i % nx);
+  out[i] = ((bits[(size_t)y * stride + (x >> 5)] >> (x & 31)) & 1u) ? 255 : 0;
+}
+
+// ---- the working set of a batch: one slot per distinct grid, everything derived from the
+// stored width-1 grid on the device, batched over the slots (blockIdx.y = slot)
+
+__device__ __forceinline__ unsigned hash_gid(int gid) {
+  unsigned h = (unsigned)gid * 0x9E3779B1u;
+  return h ^ (h >> 15);
+}
+
+__global__ void csm_slot_insert_kernel(const CsmPairDev* __restrict__ pairs, int n_pairs,
+                                       int* __restrict__ keys, int* __restrict__ hslot, int hmask,
+                                       int* __restrict__ slot_gid, int* __restrict__ n_slots) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int gid = pairs[i].gid;
+  unsigned h = hash_gid(gid) & (unsigned)hmask;
+  for (;;) {
+    const int prev = atomicCAS(keys + h, -1, gid);
+    if (prev == -1) {
+      const int slot = atomicAdd(n_slots, 1);
+      hslot[h] = slot;
+      slot_gid[slot] = gid;
+      return;
+    }
+    if (prev == gid) return;
+    h = (h + 1) & (unsigned)hmask;
+  }
+}
+
+__global__ void csm_slot_lookup_kernel(CsmPairDev* __restrict__ pairs, int n_pairs,
+                                       const int* __restrict__ keys, const int* __restrict__ hslot,
+                                       int hmask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs) return;
+  const int gid = pairs[i].gid;
+  unsigned h = hash_gid(gid) & (unsigned)hmask;
+  while (keys[h] != gid) h = (h + 1) & (unsigned)hmask;
+  pairs[i].grid = hslot[h];
+}
+
+__device__ __forceinline__ int bit_stride(int wide_nx) { return (wide_nx + 31) / 32 + 1; }
+
+__global__ void csm_prepare_slots_kernel(const CsmGridRec* __restrict__ recs,
+                                         const int* __restrict__ slot_gid,
+                                         const int* __restrict__ n_slots, CsmPlan plan,
+                                         unsigned char* __restrict__ ws, CsmGridDev* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= *n_slots) return;
+  const CsmGridRec r = recs[slot_gid[j]];
+  unsigned char* base = ws + (size_t)j * plan.slot_bytes;
+  CsmGridDev g;
+  g.nx = r.nx; g.ny = r.ny; g.resolution = r.resolution; g.max_x = r.max_x; g.max_y = r.max_y;
+  g.binary = plan.bits;
+  g.stack = nullptr; g.pm = nullptr; g.pmb = nullptr;
+  g.pm_pad = g.pm_pw = g.pm_ph = g.pm_log2w = 0;
+  g.pmb_rows = g.pmb_px = g.pmb_py = g.pmb_log2w = 0;
+  for (int l = 0; l < kCsmMaxDepth; ++l) { g.off[l] = 0; g.lvl[l] = nullptr; g.lvs[l] = 0; }
+  const int top = plan.depth - 1, w = 1 << top;
+  if (plan.bits) {
+    g.lvl[0] = reinterpret_cast<const unsigned*>(r.data);
+    g.lvs[0] = bit_stride(r.nx);
+    for (int l = 1; l < plan.depth; ++l) {
+      g.lvl[l] = reinterpret_cast<const unsigned*>(base + plan.lvl_off[l]);
+      g.lvs[l] = bit_stride(r.nx + (1 << l) - 1);
+    }
+    g.pmb = reinterpret_cast<const unsigned long long*>(base + plan.pmb_off);
+    g.pmb_rows = ((r.ny + w - 1 + 3 * plan.n_lin - 1) >> top) + 1 + kBitRowSlack;
+    g.pmb_px = plan.n_lin; g.pmb_py = 2 * plan.n_lin; g.pmb_log2w = top;
+  } else {
+    g.stack = base;
+    long long total = 0;
+    for (int l = 0; l < plan.depth; ++l) {
+      const int wl = 1 << l;
+      g.off[l] = total;
+      total += (long long)(r.nx + wl - 1) * (long long)(r.ny + wl - 1);
+      total = (total + 15) & ~15ll;
+    }
+    if (plan.use_pm) {
+      const int wide_nx = r.nx + w - 1, wide_ny = r.ny + w - 1, pad = plan.n_lin;
+      g.pm = base + plan.pm_off;
+      g.pm_pad = pad;
+      g.pm_pw = (wide_nx + 2 * pad + w - 1) / w;
+      g.pm_ph = (wide_ny + 2 * pad + w - 1) / w;
+      g.pm_log2w = top;
+    }
+  }
+  out[j] = g;
+}
+
+// bit level l from bit level l-1: the max over a w x w window is the OR of four w/2 x w/2
+// windows, i.e. out = A | (A << h) with A = row(y) | row(y - h) of the previous level.
+__global__ void csm_build_lvl_bits_kernel(const CsmGridDev* __restrict__ slots,
+                                          const int* __restrict__ n_slots, int l) {
+  if ((int)blockIdx.y >= *n_slots) return;
+  const CsmGridDev& g = slots[blockIdx.y];
+  const int w = 1 << l, h = w >> 1;
+  const int wny = g.ny + w - 1, pny = g.ny + h - 1;
+  const int stride = g.lvs[l], ps = g.lvs[l - 1];
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= wny * stride) return;
+  const int ly = idx / stride, j = idx % stride;
+  const unsigned* prev = g.lvl[l - 1];
+  auto A = [&](int jj) -> unsigned {
+    if (jj < 0 || jj >= ps) return 0u;
+    unsigned v = 0u;
+    if (ly < pny) v |= __ldg(prev + (size_t)ly * ps + jj);
+    if (ly - h >= 0 && ly - h < pny) v |= __ldg(prev + (size_t)(ly - h) * ps + jj);
+    return v;
+  };
+  const int hs = h >> 5, hb = h & 31;
+  const unsigned sh = hb ? __funnelshift_l(A(j - hs - 1), A(j - hs), hb) : A(j - hs);
+  const_cast<unsigned*>(g.lvl[l])[idx] = A(j) | sh;
+}
+
+// uint8 path: width-1 grid of a slot from the store's record (bits or bytes)
+__global__ void csm_slot_level0_u8_kernel(const CsmGridRec* __restrict__ recs,
+                                          const int* __restrict__ slot_gid,
+                                          const CsmGridDev* __restrict__ slots,
+                                          const int* __restrict__ n_slots) {
+  if ((int)blockIdx.y >= *n_slots) return;
+  const CsmGridDev& g = slots[blockIdx.y];
+  const CsmGridRec r = recs[slot_gid[blockIdx.y]];
+  const size_t n = (size_t)g.nx * g.ny;
+  uint8_t* out = const_cast<uint8_t*>(g.stack);
+  const int stride = (g.nx + 31) / 32 + 1;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (r.enc == 1) {
+      const int y = (int)(i / g.nx), x = (int)(i % g.nx);
+      const unsigned wd = reinterpret_cast<const unsigned*>(r.data)[(size_t)y * stride + (x >> 5)];
+      out[i] = ((wd >> (x & 31)) & 1u) ? 255 : 0;
+    } else {
+      out[i] = reinterpret_cast<const uint8_t*>(r.data)[i];
+    }
+  }
+}
+
 // Width-w grid from the width-w/2 grid: the max over a w x w window is the max of
 // four w/2 x w/2 windows.  Out-of-stack reads are windows outside the map: 0.
-__global__ void csm_build_level_kernel(const uint8_t* __restrict__ prev, int nx, int ny, int w,
-                                       uint8_t* __restrict__ out) {
+__global__ void csm_build_level_kernel(const CsmGridDev* __restrict__ slots,
+                                       const int* __restrict__ n_slots, int l) {
+  if ((int)blockIdx.y >= *n_slots) return;
+  const CsmGridDev& g = slots[blockIdx.y];
+  const int w = 1 << l, h = w >> 1, nx = g.nx, ny = g.ny;
   const int wide_nx = nx + w - 1, wide_ny = ny + w - 1;
-  const int lx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int ly = blockIdx.y * blockDim.y + threadIdx.y;
-  if (lx >= wide_nx || ly >= wide_ny) return;
-  const int h = w >> 1;
   const int pnx = nx + h - 1, pny = ny + h - 1;
-  // window origin in map cells, then position in the previous level's local frame
-  const int px = lx - (w - 1) + (h - 1), py = ly - (w - 1) + (h - 1);
-  int m = 0;
+  const uint8_t* prev = g.stack + g.off[l - 1];
+  uint8_t* out = const_cast<uint8_t*>(g.stack) + g.off[l];
+  const size_t n = (size_t)wide_nx * wide_ny;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int ly = (int)(i / wide_nx), lx = (int)(i % wide_nx);
+    // window origin in map cells, then position in the previous level's local frame
+    const int px = lx - (w - 1) + (h - 1), py = ly - (w - 1) + (h - 1);
+    int m = 0;
 #pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
+    for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      const int x = px + dx * h, y = py + dy * h;
-      if ((unsigned)x < (unsigned)pnx && (unsigned)y < (unsigned)pny)
-        m = max(m, (int)prev[(size_t)y * pnx + x]);
-    }
-  out[(size_t)ly * wide_nx + lx] = (uint8_t)m;
+      for (int dx = 0; dx < 2; ++dx) {
+        const int x = px + dx * h, y = py + dy * h;
+        if ((unsigned)x < (unsigned)pnx && (unsigned)y < (unsigned)pny)
+          m = max(m, (int)prev[(size_t)y * pnx + x]);
+      }
+    out[i] = (uint8_t)m;
+  }
 }
 
 // ------------------------------------------------------------------------- K6
@@ -278,18 +455,24 @@ csm_coarse_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
 
 // ------------------------------------------------------------- K7 coarse (phase-major)
 
-__global__ void csm_build_pm_kernel(const uint8_t* __restrict__ level, int wide_nx, int wide_ny,
-                                    int pad, int log2w, int pw, int ph, uint8_t* __restrict__ out) {
-  const int w = 1 << log2w;
-  const int X = blockIdx.x * blockDim.x + threadIdx.x;   // padded coordinates
-  const int Y = blockIdx.y * blockDim.y + threadIdx.y;
-  if (X >= pw * w || Y >= ph * w) return;
-  const int lx = X - pad, ly = Y - pad;
-  uint8_t v = 0;
-  if ((unsigned)lx < (unsigned)wide_nx && (unsigned)ly < (unsigned)wide_ny)
-    v = level[(size_t)ly * wide_nx + lx];
-  const size_t plane = (size_t)((Y & (w - 1)) * w + (X & (w - 1)));
-  out[(plane * ph + (Y >> log2w)) * pw + (X >> log2w)] = v;
+__global__ void csm_build_pm_kernel(const CsmGridDev* __restrict__ slots,
+                                    const int* __restrict__ n_slots) {
+  if ((int)blockIdx.y >= *n_slots) return;
+  const CsmGridDev& g = slots[blockIdx.y];
+  const int log2w = g.pm_log2w, w = 1 << log2w, pad = g.pm_pad, pw = g.pm_pw, ph = g.pm_ph;
+  const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1;
+  const uint8_t* level = g.stack + g.off[log2w];
+  uint8_t* out = const_cast<uint8_t*>(g.pm);
+  const size_t n = (size_t)pw * w * ph * w;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % ((size_t)pw * w)), Y = (int)(i / ((size_t)pw * w));   // padded coordinates
+    const int lx = X - pad, ly = Y - pad;
+    uint8_t v = 0;
+    if ((unsigned)lx < (unsigned)wide_nx && (unsigned)ly < (unsigned)wide_ny)
+      v = level[(size_t)ly * wide_nx + lx];
+    const size_t plane = (size_t)((Y & (w - 1)) * w + (X & (w - 1)));
+    out[(plane * ph + (Y >> log2w)) * pw + (X >> log2w)] = v;
+  }
 }
 
 constexpr int kPmThreads = 512;
@@ -474,32 +657,32 @@ csm_coarse_pm_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __r
 // the four extreme coordinates.
 
 constexpr int kBitChunk = 4080;     // points per pass: 16 x 255, so 8 high planes cannot overflow
-constexpr int kBitRowSlack = 17;    // zero rows after the last data row (candidate rows read past it)
 constexpr int kBitThreads = 384;    // 192 rotations per CTA, two lanes each
 
-__global__ void csm_build_pmb_kernel(const uint8_t* __restrict__ level, int wide_nx, int wide_ny,
-                                     int px, int py, int log2w, int rows,
-                                     unsigned long long* __restrict__ out, int* __restrict__ not_binary) {
-  const int w = 1 << log2w;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= w * w * rows) return;
-  const int plane = idx / rows, r = idx % rows;
-  const int ry = plane >> log2w, rx = plane & (w - 1);
-  const int ly = (r << log2w) + ry - py;
-  unsigned long long bits = 0;
-  bool odd = false;
-  if ((unsigned)ly < (unsigned)wide_ny) {
-    for (int c = 0; c < 64; ++c) {
-      const int lx = (c << log2w) + rx - px;
-      if ((unsigned)lx < (unsigned)wide_nx) {
-        const unsigned v = level[(size_t)ly * wide_nx + lx];
-        if (v) bits |= 1ull << c;
-        odd |= (v != 0u && v != 255u);
+__global__ void csm_build_pmb_kernel(const CsmGridDev* __restrict__ slots,
+                                     const int* __restrict__ n_slots) {
+  if ((int)blockIdx.y >= *n_slots) return;
+  const CsmGridDev& g = slots[blockIdx.y];
+  const int log2w = g.pmb_log2w, w = 1 << log2w, rows = g.pmb_rows, px = g.pmb_px, py = g.pmb_py;
+  const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1, stride = g.lvs[log2w];
+  const unsigned* level = g.lvl[log2w];
+  unsigned long long* out = const_cast<unsigned long long*>(g.pmb);
+  const int n = w * w * rows;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int plane = idx / rows, r = idx % rows;
+    const int ry = plane >> log2w, rx = plane & (w - 1);
+    const int ly = (r << log2w) + ry - py;
+    unsigned long long bits = 0;
+    if ((unsigned)ly < (unsigned)wide_ny) {
+      const unsigned* row = level + (size_t)ly * stride;
+      for (int c = 0; c < 64; ++c) {
+        const int lx = (c << log2w) + rx - px;
+        if ((unsigned)lx < (unsigned)wide_nx)
+          bits |= (unsigned long long)((__ldg(row + (lx >> 5)) >> (lx & 31)) & 1u) << c;
       }
     }
+    out[idx] = bits;
   }
-  out[idx] = bits;
-  if (odd) atomicOr(not_binary, 1);
 }
 
 // map_limits.h:69-76 on an already transformed point (double arithmetic, lround)
@@ -856,20 +1039,6 @@ __global__ void csm_filter_kernel(const CsmPairDev* __restrict__ pairs, int n_pa
 
 constexpr int kExpChunk = 2048;   // points staged per pass of the expand kernel
 
-// Binary grids: level -> bit-packed rows (bit x of row y at word y * stride + x / 32).
-__global__ void csm_build_lvb_kernel(const uint8_t* __restrict__ level, int wide_nx, int wide_ny,
-                                     int stride, unsigned* __restrict__ out) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= wide_ny * stride) return;
-  const int y = idx / stride, wx = idx % stride;
-  unsigned bits = 0;
-  for (int i = 0; i < 32; ++i) {
-    const int x = wx * 32 + i;
-    if (x < wide_nx && level[(size_t)y * wide_nx + x]) bits |= 1u << i;
-  }
-  out[idx] = bits;
-}
-
 // Survivors of grids without bit planes go to the depth-first refinement unexpanded.
 __global__ void csm_survivors_to_nodes_kernel(const CsmPairDev* __restrict__ pairs, CsmParams prm,
                                               const CsmBounds* __restrict__ bounds,
@@ -925,14 +1094,15 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
   const float* sp = pts + 3 * (size_t)pr.pt_begin;
   const int d = prm.depth - 2;                   // level of the children
   const int h = 1 << d, wm1 = h - 1;
-  const int wide_nx = g.nx + wm1, wide_ny = g.ny + wm1, stride = g.lvb_stride;
+  const int wide_nx = g.nx + wm1, wide_ny = g.ny + wm1, stride = g.lvs[d];
+  const unsigned* lvb = g.lvl[d];
   float2* P0 = reinterpret_cast<float2*>(csm_smem);                       // [kExpChunk]
   // rows 16 k apart (neighbouring coarse candidates of one scan) would share two banks with a
   // plain row stride: one extra word every 16 rows spreads them over all banks
   unsigned* bits = reinterpret_cast<unsigned*>(P0 + kExpChunk);          // [wide_ny][stride] (+ row / 16)
   for (int i = tid; i < wide_ny * stride; i += 256) {
     const int row = i / stride;
-    bits[i + (row >> 4)] = __ldg(g.lvb + i);
+    bits[i + (row >> 4)] = __ldg(lvb + i);
   }
   const float mx_f = (float)g.max_x, my_f = (float)g.max_y, ir = (float)(1.0 / g.resolution);
   const float U = (float)(max(g.nx, g.ny) + 2 * prm.n_lin + 64 + 2 * prm.step);
@@ -1182,11 +1352,75 @@ cudaError_t launch_csm_level1_from_cells(const uint16_t* cells, const uint8_t* l
   return cudaGetLastError();
 }
 
-cudaError_t launch_csm_build_level(const uint8_t* prev, int nx, int ny, int w, uint8_t* out,
-                                   cudaStream_t stream) {
-  dim3 blk(64, 4);
-  dim3 grd((nx + w - 1 + blk.x - 1) / blk.x, (ny + w - 1 + blk.y - 1) / blk.y);
-  csm_build_level_kernel<<<grd, blk, 0, stream>>>(prev, nx, ny, w, out);
+cudaError_t launch_csm_pack_bits(const uint8_t* level1, int nx, int ny, unsigned* out, int* not_binary,
+                                 cudaStream_t stream) {
+  const int stride = (nx + 31) / 32 + 1, n = ny * stride;
+  csm_pack_bits_kernel<<<(n + 255) / 256, 256, 0, stream>>>(level1, nx, ny, stride, out, not_binary);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_unpack_bits(const unsigned* bits, int nx, int ny, uint8_t* out, cudaStream_t stream) {
+  const size_t n = (size_t)nx * ny;
+  csm_unpack_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bits, nx, ny, (nx + 31) / 32 + 1, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_assign_slots(CsmPairDev* pairs, int n_pairs, int* hash_keys, int* hash_slot,
+                                    int hash_size, int* slot_gid, int* n_slots, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(hash_keys, 0xFF, (size_t)hash_size * sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(n_slots, 0, sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  const int blocks = (n_pairs + 255) / 256;
+  csm_slot_insert_kernel<<<blocks, 256, 0, stream>>>(pairs, n_pairs, hash_keys, hash_slot, hash_size - 1,
+                                                     slot_gid, n_slots);
+  csm_slot_lookup_kernel<<<blocks, 256, 0, stream>>>(pairs, n_pairs, hash_keys, hash_slot, hash_size - 1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_prepare_slots(const CsmGridRec* recs, const int* slot_gid, const int* n_slots,
+                                     int max_slots, CsmPlan plan, unsigned char* ws, CsmGridDev* out,
+                                     cudaStream_t stream) {
+  csm_prepare_slots_kernel<<<(max_slots + 127) / 128, 128, 0, stream>>>(recs, slot_gid, n_slots, plan, ws, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_csm_build_slots(const CsmGridRec* recs, const int* slot_gid, const CsmGridDev* slots,
+                                   const int* n_slots, int max_slots, CsmPlan plan, cudaStream_t stream,
+                                   uint64_t* launches) {
+  // grid.y = slot (early exit beyond the device-side count); grid.x sized for the largest grid
+  auto blocks = [](size_t elems, int per_block) {
+    return (unsigned)std::min<size_t>((elems + per_block - 1) / per_block, 1u << 20);
+  };
+  const int top = plan.depth - 1;
+  if (plan.bits) {
+    for (int l = 1; l < plan.depth; ++l) {
+      const int w = 1 << l;
+      const size_t words = (size_t)(plan.max_ny + w - 1) * (size_t)((plan.max_nx + w - 1 + 31) / 32 + 1);
+      csm_build_lvl_bits_kernel<<<dim3(blocks(words, 256), max_slots), 256, 0, stream>>>(slots, n_slots, l);
+      ++*launches;
+    }
+    const int w = 1 << top;
+    const size_t words = (size_t)w * w * (size_t)csm_pmb_rows(plan.max_ny + w - 1, plan.n_lin, top);
+    csm_build_pmb_kernel<<<dim3(blocks(words, 128), max_slots), 128, 0, stream>>>(slots, n_slots);
+    ++*launches;
+  } else {
+    const size_t n0 = (size_t)plan.max_nx * plan.max_ny;
+    csm_slot_level0_u8_kernel<<<dim3(blocks(n0, 1024), max_slots), 256, 0, stream>>>(recs, slot_gid, slots, n_slots);
+    ++*launches;
+    for (int l = 1; l < plan.depth; ++l) {
+      const int w = 1 << l;
+      const size_t n = (size_t)(plan.max_nx + w - 1) * (size_t)(plan.max_ny + w - 1);
+      csm_build_level_kernel<<<dim3(blocks(n, 1024), max_slots), 256, 0, stream>>>(slots, n_slots, l);
+      ++*launches;
+    }
+    if (plan.use_pm) {
+      const int w = 1 << top;
+      const size_t n = (size_t)(plan.max_nx + 2 * w + 2 * plan.n_lin) * (size_t)(plan.max_ny + 2 * w + 2 * plan.n_lin);
+      csm_build_pm_kernel<<<dim3(blocks(n, 1024), max_slots), 256, 0, stream>>>(slots, n_slots);
+      ++*launches;
+    }
+  }
   return cudaGetLastError();
 }
 
@@ -1197,14 +1431,6 @@ cudaError_t launch_csm_discretize(const float* pts, int n_pts, float w0, float z
   dim3 grd((n_pts + 255) / 256, S);
   csm_discretize_kernel<<<grd, 256, 0, stream>>>(pts, n_pts, w0, z0, tx, ty, rot, S, resolution,
                                                  max_x, max_y, out_cells);
-  return cudaGetLastError();
-}
-
-cudaError_t launch_csm_build_pm(const uint8_t* level, int wide_nx, int wide_ny, int pad, int log2w,
-                                int pw, int ph, uint8_t* out, cudaStream_t stream) {
-  dim3 blk(64, 4);
-  dim3 grd(((pw << log2w) + blk.x - 1) / blk.x, ((ph << log2w) + blk.y - 1) / blk.y);
-  csm_build_pm_kernel<<<grd, blk, 0, stream>>>(level, wide_nx, wide_ny, pad, log2w, pw, ph, out);
   return cudaGetLastError();
 }
 
@@ -1227,15 +1453,6 @@ cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, 
     csm_coarse_kernel<<<grd, kCoarseThreads, 0, stream>>>(grids, pairs, pts, rot, prm, bounds,
                                                           coarse, top_coarse);
   }
-  return cudaGetLastError();
-}
-
-cudaError_t launch_csm_build_pmb(const uint8_t* level, int wide_nx, int wide_ny, int px, int py,
-                                 int log2w, int rows, unsigned long long* out, int* not_binary,
-                                 cudaStream_t stream) {
-  const int n = (1 << (2 * log2w)) * rows;
-  csm_build_pmb_kernel<<<(n + 127) / 128, 128, 0, stream>>>(level, wide_nx, wide_ny, px, py, log2w,
-                                                            rows, out, not_binary);
   return cudaGetLastError();
 }
 
@@ -1305,18 +1522,11 @@ cudaError_t launch_csm_filter(const CsmPairDev* pairs, int n_pairs, CsmParams pr
   return cudaGetLastError();
 }
 
-cudaError_t launch_csm_build_lvb(const uint8_t* level, int wide_nx, int wide_ny, int stride,
-                                 unsigned* out, cudaStream_t stream) {
-  const int n = wide_ny * stride;
-  csm_build_lvb_kernel<<<(n + 255) / 256, 256, 0, stream>>>(level, wide_nx, wide_ny, stride, out);
-  return cudaGetLastError();
-}
-
 size_t csm_expand_smem(int wide_ny, int stride) {
   return (size_t)kExpChunk * sizeof(float2) + ((size_t)wide_ny * stride + (size_t)(wide_ny >> 4) + 1) * 4;
 }
 
-// bits == true: every grid of the batch carries the bit-packed level depth-2 (lvb), and
+// bits == true: every grid of the batch carries bit-packed levels (binary slots), and
 // `smem` is the largest footprint; else the survivors become nodes unexpanded.
 cudaError_t launch_csm_expand(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                               const float* pts, const float2* rot, CsmParams prm,

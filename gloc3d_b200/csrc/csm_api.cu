@@ -8,7 +8,7 @@
 #include <new>
 #include <vector>
 
-#include "csm_kernels.cuh"
+#include "csm_store.cuh"
 
 using namespace gloc;
 
@@ -34,24 +34,6 @@ float value_to_cost(uint16_t value) {
   return v * kScale + (kMinCorrespondenceCost - kScale);
 }
 
-struct HostGrid {
-  int nx = 0, ny = 0;
-  double resolution = 0, max_x = 0, max_y = 0;
-  uint8_t* d_stack = nullptr;  // levels 0..depth-1 concatenated; level 0 is the width-1 grid
-  int depth = 0;               // levels currently built
-  size_t bytes = 0;
-  long long off[kCsmMaxDepth] = {0};
-  // padded phase-major copy of the coarsest level used by the last batches (CsmGridDev::pm)
-  uint8_t* d_pm = nullptr;
-  int pm_level = -1, pm_pad = 0, pm_pw = 0, pm_ph = 0;
-  // bit planes of the coarsest level (binary grids; CsmGridDev::pmb)
-  unsigned long long* d_pmb = nullptr;
-  int pmb_level = -1, pmb_nlin = -1, pmb_rows = 0;
-  int binary = -1;   // -1 unknown, 0 some cell is neither 0 nor 255, 1 binary
-  unsigned* d_lvb = nullptr;   // bit-packed level depth-2 (CsmGridDev::lvb)
-  int lvb_level = -1, lvb_stride = 0;
-};
-
 size_t stack_bytes(int nx, int ny, int depth, long long* off) {
   size_t total = 0;
   for (int i = 0; i < depth; ++i) {
@@ -63,38 +45,7 @@ size_t stack_bytes(int nx, int ny, int depth, long long* off) {
   return total;
 }
 
-struct Buf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t reserve(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMalloc(&p, need + need / 4 + 256);
-    if (e == cudaSuccess) bytes = need + need / 4 + 256; else p = nullptr;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-  }
-};
-
-}  // namespace
-
-struct gloc_csm_store {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::vector<HostGrid> grids;
-  uint8_t* d_lut = nullptr;  // uint16 cost value -> uint8 width-1 cell
-  Buf pts, pairs, gridtab, rot, bounds, coarse, top, best, survivors, nsurv, nodes, misc, cells16, disc;
-  gloc_csm_stats stats{};
-  EventProfiler prof;
-};
-
-namespace {
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // Build the uint16 -> uint8 table exactly as PrecomputationGrid2D does per cell:
 // ComputeCellValue(1.f - |cost|), fast_..._2d.cpp:118-119,130-131,184-190.
@@ -109,44 +60,334 @@ void build_lut(std::vector<uint8_t>& lut) {
   }
 }
 
-int ensure_stack(gloc_csm_store* st, HostGrid& g, int depth) {
-  if (g.depth >= depth) return GLOC_OK;
-  long long off[kCsmMaxDepth] = {0};
-  const size_t bytes = stack_bytes(g.nx, g.ny, depth, off);
-  uint8_t* ns = nullptr;
-  GLOC_CUDA_TRY(cudaMalloc((void**)&ns, bytes));
-  const size_t l1 = (size_t)g.nx * g.ny;
-  cudaError_t e = cudaMemcpyAsync(ns, g.d_stack, l1, cudaMemcpyDeviceToDevice, st->stream);
-  for (int i = 1; i < depth && e == cudaSuccess; ++i) {
-    e = launch_csm_build_level(ns + off[i - 1], g.nx, g.ny, 1 << i, ns + off[i], st->stream);
-    st->stats.kernel_launches++;
+CsmBuf* all_bufs(gloc_csm_store* st, int i) {
+  CsmBuf* b[] = {&st->d_recs, &st->pts, &st->pairs, &st->slots, &st->slot_gid, &st->hkeys, &st->hslot,
+                 &st->ws, &st->rot, &st->bounds, &st->coarse, &st->top, &st->best, &st->survivors,
+                 &st->nsurv, &st->nodes, &st->misc, &st->cells16, &st->stage_u8, &st->disc};
+  return i < (int)(sizeof(b) / sizeof(b[0])) ? b[i] : nullptr;
+}
+
+// The width-1 grid sits in st->stage_u8 (device): pack it into the arena (bits when every
+// cell is 0 or 255, else the bytes) and record it.  One host round trip when the encoding is
+// not known in advance; none for grids that are binary by construction.
+int add_from_stage(gloc_csm_store* st, int nx, int ny, double resolution, double max_x, double max_y,
+                   bool known_binary, int* grid_id, const char* who) {
+  const int stride = (nx + 31) / 32 + 1;
+  const size_t bit_bytes = (size_t)ny * stride * 4, n = (size_t)nx * ny;
+  void* d_bits = nullptr;
+  cudaError_t e = st->arena.alloc(bit_bytes, &d_bits);
+  if (e == cudaSuccess) e = st->misc.reserve(64);
+  if (e == cudaSuccess) e = cudaMemsetAsync(st->misc.p, 0, 4, st->stream);
+  if (e == cudaSuccess)
+    e = launch_csm_pack_bits((const uint8_t*)st->stage_u8.p, nx, ny, (unsigned*)d_bits, (int*)st->misc.p,
+                             st->stream);
+  st->stats.kernel_launches++;
+  int not_binary = 0;
+  if (e == cudaSuccess && !known_binary) {
+    e = cudaMemcpyAsync(&not_binary, st->misc.p, 4, cudaMemcpyDeviceToHost, st->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);
   }
+  CsmGridRec r{};
+  r.nx = nx; r.ny = ny; r.resolution = resolution; r.max_x = max_x; r.max_y = max_y;
+  r.data = d_bits;
+  r.enc = 1;
+  if (e == cudaSuccess && not_binary) {
+    st->arena.rollback(d_bits, bit_bytes);
+    void* d_raw = nullptr;
+    e = st->arena.alloc(n, &d_raw);
+    if (e == cudaSuccess)
+      e = cudaMemcpyAsync(d_raw, st->stage_u8.p, n, cudaMemcpyDeviceToDevice, st->stream);
+    r.data = d_raw;
+    r.enc = 0;
+  }
+  // the staging buffer is reused by the next add: the kernels reading it must have finished
   if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);
-  if (e != cudaSuccess) {
-    cudaFree(ns);
-    return fail(GLOC_ERR_CUDA, std::string("precomputation stack: ") + cudaGetErrorString(e));
-  }
-  cudaFree(g.d_stack);
-  g.d_stack = ns;
-  g.depth = depth;
-  g.bytes = bytes;
-  std::memcpy(g.off, off, sizeof(off));
+  if (e != cudaSuccess) return fail(GLOC_ERR_CUDA, std::string(who) + ": " + cudaGetErrorString(e));
+  if (r.enc == 0) st->n_graded++;
+  st->max_nx = std::max(st->max_nx, nx);
+  st->max_ny = std::max(st->max_ny, ny);
+  st->recs.push_back(r);
+  if (grid_id) *grid_id = (int)st->recs.size() - 1;
   return GLOC_OK;
 }
 
-int add_grid_common(gloc_csm_store* st, int nx, int ny, double resolution, double max_x,
-                    double max_y, uint8_t** d_level1) {
+int check_limits(int nx, int ny, double resolution, const char* who) {
   if (nx < 1 || ny < 1 || !(resolution > 0.))  // MapLimits ctor CHECKs, map_limits.h:44-46
-    return fail(GLOC_ERR_INVALID, "gloc_csm_add_grid: bad limits");
-  if ((long long)nx * ny > (1ll << 30)) return fail(GLOC_ERR_RANGE, "gloc_csm_add_grid: grid too large");
-  (void)max_x;
-  (void)max_y;
-  GLOC_CUDA_TRY(cudaMalloc((void**)d_level1, (size_t)nx * ny));
-  (void)st;
+    return fail(GLOC_ERR_INVALID, std::string(who) + ": bad limits");
+  if ((long long)nx * ny > (1ll << 30)) return fail(GLOC_ERR_RANGE, std::string(who) + ": grid too large");
   return GLOC_OK;
 }
 
 }  // namespace
+
+namespace gloc {
+
+int csm_sync_recs(gloc_csm_store* st) {
+  const size_t n = st->recs.size();
+  if (st->recs_on_device == n) return GLOC_OK;
+  const size_t need = n * sizeof(CsmGridRec);
+  size_t first = st->recs_on_device;
+  if (need > st->d_recs.bytes) {   // a growth drops the old contents: upload everything again
+    GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
+    GLOC_CUDA_TRY(st->d_recs.reserve(std::max(need * 2, (size_t)4096)));
+    first = 0;
+  }
+  GLOC_CUDA_TRY(cudaMemcpyAsync((char*)st->d_recs.p + first * sizeof(CsmGridRec), st->recs.data() + first,
+                                (n - first) * sizeof(CsmGridRec), cudaMemcpyHostToDevice, st->stream));
+  // the records live in a std::vector that may reallocate: the copy must not outlive this call
+  GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
+  st->recs_on_device = n;
+  return GLOC_OK;
+}
+
+CsmParams csm_make_params(int n_lin, int n_ang, int depth, float min_score) {
+  CsmParams prm;
+  prm.n_lin = n_lin;
+  prm.n_ang = n_ang;
+  prm.S = 2 * n_ang + 1;
+  prm.depth = depth;
+  prm.step = 1 << (depth - 1);
+  prm.max_side = (2 * n_lin) / prm.step + 1;
+  prm.maxc = prm.max_side * prm.max_side;
+  prm.W = (unsigned)(2 * n_lin + 1);
+  prm.min_score = min_score;
+  prm.min_s = 1.f - kMaxCorrespondenceCost;
+  prm.coef = ((1.f - kMinCorrespondenceCost) - (1.f - kMaxCorrespondenceCost)) / 255.f;
+  return prm;
+}
+
+void csm_host_rotations(int n_ang, double ang_step, std::vector<float2>* rot) {
+  const long long S = 2ll * n_ang + 1;
+  rot->resize((size_t)S);
+  double delta_theta = -n_ang * ang_step;
+  for (long long s = 0; s < S; ++s, delta_theta += ang_step) {
+    const float ha = 0.5f * (float)delta_theta;
+    (*rot)[(size_t)s] = make_float2(std::cos(ha), std::sin(ha));
+  }
+}
+
+int csm_make_plan(int max_nx, int max_ny, bool all_binary, int n_lin, int depth, CsmBatchPlan* out) {
+  CsmBatchPlan P;
+  const int top = depth - 1, w = 1 << top;
+  const int max_side = (2 * n_lin) / w + 1;
+  const int wide_nx = max_nx + w - 1, wide_ny = max_ny + w - 1;
+  P.dev.depth = depth;
+  P.dev.n_lin = n_lin;
+  P.dev.max_nx = max_nx;
+  P.dev.max_ny = max_ny;
+  // bit-sliced coarse scorer: binary grids whose coarsest level fits 64 columns per plane row
+  // and shared memory, at most 16 lattice candidates per axis
+  bool use_bits = all_binary && std::getenv("GLOC_CSM_NO_BITS") == nullptr && max_side <= 16;
+  if (use_bits) {
+    const int rows = csm_pmb_rows(wide_ny, n_lin, top);
+    const size_t smem = csm_coarse_bits_smem(top, rows);
+    if (((wide_nx + n_lin - 1) >> top) >= 64 || smem > (size_t)225 * 1024) use_bits = false;
+    else P.bits_smem = smem;
+  }
+  P.use_bits = use_bits;
+  if (use_bits) {
+    P.dev.bits = 1;
+    size_t off = 0;
+    for (int l = 1; l < depth; ++l) {
+      const int wl = 1 << l;
+      P.dev.lvl_off[l] = off;
+      off += align256((size_t)(max_ny + wl - 1) * (size_t)((max_nx + wl - 1 + 31) / 32 + 1) * 4);
+    }
+    P.dev.pmb_off = off;
+    off += align256((size_t)w * w * (size_t)csm_pmb_rows(wide_ny, n_lin, top) * 8);
+    P.dev.slot_bytes = std::max(off, (size_t)256);
+    if (depth >= 2) {   // expand stage on the bit-packed level depth-2
+      const int l2 = depth - 2, w2 = 1 << l2;
+      const size_t smem = csm_expand_smem(max_ny + w2 - 1, (max_nx + w2 - 1 + 31) / 32 + 1);
+      if (smem <= (size_t)112 * 1024) {
+        P.exp_bits = true;
+        P.exp_smem = smem;
+      }
+    }
+  } else {
+    P.dev.bits = 0;
+    const size_t sb = align256(stack_bytes(max_nx, max_ny, depth, nullptr));
+    const size_t pw = (size_t)(wide_nx + 2 * n_lin + w - 1) / w, ph = (size_t)(wide_ny + 2 * n_lin + w - 1) / w;
+    const size_t cells = pw * ph * w * w;
+    // absurd windows: bounds-checked kernel
+    const bool use_pm = std::getenv("GLOC_CSM_NO_PM") == nullptr && cells <= ((size_t)1 << 27);
+    P.dev.use_pm = use_pm ? 1 : 0;
+    P.dev.pm_off = sb;
+    P.dev.slot_bytes = sb + (use_pm ? align256(cells) : 0);
+    P.pm_kernel = use_pm && (size_t)max_side * max_side * 4 + 20 * 4096 <= 150 * 1024;
+  }
+  *out = P;
+  return GLOC_OK;
+}
+
+int csm_match_core(gloc_csm_store* st, const CsmBatchPlan& plan, const float* d_pts, CsmPairDev* d_pairs,
+                   int n_pairs, const CsmParams& prm, const float2* d_rot, unsigned long long* h_best) {
+  cudaStream_t stream = st->stream;
+  int rc = csm_sync_recs(st);
+  if (rc != GLOC_OK) return rc;
+  const long long S = prm.S;
+  const int depth = prm.depth;
+  // sub-batches bound the coarse-score workspace and the working set, and keep candidate ids in 32 bits
+  const long long per_pair = S * prm.maxc;
+  long long sub = std::min<long long>(n_pairs, std::max<long long>(1, (1ll << 28) / per_pair));
+  sub = std::min<long long>(sub, 65535);
+  const size_t ws_budget = (size_t)(plan.use_bits ? 6 : 8) << 30;
+  sub = std::min<long long>(sub, std::max<long long>(1, (long long)(ws_budget / plan.dev.slot_bytes)));
+  if (const char* e = std::getenv("GLOC_CSM_SUB")) sub = std::max(1, std::min((int)sub, std::atoi(e)));
+  unsigned long long init_key = 0ull;  // incumbent starts at (min_score, worst rank)
+  if (prm.min_score > 0.f) {
+    uint32_t u;
+    std::memcpy(&u, &prm.min_score, 4);
+    init_key = (unsigned long long)u << 32;
+  }
+  const int n_ctas = sm_count(st->device) * 8;   // persistent refinement CTAs (128 threads)
+  int bits_warps = 12;   // rotations per CTA = 16 x warps (two lanes per rotation)
+  if (const char* e = std::getenv("GLOC_CSM_BITS_WARPS")) bits_warps = std::min(12, std::max(1, std::atoi(e)));
+  int hsize = 64;
+  while (hsize < 2 * sub) hsize <<= 1;
+  GLOC_CUDA_TRY(st->slots.reserve((size_t)sub * sizeof(CsmGridDev)));
+  GLOC_CUDA_TRY(st->slot_gid.reserve((size_t)sub * sizeof(int)));
+  GLOC_CUDA_TRY(st->hkeys.reserve((size_t)hsize * sizeof(int)));
+  GLOC_CUDA_TRY(st->hslot.reserve((size_t)hsize * sizeof(int)));
+  GLOC_CUDA_TRY(st->ws.reserve((size_t)sub * plan.dev.slot_bytes));
+  GLOC_CUDA_TRY(st->bounds.reserve((size_t)sub * S * sizeof(CsmBounds)));
+  GLOC_CUDA_TRY(st->coarse.reserve((size_t)sub * per_pair * sizeof(int)));
+  GLOC_CUDA_TRY(st->survivors.reserve((size_t)sub * per_pair * sizeof(unsigned)));
+  GLOC_CUDA_TRY(st->top.reserve((size_t)sub * 8));
+  GLOC_CUDA_TRY(st->best.reserve((size_t)sub * 8));
+  GLOC_CUDA_TRY(st->nsurv.reserve((size_t)sub * 4));
+  // nodes handed from the expand stage to the depth-first refinement (24 B each)
+  const unsigned node_cap = (unsigned)std::min<long long>(4ll * sub * per_pair, 16ll << 20);
+  GLOC_CUDA_TRY(st->nodes.reserve((size_t)node_cap * sizeof(CsmNode)));
+  GLOC_CUDA_TRY(st->misc.reserve(64));
+  std::vector<unsigned long long> init((size_t)sub, init_key);
+  const bool timing = std::getenv("GLOC_CSM_TIMING") != nullptr;
+  for (long long p0 = 0; p0 < n_pairs; p0 += sub) {
+    const int np = (int)std::min<long long>(sub, n_pairs - p0);
+    CsmPairDev* dp = d_pairs + p0;
+    GLOC_CUDA_TRY(cudaMemsetAsync(st->top.p, 0, (size_t)np * 8, stream));
+    GLOC_CUDA_TRY(cudaMemsetAsync(st->nsurv.p, 0, (size_t)np * 4, stream));
+    GLOC_CUDA_TRY(cudaMemsetAsync(st->misc.p, 0, 64, stream));
+    GLOC_CUDA_TRY(cudaMemcpyAsync(st->best.p, init.data(), (size_t)np * 8, cudaMemcpyHostToDevice, stream));
+    unsigned* n_surv = (unsigned*)st->nsurv.p;
+    unsigned* n_nodes = (unsigned*)st->misc.p;
+    unsigned* cursor = n_nodes + 1;
+    int* n_slots = (int*)st->misc.p + 2;
+    unsigned long long* counters = (unsigned long long*)((char*)st->misc.p + 16);
+    const CsmGridDev* dg = (const CsmGridDev*)st->slots.p;
+    // tuning aid: GLOC_CSM_TIMING=1 prints the duration of every stage of this sub-batch
+    cudaEvent_t tev[7];
+    if (timing) {
+      for (auto& e : tev) cudaEventCreate(&e);
+      cudaEventRecord(tev[6], stream);
+    }
+    // ---- working set: distinct grids -> slots, derived structures rebuilt on the device
+    GLOC_CUDA_TRY(launch_csm_assign_slots(dp, np, (int*)st->hkeys.p, (int*)st->hslot.p, hsize,
+                                          (int*)st->slot_gid.p, n_slots, stream));
+    GLOC_CUDA_TRY(launch_csm_prepare_slots((const CsmGridRec*)st->d_recs.p, (const int*)st->slot_gid.p,
+                                           n_slots, np, plan.dev, (unsigned char*)st->ws.p,
+                                           (CsmGridDev*)st->slots.p, stream));
+    st->stats.kernel_launches += 3;
+    GLOC_CUDA_TRY(launch_csm_build_slots((const CsmGridRec*)st->d_recs.p, (const int*)st->slot_gid.p, dg,
+                                         n_slots, np, plan.dev, stream, &st->stats.kernel_launches));
+    if (timing) cudaEventRecord(tev[0], stream);
+    st->prof.begin(stream);
+    cudaError_t ce;
+    if (plan.use_bits)
+      ce = launch_csm_coarse_bits(dg, dp, np, d_pts, d_rot, prm, (CsmBounds*)st->bounds.p,
+                                  (int*)st->coarse.p, (unsigned long long*)st->top.p, plan.bits_smem,
+                                  bits_warps, stream);
+    else
+      ce = launch_csm_coarse(dg, dp, np, d_pts, d_rot, prm, (CsmBounds*)st->bounds.p, (int*)st->coarse.p,
+                             (unsigned long long*)st->top.p, stream, plan.pm_kernel);
+    st->prof.end(stream);
+    GLOC_CUDA_TRY(ce);
+    if (timing) cudaEventRecord(tev[1], stream);
+    GLOC_CUDA_TRY(launch_csm_seed(dg, dp, np, d_pts, d_rot, prm, (const CsmBounds*)st->bounds.p,
+                                  (const unsigned long long*)st->top.p, (unsigned long long*)st->best.p,
+                                  stream));
+    if (timing) cudaEventRecord(tev[2], stream);
+    GLOC_CUDA_TRY(launch_csm_filter(dp, np, prm, (const CsmBounds*)st->bounds.p, (const int*)st->coarse.p,
+                                    (const unsigned long long*)st->best.p, (unsigned*)st->survivors.p,
+                                    n_surv, stream));
+    if (timing) cudaEventRecord(tev[3], stream);
+    if (depth >= 2) {
+      GLOC_CUDA_TRY(launch_csm_expand(dg, dp, np, d_pts, d_rot, prm, (const CsmBounds*)st->bounds.p,
+                                      (const int*)st->coarse.p, (const unsigned*)st->survivors.p, n_surv,
+                                      (unsigned long long*)st->best.p, (CsmNode*)st->nodes.p, n_nodes,
+                                      node_cap, counters, 128, plan.exp_bits && plan.use_bits,
+                                      plan.exp_smem, stream));
+      if (timing) cudaEventRecord(tev[5], stream);
+      GLOC_CUDA_TRY(launch_csm_refine(dg, dp, d_pts, d_rot, prm, (const CsmBounds*)st->bounds.p,
+                                      (const CsmNode*)st->nodes.p, n_nodes, node_cap, cursor,
+                                      (unsigned long long*)st->best.p, counters, n_ctas, stream));
+    }
+    if (timing) cudaEventRecord(tev[4], stream);
+    GLOC_CUDA_TRY(cudaMemcpyAsync(h_best + p0, st->best.p, (size_t)np * 8, cudaMemcpyDeviceToHost, stream));
+    unsigned long long hc = 0;
+    unsigned hn = 0;
+    GLOC_CUDA_TRY(cudaMemcpyAsync(&hc, counters, 8, cudaMemcpyDeviceToHost, stream));
+    GLOC_CUDA_TRY(cudaMemcpyAsync(&hn, n_nodes, 4, cudaMemcpyDeviceToHost, stream));
+    GLOC_CUDA_TRY(cudaStreamSynchronize(stream));
+    if (hn > node_cap)
+      return fail(GLOC_ERR_RANGE, "gloc_csm_match_batch: branch-and-bound node list overflowed "
+                                  "(more than 16M open nodes in one sub-batch); match fewer pairs per call");
+    if (timing) {
+      float t[4] = {0, 0, 0, 0}, t_build = 0.f;
+      std::vector<unsigned> hs((size_t)np);
+      cudaMemcpy(hs.data(), n_surv, (size_t)np * 4, cudaMemcpyDeviceToHost);
+      int hslots = 0;
+      cudaMemcpy(&hslots, n_slots, 4, cudaMemcpyDeviceToHost);
+      unsigned long long ns = 0;
+      for (unsigned v : hs) ns += v;
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+      cudaEventElapsedTime(&t_build, tev[6], tev[0]);
+      float t_exp = 0.f;
+      if (depth >= 2) cudaEventElapsedTime(&t_exp, tev[3], tev[5]);
+      fprintf(stderr, "[csm] pairs=%d grids=%d build=%.3f ms coarse(%s)=%.3f ms seed=%.3f filter=%.3f "
+                      "expand+refine=%.3f (expand %.3f) | survivors=%llu nodes=%u expanded=%llu\n",
+              np, hslots, t_build, plan.use_bits ? "bits" : "u8", t[0], t[1], t[2], t[3], t_exp, ns, hn, hc);
+      unsigned mx = 0;
+      for (unsigned v : hs) mx = std::max(mx, v);
+      fprintf(stderr, "[csm] max survivors in one pair = %u\n", mx);
+      for (auto& e : tev) cudaEventDestroy(e);
+    }
+    st->stats.kernel_launches += depth >= 2 ? 5 : 3;
+    st->stats.refined_nodes += hc;
+    st->stats.coarse_candidates += (uint64_t)np * (uint64_t)per_pair;  // upper bound (slots)
+  }
+  st->stats.matches += (uint64_t)n_pairs;
+  return GLOC_OK;
+}
+
+void csm_decode(unsigned long long key, const CsmParams& prm, double ang_step, double resolution,
+                const double* init, float min_score, gloc_csm_result* rp) {
+  gloc_csm_result& r = *rp;
+  std::memset(&r, 0, sizeof(r));
+  uint32_t sb = (uint32_t)(key >> 32);
+  float score;
+  std::memcpy(&score, &sb, 4);
+  r.score = min_score;
+  if (key != 0 && score > min_score) {
+    const uint32_t rank = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+    const int s = (int)(rank / (prm.W * prm.W));
+    const int xo = (int)((rank / prm.W) % prm.W) - prm.n_lin;
+    const int yo = (int)(rank % prm.W) - prm.n_lin;
+    const double cx = -yo * resolution;
+    const double cy = -xo * resolution;
+    const double orientation = (s - prm.n_ang) * ang_step;
+    r.found = 1;
+    r.score = score;
+    r.scan_index = s;
+    r.x_offset = xo;
+    r.y_offset = yo;
+    r.pose_x = init[0] + cx;
+    r.pose_y = init[1] + cy;
+    r.pose_yaw = init[2] + orientation;
+  }
+}
+
+}  // namespace gloc
 
 extern "C" {
 
@@ -190,64 +431,38 @@ void gloc_csm_destroy(gloc_csm_store* st) {
     cudaStreamSynchronize(st->stream);
     cudaStreamDestroy(st->stream);
   }
-  for (auto& gr : st->grids) {
-    if (gr.d_stack) cudaFree(gr.d_stack);
-    if (gr.d_pm) cudaFree(gr.d_pm);
-    if (gr.d_pmb) cudaFree(gr.d_pmb);
-    if (gr.d_lvb) cudaFree(gr.d_lvb);
-  }
+  st->arena.release();
   if (st->d_lut) cudaFree(st->d_lut);
-  for (Buf* b : {&st->pts, &st->pairs, &st->gridtab, &st->rot, &st->bounds, &st->coarse, &st->top,
-                 &st->best, &st->survivors, &st->nsurv, &st->nodes, &st->misc, &st->cells16, &st->disc})
-    b->release();
+  for (int i = 0; CsmBuf* b = all_bufs(st, i); ++i) b->release();
   delete st;
 }
 
 int gloc_csm_add_grid_cells(gloc_csm_store* st, const uint16_t* cells, int nx, int ny,
                             double resolution, double max_x, double max_y, int* grid_id) {
   if (!st || !cells) return fail(GLOC_ERR_INVALID, "gloc_csm_add_grid_cells: null argument");
-  DeviceGuard g(st->device);
-  uint8_t* d_l1 = nullptr;
-  int rc = add_grid_common(st, nx, ny, resolution, max_x, max_y, &d_l1);
+  int rc = check_limits(nx, ny, resolution, "gloc_csm_add_grid_cells");
   if (rc != GLOC_OK) return rc;
+  DeviceGuard g(st->device);
   const size_t n = (size_t)nx * ny;
-  cudaError_t e = st->cells16.reserve(n * 2);
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(st->cells16.p, cells, n * 2, cudaMemcpyHostToDevice, st->stream);
-  if (e == cudaSuccess)
-    e = launch_csm_level1_from_cells((const uint16_t*)st->cells16.p, st->d_lut, n, d_l1, st->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);
-  if (e != cudaSuccess) {
-    cudaFree(d_l1);
-    return fail(GLOC_ERR_CUDA, std::string("gloc_csm_add_grid_cells: ") + cudaGetErrorString(e));
-  }
+  GLOC_CUDA_TRY(st->cells16.reserve(n * 2));
+  GLOC_CUDA_TRY(st->stage_u8.reserve(n));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(st->cells16.p, cells, n * 2, cudaMemcpyHostToDevice, st->stream));
+  GLOC_CUDA_TRY(launch_csm_level1_from_cells((const uint16_t*)st->cells16.p, st->d_lut, n,
+                                             (uint8_t*)st->stage_u8.p, st->stream));
   st->stats.kernel_launches++;
-  HostGrid hg;
-  hg.nx = nx; hg.ny = ny; hg.resolution = resolution; hg.max_x = max_x; hg.max_y = max_y;
-  hg.d_stack = d_l1; hg.depth = 1; hg.bytes = n;
-  st->grids.push_back(hg);
-  if (grid_id) *grid_id = (int)st->grids.size() - 1;
-  return GLOC_OK;
+  return add_from_stage(st, nx, ny, resolution, max_x, max_y, false, grid_id, "gloc_csm_add_grid_cells");
 }
 
 int gloc_csm_add_grid_u8(gloc_csm_store* st, const uint8_t* level1, int nx, int ny,
                          double resolution, double max_x, double max_y, int* grid_id) {
   if (!st || !level1) return fail(GLOC_ERR_INVALID, "gloc_csm_add_grid_u8: null argument");
-  DeviceGuard g(st->device);
-  uint8_t* d_l1 = nullptr;
-  int rc = add_grid_common(st, nx, ny, resolution, max_x, max_y, &d_l1);
+  int rc = check_limits(nx, ny, resolution, "gloc_csm_add_grid_u8");
   if (rc != GLOC_OK) return rc;
-  cudaError_t e = cudaMemcpy(d_l1, level1, (size_t)nx * ny, cudaMemcpyHostToDevice);
-  if (e != cudaSuccess) {
-    cudaFree(d_l1);
-    return fail(GLOC_ERR_CUDA, std::string("gloc_csm_add_grid_u8: ") + cudaGetErrorString(e));
-  }
-  HostGrid hg;
-  hg.nx = nx; hg.ny = ny; hg.resolution = resolution; hg.max_x = max_x; hg.max_y = max_y;
-  hg.d_stack = d_l1; hg.depth = 1; hg.bytes = (size_t)nx * ny;
-  st->grids.push_back(hg);
-  if (grid_id) *grid_id = (int)st->grids.size() - 1;
-  return GLOC_OK;
+  DeviceGuard g(st->device);
+  const size_t n = (size_t)nx * ny;
+  GLOC_CUDA_TRY(st->stage_u8.reserve(n));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(st->stage_u8.p, level1, n, cudaMemcpyHostToDevice, st->stream));
+  return add_from_stage(st, nx, ny, resolution, max_x, max_y, false, grid_id, "gloc_csm_add_grid_u8");
 }
 
 int gloc_csm_add_grid_from_bev(gloc_csm_store* st, gloc_bev_projector* bev, int* grid_id) {
@@ -262,23 +477,14 @@ int gloc_csm_add_grid_from_bev(gloc_csm_store* st, gloc_bev_projector* bev, int*
   // ProjectToGrid, 3d/submap_3d.cpp:376-388: limits from the voxel bounding box
   const double max_x = (I.min_ix + I.width - 1) * I.resolution;
   const double max_y = (I.min_iy + I.height - 1) * I.resolution;
-  uint8_t* d_l1 = nullptr;
-  int rc = add_grid_common(st, I.width, I.height, I.resolution, max_x, max_y, &d_l1);
+  int rc = check_limits(I.width, I.height, I.resolution, "gloc_csm_add_grid_from_bev");
   if (rc != GLOC_OK) return rc;
   const size_t n = (size_t)I.width * I.height;
-  cudaError_t e = gloc_bev_launch_level1(d_img, n, d_l1, st->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);
-  if (e != cudaSuccess) {
-    cudaFree(d_l1);
-    return fail(GLOC_ERR_CUDA, std::string("gloc_csm_add_grid_from_bev: ") + cudaGetErrorString(e));
-  }
+  GLOC_CUDA_TRY(st->stage_u8.reserve(n));
+  GLOC_CUDA_TRY(gloc_bev_launch_level1(d_img, n, (uint8_t*)st->stage_u8.p, st->stream));
   st->stats.kernel_launches++;
-  HostGrid hg;
-  hg.nx = I.width; hg.ny = I.height; hg.resolution = I.resolution; hg.max_x = max_x; hg.max_y = max_y;
-  hg.d_stack = d_l1; hg.depth = 1; hg.bytes = n;
-  st->grids.push_back(hg);
-  if (grid_id) *grid_id = (int)st->grids.size() - 1;
-  return GLOC_OK;
+  return add_from_stage(st, I.width, I.height, I.resolution, max_x, max_y, true, grid_id,
+                        "gloc_csm_add_grid_from_bev");
 }
 
 int gloc_csm_add_grid_from_bev_aligned(gloc_csm_store* st, gloc_bev_projector* bev, int* grid_id) {
@@ -295,53 +501,81 @@ int gloc_csm_add_grid_from_bev_aligned(gloc_csm_store* st, gloc_bev_projector* b
   const int nx = I.height, ny = I.width;
   const double max_x = (I.min_ix + I.width - 1 + 0.5) * I.resolution;
   const double max_y = (I.min_iy + I.height - 1 + 0.5) * I.resolution;
-  uint8_t* d_l1 = nullptr;
-  int rc = add_grid_common(st, nx, ny, I.resolution, max_x, max_y, &d_l1);
+  int rc = check_limits(nx, ny, I.resolution, "gloc_csm_add_grid_from_bev_aligned");
   if (rc != GLOC_OK) return rc;
-  cudaError_t e = gloc_bev_launch_level1_aligned(d_img, I.width, I.height, d_l1, st->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);
-  if (e != cudaSuccess) {
-    cudaFree(d_l1);
-    return fail(GLOC_ERR_CUDA, std::string("gloc_csm_add_grid_from_bev_aligned: ") + cudaGetErrorString(e));
-  }
+  GLOC_CUDA_TRY(st->stage_u8.reserve((size_t)nx * ny));
+  GLOC_CUDA_TRY(gloc_bev_launch_level1_aligned(d_img, I.width, I.height, (uint8_t*)st->stage_u8.p, st->stream));
   st->stats.kernel_launches++;
-  HostGrid hg;
-  hg.nx = nx; hg.ny = ny; hg.resolution = I.resolution; hg.max_x = max_x; hg.max_y = max_y;
-  hg.d_stack = d_l1; hg.depth = 1; hg.bytes = (size_t)nx * ny;
-  st->grids.push_back(hg);
-  if (grid_id) *grid_id = (int)st->grids.size() - 1;
-  return GLOC_OK;
+  return add_from_stage(st, nx, ny, I.resolution, max_x, max_y, true, grid_id,
+                        "gloc_csm_add_grid_from_bev_aligned");
 }
 
-int gloc_csm_num_grids(const gloc_csm_store* st) { return st ? (int)st->grids.size() : 0; }
+int gloc_csm_num_grids(const gloc_csm_store* st) { return st ? (int)st->recs.size() : 0; }
 
 int gloc_csm_get_grid_info(const gloc_csm_store* st, int grid_id, gloc_grid_info* out) {
   if (!st || !out) return fail(GLOC_ERR_INVALID, "gloc_csm_get_grid_info: null argument");
-  if (grid_id < 0 || grid_id >= (int)st->grids.size())
+  if (grid_id < 0 || grid_id >= (int)st->recs.size())
     return fail(GLOC_ERR_INVALID, "gloc_csm_get_grid_info: bad grid id");
-  const HostGrid& hg = st->grids[grid_id];
-  out->nx = hg.nx;
-  out->ny = hg.ny;
-  out->resolution = hg.resolution;
-  out->max_x = hg.max_x;
-  out->max_y = hg.max_y;
+  const CsmGridRec& r = st->recs[grid_id];
+  out->nx = r.nx;
+  out->ny = r.ny;
+  out->resolution = r.resolution;
+  out->max_x = r.max_x;
+  out->max_y = r.max_y;
+  return GLOC_OK;
+}
+
+int gloc_csm_store_bytes(const gloc_csm_store* st, uint64_t* grid_bytes, uint64_t* workspace_bytes) {
+  if (!st) return fail(GLOC_ERR_INVALID, "gloc_csm_store_bytes: null store");
+  if (grid_bytes) *grid_bytes = st->arena.total;
+  if (workspace_bytes) {
+    uint64_t t = 0;
+    for (int i = 0; const CsmBuf* b = all_bufs(const_cast<gloc_csm_store*>(st), i); ++i) t += b->bytes;
+    *workspace_bytes = t;
+  }
   return GLOC_OK;
 }
 
 int gloc_csm_get_precomputation_grid(gloc_csm_store* st, int grid_id, int width, uint8_t* out) {
   if (!st || !out) return fail(GLOC_ERR_INVALID, "gloc_csm_get_precomputation_grid: null argument");
-  if (grid_id < 0 || grid_id >= (int)st->grids.size())
+  if (grid_id < 0 || grid_id >= (int)st->recs.size())
     return fail(GLOC_ERR_INVALID, "gloc_csm_get_precomputation_grid: bad grid id");
   int level = 0;
   while ((1 << level) < width) ++level;
   if (width < 1 || (1 << level) != width || level >= kCsmMaxDepth)  // CHECK_GE(width, 1)
     return fail(GLOC_ERR_RANGE, "gloc_csm_get_precomputation_grid: width must be 1,2,4,...,128");
   DeviceGuard g(st->device);
-  HostGrid& hg = st->grids[grid_id];
-  int rc = ensure_stack(st, hg, level + 1);
+  const CsmGridRec& r = st->recs[grid_id];
+  int rc = csm_sync_recs(st);
   if (rc != GLOC_OK) return rc;
-  const size_t n = (size_t)(hg.nx + width - 1) * (size_t)(hg.ny + width - 1);
-  GLOC_CUDA_TRY(cudaMemcpy(out, hg.d_stack + hg.off[level], n, cudaMemcpyDeviceToHost));
+  // one slot of the uint8 working set, built exactly as a batch builds it
+  CsmPlan plan{};
+  plan.bits = 0;
+  plan.depth = level + 1;
+  plan.n_lin = 0;
+  plan.use_pm = 0;
+  plan.max_nx = r.nx;
+  plan.max_ny = r.ny;
+  long long off[kCsmMaxDepth] = {0};
+  plan.slot_bytes = align256(stack_bytes(r.nx, r.ny, level + 1, off));
+  GLOC_CUDA_TRY(st->ws.reserve(plan.slot_bytes));
+  GLOC_CUDA_TRY(st->slots.reserve(sizeof(CsmGridDev)));
+  GLOC_CUDA_TRY(st->slot_gid.reserve(sizeof(int)));
+  GLOC_CUDA_TRY(st->misc.reserve(64));
+  const int one = 1;
+  GLOC_CUDA_TRY(cudaMemcpyAsync(st->slot_gid.p, &grid_id, 4, cudaMemcpyHostToDevice, st->stream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(st->misc.p, &one, 4, cudaMemcpyHostToDevice, st->stream));
+  GLOC_CUDA_TRY(launch_csm_prepare_slots((const CsmGridRec*)st->d_recs.p, (const int*)st->slot_gid.p,
+                                         (const int*)st->misc.p, 1, plan, (unsigned char*)st->ws.p,
+                                         (CsmGridDev*)st->slots.p, st->stream));
+  st->stats.kernel_launches++;
+  GLOC_CUDA_TRY(launch_csm_build_slots((const CsmGridRec*)st->d_recs.p, (const int*)st->slot_gid.p,
+                                       (const CsmGridDev*)st->slots.p, (const int*)st->misc.p, 1, plan,
+                                       st->stream, &st->stats.kernel_launches));
+  const size_t n = (size_t)(r.nx + width - 1) * (size_t)(r.ny + width - 1);
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out, (const uint8_t*)st->ws.p + off[level], n, cudaMemcpyDeviceToHost,
+                                st->stream));
+  GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
   return GLOC_OK;
 }
 
@@ -362,143 +596,31 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
     return fail(GLOC_ERR_RANGE, "gloc_csm_match_batch: search window too large (scans*(2*n_lin+1)^2 must be < 2^32)");
   DeviceGuard guard(st->device);
   if (!guard.ok) return fail(GLOC_ERR_CUDA, "gloc_csm_match_batch: cudaSetDevice failed");
-
-  CsmParams prm;
-  prm.n_lin = n_lin;
-  prm.n_ang = n_ang;
-  prm.S = (int)S;
-  prm.depth = depth;
-  prm.step = 1 << (depth - 1);
-  prm.max_side = (2 * n_lin) / prm.step + 1;
-  prm.maxc = prm.max_side * prm.max_side;
-  prm.W = (unsigned)W;
-  prm.min_score = min_score;
-  prm.min_s = 1.f - kMaxCorrespondenceCost;
-  prm.coef = ((1.f - kMinCorrespondenceCost) - (1.f - kMaxCorrespondenceCost)) / 255.f;
-
-  // per-angle quaternions from the host libm, theta accumulated in double exactly as
-  // GenerateRotatedScans does (correlative_scan_matcher_2d.cpp:99-107)
-  std::vector<float2> rot((size_t)S);
-  {
-    double delta_theta = -n_ang * ang_step;
-    for (long long s = 0; s < S; ++s, delta_theta += ang_step) {
-      const float ha = 0.5f * (float)delta_theta;
-      rot[(size_t)s] = make_float2(std::cos(ha), std::sin(ha));
-    }
-  }
+  const CsmParams prm = csm_make_params(n_lin, n_ang, depth, min_score);
+  std::vector<float2> rot;
+  csm_host_rotations(n_ang, ang_step, &rot);
   const int64_t total_pts = scan_offsets[n_scans];
   if (total_pts < 0) return fail(GLOC_ERR_INVALID, "gloc_csm_match_batch: bad scan offsets");
 
-  // validate + device tables
+  // validate; the plan depends on the dimensions of the batch's grids only
   std::vector<CsmPairDev> hp((size_t)n_pairs);
-  bool use_pm = std::getenv("GLOC_CSM_NO_PM") == nullptr;
-  // bit-sliced coarse scorer: binary grids whose coarsest level fits 64 columns per plane
-  // row and shared memory, at most 16 lattice candidates per axis
-  bool use_bits = std::getenv("GLOC_CSM_NO_BITS") == nullptr && prm.max_side <= 16;
-  size_t bits_smem = 0, exp_smem = 0;
-  bool exp_bits = use_bits && depth >= 2;   // expand stage on bit-packed level depth-2
-  std::map<int, int> grid_slot;
-  std::vector<CsmGridDev> hg;
+  int max_nx = 0, max_ny = 0;
+  bool all_binary = true;
   for (int i = 0; i < n_pairs; ++i) {
     const int gi = grid_ids[i], si = scan_ids[i];
-    if (gi < 0 || gi >= (int)st->grids.size() || si < 0 || si >= n_scans)
+    if (gi < 0 || gi >= (int)st->recs.size() || si < 0 || si >= n_scans)
       return fail(GLOC_ERR_INVALID, "gloc_csm_match_batch: bad grid or scan id");
     const int64_t b = scan_offsets[si], e = scan_offsets[si + 1];
     if (b < 0 || e < b || e > total_pts || e - b > INT32_MAX)
       return fail(GLOC_ERR_INVALID, "gloc_csm_match_batch: bad scan offsets");
     if (e == b) return fail(GLOC_ERR_INVALID, "gloc_csm_match_batch: empty scan");
-    auto it = grid_slot.find(gi);
-    if (it == grid_slot.end()) {
-      HostGrid& g = st->grids[gi];
-      int rc = ensure_stack(st, g, depth);
-      if (rc != GLOC_OK) return rc;
-      CsmGridDev d;
-      d.stack = g.d_stack;
-      std::memcpy(d.off, g.off, sizeof(d.off));
-      d.nx = g.nx; d.ny = g.ny; d.resolution = g.resolution; d.max_x = g.max_x; d.max_y = g.max_y;
-      {  // padded phase-major coarsest level (rebuilt when depth or window change)
-        const int level = depth - 1, w = 1 << level, pad = n_lin;
-        const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1;
-        const int pw = (wide_nx + 2 * pad + w - 1) / w, ph = (wide_ny + 2 * pad + w - 1) / w;
-        const size_t cells = (size_t)pw * ph * w * w;
-        if (cells > ((size_t)1 << 27)) use_pm = false;  // absurd windows: bounds-checked kernel
-        if (use_pm && (g.pm_level != level || g.pm_pad != pad)) {
-          if (g.d_pm) cudaFree(g.d_pm);
-          g.d_pm = nullptr;
-          g.pm_level = -1;
-          GLOC_CUDA_TRY(cudaMalloc((void**)&g.d_pm, cells));
-          GLOC_CUDA_TRY(launch_csm_build_pm(g.d_stack + g.off[level], wide_nx, wide_ny, pad, level,
-                                            pw, ph, g.d_pm, st->stream));
-          st->stats.kernel_launches++;
-          g.pm_level = level; g.pm_pad = pad; g.pm_pw = pw; g.pm_ph = ph;
-        }
-        d.pm = g.d_pm; d.pm_pad = g.pm_pad; d.pm_pw = g.pm_pw; d.pm_ph = g.pm_ph; d.pm_log2w = level;
-      }
-      d.pmb = nullptr; d.pmb_rows = 0; d.pmb_px = 0; d.pmb_py = 0; d.pmb_log2w = 0;
-      d.lvb = nullptr; d.lvb_stride = 0;
-      if (use_bits && g.binary != 0) {
-        const int level = depth - 1, w = 1 << level;
-        const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1;
-        const int rows = csm_pmb_rows(wide_ny, n_lin, level);
-        const size_t smem = csm_coarse_bits_smem(level, rows);
-        if (((wide_nx + n_lin - 1) >> level) >= 64 || smem > (size_t)225 * 1024) {
-          use_bits = false;
-        } else {
-          if (g.pmb_level != level || g.pmb_nlin != n_lin) {
-            if (g.d_pmb) cudaFree(g.d_pmb);
-            g.d_pmb = nullptr;
-            g.pmb_level = -1;
-            GLOC_CUDA_TRY(cudaMalloc((void**)&g.d_pmb, (size_t)w * w * rows * 8));
-            GLOC_CUDA_TRY(st->misc.reserve(64));
-            GLOC_CUDA_TRY(cudaMemsetAsync(st->misc.p, 0, 4, st->stream));
-            GLOC_CUDA_TRY(launch_csm_build_pmb(g.d_stack + g.off[level], wide_nx, wide_ny, n_lin,
-                                               2 * n_lin, level, rows, g.d_pmb, (int*)st->misc.p,
-                                               st->stream));
-            int not_binary = 0;
-            GLOC_CUDA_TRY(cudaMemcpyAsync(&not_binary, st->misc.p, 4, cudaMemcpyDeviceToHost, st->stream));
-            GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
-            st->stats.kernel_launches++;
-            g.binary = not_binary ? 0 : 1;
-            g.pmb_level = level; g.pmb_nlin = n_lin; g.pmb_rows = rows;
-          }
-          if (g.binary == 1) {
-            d.pmb = g.d_pmb; d.pmb_rows = g.pmb_rows; d.pmb_px = n_lin; d.pmb_py = 2 * n_lin;
-            d.pmb_log2w = level;
-            bits_smem = std::max(bits_smem, smem);
-          } else {
-            use_bits = false;
-          }
-          d.lvb = nullptr; d.lvb_stride = 0;
-          if (g.binary == 1 && depth >= 2) {   // the level below, bit-packed, for the expand stage
-            const int l2 = depth - 2, w2 = 1 << l2;
-            const int wnx = g.nx + w2 - 1, wny = g.ny + w2 - 1, stride = (wnx + 31) / 32 + 1;
-            if (csm_expand_smem(wny, stride) > (size_t)112 * 1024) {
-              exp_bits = false;
-            } else {
-              if (g.lvb_level != l2) {
-                if (g.d_lvb) cudaFree(g.d_lvb);
-                g.d_lvb = nullptr;
-                g.lvb_level = -1;
-                GLOC_CUDA_TRY(cudaMalloc((void**)&g.d_lvb, (size_t)wny * stride * 4));
-                GLOC_CUDA_TRY(launch_csm_build_lvb(g.d_stack + g.off[l2], wnx, wny, stride, g.d_lvb,
-                                                   st->stream));
-                st->stats.kernel_launches++;
-                g.lvb_level = l2; g.lvb_stride = stride;
-              }
-              d.lvb = g.d_lvb; d.lvb_stride = g.lvb_stride;
-              exp_smem = std::max(exp_smem, csm_expand_smem(wny, stride));
-            }
-          }
-        }
-      } else {
-        use_bits = false;
-      }
-      if (!use_bits) exp_bits = false;
-      it = grid_slot.emplace(gi, (int)hg.size()).first;
-      hg.push_back(d);
-    }
+    const CsmGridRec& r = st->recs[gi];
+    max_nx = std::max(max_nx, r.nx);
+    max_ny = std::max(max_ny, r.ny);
+    all_binary = all_binary && r.enc == 1;
     CsmPairDev& p = hp[(size_t)i];
-    p.grid = it->second;
+    p.grid = 0;
+    p.gid = gi;
     p.pt_begin = b;
     p.n_pts = (int)(e - b);
     // initial_rotation.cast<float>().angle() -> Quaternionf(AngleAxisf) (fast_..._2d.cpp:278-283)
@@ -508,163 +630,26 @@ int gloc_csm_match_batch(gloc_csm_store* st, const float* pts, const int64_t* sc
     p.tx = (float)init_xyyaw[3 * i];      // Eigen::Translation2f(double, double), :287-288
     p.ty = (float)init_xyyaw[3 * i + 1];
   }
+  CsmBatchPlan plan;
+  csm_make_plan(max_nx, max_ny, all_binary, n_lin, depth, &plan);
 
   cudaStream_t stream = st->stream;
   GLOC_CUDA_TRY(st->pts.reserve((size_t)total_pts * 3 * sizeof(float)));
   GLOC_CUDA_TRY(st->rot.reserve((size_t)S * sizeof(float2)));
-  GLOC_CUDA_TRY(st->gridtab.reserve(hg.size() * sizeof(CsmGridDev)));
+  GLOC_CUDA_TRY(st->pairs.reserve((size_t)n_pairs * sizeof(CsmPairDev)));
   GLOC_CUDA_TRY(cudaMemcpyAsync(st->pts.p, pts, (size_t)total_pts * 3 * sizeof(float),
                                 cudaMemcpyHostToDevice, stream));
   GLOC_CUDA_TRY(cudaMemcpyAsync(st->rot.p, rot.data(), (size_t)S * sizeof(float2),
                                 cudaMemcpyHostToDevice, stream));
-  GLOC_CUDA_TRY(cudaMemcpyAsync(st->gridtab.p, hg.data(), hg.size() * sizeof(CsmGridDev),
+  GLOC_CUDA_TRY(cudaMemcpyAsync(st->pairs.p, hp.data(), (size_t)n_pairs * sizeof(CsmPairDev),
                                 cudaMemcpyHostToDevice, stream));
-
-  // sub-batches bound the coarse-score workspace and keep candidate ids in 32 bits
-  const long long per_pair = S * prm.maxc;
-  long long sub = std::min<long long>(n_pairs, std::max<long long>(1, (1ll << 28) / per_pair));
-  sub = std::min<long long>(sub, 65535);
-  unsigned long long init_key = 0ull;  // incumbent starts at (min_score, worst rank)
-  if (min_score > 0.f) {
-    uint32_t u;
-    std::memcpy(&u, &min_score, 4);
-    init_key = (unsigned long long)u << 32;
-  }
   std::vector<unsigned long long> hbest((size_t)n_pairs);
-  const int n_ctas = sm_count(st->device) * 8;   // persistent refinement CTAs (128 threads)
-  int bits_warps = 12;   // rotations per CTA = 16 x warps (two lanes per rotation)
-  if (const char* e = std::getenv("GLOC_CSM_BITS_WARPS")) bits_warps = std::min(12, std::max(1, std::atoi(e)));
-  for (long long p0 = 0; p0 < n_pairs; p0 += sub) {
-    const int np = (int)std::min<long long>(sub, n_pairs - p0);
-    GLOC_CUDA_TRY(st->pairs.reserve((size_t)np * sizeof(CsmPairDev)));
-    GLOC_CUDA_TRY(st->bounds.reserve((size_t)np * S * sizeof(CsmBounds)));
-    GLOC_CUDA_TRY(st->coarse.reserve((size_t)np * per_pair * sizeof(int)));
-    GLOC_CUDA_TRY(st->survivors.reserve((size_t)np * per_pair * sizeof(unsigned)));
-    GLOC_CUDA_TRY(st->top.reserve((size_t)np * 8));
-    GLOC_CUDA_TRY(st->best.reserve((size_t)np * 8));
-    GLOC_CUDA_TRY(st->nsurv.reserve((size_t)np * 4));
-    // nodes handed from the expand stage to the depth-first refinement (24 B each)
-    const unsigned node_cap = (unsigned)std::min<long long>(4ll * np * per_pair, 16ll << 20);
-    GLOC_CUDA_TRY(st->nodes.reserve((size_t)node_cap * sizeof(CsmNode)));
-    GLOC_CUDA_TRY(st->misc.reserve(64));
-    GLOC_CUDA_TRY(cudaMemcpyAsync(st->pairs.p, hp.data() + p0, (size_t)np * sizeof(CsmPairDev),
-                                  cudaMemcpyHostToDevice, stream));
-    GLOC_CUDA_TRY(cudaMemsetAsync(st->top.p, 0, (size_t)np * 8, stream));
-    GLOC_CUDA_TRY(cudaMemsetAsync(st->nsurv.p, 0, (size_t)np * 4, stream));
-    GLOC_CUDA_TRY(cudaMemsetAsync(st->misc.p, 0, 64, stream));
-    std::vector<unsigned long long> init((size_t)np, init_key);
-    GLOC_CUDA_TRY(cudaMemcpyAsync(st->best.p, init.data(), (size_t)np * 8, cudaMemcpyHostToDevice,
-                                  stream));
-    unsigned* n_surv = (unsigned*)st->nsurv.p;
-    unsigned* n_nodes = (unsigned*)st->misc.p;
-    unsigned* cursor = n_nodes + 1;
-    unsigned long long* counters = (unsigned long long*)((char*)st->misc.p + 16);
-    const CsmGridDev* dg = (const CsmGridDev*)st->gridtab.p;
-    const CsmPairDev* dp = (const CsmPairDev*)st->pairs.p;
-    // tuning aid: GLOC_CSM_TIMING=1 prints the duration of every stage of this sub-batch
-    const bool timing = std::getenv("GLOC_CSM_TIMING") != nullptr;
-    cudaEvent_t tev[6];
-    if (timing) {
-      for (auto& e : tev) cudaEventCreate(&e);
-      cudaEventRecord(tev[0], stream);
-    }
-    st->prof.begin(stream);
-    cudaError_t ce;
-    if (use_bits)
-      ce = launch_csm_coarse_bits(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p, prm,
-                                  (CsmBounds*)st->bounds.p, (int*)st->coarse.p,
-                                  (unsigned long long*)st->top.p, bits_smem, bits_warps, stream);
-    else
-      ce = launch_csm_coarse(dg, dp, np, (const float*)st->pts.p,
-                             (const float2*)st->rot.p, prm, (CsmBounds*)st->bounds.p,
-                             (int*)st->coarse.p, (unsigned long long*)st->top.p, stream,
-                             use_pm && (size_t)prm.maxc * 4 + 20 * 4096 <= 150 * 1024);
-    st->prof.end(stream);
-    GLOC_CUDA_TRY(ce);
-    if (timing) cudaEventRecord(tev[1], stream);
-    GLOC_CUDA_TRY(launch_csm_seed(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,
-                                  prm, (const CsmBounds*)st->bounds.p,
-                                  (const unsigned long long*)st->top.p,
-                                  (unsigned long long*)st->best.p, stream));
-    if (timing) cudaEventRecord(tev[2], stream);
-    GLOC_CUDA_TRY(launch_csm_filter(dp, np, prm, (const CsmBounds*)st->bounds.p,
-                                    (const int*)st->coarse.p, (const unsigned long long*)st->best.p,
-                                    (unsigned*)st->survivors.p, n_surv, stream));
-    if (timing) cudaEventRecord(tev[3], stream);
-    if (depth >= 2) {
-      GLOC_CUDA_TRY(launch_csm_expand(dg, dp, np, (const float*)st->pts.p, (const float2*)st->rot.p,
-                                      prm, (const CsmBounds*)st->bounds.p, (const int*)st->coarse.p,
-                                      (const unsigned*)st->survivors.p, n_surv,
-                                      (unsigned long long*)st->best.p, (CsmNode*)st->nodes.p, n_nodes,
-                                      node_cap, counters, 128, exp_bits && use_bits, exp_smem, stream));
-      if (timing) cudaEventRecord(tev[5], stream);
-      GLOC_CUDA_TRY(launch_csm_refine(dg, dp, (const float*)st->pts.p, (const float2*)st->rot.p, prm,
-                                      (const CsmBounds*)st->bounds.p, (const CsmNode*)st->nodes.p,
-                                      n_nodes, node_cap, cursor, (unsigned long long*)st->best.p,
-                                      counters, n_ctas, stream));
-    }
-    if (timing) cudaEventRecord(tev[4], stream);
-    GLOC_CUDA_TRY(cudaMemcpyAsync(hbest.data() + p0, st->best.p, (size_t)np * 8,
-                                  cudaMemcpyDeviceToHost, stream));
-    unsigned long long hc = 0;
-    unsigned hn = 0;
-    GLOC_CUDA_TRY(cudaMemcpyAsync(&hc, counters, 8, cudaMemcpyDeviceToHost, stream));
-    GLOC_CUDA_TRY(cudaMemcpyAsync(&hn, n_nodes, 4, cudaMemcpyDeviceToHost, stream));
-    GLOC_CUDA_TRY(cudaStreamSynchronize(stream));
-    if (hn > node_cap)
-      return fail(GLOC_ERR_RANGE, "gloc_csm_match_batch: branch-and-bound node list overflowed "
-                                  "(more than 16M open nodes in one sub-batch); match fewer pairs per call");
-    if (timing) {
-      float t[4] = {0, 0, 0, 0};
-      std::vector<unsigned> hs((size_t)np);
-      cudaMemcpy(hs.data(), n_surv, (size_t)np * 4, cudaMemcpyDeviceToHost);
-      unsigned long long ns = 0;
-      for (unsigned v : hs) ns += v;
-      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
-      float t_exp = 0.f;
-      if (depth >= 2) cudaEventElapsedTime(&t_exp, tev[3], tev[5]);
-      fprintf(stderr, "[csm] pairs=%d coarse(%s)=%.3f ms seed=%.3f filter=%.3f expand+refine=%.3f (expand %.3f) | "
-                      "survivors=%llu nodes=%u expanded=%llu\n", np, use_bits ? "bits" : "u8", t[0], t[1],
-              t[2], t[3], t_exp, ns, hn, hc);
-      unsigned mx = 0;
-      for (unsigned v : hs) mx = std::max(mx, v);
-      fprintf(stderr, "[csm] max survivors in one pair = %u\n", mx);
-      for (auto& e : tev) cudaEventDestroy(e);
-    }
-    st->stats.kernel_launches += depth >= 2 ? 5 : 3;
-    st->stats.refined_nodes += hc;
-    st->stats.coarse_candidates += (uint64_t)np * (uint64_t)per_pair;  // upper bound (slots)
-  }
-  st->stats.matches += (uint64_t)n_pairs;
-
-  // decode: Candidate2D (correlative_scan_matcher_2d.h:74-87) + pose (fast_..._2d.cpp:311-318)
-  for (int i = 0; i < n_pairs; ++i) {
-    gloc_csm_result& r = results[i];
-    std::memset(&r, 0, sizeof(r));
-    const unsigned long long key = hbest[(size_t)i];
-    uint32_t sb = (uint32_t)(key >> 32);
-    float score;
-    std::memcpy(&score, &sb, 4);
-    r.score = min_score;
-    if (key != 0 && score > min_score) {
-      const uint32_t rank = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
-      const int s = (int)(rank / (prm.W * prm.W));
-      const int xo = (int)((rank / prm.W) % prm.W) - n_lin;
-      const int yo = (int)(rank % prm.W) - n_lin;
-      const double resolution = st->grids[grid_ids[i]].resolution;
-      const double cx = -yo * resolution;
-      const double cy = -xo * resolution;
-      const double orientation = (s - n_ang) * ang_step;
-      r.found = 1;
-      r.score = score;
-      r.scan_index = s;
-      r.x_offset = xo;
-      r.y_offset = yo;
-      r.pose_x = init_xyyaw[3 * i] + cx;
-      r.pose_y = init_xyyaw[3 * i + 1] + cy;
-      r.pose_yaw = init_xyyaw[3 * i + 2] + orientation;
-    }
-  }
+  int rc = csm_match_core(st, plan, (const float*)st->pts.p, (CsmPairDev*)st->pairs.p, n_pairs, prm,
+                          (const float2*)st->rot.p, hbest.data());
+  if (rc != GLOC_OK) return rc;
+  for (int i = 0; i < n_pairs; ++i)
+    csm_decode(hbest[(size_t)i], prm, ang_step, st->recs[grid_ids[i]].resolution, init_xyyaw + 3 * i,
+               min_score, &results[i]);
   return GLOC_OK;
 }
 

@@ -484,3 +484,10 @@ int gloc_knn_merge_topk_device(const uint64_t* d_idx, const float* d_d2, size_t 
 }
 
 }  // extern "C"
+
+// internal accessors for the localizer (loc_api.cu)
+namespace gloc {
+int knn_device_of(const gloc_knn_index* ix) { return ix->device; }
+uint64_t knn_offset_of(const gloc_knn_index* ix) { return ix->offset; }
+size_t knn_searchable_rows(const gloc_knn_index* ix) { return std::min(ix->n, ix->search_limit); }
+}  // namespace gloc

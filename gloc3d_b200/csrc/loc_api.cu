@@ -1,0 +1,341 @@
+// loc_api.cu -- the whole query path in one call: top-k retrieval -> the k candidates' map grids
+// gathered on the device -> scan-match verification of every (query, candidate) pair -> the located
+// frame and pose per query.  Replaces the evaluation loop of the reference driver:
+//   GlocEvaluator::detect_all_query    global_localization.cpp:482-509  (RpyPCLoopDetector::detect,
+//                                      loop_detector.cpp:22-46 -> InvKeyTree::query)
+//   GlocEvaluator::global_registraion  global_localization.cpp:511-574  (candidates in retrieval
+//                                      order, loop_detector_.match(...) :519-524, first match wins)
+// with FastCorrelativeScanMatcher2D::MatchWithSearchParameters (2d/fast_..._2d.cpp:270-320) as the
+// verifier.  Nothing of a batch goes through the host between the stages.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "csm_store.cuh"
+
+namespace gloc {
+int knn_device_of(const gloc_knn_index* ix);
+uint64_t knn_offset_of(const gloc_knn_index* ix);
+size_t knn_searchable_rows(const gloc_knn_index* ix);
+}  // namespace gloc
+
+using namespace gloc;
+
+namespace {
+
+struct QueryScan {     // per query: its scan and initial pose (host libm quaternion, as match_batch)
+  long long pt_begin;
+  int n_pts;
+  float w0, z0, tx, ty;
+};
+
+// pair (q, c) = candidate c of query q: the map grid of the retrieved row, the query's scan
+__global__ void loc_make_pairs_kernel(const uint64_t* __restrict__ idx, int nq, int k, uint64_t offset,
+                                      const int* __restrict__ grid_of_row, const QueryScan* __restrict__ qs,
+                                      CsmPairDev* __restrict__ pairs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nq * k) return;
+  const QueryScan s = qs[i / k];
+  const uint64_t row = idx[i] - offset;
+  CsmPairDev p;
+  p.grid = 0;
+  p.gid = grid_of_row ? grid_of_row[row] : (int)row;
+  p.pt_begin = s.pt_begin;
+  p.n_pts = s.n_pts;
+  p.w0 = s.w0; p.z0 = s.z0; p.tx = s.tx; p.ty = s.ty;
+  pairs[i] = p;
+}
+
+}  // namespace
+
+struct gloc_localizer {
+  gloc_knn_index* knn = nullptr;
+  gloc_csm_store* csm = nullptr;
+  int device = 0;
+  std::vector<int32_t> h_map;   // row -> grid (empty: identity, the reference's db_grids_[db_idx])
+  CsmBuf d_map, d_q, d_idx, d_d2, d_qs, d_pairs, d_pts;
+  gloc_loc_stats stats{};
+  EventProfiler prof_total, prof_retrieval;   // device-side spans on the store's stream
+};
+
+namespace {
+
+int loc_run(gloc_localizer* L, const float* d_queries, size_t nq, const float* d_pts,
+            const int64_t* scan_offsets, const double* init_xyyaw, const gloc_loc_params* P,
+            uint64_t* out_idx, float* out_d2, gloc_csm_result* cand_results, gloc_loc_result* results) {
+  gloc_csm_store* st = L->csm;
+  const int k = P->k;
+  if (k < 1 || k > 128) return fail(GLOC_ERR_RANGE, "gloc_loc_localize: k must be in [1, 128]");
+  if (P->depth < 1 || P->depth > kCsmMaxDepth)
+    return fail(GLOC_ERR_RANGE, "gloc_loc_localize: depth must be in [1, 8]");
+  if (P->n_lin < 0 || P->n_ang < 0) return fail(GLOC_ERR_INVALID, "gloc_loc_localize: negative window");
+  const long long S = 2ll * P->n_ang + 1, W = 2ll * P->n_lin + 1;
+  if (S * W * W >= (1ll << 32) || S > 65535)
+    return fail(GLOC_ERR_RANGE, "gloc_loc_localize: search window too large (scans*(2*n_lin+1)^2 must be < 2^32)");
+  if (P->policy != GLOC_LOC_VERIFY_ALL && P->policy != GLOC_LOC_FIRST_MATCH)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize: unknown policy");
+  if (nq * (size_t)k > (size_t)INT32_MAX) return fail(GLOC_ERR_RANGE, "gloc_loc_localize: too many pairs in one call");
+  // RpyPCLoopDetector::detect leaves its outputs untouched when the database is too small
+  // (loop_detector.cpp:27-30); here a database with fewer than k searchable rows is an error
+  const size_t rows = knn_searchable_rows(L->knn);
+  if (rows < (size_t)k)
+    return fail(GLOC_ERR_NOT_BUILT, "gloc_loc_localize: fewer than k searchable rows in the database");
+  const size_t n_grids = st->recs.size();
+  if (n_grids == 0) return fail(GLOC_ERR_NOT_BUILT, "gloc_loc_localize: the grid store is empty");
+  if (L->h_map.empty() ? gloc_knn_size(L->knn) > n_grids : gloc_knn_size(L->knn) > L->h_map.size())
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize: database rows without a map grid (add the grids or set the row -> grid table)");
+  const int64_t total_pts = scan_offsets[nq];
+  std::vector<QueryScan> hq(nq);
+  for (size_t q = 0; q < nq; ++q) {
+    const int64_t b = scan_offsets[q], e = scan_offsets[q + 1];
+    if (b < 0 || e <= b || e > total_pts || e - b > INT32_MAX)
+      return fail(GLOC_ERR_INVALID, "gloc_loc_localize: bad scan offsets (every query needs a non-empty scan)");
+    const double* in = init_xyyaw ? init_xyyaw + 3 * q : nullptr;
+    const float ha = 0.5f * (float)(in ? in[2] : 0.0);
+    hq[q].pt_begin = b;
+    hq[q].n_pts = (int)(e - b);
+    hq[q].w0 = std::cos(ha);
+    hq[q].z0 = std::sin(ha);
+    hq[q].tx = (float)(in ? in[0] : 0.0);
+    hq[q].ty = (float)(in ? in[1] : 0.0);
+  }
+  const CsmParams prm = csm_make_params(P->n_lin, P->n_ang, P->depth, P->min_score);
+  std::vector<float2> rot;
+  csm_host_rotations(P->n_ang, P->ang_step, &rot);
+  // the candidates can be any grid of the store: plan for the largest
+  CsmBatchPlan plan;
+  csm_make_plan(st->max_nx, st->max_ny, st->n_graded == 0, P->n_lin, P->depth, &plan);
+
+  cudaStream_t stream = st->stream;
+  const size_t n_pairs = nq * (size_t)k;
+  GLOC_CUDA_TRY(L->d_idx.reserve(n_pairs * sizeof(uint64_t)));
+  GLOC_CUDA_TRY(L->d_d2.reserve(n_pairs * sizeof(float)));
+  GLOC_CUDA_TRY(L->d_qs.reserve(nq * sizeof(QueryScan)));
+  GLOC_CUDA_TRY(L->d_pairs.reserve(n_pairs * sizeof(CsmPairDev)));
+  GLOC_CUDA_TRY(st->rot.reserve((size_t)S * sizeof(float2)));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(st->rot.p, rot.data(), (size_t)S * sizeof(float2), cudaMemcpyHostToDevice, stream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_qs.p, hq.data(), nq * sizeof(QueryScan), cudaMemcpyHostToDevice, stream));
+  // ---- stage 1 on the store's stream: the pairs are made from its output without leaving the device
+  L->prof_retrieval.begin(stream);
+  int rc = gloc_knn_query_device(L->knn, d_queries, nq, (size_t)k, (uint64_t*)L->d_idx.p, (float*)L->d_d2.p, stream);
+  L->prof_retrieval.end(stream);
+  if (rc != GLOC_OK) return rc;
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_idx, L->d_idx.p, n_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_d2, L->d_d2.p, n_pairs * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  const int* d_map = L->h_map.empty() ? nullptr : (const int*)L->d_map.p;
+  const uint64_t offset = knn_offset_of(L->knn);
+  std::vector<unsigned long long> hbest(n_pairs, 0ull);
+  std::vector<unsigned char> verified(n_pairs, 0);
+
+  if (P->policy == GLOC_LOC_VERIFY_ALL) {
+    loc_make_pairs_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream>>>(
+        (const uint64_t*)L->d_idx.p, (int)nq, k, offset, d_map, (const QueryScan*)L->d_qs.p,
+        (CsmPairDev*)L->d_pairs.p);
+    GLOC_CUDA_TRY(cudaGetLastError());
+    L->stats.kernel_launches++;
+    rc = csm_match_core(st, plan, d_pts, (CsmPairDev*)L->d_pairs.p, (int)n_pairs, prm,
+                        (const float2*)st->rot.p, hbest.data());
+    if (rc != GLOC_OK) return rc;
+    std::fill(verified.begin(), verified.end(), 1);
+    L->stats.pairs_verified += n_pairs;
+  } else {
+    // the reference's order of evaluation: candidate c is tried only when candidates 0..c-1 failed
+    // (global_localization.cpp:519-524).  Waves of candidates [c0, c1) over the queries still
+    // unlocated give the same located frame and pose with one device batch per wave.
+    GLOC_CUDA_TRY(cudaStreamSynchronize(stream));   // out_idx is on the host now
+    std::vector<char> done(nq, 0);
+    std::vector<CsmPairDev> hp;
+    std::vector<size_t> where;
+    for (int c0 = 0; c0 < k;) {
+      const int c1 = std::min(k, c0 == 0 ? 1 : 2 * c0);
+      hp.clear();
+      where.clear();
+      for (size_t q = 0; q < nq; ++q) {
+        if (done[q]) continue;
+        for (int c = c0; c < c1; ++c) {
+          const uint64_t row = out_idx[q * k + c] - offset;
+          CsmPairDev p;
+          p.grid = 0;
+          p.gid = L->h_map.empty() ? (int)row : L->h_map[row];
+          p.pt_begin = hq[q].pt_begin;
+          p.n_pts = hq[q].n_pts;
+          p.w0 = hq[q].w0; p.z0 = hq[q].z0; p.tx = hq[q].tx; p.ty = hq[q].ty;
+          hp.push_back(p);
+          where.push_back(q * k + c);
+        }
+      }
+      if (hp.empty()) break;
+      GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_pairs.p, hp.data(), hp.size() * sizeof(CsmPairDev),
+                                    cudaMemcpyHostToDevice, stream));
+      std::vector<unsigned long long> wb(hp.size());
+      rc = csm_match_core(st, plan, d_pts, (CsmPairDev*)L->d_pairs.p, (int)hp.size(), prm,
+                          (const float2*)st->rot.p, wb.data());
+      if (rc != GLOC_OK) return rc;
+      L->stats.pairs_verified += hp.size();
+      L->stats.waves++;
+      for (size_t i = 0; i < hp.size(); ++i) {
+        hbest[where[i]] = wb[i];
+        verified[where[i]] = 1;
+        uint32_t sb = (uint32_t)(wb[i] >> 32);
+        float sc;
+        std::memcpy(&sc, &sb, 4);
+        if (wb[i] != 0 && sc > P->min_score) done[where[i] / k] = 1;
+      }
+      c0 = c1;
+    }
+  }
+  L->prof_total.end(stream);
+  GLOC_CUDA_TRY(cudaStreamSynchronize(stream));
+
+  // ---- decode: Candidate2D + pose per verified pair, then global_registraion's choice per query
+  static const double zero3[3] = {0, 0, 0};
+  for (size_t q = 0; q < nq; ++q) {
+    gloc_loc_result& R = results[q];
+    std::memset(&R, 0, sizeof(R));
+    R.candidate = -1;
+    R.best_candidate = -1;
+    R.db_index = UINT64_MAX;
+    const double* in = init_xyyaw ? init_xyyaw + 3 * q : zero3;
+    float best_score = 0.f;
+    for (int c = 0; c < k; ++c) {
+      const size_t i = q * k + c;
+      gloc_csm_result r;
+      std::memset(&r, 0, sizeof(r));
+      r.score = P->min_score;
+      if (verified[i]) {
+        const uint64_t row = out_idx[i] - offset;
+        const int gid = L->h_map.empty() ? (int)row : L->h_map[row];
+        csm_decode(hbest[i], prm, P->ang_step, st->recs[gid].resolution, in, P->min_score, &r);
+        R.n_verified++;
+      } else {
+        r.reserved = -1;   // not evaluated (GLOC_LOC_FIRST_MATCH: an earlier candidate matched)
+      }
+      if (cand_results) cand_results[i] = r;
+      if (r.found) {
+        if (R.candidate < 0) {
+          R.located = 1;
+          R.candidate = c;
+          R.db_index = out_idx[i];
+          R.match = r;
+        }
+        if (R.best_candidate < 0 || r.score > best_score) {
+          R.best_candidate = c;
+          best_score = r.score;
+        }
+      }
+    }
+  }
+  L->stats.queries += nq;
+  return GLOC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gloc_loc_create(gloc_localizer** out, gloc_knn_index* knn, gloc_csm_store* csm) {
+  if (!out) return fail(GLOC_ERR_INVALID, "gloc_loc_create: out is null");
+  *out = nullptr;
+  if (!knn || !csm) return fail(GLOC_ERR_INVALID, "gloc_loc_create: null index or store");
+  if (knn_device_of(knn) != csm->device)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_create: index and grid store live on different devices");
+  gloc_localizer* L = new (std::nothrow) gloc_localizer;
+  if (!L) return fail(GLOC_ERR_NOMEM, "gloc_loc_create: out of host memory");
+  L->knn = knn;
+  L->csm = csm;
+  L->device = csm->device;
+  *out = L;
+  return GLOC_OK;
+}
+
+void gloc_loc_destroy(gloc_localizer* L) {
+  if (!L) return;
+  DeviceGuard g(L->device);
+  for (CsmBuf* b : {&L->d_map, &L->d_q, &L->d_idx, &L->d_d2, &L->d_qs, &L->d_pairs, &L->d_pts}) b->release();
+  delete L;
+}
+
+int gloc_loc_set_row_grids(gloc_localizer* L, const int32_t* grid_of_row, size_t n_rows) {
+  if (!L) return fail(GLOC_ERR_INVALID, "gloc_loc_set_row_grids: null localizer");
+  DeviceGuard g(L->device);
+  if (!grid_of_row || n_rows == 0) {   // back to the identity (db_grids_[db_idx], loop_detector.h:36-39)
+    L->h_map.clear();
+    return GLOC_OK;
+  }
+  const int n_grids = gloc_csm_num_grids(L->csm);
+  for (size_t i = 0; i < n_rows; ++i)
+    if (grid_of_row[i] < 0 || grid_of_row[i] >= n_grids)
+      return fail(GLOC_ERR_INVALID, "gloc_loc_set_row_grids: grid id out of range at row " + std::to_string(i));
+  try {
+    L->h_map.assign(grid_of_row, grid_of_row + n_rows);
+  } catch (...) {
+    return fail(GLOC_ERR_NOMEM, "gloc_loc_set_row_grids: out of host memory");
+  }
+  GLOC_CUDA_TRY(cudaStreamSynchronize(L->csm->stream));
+  GLOC_CUDA_TRY(L->d_map.reserve(n_rows * sizeof(int32_t)));
+  GLOC_CUDA_TRY(cudaMemcpy(L->d_map.p, grid_of_row, n_rows * sizeof(int32_t), cudaMemcpyHostToDevice));
+  GLOC_CUDA_TRY(cudaStreamSynchronize(0));
+  return GLOC_OK;
+}
+
+int gloc_loc_localize_device(gloc_localizer* L, const float* d_queries, size_t nq, const float* d_pts,
+                             const int64_t* scan_offsets, const double* init_xyyaw,
+                             const gloc_loc_params* prm, uint64_t* out_idx, float* out_d2,
+                             gloc_csm_result* cand_results, gloc_loc_result* results) {
+  if (!L || !prm) return fail(GLOC_ERR_INVALID, "gloc_loc_localize: null argument");
+  if (nq == 0) return GLOC_OK;
+  if (!d_queries || !d_pts || !scan_offsets || !out_idx || !out_d2 || !results)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize: null buffer");
+  DeviceGuard g(L->device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_loc_localize: cudaSetDevice failed");
+  L->prof_total.begin(L->csm->stream);
+  return loc_run(L, d_queries, nq, d_pts, scan_offsets, init_xyyaw, prm, out_idx, out_d2, cand_results, results);
+}
+
+int gloc_loc_localize(gloc_localizer* L, const float* queries, size_t nq, const float* pts,
+                      const int64_t* scan_offsets, const double* init_xyyaw, const gloc_loc_params* prm,
+                      uint64_t* out_idx, float* out_d2, gloc_csm_result* cand_results,
+                      gloc_loc_result* results) {
+  if (!L || !prm) return fail(GLOC_ERR_INVALID, "gloc_loc_localize: null argument");
+  if (nq == 0) return GLOC_OK;
+  if (!queries || !pts || !scan_offsets || !out_idx || !out_d2 || !results)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize: null buffer");
+  DeviceGuard g(L->device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_loc_localize: cudaSetDevice failed");
+  const size_t dim = gloc_knn_dim(L->knn);
+  const int64_t total_pts = scan_offsets[nq];
+  if (total_pts <= 0) return fail(GLOC_ERR_INVALID, "gloc_loc_localize: bad scan offsets");
+  cudaStream_t stream = L->csm->stream;
+  GLOC_CUDA_TRY(L->d_q.reserve(nq * dim * sizeof(float)));
+  GLOC_CUDA_TRY(L->d_pts.reserve((size_t)total_pts * 3 * sizeof(float)));
+  L->prof_total.begin(stream);
+  GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_q.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_pts.p, pts, (size_t)total_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+  return loc_run(L, (const float*)L->d_q.p, nq, (const float*)L->d_pts.p, scan_offsets, init_xyyaw, prm,
+                 out_idx, out_d2, cand_results, results);
+}
+
+int gloc_loc_set_profiling(gloc_localizer* L, int enabled) {
+  if (!L) return fail(GLOC_ERR_INVALID, "gloc_loc_set_profiling: null localizer");
+  L->prof_total.enabled = L->prof_retrieval.enabled = enabled != 0;
+  return GLOC_OK;
+}
+
+int gloc_loc_get_profile(gloc_localizer* L, gloc_loc_profile* out) {
+  if (!L || !out) return fail(GLOC_ERR_INVALID, "gloc_loc_get_profile: null argument");
+  DeviceGuard g(L->device);
+  uint64_t n = 0;
+  L->prof_total.collect(&out->total_ms, &out->calls);
+  L->prof_retrieval.collect(&out->retrieval_ms, &n);
+  return GLOC_OK;
+}
+
+int gloc_loc_get_stats(const gloc_localizer* L, gloc_loc_stats* out) {
+  if (!L || !out) return fail(GLOC_ERR_INVALID, "gloc_loc_get_stats: null argument");
+  *out = L->stats;
+  return GLOC_OK;
+}
+
+}  // extern "C"

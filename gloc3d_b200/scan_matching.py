@@ -87,6 +87,12 @@ class CsmStore:
     def __len__(self) -> int:
         return int(_lib.lib().gloc_csm_num_grids(self._h))
 
+    def store_bytes(self):
+        """(bytes of the resident grids, bytes of the store's reusable work buffers)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        check(_lib.lib().gloc_csm_store_bytes(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def grid_info(self, grid_id: int) -> MapLimits:
         info = _lib.GridInfo()
         check(_lib.lib().gloc_csm_get_grid_info(self._h, grid_id, C.byref(info)))

@@ -137,6 +137,11 @@ int gloc_knn_merge_topk_device(const uint64_t* d_idx, const float* d_d2, size_t 
  * the shrunk search window -- what BranchAndBound returns -- with ties
  * resolved to the smallest (scan, x, y).
  */
+/* What a store keeps per map grid is the width-1 precomputation grid only, bit-packed (one bit
+ * per cell) when every cell is 0 or 255 -- 49 KB for a KITTI-sized 781 x 504 BEV grid -- in a
+ * pooled device arena.  The reference builds a PrecomputationGridStack2D per matcher instance
+ * (fast_..._2d.cpp:192-215); here the coarser levels are rebuilt on the device for the distinct
+ * grids of each batch, so that a database of a million frames stays resident. */
 typedef struct gloc_csm_store gloc_csm_store;
 
 typedef struct {
@@ -173,6 +178,8 @@ int gloc_csm_add_grid_cells(gloc_csm_store* store, const uint16_t* cells, int nx
 int gloc_csm_add_grid_u8(gloc_csm_store* store, const uint8_t* level1, int nx, int ny,
                          double resolution, double max_x, double max_y, int* grid_id);
 int gloc_csm_num_grids(const gloc_csm_store* store);
+/* Device memory held by the store: the grids themselves, and its (reused) work buffers. */
+int gloc_csm_store_bytes(const gloc_csm_store* store, uint64_t* grid_bytes, uint64_t* workspace_bytes);
 /* Copy the width-`width` precomputation grid of grid_id back to the host
  * ((nx+width-1)*(ny+width-1) bytes) -- PrecomputationGridStack2D::Get. */
 int gloc_csm_get_precomputation_grid(gloc_csm_store* store, int grid_id, int width,
@@ -215,6 +222,81 @@ int gloc_csm_get_stats(const gloc_csm_store* store, gloc_csm_stats* stats);
 /* Same live timing for stage 2; the dominant kernel is the coarse-level scorer. */
 int gloc_csm_set_profiling(gloc_csm_store* store, int enabled);
 int gloc_csm_get_profile(gloc_csm_store* store, gloc_profile* out);
+
+/* ============================================================ whole query path
+ * One call from descriptors + scans to located frames and poses.  Replaces the evaluation loop
+ * of the reference driver:
+ *   GlocEvaluator::detect_all_query    global_localization.cpp:482-509 (RpyPCLoopDetector::detect,
+ *                                      loop_detector.cpp:22-46 -> InvKeyTree::query, top_k_)
+ *   GlocEvaluator::global_registraion  global_localization.cpp:511-574 (candidates in retrieval
+ *                                      order; loop_detector_.match(q_grid, db_idx, ...) :519-524;
+ *                                      the first candidate that matches is the located frame)
+ * with FastCorrelativeScanMatcher2D::MatchWithSearchParameters as the verifier.  Retrieval, the
+ * gather of the candidates' map grids, verification and the per-query choice run on the device
+ * without a host round trip between the stages.  The index and the store are borrowed (they must
+ * outlive the localizer and live on the same device); database row r is verified against grid
+ * grid_of_row[r] (default: grid r -- db_grids_[db_idx], loop_detector.h:36-39).
+ */
+typedef struct gloc_localizer gloc_localizer;
+
+#define GLOC_LOC_VERIFY_ALL 0   /* every one of the k candidates is verified (BASELINE config:   */
+                                /* "25 candidates/query"); per-candidate results available       */
+#define GLOC_LOC_FIRST_MATCH 1  /* the reference's evaluation order: candidate c is verified only */
+                                /* if candidates 0..c-1 did not match; same located frame and pose */
+
+typedef struct {
+  int k;              /* candidates per query: top_k_ (loop_detector.h:98; 20 there, 25 in BASELINE) */
+  int n_lin, n_ang;   /* SearchParameters "for testing" ctor, as gloc_csm_match_batch               */
+  double ang_step;
+  int depth;          /* branch_and_bound_depth; only affects speed                                 */
+  float min_score;
+  int policy;         /* GLOC_LOC_*                                                                 */
+} gloc_loc_params;
+
+typedef struct {
+  int located;            /* global_registraion's return value                                     */
+  int candidate;          /* position in the top-k of the located frame = the first candidate, in  */
+                          /* retrieval order, whose match succeeded; -1 if none                    */
+  int best_candidate;     /* the candidate with the highest score among those verified; -1 if none */
+  int n_verified;         /* candidates verified for this query                                    */
+  uint64_t db_index;      /* located_db_idx (UINT64_MAX if not located)                            */
+  gloc_csm_result match;  /* the match of `candidate`: pose of the query in the located frame      */
+} gloc_loc_result;
+
+typedef struct {
+  uint64_t queries, pairs_verified, waves, kernel_launches;
+} gloc_loc_stats;
+
+int gloc_loc_create(gloc_localizer** out, gloc_knn_index* knn, gloc_csm_store* csm);
+void gloc_loc_destroy(gloc_localizer* loc);
+/* Row -> grid table (n_rows >= rows of the index; ids must exist in the store).  NULL: identity. */
+int gloc_loc_set_row_grids(gloc_localizer* loc, const int32_t* grid_of_row, size_t n_rows);
+/* nq queries (row-major nq x dim) with one scan each (pts: concatenated float32 xyz triples,
+ * scan_offsets: nq+1 prefix offsets in points) and an initial pose estimate per query
+ * (init_xyyaw: nq x 3, NULL = zeros), all in HOST memory.  Outputs (host, caller-allocated):
+ *   out_idx / out_d2  nq x k    the retrieval result, as gloc_knn_query
+ *   cand_results      nq x k    per-candidate match (may be NULL); reserved = -1 marks candidates
+ *                               GLOC_LOC_FIRST_MATCH did not evaluate
+ *   results           nq        located frame and pose per query                                  */
+int gloc_loc_localize(gloc_localizer* loc, const float* queries, size_t nq, const float* pts,
+                      const int64_t* scan_offsets, const double* init_xyyaw,
+                      const gloc_loc_params* params, uint64_t* out_idx, float* out_d2,
+                      gloc_csm_result* cand_results, gloc_loc_result* results);
+/* Same with the descriptors and the scan points already in DEVICE memory (scan offsets, initial
+ * poses and all outputs stay on the host: a few hundred bytes per query). */
+int gloc_loc_localize_device(gloc_localizer* loc, const float* d_queries, size_t nq, const float* d_pts,
+                             const int64_t* scan_offsets, const double* init_xyyaw,
+                             const gloc_loc_params* params, uint64_t* out_idx, float* out_d2,
+                             gloc_csm_result* cand_results, gloc_loc_result* results);
+int gloc_loc_get_stats(const gloc_localizer* loc, gloc_loc_stats* out);
+/* Live device-side timing (CUDA events on the stream the work is launched on) of whole calls and
+ * of their retrieval stage; the rest of a call is verification.  Summed since the last get. */
+typedef struct {
+  double total_ms, retrieval_ms;
+  uint64_t calls;
+} gloc_loc_profile;
+int gloc_loc_set_profiling(gloc_localizer* loc, int enabled);
+int gloc_loc_get_profile(gloc_localizer* loc, gloc_loc_profile* out);
 
 /* ============================================================ BEV projection
  * (the producer of both stages' inputs.)  One LiDAR scan ->
