@@ -3,12 +3,20 @@
  * Cartographer fast correlative scan matcher in registration/2d (plus the
  * author's Grid2D additions).  TEST INFRASTRUCTURE ONLY (see gloc_oracle.h).
  *
- * PARITY UNPINNED: registration/2d needs Eigen + glog + OpenCV, none of which
- * exist in this image, and the reference ships no tests/golden vectors.  Every
- * function cites the source lines it restates; Eigen's quaternion arithmetic
- * (not under /root/reference, version unpinned by the reference's CMake) is
- * restated from Eigen 3.3/3.4's QuaternionBase::_transformVector and
- * Quaternion(AngleAxis).
+ * PARITY PINNED against the reference's own code: registration/2d/*.cpp,
+ * 3d/probability_values.cpp and 3d/point_cloud.cpp compile UNMODIFIED into
+ * oracle/_ref/libcsm_ref.so (oracle/csm_ref.cpp; oracle/shim/ stands in for the
+ * Eigen / glog / OpenCV / boost / ceres headers this image lacks), and
+ * tests/test_oracle_csm_ref.py holds this file equal to it: precomputation grids,
+ * value codec, SearchParameters, rotated + discretised scans, and the result of
+ * MatchWithSearchParameters / MatchFullSubmap (score, candidate, pose) bit for bit;
+ * tests/golden/csm_*.npz are minted from the reference.  What remains a
+ * restatement is Eigen's own arithmetic (not under /root/reference, version
+ * unpinned by the reference's CMake): Quaternion(AngleAxis),
+ * QuaternionBase::_transformVector and Transform * vector as in Eigen 3.3/3.4,
+ * stated once in oracle/shim/Eigen/eigen_shim.h (general form) and once here
+ * (specialised to rotations about z); the two agree bit for bit.  Every function
+ * cites the source lines it restates.
  *
  * Compile with -ffp-contract=off and no -ffast-math: float32 arithmetic must
  * stay un-fused and un-reassociated.

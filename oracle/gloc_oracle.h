@@ -11,12 +11,15 @@
  *     KDTreeVectorOfVectorsAdaptor compiled from /root/reference
  *     (oracle/_ref/libnanoflann_ref.so, see oracle/Makefile) and against the
  *     golden vectors minted from it (tests/golden/knn_*.npz).
- *   stage 2 (scan matching): PARITY UNPINNED -- registration/2d cannot be
- *     compiled here (needs Eigen, glog, OpenCV; none installed) and the
- *     reference ships no tests or golden vectors for it.  The
- *     restatement follows the sources line by line (citations below) and is
- *     checked for self-consistency only (B&B == exhaustive, level_w == sliding
- *     max of level_1, float path == u8 path).
+ *   stage 2 (scan matching): pinned against the reference's own
+ *     registration/2d/*.cpp (+ 3d/probability_values.cpp, 3d/point_cloud.cpp)
+ *     compiled unmodified from /root/reference into oracle/_ref/libcsm_ref.so
+ *     (oracle/csm_ref.cpp, against the stand-in headers of oracle/shim/ for the
+ *     absent Eigen / glog / OpenCV / boost / ceres) -- tests/test_oracle_csm_ref.py,
+ *     tests/golden/csm_*.npz.  Eigen's arithmetic inside the shim is a
+ *     restatement of Eigen 3.3/3.4 (Eigen is not under /root/reference).  Also
+ *     checked for self-consistency (B&B == exhaustive, level_w == sliding max
+ *     of level_1, float path == u8 path).
  *
  * All file:line citations are relative to /root/reference/registration/.
  */

@@ -333,3 +333,119 @@ def crop_pad(img: np.ndarray, width: int = 768, height: int = 768) -> np.ndarray
     lib().gloc_oracle_crop_pad(img.ctypes.data, img.shape[1], img.shape[0], width, height,
                                out.ctypes.data)
     return out
+
+
+# ------------------------------------------------- stage 2: the REFERENCE's own matcher
+# oracle/_ref/libcsm_ref.so = registration/2d/*.cpp (+ 3d/probability_values.cpp, point_cloud.cpp)
+# compiled unmodified from /root/reference against oracle/shim/ (see oracle/csm_ref.cpp).
+
+_CSM_REF = os.path.join(_HERE, "_ref", "libcsm_ref.so")
+_csm_ref = None
+
+
+class RefMatchResult(C.Structure):
+    _fields_ = [("found", C.c_int), ("score", C.c_float), ("pose_x", C.c_double), ("pose_y", C.c_double),
+                ("pose_yaw", C.c_double), ("scan_index", C.c_int), ("x_offset", C.c_int),
+                ("y_offset", C.c_int), ("cand_score", C.c_float)]
+
+
+def have_csm_ref() -> bool:
+    if not os.path.exists(_CSM_REF):
+        try:
+            build()
+        except Exception:
+            return False
+    return os.path.exists(_CSM_REF)
+
+
+def csm_ref():
+    global _csm_ref
+    if _csm_ref is None:
+        if not have_csm_ref():
+            raise RuntimeError("oracle/_ref/libcsm_ref.so is missing")
+        R = C.CDLL(_CSM_REF)
+        d, i, f, vp = C.c_double, C.c_int, C.c_float, C.c_void_p
+        R.gloc_ref_value_to_cost.restype = f
+        R.gloc_ref_value_to_cost.argtypes = [C.c_uint16]
+        R.gloc_ref_cost_to_value.restype = C.c_uint16
+        R.gloc_ref_cost_to_value.argtypes = [f]
+        R.gloc_ref_csm_precomp.argtypes = [vp, i, i, d, d, d, i, i, vp]
+        R.gloc_ref_csm_search_params.argtypes = [d, d, vp, i, d, C.POINTER(i), C.POINTER(i), C.POINTER(d)]
+        R.gloc_ref_csm_discretize.argtypes = [vp, i, d, d, d, i, d, d, d, d, vp]
+        R.gloc_ref_csm_match.restype = i
+        R.gloc_ref_csm_match.argtypes = [vp, i, i, d, d, d, i, vp, i, d, d, d, i, i, d, f, C.POINTER(RefMatchResult)]
+        R.gloc_ref_csm_match_grid.restype = i
+        R.gloc_ref_csm_match_grid.argtypes = [vp, i, i, d, d, d, i, d, d, vp, i, i, d, d, d, d, d, d, d, f,
+                                              C.POINTER(RefMatchResult)]
+        R.gloc_ref_csm_match_full_submap.restype = i
+        R.gloc_ref_csm_match_full_submap.argtypes = [vp, i, i, d, d, d, i, vp, i, f, C.POINTER(RefMatchResult)]
+        R.gloc_ref_csm_match_batch_mt.argtypes = [C.POINTER(vp), i, i, d, d, d, i, C.POINTER(vp), C.POINTER(i),
+                                                  C.POINTER(d), i, i, i, d, f, i, C.POINTER(RefMatchResult)]
+        _csm_ref = R
+    return _csm_ref
+
+
+def ref_precomp(cells: np.ndarray, depth: int, index: int) -> np.ndarray:
+    cells = np.ascontiguousarray(cells, np.uint16)
+    ny, nx = cells.shape
+    w = 1 << index
+    out = np.empty((ny + w - 1, nx + w - 1), np.uint8)
+    csm_ref().gloc_ref_csm_precomp(cells.ctypes.data, nx, ny, 0.2, 10.0, 10.0, depth, index, out.ctypes.data)
+    return out
+
+
+def ref_search_params(lin_window, ang_window, pts, resolution):
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    nl, na, st = C.c_int(), C.c_int(), C.c_double()
+    csm_ref().gloc_ref_csm_search_params(lin_window, ang_window, pts.ctypes.data, pts.shape[0], resolution,
+                                         C.byref(nl), C.byref(na), C.byref(st))
+    return nl.value, na.value, st.value
+
+
+def ref_discretize(pts, init, n_ang, ang_step, resolution, max_x, max_y) -> np.ndarray:
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    out = np.empty((2 * n_ang + 1, pts.shape[0], 2), np.int32)
+    csm_ref().gloc_ref_csm_discretize(pts.ctypes.data, pts.shape[0], init[0], init[1], init[2], n_ang, ang_step,
+                                      resolution, max_x, max_y, out.ctypes.data)
+    return out
+
+
+def ref_csm_match(cells, resolution, max_x, max_y, depth, pts, init, n_lin, n_ang, ang_step,
+                  min_score) -> RefMatchResult:
+    """cells: Grid2D's uint16 correspondence-cost cells [ny, nx]."""
+    cells = np.ascontiguousarray(cells, np.uint16)
+    ny, nx = cells.shape
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    r = RefMatchResult()
+    csm_ref().gloc_ref_csm_match(cells.ctypes.data, nx, ny, resolution, max_x, max_y, depth, pts.ctypes.data,
+                                 pts.shape[0], init[0], init[1], init[2], n_lin, n_ang, ang_step, min_score,
+                                 C.byref(r))
+    return r
+
+
+def ref_csm_match_full_submap(cells, resolution, max_x, max_y, depth, pts, min_score) -> RefMatchResult:
+    cells = np.ascontiguousarray(cells, np.uint16)
+    ny, nx = cells.shape
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    r = RefMatchResult()
+    csm_ref().gloc_ref_csm_match_full_submap(cells.ctypes.data, nx, ny, resolution, max_x, max_y, depth,
+                                             pts.ctypes.data, pts.shape[0], min_score, C.byref(r))
+    return r
+
+
+def ref_csm_match_batch(cells_list, resolution, max_x, max_y, depth, pts_list, inits, n_lin, n_ang, ang_step,
+                        min_score, nthreads=1):
+    """The reference matcher over independent (grid, scan) pairs, one matcher per pair."""
+    cells_list = [np.ascontiguousarray(c, np.uint16) for c in cells_list]
+    pts_list = [np.ascontiguousarray(p, np.float32).reshape(-1, 3) for p in pts_list]
+    n = len(cells_list)
+    ny, nx = cells_list[0].shape
+    gp = (C.c_void_p * n)(*[c.ctypes.data for c in cells_list])
+    pp = (C.c_void_p * n)(*[p.ctypes.data for p in pts_list])
+    npts = (C.c_int * n)(*[p.shape[0] for p in pts_list])
+    init = np.ascontiguousarray(inits, np.float64).reshape(n, 3)
+    out = (RefMatchResult * n)()
+    csm_ref().gloc_ref_csm_match_batch_mt(gp, nx, ny, resolution, max_x, max_y, depth, pp, npts,
+                                          init.ctypes.data_as(C.POINTER(C.c_double)), n, n_lin, n_ang, ang_step,
+                                          min_score, nthreads, out)
+    return list(out)

@@ -7,9 +7,10 @@ knn_*.npz   outputs of the REFERENCE ITSELF (its nanoflann + adaptor compiled un
             from /root/reference/registration, oracle/nanoflann_ref.cpp) on seeded inputs;
             inputs are stored too so the fixtures do not depend on numpy's RNG stream.
 vlad_*.npz  outputs of the REFERENCE ITSELF (model/netvlad_fc.py, torch CPU) on hashed weights.
-csm_*.npz   outputs of the stage-2 restatement (oracle/csm_oracle.c); the reference's
-            registration/2d cannot be built here, so these pin the restatement against
-            regressions only (parity unpinned, see oracle/gloc_oracle.h).
+csm_*.npz   outputs of the REFERENCE ITSELF: registration/2d/*.cpp compiled unmodified into
+            oracle/_ref/libcsm_ref.so (oracle/csm_ref.cpp + oracle/shim/): match result, rotated
+            and discretised scans, precomputation grids.  The restatement (oracle/csm_oracle.c) is
+            asserted equal at mint time.
 """
 import os
 import sys
@@ -36,17 +37,28 @@ def knn_case(name, n, dim, nq, k, seed, dup_run=0, sigma=None):
 def csm_case(name, nx, ny, seed, yaw, dx, dy, n_lin, n_ang, step, depth, min_score, graded=False):
     res = 0.2
     g = synth.make_bev_grid(nx, ny, seed=seed, n_segments=14, n_blobs=8, graded=graded)
+    cells = synth.level1_to_cells(g)                      # Grid2D's uint16 cells
+    g = po.level1_from_cells(cells)                       # the width-1 grid the reference derives
+    assert np.array_equal(g, po.ref_precomp(cells, depth, 0))
     mx, my = synth.centered_limits(nx, ny, res)
-    scan = synth.planted_scan(g, res, mx, my, yaw, dx, dy, dropout=0.2, seed=seed + 1)
-    r = po.csm_match(g, res, mx, my, depth, scan, (0.1, -0.05, 0.02), n_lin, n_ang, step,
-                     min_score, 0)
-    cells = po.discretize(scan, (0.1, -0.05, 0.02), n_ang, step, res, mx, my)
-    levels = {f"level{w}": po.precomp_from_level1(g, w) for w in (2, 4, 16)}
-    np.savez_compressed(os.path.join(OUT, name), grid=g, scan=scan, res=res, max_x=mx, max_y=my,
-                        init=np.array([0.1, -0.05, 0.02]), n_lin=n_lin, n_ang=n_ang, step=step,
-                        depth=depth, min_score=min_score, result=np.array(r.as_tuple(), np.float64),
-                        cells_first=cells[0], cells_last=cells[-1], **levels)
-    print(name, r.as_tuple())
+    scan = synth.planted_scan(np.where(g > 0, 255, 0).astype(np.uint8), res, mx, my, yaw, dx, dy,
+                              dropout=0.2, seed=seed + 1)
+    init = (0.1, -0.05, 0.02)
+    r = po.ref_csm_match(cells, res, mx, my, depth, scan, init, n_lin, n_ang, step, min_score)
+    o = po.csm_match(g, res, mx, my, depth, scan, init, n_lin, n_ang, step, min_score, 0)
+    result = (r.found, r.score, r.scan_index, r.x_offset, r.y_offset, r.pose_x, r.pose_y, r.pose_yaw)
+    assert result == o.as_tuple(), (result, o.as_tuple())
+    disc = po.ref_discretize(scan, init, n_ang, step, res, mx, my)
+    assert np.array_equal(disc, po.discretize(scan, init, n_ang, step, res, mx, my))
+    levels = {}
+    for w in (2, 4, 16):
+        levels[f"level{w}"] = po.ref_precomp(cells, 5, w.bit_length() - 1)
+        assert np.array_equal(levels[f"level{w}"], po.precomp_from_level1(g, w))
+    np.savez_compressed(os.path.join(OUT, name), grid=g, cells=cells, scan=scan, res=res, max_x=mx, max_y=my,
+                        init=np.array(init), n_lin=n_lin, n_ang=n_ang, step=step,
+                        depth=depth, min_score=min_score, result=np.array(result, np.float64),
+                        cells_first=disc[0], cells_last=disc[-1], **levels)
+    print(name, result)
 
 
 def bev_case(name, every=4):

@@ -1,5 +1,6 @@
-"""CPU: self-consistency of the stage-2 restatement (the reference ships no tests or
-golden vectors for registration/2d and it cannot be compiled here: parity unpinned)."""
+"""CPU: self-consistency of the stage-2 restatement and its golden vectors (minted from the
+reference's own registration/2d compiled into oracle/_ref/libcsm_ref.so; the direct comparison
+with that library is tests/test_oracle_csm_ref.py)."""
 import glob
 import os
 
@@ -153,8 +154,8 @@ def _numpy_matcher(level1, res, max_x, max_y, pts, init, n_lin, n_ang, step, min
     """A second, independently written restatement of MatchWithSearchParameters (numpy, brute
     force) from SURVEY.md Appendix B: Eigen's quaternion rotation in float32, GetCellIndex in
     double with lround, ShrinkToFit, integer sums, float32 score, ties to the smallest
-    (scan, x, y).  Used to cross-check oracle/csm_oracle.c, whose parity with the reference is
-    otherwise unpinned (registration/2d does not compile here)."""
+    (scan, x, y).  A third opinion next to oracle/csm_oracle.c and the compiled reference
+    (tests/test_oracle_csm_ref.py)."""
     f32 = np.float32
     ny, nx = level1.shape
     P = pts.shape[0]
