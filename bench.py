@@ -117,11 +117,13 @@ def hold_steps(ms_per_step: float) -> int:
     return int(min(4000, max(1, round(250.0 / max(ms_per_step, 0.05)))))
 
 
-def make_retrieval_inputs(world: int):
+def make_retrieval_inputs(world: int, rows: int = 0, queries: int = 0):
     from gloc3d_b200 import synth
 
-    db = synth.make_descriptors(DB_ROWS, DIM, seed=1234, dup_run=DUP_RUN)
-    nq = Q_PER_GPU * world
+    rows = rows or DB_ROWS
+    db = (synth.make_descriptors(rows, DIM, seed=1234, dup_run=DUP_RUN) if rows <= 200_000
+          else synth.make_descriptors_mt(rows, DIM, seed=1234, dup_run=max(DUP_RUN, 1)))
+    nq = queries or Q_PER_GPU * world
     qa = synth.make_queries(db, nq // 2, seed=5678)                    # set A: independent
     qb = synth.make_queries(db, nq - nq // 2, seed=5679, sigma=0.01)   # set B: perturbed copies
     return db, np.ascontiguousarray(np.concatenate([qa, qb]))
@@ -133,12 +135,12 @@ def run_retrieval(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import gloc3d_b200 as g
-    from gloc3d_b200.distributed import ShardedRetrieval, shard_bounds
+    from gloc3d_b200.distributed import shard_bounds
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     peaks = load_peaks()
-    db, q_all = make_retrieval_inputs(world)
+    db, q_all = make_retrieval_inputs(world, args.rows, args.queries)
     mode = {"auto": g.KNN_AUTO, "exact": g.KNN_EXACT_SCAN, "shortlist": g.KNN_SHORTLIST}[args.mode]
 
     def barrier():
@@ -153,33 +155,53 @@ def run_retrieval(args, rank, world, local_rank):
         dist.all_reduce(t, op=op)
         return float(t.item())
 
+    rows_total = args.rows or DB_ROWS
+    strong = bool(args.queries)             # a fixed total batch (configs[3]) instead of 10k per GPU
+    comm = None
+    if world > 1:
+        from gloc3d_b200.distributed import Comm
+
+        comm = Comm.from_torch(local_rank)
+
     def measure(sharding: str, steps: int, warmup: int):
-        """sharding "queries": every rank holds the whole DB and answers its own 10k-query slice
-        (no data-path collective).  "db": the north-star protocol -- rows sharded, every rank
-        answers all N x 10k queries on its shard, one all-gather of the local top-k, K4 merge."""
-        if sharding == "db" and world > 1:
-            b = shard_bounds(DB_ROWS, world)
+        """sharding "queries": every rank holds the whole DB and answers its own query slice (no
+        data-path collective).  "db": the north-star protocol through the C ABI
+        (gloc_knn_query_sharded*): rows sharded; every rank uploads ITS slice of the batch, the
+        queries are all-gathered over NVLink, every rank searches the whole batch on its shard, the
+        local top-k lists go to the rank that owns the query (all-to-all) and are merged there."""
+        from gloc3d_b200.distributed import query_sharded_device, query_sharded_host
+
+        nq_job = args.queries if strong else Q_PER_GPU * world
+        nq = nq_job // world                  # queries this rank uploads / downloads per step
+        q = np.ascontiguousarray(q_all[rank * nq:(rank + 1) * nq])
+        db_sharded = sharding == "db" and world > 1
+        if db_sharded:
+            b = shard_bounds(rows_total, world)
             lo, hi = b[rank], b[rank + 1]
-            sr = ShardedRetrieval(rank, world).load_shard(torch.from_numpy(db[lo:hi]).to(dev), lo,
-                                                          local_rank, mode)
-            q = q_all
         else:
-            lo, hi = 0, DB_ROWS
-            sr = ShardedRetrieval(0, 1).load_shard(torch.from_numpy(db).to(dev), 0, local_rank, mode)
-            q = np.ascontiguousarray(q_all[rank * Q_PER_GPU:(rank + 1) * Q_PER_GPU])
-        nq = q.shape[0]                       # queries this rank answers per step
-        nq_job = Q_PER_GPU * world            # queries the whole job answers per step
+            lo, hi = 0, rows_total
+        ix = g.KnnIndex(DIM, local_rank)
+        ix.set_db(db[lo:hi])
+        ix.set_index_offset(lo)
+        ix.set_mode(mode)
         q_dev = torch.from_numpy(q).to(dev)
         q_pin = torch.from_numpy(q).pin_memory()
         oi_pin = torch.empty((nq, K_NN), dtype=torch.int64).pin_memory()
         od_pin = torch.empty((nq, K_NN), dtype=torch.float32).pin_memory()
+        oi_dev = torch.empty((nq, K_NN), dtype=torch.int64, device=dev)
+        od_dev = torch.empty((nq, K_NN), dtype=torch.float32, device=dev)
+
+        def dev_step():
+            if db_sharded:
+                return query_sharded_device(ix, comm, q_dev, K_NN, False, oi_dev, od_dev)
+            return ix.query_device(q_dev, K_NN, oi_dev, od_dev)
 
         # ---- device-resident timing (value)
         for _ in range(warmup):
-            out = sr.query(q_dev, K_NN)
+            out = dev_step()
         barrier()
-        sr.index.set_profiling(True)
-        launches0 = sr.index.stats().kernel_launches
+        ix.set_profiling(True)
+        launches0 = ix.stats().kernel_launches
         clocks = ClockSampler(local_rank)
         if rank == 0:
             clocks.start()
@@ -187,27 +209,26 @@ def run_retrieval(args, rank, world, local_rank):
         barrier()
         e0.record()
         for _ in range(steps):
-            out = sr.query(q_dev, K_NN)
+            out = dev_step()
         e1.record()
         barrier()
-        dom_ms, dom_n = sr.index.profile()
-        sr.index.set_profiling(False)
-        st = sr.index.stats()
+        dom_ms, dom_n = ix.profile()
+        ix.set_profiling(False)
+        st = ix.stats()
         ms_total = reduce_ranks(e0.elapsed_time(e1), dist.ReduceOp.MAX)
         for _ in range(hold_steps(ms_total / steps)):   # every rank: the same count (see hold_steps)
-            sr.query(q_dev, K_NN)
+            dev_step()
         barrier()
         clk = clocks.stop() if rank == 0 else None
-        own = (st.kernel_launches - launches0) + (steps if sr.world_size > 1 else 0)   # + K4 merge
-        launches = int(reduce_ranks(float(own), dist.ReduceOp.SUM))
+        launches = int(reduce_ranks(float(st.kernel_launches - launches0), dist.ReduceOp.SUM))
         ms_per_step = ms_total / steps
 
         # ---- end to end with host buffers (e2e): pinned H2D of the queries, D2H of the result
         def e2e_step():
-            if sr.world_size == 1:
-                sr.index.query_ptr(q_pin.data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
+            if db_sharded:
+                query_sharded_host(ix, comm, q_pin.data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
             else:
-                sr.query_host(q_pin, K_NN, oi_pin, od_pin)
+                ix.query_ptr(q_pin.data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
 
         for _ in range(max(1, min(warmup, 3))):
             e2e_step()
@@ -224,8 +245,10 @@ def run_retrieval(args, rank, world, local_rank):
         res = dict(sharding=sharding, nq=nq, nq_job=nq_job, rows=hi - lo, ms_per_step=ms_per_step,
                    value=nq_job / (ms_per_step * 1e-3), e2e_ms=e2e_ms, e2e_value=nq_job / (e2e_ms * 1e-3),
                    h2d=int(q.nbytes) * world, d2h=int(nq * K_NN * 12) * world, launches=launches, clk=clk,
-                   dom_ms=dom_ms, dom_n=dom_n, st=st, steps=steps, sample=(q, out[0].cpu().numpy(), out[1].cpu().numpy()))
-        sr.close()
+                   dom_ms=dom_ms, dom_n=dom_n, st=st, steps=steps, db_sharded=db_sharded,
+                   nq_searched=nq * world if db_sharded else nq,
+                   sample=(q, out[0].cpu().numpy().view(np.uint64), out[1].cpu().numpy()))
+        ix.close()
         return res
 
     primary = args.sharding if world > 1 else "queries"
@@ -239,8 +262,8 @@ def run_retrieval(args, rank, world, local_rank):
     last_mode = int(st.last_mode)
     # the library may split a batch into several launches: algorithmic work per LAUNCH
     launches_per_step = max(r["dom_n"], 1) / r["steps"]
-    flops = 2.0 * r["nq"] * r["rows"] * DIM / launches_per_step
-    alg_bytes = r["rows"] * DIM * 4 + (r["nq"] * DIM * 4 + r["nq"] * K_NN * 12) / launches_per_step
+    flops = 2.0 * r["nq_searched"] * r["rows"] * DIM / launches_per_step
+    alg_bytes = r["rows"] * DIM * 4 + (r["nq_searched"] * DIM * 4 + r["nq_searched"] * K_NN * 12) / launches_per_step
     avg_ms = r["dom_ms"] / max(r["dom_n"], 1)
     peak_tf = peaks["bf16_tflops"]
     traffic = None
@@ -248,17 +271,20 @@ def run_retrieval(args, rank, world, local_rank):
     if os.path.exists(tp) and world == 1:
         traffic = json.load(open(tp)).get({1: "exact_scan", 2: "shortlist_gemm"}.get(last_mode, ""), None)
     nq_job = r["nq_job"]
-    shard_txt = {"queries": f"queries/{world} (each rank: whole DB replicated, its own 10k queries; no collective)",
-                 "db": f"rows/{world} + all-gather top-k + K4 merge (north-star protocol)"}
+    shard_txt = {"queries": f"queries/{world} (each rank: whole DB replicated, its own query slice; no collective)",
+                 "db": f"rows/{world}: queries all-gathered over NVLink, local top-k per shard, all-to-all of the lists to "
+                       f"the query's owner, K4 merge there (gloc_knn_query_sharded, NCCL inside libgloc3d.so)"}
     line = {
         "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32" if last_mode == g.KNN_EXACT_SCAN else "fp16 tensor shortlist + f32 exact re-rank",
         "data": "synthetic",
-        "config": {"workload": "configs[1]: 100k x 512-d f32 descriptor DB, 10k-query batch per GPU, "
+        "config": {"workload": (f"configs[3]: {rows_total} x 512-d f32 descriptor DB, {nq_job}-query batch (whole job), "
+                                if strong else
+                                f"configs[1]: {rows_total} x 512-d f32 descriptor DB, 10k-query batch per GPU, ") +
                                "top-25 exact L2 retrieval (bit-exact vs nanoflann)",
-                   "db_rows": DB_ROWS, "queries_per_step": nq_job, "k": K_NN, "dim": DIM,
+                   "db_rows": rows_total, "queries_per_step": nq_job, "k": K_NN, "dim": DIM,
                    "sharding": shard_txt[r["sharding"]] if world > 1 else "none",
                    "strategy": {1: "exact_scan", 2: "tensor_shortlist"}.get(last_mode, str(last_mode)),
                    "gemm_variant": "cta_pair (GLOC_KNN_PAIR)" if os.environ.get("GLOC_KNN_PAIR", "0") not in ("", "0")
@@ -279,6 +305,14 @@ def run_retrieval(args, rank, world, local_rank):
         "stats": {"fallback_queries": int(st.fallback_queries), "shortlist_rows_per_query":
                   (st.shortlist_rows / max(st.shortlist_queries, 1))},
     }
+    # a sample of the timed step's answers against the brute-force oracle (bit-exact indices and distances)
+    from oracle import pyoracle as po
+    sq, sidx, sd2 = r["sample"]
+    n_chk = min(32, sq.shape[0])
+    ref_idx, ref_d2 = po.knn(db, sq[:n_chk], K_NN, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(sidx[:n_chk], ref_idx) and np.array_equal(sd2[:n_chk].view(np.uint32), ref_d2.view(np.uint32)), \
+        "retrieval: result differs from the oracle"
+    line["stats"]["checked_against_oracle"] = f"{n_chk} queries of rank 0's slice, indices and distances bit-equal"
     if other is not None:
         line["other_sharding"] = {"sharding": shard_txt[other["sharding"]], "value": other["value"],
                                   "ms_per_step": other["ms_per_step"], "e2e_value": other["e2e_value"],
@@ -363,22 +397,30 @@ STREAM_ROWS = 1_000_000
 
 def run_stream(args, rank, world, local_rank):
     """Online localisation as the reference issues it: ONE query per call against a resident
-    1M-descriptor database (configs[3] size on one GPU).  HBM-bound: every step streams the
-    2 GB float32 database once.  N > 1 runs independent replicas (no collective)."""
+    1M-descriptor database (configs[3] size; --rows 5000000 for configs[4]).  HBM-bound: every
+    step streams the float32 database once.  N > 1: rows sharded over the ranks, the same query
+    on every rank, per-GPU streaming scan of the shard, NCCL all-gather of the N x 25-entry lists,
+    merge (gloc_knn_query_sharded, replicated) -- strong scaling of a single query's latency."""
     import torch
     import torch.distributed as dist
 
     import gloc3d_b200 as g
     from gloc3d_b200 import synth
+    from gloc3d_b200.distributed import Comm, query_sharded_device, query_sharded_host, shard_bounds
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     peaks = load_peaks()
     nq = max(1, min(4, args.stream_queries))
-    db = synth.make_descriptors(STREAM_ROWS, DIM, seed=1234, dup_run=DUP_RUN)
-    qs = synth.make_queries(db, 64, seed=5678 + rank, sigma=0.01)
+    rows_total = args.rows or STREAM_ROWS
+    db = synth.make_descriptors_mt(rows_total, DIM, seed=1234, dup_run=max(DUP_RUN, 1))
+    qs = synth.make_queries(db, 64, seed=5678, sigma=0.01)
+    b = shard_bounds(rows_total, world)
+    lo, hi = b[rank], b[rank + 1]
+    comm = Comm.from_torch(local_rank) if world > 1 else None
     ix = g.KnnIndex(DIM, local_rank)
-    ix.set_db(db)
+    ix.set_db(db[lo:hi])
+    ix.set_index_offset(lo)
     q_dev = torch.from_numpy(qs).to(dev)
     q_pin = torch.from_numpy(qs).pin_memory()
     oi_pin = torch.empty((nq, K_NN), dtype=torch.int64).pin_memory()
@@ -391,6 +433,8 @@ def run_stream(args, rank, world, local_rank):
 
     def step(i):
         j = (i * nq) % (64 - nq + 1)
+        if comm is not None:
+            return query_sharded_device(ix, comm, q_dev[j:j + nq], K_NN, True)
         return ix.query_device(q_dev[j:j + nq], K_NN)
 
     for i in range(args.warmup):
@@ -425,7 +469,10 @@ def run_stream(args, rank, world, local_rank):
 
     def e2e_step(i):
         j = (i * nq) % (64 - nq + 1)
-        ix.query_ptr(q_pin[j:j + nq].data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
+        if comm is not None:
+            query_sharded_host(ix, comm, q_pin[j:j + nq].data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr(), True)
+        else:
+            ix.query_ptr(q_pin[j:j + nq].data_ptr(), nq, K_NN, oi_pin.data_ptr(), od_pin.data_ptr())
 
     for i in range(3):
         e2e_step(i)
@@ -440,40 +487,50 @@ def run_stream(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     barrier()
-    j = ((args.steps - 1) * nq) % (64 - nq + 1)
     assert np.array_equal(out[0].cpu().numpy(), oi_pin.numpy()) and \
         np.array_equal(out[1].cpu().numpy(), od_pin.numpy())
+    # the sharded answer is the single-GPU answer: checked against the brute-force oracle on rank 0
     if rank != 0:
         ix.close()
         return None
     avg_ms = dom_ms / max(dom_n, 1)
-    alg_bytes = STREAM_ROWS * DIM * 4 + nq * DIM * 4 + nq * K_NN * 12
+    alg_bytes = (hi - lo) * DIM * 4 + nq * DIM * 4 + nq * K_NN * 12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and rows_total == STREAM_ROWS and world == 1:
         traffic = json.load(open(tp)).get("stream_scan", None)
     line = {
-        "metric": METRIC, "value": nq * world / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+        "metric": METRIC, "value": nq / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"online localisation: {nq} query per call (the reference's call pattern, "
-                               "loop_detector.cpp:42-45) against a resident 1M x 512-d f32 database, "
+                               f"loop_detector.cpp:42-45) against a resident {rows_total} x 512-d f32 database, "
                                "top-25 exact L2 (bit-exact vs nanoflann)",
-                   "db_rows": STREAM_ROWS, "queries_per_step": nq * world, "k": K_NN, "dim": DIM,
-                   "sharding": "none" if world == 1 else f"{world} independent replicas, no collective",
+                   "db_rows": rows_total, "queries_per_step": nq, "k": K_NN, "dim": DIM,
+                   "sharding": "none" if world == 1 else
+                               f"rows/{world}: per-GPU streaming scan of {hi - lo} rows, all-gather of the {world} x {K_NN}-entry "
+                               "lists, merge (gloc_knn_query_sharded, NCCL inside libgloc3d.so)",
                    "strategy": "stream_scan",
-                   "l2": "every step streams the 2 GB database (16x L2); no flush needed"},
-        "e2e": {"value": nq * world / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                   "l2": f"every step streams the {(hi - lo) * DIM * 4 / 1e9:.2f} GB shard (> L2); no flush needed"},
+        "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": nq * DIM * 4 * world, "d2h_bytes_per_step": nq * K_NN * 12 * world},
         "gpu_launches": int(launches), "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "knn_stream_kernel",
+        "roofline": {"bound": "hbm", "kernel": "knn_stream_kernel (per GPU, its shard)",
                      "achieved": alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": (alg_bytes / (avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if avg_ms else None,
                      "traffic": traffic, "peak_source": peaks["source"] + " (copy, read+write)",
                      "kernel_ms": avg_ms, "kernel_launches_timed": dom_n,
-                     "algorithmic_bytes_per_launch": alg_bytes},
+                     "algorithmic_bytes_per_launch": alg_bytes,
+                     "whole_step_hbm_frac": (alg_bytes / (ms * 1e-3) / 1e9) / peaks["hbm_gbs"],
+                     "aggregate_gbs_all_gpus": rows_total * DIM * 4 / (ms * 1e-3) / 1e9},
     }
+    from oracle import pyoracle as po
+    j = ((args.steps - 1) * nq) % (64 - nq + 1)
+    ref_idx, ref_d2 = po.knn(db, qs[j:j + nq], K_NN, nthreads=os.cpu_count() or 1)
+    assert np.array_equal(oi_pin.numpy().view(np.uint64), ref_idx) and \
+        np.array_equal(od_pin.numpy().view(np.uint32), ref_d2.view(np.uint32)), "stream: result differs from the oracle"
+    line["stats"] = {"checked_against_oracle": f"{nq} queries of the last step, indices and distances bit-equal"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_stream(db, qs, args.cpu_budget)
     ix.close()
@@ -512,7 +569,7 @@ def cpu_baseline_stream(db, q, budget_s: float):
 def run_reference_stream(args):
     from gloc3d_b200 import synth
 
-    db = synth.make_descriptors(STREAM_ROWS, DIM, seed=1234, dup_run=DUP_RUN)
+    db = synth.make_descriptors_mt(args.rows or STREAM_ROWS, DIM, seed=1234, dup_run=max(DUP_RUN, 1))
     q = synth.make_queries(db, 64, seed=5678, sigma=0.01)
     cb = None
     for _ in range(max(1, args.warmup)):
@@ -721,10 +778,14 @@ LOC = dict(rows=1_000_000, grids=8192, base_grids=1024, q_per_gpu=64, nx=800, ny
 
 class LocWorld:
     """1M-descriptor database (runs of 8 near-duplicate rows = consecutive frames), 8192 distinct
-    800 x 800 BEV grids (1024 seeded wall/blob layouts x the 8 dihedral variants), row r taken at
-    place r % 8192.  A query revisits the place of a random row: its descriptor is that row plus
-    N(0, 0.01^2) noise, its scan is the place's grid seen from a planted pose (yaw in [-pi, pi),
-    |dx|, |dy| <= 18 m, 20 % dropout, +-1 cell jitter)."""
+    800 x 800 BEV grids (1024 seeded wall/blob layouts x the 8 dihedral variants).  The rows form 8
+    contiguous super-blocks (sessions); block b's rows cycle through places [1024 b, 1024 (b + 1)),
+    so a contiguous row shard of 1/N of the database (N in 1, 2, 4, 8) owns whole place ranges and
+    the world is the same for every N.  A query revisits the place of a random row: its descriptor
+    is that row plus N(0, 0.01^2) noise, its scan is the place's grid seen from a planted pose (yaw
+    in [-pi, pi), |dx|, |dy| <= 18 m, 20 % dropout, +-1 cell jitter)."""
+
+    BLOCKS = 8
 
     def __init__(self, rows=None, grids=None):
         from gloc3d_b200 import synth
@@ -732,7 +793,9 @@ class LocWorld:
         self.synth = synth
         self.rows = rows or LOC["rows"]
         self.n_grids = grids or LOC["grids"]
-        self.n_base = max(1, self.n_grids // 8)
+        assert self.rows % self.BLOCKS == 0 and self.n_grids % self.BLOCKS == 0
+        self.n_base = self.n_grids // self.BLOCKS
+        self.rpb = self.rows // self.BLOCKS
         self.mx, self.my = synth.centered_limits(LOC["nx"], LOC["ny"], LOC["res"])
         self.db = synth.make_descriptors_mt(self.rows, DIM, seed=1234, dup_run=8)
         self.base = [synth.make_bev_grid(LOC["nx"], LOC["ny"], seed=2222 + i) for i in range(self.n_base)]
@@ -748,8 +811,21 @@ class LocWorld:
             g = g.T
         return np.ascontiguousarray(g)
 
-    def grid_of_row(self) -> np.ndarray:
-        return (np.arange(self.rows, dtype=np.int64) % self.n_grids).astype(np.int32)
+    def place_of_rows(self, r) -> np.ndarray:
+        r = np.asarray(r, np.int64)
+        blk = r // self.rpb
+        return (blk * self.n_base + (r - blk * self.rpb) % self.n_base).astype(np.int64)
+
+    def grid_of_row(self, lo=0, hi=None) -> np.ndarray:
+        """Row -> grid table of the shard [lo, hi) in LOCAL grid ids (the shard's first place = 0)."""
+        hi = self.rows if hi is None else hi
+        return (self.place_of_rows(np.arange(lo, hi)) - (lo // self.rpb) * self.n_base).astype(np.int32)
+
+    def shard(self, rank, world):
+        """(first row, end row, first place, end place) of rank's contiguous shard."""
+        assert self.BLOCKS % world == 0, "the sharded bench wants 1, 2, 4 or 8 GPUs"
+        b0, b1 = rank * self.BLOCKS // world, (rank + 1) * self.BLOCKS // world
+        return b0 * self.rpb, b1 * self.rpb, b0 * self.n_base, b1 * self.n_base
 
     def batch(self, b: int, nq: int):
         """Query batch b: (descriptors [nq, 512], scans list, rows)."""
@@ -759,7 +835,7 @@ class LocWorld:
         scans = []
         for i, r in enumerate(rows):
             yaw, dx, dy = rng.uniform(-np.pi, np.pi), rng.uniform(-18, 18), rng.uniform(-18, 18)
-            scans.append(self.synth.planted_scan(self.grid(int(r) % self.n_grids), LOC["res"], self.mx, self.my,
+            scans.append(self.synth.planted_scan(self.grid(int(self.place_of_rows(r))), LOC["res"], self.mx, self.my,
                                                  yaw, dx, dy, dropout=0.2, jitter_cells=1.0, seed=3333 + 1000 * b + i))
         return q, scans, rows
 
@@ -788,22 +864,29 @@ def run_localize(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     peaks = load_peaks()
     W = LocWorld(args.loc_rows, args.loc_grids)
-    nq = args.loc_queries
+    nq = args.loc_queries * world        # queries of the whole job per step (weak scaling)
+    lo, hi, p0, p1 = W.shard(rank, world)
+    comm = None
+    if world > 1:
+        from gloc3d_b200.distributed import Comm
+
+        comm = Comm.from_torch(local_rank)
     ix = g.KnnIndex(DIM, local_rank)
-    ix.set_db(W.db)
+    ix.set_db(W.db[lo:hi])
+    ix.set_index_offset(lo)
     st = g.CsmStore(local_rank)
     t0 = time.perf_counter()
-    for gid in range(W.n_grids):
+    for gid in range(p0, p1):            # this rank's rows and their places' grids only
         st.add_grid_u8(W.grid(gid), LOC["res"], W.mx, W.my)
     t_add = time.perf_counter() - t0
     loc = g.Localizer(ix, st)
-    loc.set_row_grids(W.grid_of_row())
+    loc.set_row_grids(W.grid_of_row(lo, hi))
     prm = loc.params(LOC["k"], LOC["n_lin"], LOC["n_ang"], LOC["step"], args.verify_depth or LOC["depth"],
                      LOC["min_score"], g.LOC_FIRST_MATCH if args.loc_policy == "first" else g.LOC_VERIFY_ALL)
-    n_batches = min(LOC["batches"], args.steps + args.warmup)
+    n_batches = min(LOC["batches"] if world == 1 else 6, args.steps + args.warmup)
     batches = []
-    for b in range(n_batches):                      # every rank works on its own query batches
-        q, scans, rows = W.batch(b * world + rank, nq)
+    for b in range(n_batches):                      # N > 1: the same batches on every rank (collective call)
+        q, scans, rows = W.batch(b, nq)
         pts, offs = g.Localizer.pack_scans(scans)
         batches.append(dict(q=q, pts=pts, offs=offs, rows=rows, scans=scans,
                             q_dev=torch.from_numpy(q).to(dev), pts_dev=torch.from_numpy(pts).to(dev),
@@ -827,7 +910,14 @@ def run_localize(args, rank, world, local_rank):
 
     def step(i, host=False, keep=False):
         B = batches[i % n_batches]
-        if host:
+        if comm is not None:
+            if host:
+                loc.localize_sharded_ptr(comm, B["q_pin"].data_ptr(), nq, B["pts_pin"].data_ptr(), B["offs"], prm,
+                                         oi.data_ptr(), od.data_ptr(), res, cand if keep else None)
+            else:
+                loc.localize_sharded_ptr(comm, B["q_dev"].data_ptr(), nq, B["pts_dev"].data_ptr(), B["offs"], prm,
+                                         oi.data_ptr(), od.data_ptr(), res, cand if keep else None, device=True)
+        elif host:
             loc.localize_ptr(B["q_pin"].data_ptr(), nq, B["pts_pin"].data_ptr(), B["offs"], prm, oi.data_ptr(),
                              od.data_ptr(), res, cand if keep else None)
         else:
@@ -842,6 +932,7 @@ def run_localize(args, rank, world, local_rank):
     st.set_profiling(True)
     ix.set_profiling(True)
     l0 = st.stats().kernel_launches + ix.stats().kernel_launches + loc.stats().kernel_launches
+    pv0 = loc.stats().pairs_verified
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -859,6 +950,7 @@ def run_localize(args, rank, world, local_rank):
     st.set_profiling(False)
     ix.set_profiling(False)
     launches = st.stats().kernel_launches + ix.stats().kernel_launches + loc.stats().kernel_launches - l0
+    pairs_verified = loc.stats().pairs_verified - pv0
     ms_total = reduce_ranks(wall_ms, dist.ReduceOp.MAX)        # host clock >= device events (conservative)
     dev_ms = reduce_ranks(total_ms, dist.ReduceOp.MAX)
     for i in range(hold_steps(ms_total / args.steps)):
@@ -883,15 +975,16 @@ def run_localize(args, rank, world, local_rank):
     grid_bytes, ws_bytes = st.store_bytes()
     if rank != 0:
         return None
-    nq_job = nq * world
+    nq_job = nq
     ms = ms_total / args.steps
     located = sum(r[0] for r in got_res)
-    # did the query find its own place?  (rows r and r' share a place iff r % grids == r' % grids)
-    right_place = sum(1 for r, row in zip(got_res, last["rows"]) if r[0] and int(r[2]) % W.n_grids == int(row) % W.n_grids)
+    # did the query find its own place?
+    right_place = sum(1 for r, row in zip(got_res, last["rows"])
+                      if r[0] and int(W.place_of_rows(int(r[2]))) == int(W.place_of_rows(int(row))))
     P = float(np.mean([s.shape[0] for b in batches for s in b["scans"]]))
     side = (2 * LOC["n_lin"]) // (1 << (LOC["depth"] - 1)) + 1
     S = 2 * LOC["n_ang"] + 1
-    pairs_per_launch = nq * LOC["k"] * args.steps / max(coarse_n, 1)
+    pairs_per_launch = pairs_verified / max(coarse_n, 1)
     lds_per_launch = S * side * P * pairs_per_launch            # one LDS.64 per (rotation, point, candidate row)
     avg_coarse = coarse_ms / max(coarse_n, 1)
     lsu = {}
@@ -920,7 +1013,7 @@ def run_localize(args, rank, world, local_rank):
                                    "coarse_scorer": coarse_ms / args.steps},
             "retrieval_gemm": {"bound": "tensor", "kernel": "knn_shortlist_gemm_kernel",
                                "kernel_ms": gemm_ms / max(gemm_n, 1), "launches": gemm_n,
-                               "achieved_tflops": (2.0 * nq * W.rows * DIM * args.steps / max(gemm_n, 1)) /
+                               "achieved_tflops": (2.0 * nq * (hi - lo) * DIM * args.steps / max(gemm_n, 1)) /
                                                   (gemm_ms / max(gemm_n, 1) * 1e-3) / 1e12 if gemm_ms else None,
                                "peak_tflops": peaks["bf16_tflops"],
                                "note": "64 queries fill half of one 128-row query tile: this launch is latency-, "
@@ -930,10 +1023,13 @@ def run_localize(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp16 tensor shortlist + f32 exact re-rank; u8/bit sums -> f32 score", "data": "synthetic",
         "config": loc_config(W, nq_job, "none" if world == 1 else
-                             f"{world} replicas: database + grids replicated, every rank its own {nq} queries"),
+                             f"rows/{world}: every rank holds {hi - lo} descriptor rows and the {p1 - p0} map grids of their "
+                             f"places; local top-k -> NCCL all-gather + merge; a (query, candidate) pair is verified by the "
+                             f"rank that owns the candidate; all-reduce of the 8-byte pair results (gloc_loc_localize_sharded)"),
         "e2e": {"value": nq_job / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(last["q"].nbytes + last["pts"].nbytes) * world,
-                "d2h_bytes_per_step": int(nq * LOC["k"] * 12 + nq * LOC["k"] * 8) * world},
+                "d2h_bytes_per_step": int(nq * LOC["k"] * 12 + nq * LOC["k"] * 8) * world,
+                "note": "N > 1: the batch (descriptors 2 KB + scan ~52 KB per query) is uploaded by every rank"},
         "gpu_launches": launches, "clocks": clk, "roofline": roof,
         "timing": "value: host clock around K synchronous C-ABI calls between device synchronisations "
                   f"(device events on the library's stream: {dev_ms / args.steps:.3f} ms/step)",
@@ -946,6 +1042,8 @@ def run_localize(args, rank, world, local_rank):
     loc.close()
     st.close()
     ix.close()
+    if comm is not None:
+        comm.close()
     return line
 
 
@@ -974,16 +1072,29 @@ def cpu_baseline_localize(W, B, gpu_idx, gpu_cand, budget_s, check, tree=None):
         ref_idx, ref_d2 = po.knn(W.db, B["q"][:n_r], k, nthreads=cores)
     t_r = time.perf_counter() - t0
     # verification sample: the first candidates of the first queries (the planted place is usually among them)
-    n_v = int(max(cores, min(n_r * k, (budget_s / 0.7) * cores)))
+    n_v = int(max(cores, min(n_r * k, (budget_s / 1.5) * cores)))
     n_v = min(n_r * k, n_v // cores * cores)
     per_q = max(1, n_v // n_r)
     sel = [(qi, c) for qi in range(n_r) for c in range(per_q)][:n_v]
-    grids = [W.grid(int(ref_idx[qi, c]) % W.n_grids) for qi, c in sel]
-    t0 = time.perf_counter()
-    out = po.csm_match_batch(grids, LOC["res"], W.mx, W.my, LOC["depth"], [B["scans"][qi] for qi, _ in sel],
-                             [(0, 0, 0)] * len(sel), LOC["n_lin"], LOC["n_ang"], LOC["step"], LOC["min_score"], 0, cores)
-    t_v = time.perf_counter() - t0
+    grids = [W.grid(int(W.place_of_rows(int(ref_idx[qi, c])))) for qi, c in sel]
+    scans_sel = [B["scans"][qi] for qi, _ in sel]
+    if po.have_csm_ref():
+        # the reference's own FastCorrelativeScanMatcher2D (registration/2d compiled unmodified), one
+        # matcher -- hence one PrecomputationGridStack2D -- per (query, candidate) pair
+        cells = [W.synth.level1_to_cells(gr) for gr in grids]
+        t0 = time.perf_counter()
+        out = po.ref_csm_match_batch(cells, LOC["res"], W.mx, W.my, LOC["depth"], scans_sel, [(0, 0, 0)] * len(sel),
+                                     LOC["n_lin"], LOC["n_ang"], LOC["step"], LOC["min_score"], cores)
+        t_v = time.perf_counter() - t0
+        vkind = "reference"
+    else:
+        t0 = time.perf_counter()
+        out = po.csm_match_batch(grids, LOC["res"], W.mx, W.my, LOC["depth"], scans_sel, [(0, 0, 0)] * len(sel),
+                                 LOC["n_lin"], LOC["n_ang"], LOC["step"], LOC["min_score"], 0, cores)
+        t_v = time.perf_counter() - t0
+        vkind = "port"
     checked = None
+    same_pose = 0
     if check:
         # nanoflann's order among exactly equal distances is traversal order; ours is (d2, idx)
         exact = po.knn(W.db, B["q"][:n_r], k, nthreads=cores)[0] if tree is not None else ref_idx
@@ -993,14 +1104,18 @@ def cpu_baseline_localize(W, B, gpu_idx, gpu_cand, budget_s, check, tree=None):
             r = gpu_cand[qi * k + c]
             assert r[0] == o.found, f"found flag differs at query {qi} candidate {c}"
             if o.found:
-                assert r[2:5] == (o.scan_index, o.x_offset, o.y_offset) and np.float32(r[1]) == np.float32(o.score) \
-                    and r[5:8] == (o.pose_x, o.pose_y, o.pose_yaw), f"pose differs at query {qi} candidate {c}"
-        checked = {"queries": n_r, "pairs": len(sel), "matched_pairs": int(sum(o.found for o in out))}
+                assert np.float32(r[1]) == np.float32(o.score), f"score differs at query {qi} candidate {c}"
+                if vkind == "port" or r[2:5] == (o.scan_index, o.x_offset, o.y_offset):   # reference: ties are unordered
+                    assert r[5:8] == (o.pose_x, o.pose_y, o.pose_yaw), f"pose differs at query {qi} candidate {c}"
+                    same_pose += 1
+        checked = {"queries": n_r, "pairs": len(sel), "matched_pairs": int(sum(o.found for o in out)),
+                   "matched_pairs_with_identical_pose": same_pose}
     v = 1.0 / (t_r / n_r + k * t_v / len(sel))
-    return {"value": v, "unit": UNIT, "cores": cores, "kind": kind + " (retrieval) + port (verification)",
+    return {"value": v, "unit": UNIT, "cores": cores,
+            "kind": "reference" if (kind, vkind) == ("reference", "reference") else f"{kind} (retrieval) + {vkind} (verification)",
             "sample": f"{n_r} queries of the step against the full {W.rows}-row DB through nanoflann (KD-tree, leaf 10, "
                       f"built once in {build_s:.1f} s, not counted): {t_r:.2f} s; {len(sel)} of their (query, candidate) "
-                      f"pairs through oracle/csm_oracle.c: {t_v:.2f} s; {cores} threads in both stages; "
+                      f"pairs through {'the reference FastCorrelativeScanMatcher2D (oracle/_ref/libcsm_ref.so)' if vkind == 'reference' else 'oracle/csm_oracle.c'}: {t_v:.2f} s; {cores} threads in both stages; "
                       f"q/s = 1 / (t_r/{n_r} + {k} * t_v/{len(sel)})",
             "retrieval_qps": n_r / t_r, "verification_pairs_per_s": len(sel) / t_v,
             "parity_checked_against_gpu": checked}, tree
@@ -1213,10 +1328,14 @@ def main():
                          "of evaluation, stop at the first candidate that matches")
     ap.add_argument("--stream-queries", type=int, default=1, help="queries per call of the stream workload (1..4)")
     ap.add_argument("--mode", default="auto", choices=["auto", "exact", "shortlist"])
-    ap.add_argument("--sharding", default="queries", choices=["queries", "db"],
+    ap.add_argument("--sharding", default="db", choices=["queries", "db"],
                     help="N > 1: 'queries' = DB replicated, queries split (no collective); 'db' = rows "
                          "sharded + all-gather top-k + merge (north-star protocol).  Both are measured; "
                          "this picks which one is the headline value.")
+    ap.add_argument("--rows", type=int, default=0, help="retrieval: database rows (default 100k; configs[3]: 1000000)")
+    ap.add_argument("--queries", type=int, default=0,
+                    help="retrieval: total queries per step for the whole job (strong scaling; configs[3]: 100000); "
+                         "default 10k per GPU (weak scaling)")
     ap.add_argument("--verify-queries", type=int, default=8, help="queries per GPU per step (verify)")
     ap.add_argument("--verify-depth", type=int, default=0,
                     help="internal branch-and-bound depth of the GPU verifier (0 = the reference's 5); "

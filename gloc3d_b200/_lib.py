@@ -111,6 +111,16 @@ SIGNATURES = {
     "gloc_csm_add_grid_u8": (_i, [_vp, _vp, _i, _i, _d, _d, _d, _ip]),
     "gloc_csm_num_grids": (_i, [_vp]),
     "gloc_csm_store_bytes": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "gloc_comm_unique_id": (_i, [_vp, _sz]),
+    "gloc_comm_create": (_i, [C.POINTER(_vp), _vp, _i, _i, _i]),
+    "gloc_comm_create_local": (_i, [C.POINTER(_vp), _i, _ip]),
+    "gloc_comm_destroy": (None, [_vp]),
+    "gloc_comm_rank": (_i, [_vp]),
+    "gloc_comm_size": (_i, [_vp]),
+    "gloc_comm_nccl_version": (_i, []),
+    "gloc_knn_query_sharded": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _i]),
+    "gloc_knn_query_sharded_device": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _i, _vp]),
+    "gloc_loc_localize_sharded": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(LocParams), _vp, _vp, _vp, _vp, _i]),
     "gloc_loc_create": (_i, [C.POINTER(_vp), _vp, _vp]),
     "gloc_loc_destroy": (None, [_vp]),
     "gloc_loc_set_row_grids": (_i, [_vp, _vp, _sz]),

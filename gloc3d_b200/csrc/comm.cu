@@ -1,0 +1,195 @@
+// comm.cu -- multi-GPU plumbing behind the C ABI: NCCL communicators owned by libgloc3d.so, so
+// that a C++ host (the reference is a single C++ process) can shard the database over the GPUs of
+// one box without Python.  The reference has no distributed code at all; this is
+// the B200 design for its north-star scaling configs.
+//
+// NCCL is resolved at run time (dlopen of libnccl.so.2): a process that already carries an NCCL
+// (PyTorch bundles its own) shares that copy, a plain C++ host gets the system library, and
+// single-GPU users never load it.
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only; every call goes through the table below
+
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+#include "comm.cuh"
+
+namespace gloc {
+
+namespace {
+
+struct NcclApi {
+  bool ok = false;
+  std::string why;
+  ncclResult_t (*GetVersion)(int*) = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+};
+
+NcclApi& api() {
+  static NcclApi A;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+      A.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+      return;
+    }
+    bool all = true;
+    auto sym = [&](const char* name) {
+      void* p = dlsym(h, name);
+      if (!p) {
+        all = false;
+        A.why = std::string("libnccl lacks ") + name;
+      }
+      return p;
+    };
+    A.GetVersion = (decltype(A.GetVersion))sym("ncclGetVersion");
+    A.GetUniqueId = (decltype(A.GetUniqueId))sym("ncclGetUniqueId");
+    A.CommInitRank = (decltype(A.CommInitRank))sym("ncclCommInitRank");
+    A.CommInitAll = (decltype(A.CommInitAll))sym("ncclCommInitAll");
+    A.CommDestroy = (decltype(A.CommDestroy))sym("ncclCommDestroy");
+    A.GetErrorString = (decltype(A.GetErrorString))sym("ncclGetErrorString");
+    A.AllGather = (decltype(A.AllGather))sym("ncclAllGather");
+    A.AllReduce = (decltype(A.AllReduce))sym("ncclAllReduce");
+    A.Send = (decltype(A.Send))sym("ncclSend");
+    A.Recv = (decltype(A.Recv))sym("ncclRecv");
+    A.GroupStart = (decltype(A.GroupStart))sym("ncclGroupStart");
+    A.GroupEnd = (decltype(A.GroupEnd))sym("ncclGroupEnd");
+    A.ok = all;
+  });
+  return A;
+}
+
+int nccl_fail(const char* what, ncclResult_t r) {
+  return fail(GLOC_ERR_CUDA, std::string(what) + ": " + (api().GetErrorString ? api().GetErrorString(r) : "NCCL error"));
+}
+
+#define GLOC_NCCL_TRY(expr)                                   \
+  do {                                                        \
+    ncclResult_t _r = (expr);                                 \
+    if (_r != ncclSuccess) return nccl_fail(#expr, _r);       \
+  } while (0)
+
+}  // namespace
+
+int comm_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s) {
+  GLOC_NCCL_TRY(api().AllGather(send, recv, bytes_per_rank, ncclUint8, (ncclComm_t)c->nccl, s));
+  return GLOC_OK;
+}
+
+int comm_all_reduce_max_u64(gloc_comm* c, const void* send, void* recv, size_t count, cudaStream_t s) {
+  GLOC_NCCL_TRY(api().AllReduce(send, recv, count, ncclUint64, ncclMax, (ncclComm_t)c->nccl, s));
+  return GLOC_OK;
+}
+
+// rank r receives block r of every rank's `send` ([size][bytes_per_block]) into recv[src]
+int comm_all_to_all(gloc_comm* c, const void* send, void* recv, size_t bytes_per_block, cudaStream_t s) {
+  GLOC_NCCL_TRY(api().GroupStart());
+  for (int r = 0; r < c->size; ++r) {
+    ncclResult_t a = api().Send((const char*)send + (size_t)r * bytes_per_block, bytes_per_block, ncclUint8, r,
+                                (ncclComm_t)c->nccl, s);
+    ncclResult_t b = api().Recv((char*)recv + (size_t)r * bytes_per_block, bytes_per_block, ncclUint8, r,
+                                (ncclComm_t)c->nccl, s);
+    if (a != ncclSuccess || b != ncclSuccess) {
+      api().GroupEnd();
+      return nccl_fail("ncclSend/ncclRecv", a != ncclSuccess ? a : b);
+    }
+  }
+  GLOC_NCCL_TRY(api().GroupEnd());
+  return GLOC_OK;
+}
+
+}  // namespace gloc
+
+using namespace gloc;
+
+extern "C" {
+
+int gloc_comm_unique_id(uint8_t* id, size_t capacity) {
+  if (!id || capacity < GLOC_COMM_ID_BYTES) return fail(GLOC_ERR_INVALID, "gloc_comm_unique_id: need a 128-byte buffer");
+  if (!api().ok) return fail(GLOC_ERR_CUDA, "gloc_comm_unique_id: " + api().why);
+  static_assert(sizeof(ncclUniqueId) == GLOC_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId u;
+  GLOC_NCCL_TRY(api().GetUniqueId(&u));
+  std::memcpy(id, &u, sizeof(u));
+  return GLOC_OK;
+}
+
+int gloc_comm_create(gloc_comm** out, const uint8_t* id, int n_ranks, int rank, int device) {
+  if (!out) return fail(GLOC_ERR_INVALID, "gloc_comm_create: out is null");
+  *out = nullptr;
+  if (!id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(GLOC_ERR_INVALID, "gloc_comm_create: bad argument");
+  if (!api().ok) return fail(GLOC_ERR_CUDA, "gloc_comm_create: " + api().why);
+  DeviceGuard g(device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_comm_create: cudaSetDevice failed");
+  gloc_comm* c = new (std::nothrow) gloc_comm;
+  if (!c) return fail(GLOC_ERR_NOMEM, "gloc_comm_create: out of host memory");
+  ncclUniqueId u;
+  std::memcpy(&u, id, sizeof(u));
+  ncclComm_t comm = nullptr;
+  ncclResult_t r = api().CommInitRank(&comm, n_ranks, u, rank);
+  if (r != ncclSuccess) {
+    delete c;
+    return nccl_fail("ncclCommInitRank", r);
+  }
+  c->nccl = comm;
+  c->rank = rank;
+  c->size = n_ranks;
+  c->device = device;
+  *out = c;
+  return GLOC_OK;
+}
+
+int gloc_comm_create_local(gloc_comm** out, int n_devices, const int* devices) {
+  if (!out || n_devices < 1) return fail(GLOC_ERR_INVALID, "gloc_comm_create_local: bad argument");
+  for (int i = 0; i < n_devices; ++i) out[i] = nullptr;
+  if (!api().ok) return fail(GLOC_ERR_CUDA, "gloc_comm_create_local: " + api().why);
+  std::vector<int> devs((size_t)n_devices);
+  for (int i = 0; i < n_devices; ++i) devs[i] = devices ? devices[i] : i;
+  std::vector<ncclComm_t> comms((size_t)n_devices, nullptr);
+  GLOC_NCCL_TRY(api().CommInitAll(comms.data(), n_devices, devs.data()));
+  for (int i = 0; i < n_devices; ++i) {
+    gloc_comm* c = new (std::nothrow) gloc_comm;
+    if (!c) return fail(GLOC_ERR_NOMEM, "gloc_comm_create_local: out of host memory");
+    c->nccl = comms[i];
+    c->rank = i;
+    c->size = n_devices;
+    c->device = devs[i];
+    out[i] = c;
+  }
+  return GLOC_OK;
+}
+
+void gloc_comm_destroy(gloc_comm* c) {
+  if (!c) return;
+  if (c->nccl && api().ok) {
+    DeviceGuard g(c->device);
+    api().CommDestroy((ncclComm_t)c->nccl);
+  }
+  delete c;
+}
+
+int gloc_comm_rank(const gloc_comm* c) { return c ? c->rank : -1; }
+int gloc_comm_size(const gloc_comm* c) { return c ? c->size : 0; }
+
+int gloc_comm_nccl_version(void) {
+  int v = 0;
+  if (!api().ok || api().GetVersion(&v) != ncclSuccess) return 0;
+  return v;
+}
+
+}  // extern "C"

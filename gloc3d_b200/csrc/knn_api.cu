@@ -8,6 +8,7 @@
 #include <new>
 #include <vector>
 
+#include "comm.cuh"
 #include "knn_kernels.cuh"
 #include "knn_shortlist.cuh"
 
@@ -81,6 +82,7 @@ struct gloc_knn_index {
   DevBuf partial;                 // exact-scan per-range lists
   DevBuf flag;                    // streaming scan: merge-overflow flag
   DevBuf stage_q, stage_idx, stage_d2;
+  DevBuf sh_allq, sh_lidx, sh_ld2, sh_gidx, sh_gd2;   // row-sharded search: gathered queries, per-shard lists
   ShortlistState* sl = nullptr;   // tensor-shortlist state (bf16 copy, norms, workspaces)
   gloc_knn_stats stats{};
   EventProfiler prof;
@@ -282,6 +284,7 @@ void gloc_knn_destroy(gloc_knn_index* ix) {
   ix->stage_q.release();
   ix->stage_idx.release();
   ix->stage_d2.release();
+  for (DevBuf* b : {&ix->sh_allq, &ix->sh_lidx, &ix->sh_ld2, &ix->sh_gidx, &ix->sh_gd2}) b->release();
   shortlist_destroy(ix->sl);
   delete ix;
 }
@@ -480,6 +483,86 @@ int gloc_knn_merge_topk_device(const uint64_t* d_idx, const float* d_d2, size_t 
   if (!guard.ok) return fail(GLOC_ERR_CUDA, "gloc_knn_merge_topk_device: cudaSetDevice failed");
   GLOC_CUDA_TRY(launch_knn_merge_pairs(d_idx, d_d2, (int)g, (int)nq, (int)k, d_out_idx, d_out_d2,
                                        (cudaStream_t)stream));
+  return GLOC_OK;
+}
+
+// Row-sharded exact top-k (BASELINE configs[3]): every rank holds rows
+// [offset, offset + n) and calls this collectively.
+//   replicated == 0: every rank passes ITS slice of the batch (nq_local queries, the same count on
+//     every rank).  Queries are all-gathered over NVLink (one PCIe upload per query instead of one
+//     per rank), every rank searches the whole batch on its shard, the local top-k lists go
+//     straight to the rank that owns the query (all-to-all), which merges its N lists (K4): the
+//     merge and the result download are sharded as well.  Output: this rank's slice.
+//   replicated != 0: every rank passes the same nq queries (online localisation: one query);
+//     local search, all-gather of the lists, merge on every rank.  Output: the whole result.
+// Results are identical to a single-GPU search of the whole database: same (d2, idx) order.
+int gloc_knn_query_sharded_device(gloc_knn_index* ix, gloc_comm* comm, const float* d_q, size_t nq,
+                                  size_t k, uint64_t* d_out_idx, float* d_out_d2, int replicated,
+                                  void* stream_v) {
+  if (!ix || !comm) return fail(GLOC_ERR_INVALID, "gloc_knn_query_sharded: null argument");
+  if (nq == 0) return GLOC_OK;
+  if (!d_q || !d_out_idx || !d_out_d2) return fail(GLOC_ERR_INVALID, "gloc_knn_query_sharded: null buffer");
+  if (comm->device != ix->device) return fail(GLOC_ERR_INVALID, "gloc_knn_query_sharded: communicator and index live on different devices");
+  if (comm->size == 1) return gloc_knn_query_device(ix, d_q, nq, k, d_out_idx, d_out_d2, stream_v);
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_knn_query_sharded: cudaSetDevice failed");
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  const size_t N = (size_t)comm->size, dim = ix->dim;
+  int rc;
+  if (replicated) {
+    GLOC_CUDA_TRY(ix->sh_lidx.reserve(nq * k * sizeof(uint64_t)));
+    GLOC_CUDA_TRY(ix->sh_ld2.reserve(nq * k * sizeof(float)));
+    GLOC_CUDA_TRY(ix->sh_gidx.reserve(N * nq * k * sizeof(uint64_t)));
+    GLOC_CUDA_TRY(ix->sh_gd2.reserve(N * nq * k * sizeof(float)));
+    rc = gloc_knn_query_device(ix, d_q, nq, k, (uint64_t*)ix->sh_lidx.p, (float*)ix->sh_ld2.p, stream);
+    if (rc != GLOC_OK) return rc;
+    rc = comm_all_gather(comm, ix->sh_lidx.p, ix->sh_gidx.p, nq * k * sizeof(uint64_t), stream);
+    if (rc != GLOC_OK) return rc;
+    rc = comm_all_gather(comm, ix->sh_ld2.p, ix->sh_gd2.p, nq * k * sizeof(float), stream);
+    if (rc != GLOC_OK) return rc;
+  } else {
+    const size_t nq_all = N * nq;
+    GLOC_CUDA_TRY(ix->sh_allq.reserve(nq_all * dim * sizeof(float)));
+    GLOC_CUDA_TRY(ix->sh_lidx.reserve(nq_all * k * sizeof(uint64_t)));
+    GLOC_CUDA_TRY(ix->sh_ld2.reserve(nq_all * k * sizeof(float)));
+    GLOC_CUDA_TRY(ix->sh_gidx.reserve(nq_all * k * sizeof(uint64_t)));
+    GLOC_CUDA_TRY(ix->sh_gd2.reserve(nq_all * k * sizeof(float)));
+    rc = comm_all_gather(comm, d_q, ix->sh_allq.p, nq * dim * sizeof(float), stream);
+    if (rc != GLOC_OK) return rc;
+    rc = gloc_knn_query_device(ix, (const float*)ix->sh_allq.p, nq_all, k, (uint64_t*)ix->sh_lidx.p,
+                               (float*)ix->sh_ld2.p, stream);
+    if (rc != GLOC_OK) return rc;
+    // block r of my lists = the queries rank r owns; I receive my queries' lists from every shard,
+    // laid out [shard][nq][k]: exactly what the merge takes
+    rc = comm_all_to_all(comm, ix->sh_lidx.p, ix->sh_gidx.p, nq * k * sizeof(uint64_t), stream);
+    if (rc != GLOC_OK) return rc;
+    rc = comm_all_to_all(comm, ix->sh_ld2.p, ix->sh_gd2.p, nq * k * sizeof(float), stream);
+    if (rc != GLOC_OK) return rc;
+  }
+  GLOC_CUDA_TRY(launch_knn_merge_pairs((const uint64_t*)ix->sh_gidx.p, (const float*)ix->sh_gd2.p, (int)N,
+                                       (int)nq, (int)k, d_out_idx, d_out_d2, stream));
+  ix->stats.kernel_launches++;
+  return GLOC_OK;
+}
+
+// Same with HOST buffers: upload of this rank's queries, download of this rank's results.
+int gloc_knn_query_sharded(gloc_knn_index* ix, gloc_comm* comm, const float* q, size_t nq, size_t k,
+                           uint64_t* out_idx, float* out_d2, int replicated) {
+  if (!ix || !comm) return fail(GLOC_ERR_INVALID, "gloc_knn_query_sharded: null argument");
+  if (nq == 0) return GLOC_OK;
+  if (!q || !out_idx || !out_d2) return fail(GLOC_ERR_INVALID, "gloc_knn_query_sharded: null buffer");
+  DeviceGuard g(ix->device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_knn_query_sharded: cudaSetDevice failed");
+  GLOC_CUDA_TRY(ix->stage_q.reserve(nq * ix->dim * sizeof(float)));
+  GLOC_CUDA_TRY(ix->stage_idx.reserve(nq * k * sizeof(uint64_t)));
+  GLOC_CUDA_TRY(ix->stage_d2.reserve(nq * k * sizeof(float)));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(ix->stage_q.p, q, nq * ix->dim * sizeof(float), cudaMemcpyHostToDevice, ix->stream));
+  int rc = gloc_knn_query_sharded_device(ix, comm, (const float*)ix->stage_q.p, nq, k, (uint64_t*)ix->stage_idx.p,
+                                         (float*)ix->stage_d2.p, replicated, ix->stream);
+  if (rc != GLOC_OK) return rc;
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_idx, ix->stage_idx.p, nq * k * sizeof(uint64_t), cudaMemcpyDeviceToHost, ix->stream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_d2, ix->stage_d2.p, nq * k * sizeof(float), cudaMemcpyDeviceToHost, ix->stream));
+  GLOC_CUDA_TRY(cudaStreamSynchronize(ix->stream));
   return GLOC_OK;
 }
 

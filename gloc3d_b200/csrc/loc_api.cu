@@ -13,6 +13,7 @@
 #include <new>
 #include <vector>
 
+#include "comm.cuh"
 #include "csm_store.cuh"
 
 namespace gloc {
@@ -55,7 +56,7 @@ struct gloc_localizer {
   gloc_csm_store* csm = nullptr;
   int device = 0;
   std::vector<int32_t> h_map;   // row -> grid (empty: identity, the reference's db_grids_[db_idx])
-  CsmBuf d_map, d_q, d_idx, d_d2, d_qs, d_pairs, d_pts;
+  CsmBuf d_map, d_q, d_idx, d_d2, d_qs, d_pairs, d_pts, d_keys;
   gloc_loc_stats stats{};
   EventProfiler prof_total, prof_retrieval;   // device-side spans on the store's stream
 };
@@ -231,6 +232,164 @@ int loc_run(gloc_localizer* L, const float* d_queries, size_t nq, const float* d
   return GLOC_OK;
 }
 
+// ---- the same path over a row-sharded database: every rank holds the descriptors
+// of rows [offset, offset + n) AND their map grids.  Collective call, same arguments on every rank:
+//   1. every rank searches the whole batch on its shard; the local top-k lists are all-gathered
+//      and merged on every rank (gloc_knn_query_sharded_device, replicated queries);
+//   2. a (query, candidate) pair is verified by the rank that owns the candidate's row -- its grid
+//      lives there; the query's scan is already everywhere;
+//   3. one all-reduce (max over ranks of the 64-bit result keys, 0 where a rank does not own the
+//      pair) gives every rank every pair's result; decode and the per-query choice are replicated.
+// GLOC_LOC_FIRST_MATCH runs the same three steps per wave of candidates.
+int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, size_t nq, const float* d_pts,
+                    const int64_t* scan_offsets, const double* init_xyyaw, const gloc_loc_params* P,
+                    uint64_t* out_idx, float* out_d2, gloc_csm_result* cand_results, gloc_loc_result* results) {
+  gloc_csm_store* st = L->csm;
+  const int k = P->k;
+  if (k < 1 || k > 128) return fail(GLOC_ERR_RANGE, "gloc_loc_localize_sharded: k must be in [1, 128]");
+  if (P->depth < 1 || P->depth > kCsmMaxDepth) return fail(GLOC_ERR_RANGE, "gloc_loc_localize_sharded: depth must be in [1, 8]");
+  if (P->n_lin < 0 || P->n_ang < 0) return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: negative window");
+  const long long S = 2ll * P->n_ang + 1, W = 2ll * P->n_lin + 1;
+  if (S * W * W >= (1ll << 32) || S > 65535) return fail(GLOC_ERR_RANGE, "gloc_loc_localize_sharded: search window too large");
+  if (P->policy != GLOC_LOC_VERIFY_ALL && P->policy != GLOC_LOC_FIRST_MATCH)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: unknown policy");
+  if (nq * (size_t)k > (size_t)INT32_MAX) return fail(GLOC_ERR_RANGE, "gloc_loc_localize_sharded: too many pairs in one call");
+  const size_t n_local = gloc_knn_size(L->knn), n_grids = st->recs.size();
+  if (n_grids == 0) return fail(GLOC_ERR_NOT_BUILT, "gloc_loc_localize_sharded: the grid store of this shard is empty");
+  if (L->h_map.empty() ? n_local > n_grids : n_local > L->h_map.size())
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: shard rows without a map grid");
+  const double resolution = st->recs[0].resolution;   // one resolution per map (the decode is replicated)
+  const int64_t total_pts = scan_offsets[nq];
+  std::vector<QueryScan> hq(nq);
+  for (size_t q = 0; q < nq; ++q) {
+    const int64_t b = scan_offsets[q], e = scan_offsets[q + 1];
+    if (b < 0 || e <= b || e > total_pts || e - b > INT32_MAX)
+      return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: bad scan offsets (every query needs a non-empty scan)");
+    const double* in = init_xyyaw ? init_xyyaw + 3 * q : nullptr;
+    const float ha = 0.5f * (float)(in ? in[2] : 0.0);
+    hq[q].pt_begin = b;
+    hq[q].n_pts = (int)(e - b);
+    hq[q].w0 = std::cos(ha);
+    hq[q].z0 = std::sin(ha);
+    hq[q].tx = (float)(in ? in[0] : 0.0);
+    hq[q].ty = (float)(in ? in[1] : 0.0);
+  }
+  const CsmParams prm = csm_make_params(P->n_lin, P->n_ang, P->depth, P->min_score);
+  std::vector<float2> rot;
+  csm_host_rotations(P->n_ang, P->ang_step, &rot);
+  CsmBatchPlan plan;
+  csm_make_plan(st->max_nx, st->max_ny, st->n_graded == 0, P->n_lin, P->depth, &plan);
+  cudaStream_t stream = st->stream;
+  const size_t n_pairs = nq * (size_t)k;
+  GLOC_CUDA_TRY(L->d_idx.reserve(n_pairs * sizeof(uint64_t)));
+  GLOC_CUDA_TRY(L->d_d2.reserve(n_pairs * sizeof(float)));
+  GLOC_CUDA_TRY(L->d_pairs.reserve(n_pairs * sizeof(CsmPairDev)));
+  GLOC_CUDA_TRY(L->d_keys.reserve(2 * n_pairs * sizeof(uint64_t)));
+  GLOC_CUDA_TRY(st->rot.reserve((size_t)S * sizeof(float2)));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(st->rot.p, rot.data(), (size_t)S * sizeof(float2), cudaMemcpyHostToDevice, stream));
+  L->prof_retrieval.begin(stream);
+  int rc = gloc_knn_query_sharded_device(L->knn, comm, d_queries, nq, (size_t)k, (uint64_t*)L->d_idx.p,
+                                         (float*)L->d_d2.p, 1, stream);
+  L->prof_retrieval.end(stream);
+  if (rc != GLOC_OK) return rc;
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_idx, L->d_idx.p, n_pairs * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(out_d2, L->d_d2.p, n_pairs * sizeof(float), cudaMemcpyDeviceToHost, stream));
+  GLOC_CUDA_TRY(cudaStreamSynchronize(stream));
+  const uint64_t lo = knn_offset_of(L->knn), hi = lo + n_local;
+  std::vector<unsigned long long> hkeys(n_pairs, 0ull), hall(n_pairs, 0ull);
+  std::vector<unsigned char> verified(n_pairs, 0);
+  std::vector<char> done(nq, 0);
+  std::vector<CsmPairDev> hp;
+  std::vector<size_t> where;
+  std::vector<unsigned long long> wb;
+  unsigned long long* d_send = (unsigned long long*)L->d_keys.p;
+  unsigned long long* d_recv = d_send + n_pairs;
+  for (int c0 = 0; c0 < k;) {
+    const int c1 = P->policy == GLOC_LOC_VERIFY_ALL ? k : std::min(k, c0 == 0 ? 1 : 2 * c0);
+    hp.clear();
+    where.clear();
+    for (size_t q = 0; q < nq; ++q) {
+      if (done[q]) continue;
+      for (int c = c0; c < c1; ++c) {
+        const size_t i = q * k + c;
+        verified[i] = 1;                          // by its owner, somewhere in the job
+        const uint64_t gi = out_idx[i];
+        if (gi < lo || gi >= hi) continue;        // another rank's row (or an empty slot)
+        CsmPairDev p;
+        p.grid = 0;
+        p.gid = L->h_map.empty() ? (int)(gi - lo) : L->h_map[gi - lo];
+        p.pt_begin = hq[q].pt_begin;
+        p.n_pts = hq[q].n_pts;
+        p.w0 = hq[q].w0; p.z0 = hq[q].z0; p.tx = hq[q].tx; p.ty = hq[q].ty;
+        hp.push_back(p);
+        where.push_back(i);
+      }
+    }
+    if (!hp.empty()) {
+      GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_pairs.p, hp.data(), hp.size() * sizeof(CsmPairDev), cudaMemcpyHostToDevice, stream));
+      wb.resize(hp.size());
+      rc = csm_match_core(st, plan, d_pts, (CsmPairDev*)L->d_pairs.p, (int)hp.size(), prm, (const float2*)st->rot.p, wb.data());
+      if (rc != GLOC_OK) return rc;
+      for (size_t i = 0; i < hp.size(); ++i) hkeys[where[i]] = wb[i];
+      L->stats.pairs_verified += hp.size();
+    }
+    L->stats.waves++;
+    // every pair has exactly one owner: max over ranks of (key | 0) is the owner's key
+    GLOC_CUDA_TRY(cudaMemcpyAsync(d_send, hkeys.data(), n_pairs * 8, cudaMemcpyHostToDevice, stream));
+    rc = comm_all_reduce_max_u64(comm, d_send, d_recv, n_pairs, stream);
+    if (rc != GLOC_OK) return rc;
+    GLOC_CUDA_TRY(cudaMemcpyAsync(hall.data(), d_recv, n_pairs * 8, cudaMemcpyDeviceToHost, stream));
+    GLOC_CUDA_TRY(cudaStreamSynchronize(stream));
+    for (size_t q = 0; q < nq; ++q)
+      for (int c = c0; c < c1 && !done[q]; ++c) {
+        const unsigned long long key = hall[q * k + c];
+        uint32_t sb = (uint32_t)(key >> 32);
+        float sc;
+        std::memcpy(&sc, &sb, 4);
+        if (key != 0 && sc > P->min_score) done[q] = 1;
+      }
+    c0 = c1;
+  }
+  L->prof_total.end(stream);
+  static const double zero3[3] = {0, 0, 0};
+  for (size_t q = 0; q < nq; ++q) {
+    gloc_loc_result& R = results[q];
+    std::memset(&R, 0, sizeof(R));
+    R.candidate = -1;
+    R.best_candidate = -1;
+    R.db_index = UINT64_MAX;
+    const double* in = init_xyyaw ? init_xyyaw + 3 * q : zero3;
+    float best_score = 0.f;
+    for (int c = 0; c < k; ++c) {
+      const size_t i = q * k + c;
+      gloc_csm_result r;
+      std::memset(&r, 0, sizeof(r));
+      r.score = P->min_score;
+      if (verified[i]) {
+        csm_decode(hall[i], prm, P->ang_step, resolution, in, P->min_score, &r);
+        R.n_verified++;
+      } else {
+        r.reserved = -1;
+      }
+      if (cand_results) cand_results[i] = r;
+      if (r.found) {
+        if (R.candidate < 0) {
+          R.located = 1;
+          R.candidate = c;
+          R.db_index = out_idx[i];
+          R.match = r;
+        }
+        if (R.best_candidate < 0 || r.score > best_score) {
+          R.best_candidate = c;
+          best_score = r.score;
+        }
+      }
+    }
+  }
+  L->stats.queries += nq;
+  return GLOC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -253,7 +412,7 @@ int gloc_loc_create(gloc_localizer** out, gloc_knn_index* knn, gloc_csm_store* c
 void gloc_loc_destroy(gloc_localizer* L) {
   if (!L) return;
   DeviceGuard g(L->device);
-  for (CsmBuf* b : {&L->d_map, &L->d_q, &L->d_idx, &L->d_d2, &L->d_qs, &L->d_pairs, &L->d_pts}) b->release();
+  for (CsmBuf* b : {&L->d_map, &L->d_q, &L->d_idx, &L->d_d2, &L->d_qs, &L->d_pairs, &L->d_pts, &L->d_keys}) b->release();
   delete L;
 }
 
@@ -315,6 +474,35 @@ int gloc_loc_localize(gloc_localizer* L, const float* queries, size_t nq, const 
   GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_pts.p, pts, (size_t)total_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
   return loc_run(L, (const float*)L->d_q.p, nq, (const float*)L->d_pts.p, scan_offsets, init_xyyaw, prm,
                  out_idx, out_d2, cand_results, results);
+}
+
+int gloc_loc_localize_sharded(gloc_localizer* L, gloc_comm* comm, const float* queries, size_t nq, const float* pts,
+                              const int64_t* scan_offsets, const double* init_xyyaw, const gloc_loc_params* prm,
+                              uint64_t* out_idx, float* out_d2, gloc_csm_result* cand_results,
+                              gloc_loc_result* results, int buffers_on_device) {
+  if (!L || !prm || !comm) return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: null argument");
+  if (nq == 0) return GLOC_OK;
+  if (!queries || !pts || !scan_offsets || !out_idx || !out_d2 || !results)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: null buffer");
+  if (comm->device != L->device) return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: communicator on another device");
+  DeviceGuard g(L->device);
+  if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_loc_localize_sharded: cudaSetDevice failed");
+  cudaStream_t stream = L->csm->stream;
+  const float* dq = queries;
+  const float* dp = pts;
+  L->prof_total.begin(stream);
+  if (!buffers_on_device) {
+    const size_t dim = gloc_knn_dim(L->knn);
+    const int64_t total_pts = scan_offsets[nq];
+    if (total_pts <= 0) return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: bad scan offsets");
+    GLOC_CUDA_TRY(L->d_q.reserve(nq * dim * sizeof(float)));
+    GLOC_CUDA_TRY(L->d_pts.reserve((size_t)total_pts * 3 * sizeof(float)));
+    GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_q.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+    GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_pts.p, pts, (size_t)total_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    dq = (const float*)L->d_q.p;
+    dp = (const float*)L->d_pts.p;
+  }
+  return loc_run_sharded(L, comm, dq, nq, dp, scan_offsets, init_xyyaw, prm, out_idx, out_d2, cand_results, results);
 }
 
 int gloc_loc_set_profiling(gloc_localizer* L, int enabled) {

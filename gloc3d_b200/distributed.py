@@ -13,6 +13,7 @@ testable on CPU with gloo by injecting a local-search and a merge function.
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import Callable
 
 import numpy as np
@@ -98,3 +99,84 @@ class ShardedRetrieval:
         if self.index is not None:
             self.index.close()
             self.index = None
+
+
+class Comm:
+    """`gloc_comm`: an NCCL communicator owned by libgloc3d.so (the multi-GPU entry points of the C
+    ABI take it, so a C++ host needs no Python).  Under torchrun the 128-byte NCCL id travels from
+    rank 0 to the other ranks through torch.distributed -- the only thing the process group is used
+    for; every data-path collective runs inside the library."""
+
+    def __init__(self, handle, rank: int, size: int):
+        self._h, self.rank, self.size = handle, rank, size
+
+    @classmethod
+    def from_torch(cls, device: int, group=None) -> "Comm":
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        rank, size = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_uint8 * 128)()
+        if rank == 0:
+            _lib.check(_lib.lib().gloc_comm_unique_id(buf, 128))
+        t = torch.tensor(list(buf), dtype=torch.uint8)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(device)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (C.c_uint8 * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        _lib.check(_lib.lib().gloc_comm_create(C.byref(h), ident, size, rank, device))
+        return cls(h, rank, size)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            from . import _lib
+
+            _lib.lib().gloc_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def query_sharded_device(index, comm: Comm, q, k: int, replicated: bool = False, out_idx=None, out_d2=None):
+    """Row-sharded top-k through the C ABI (`gloc_knn_query_sharded_device`): q is this rank's slice
+    of the batch (replicated=False) or the whole batch on every rank (replicated=True)."""
+    import torch
+
+    from . import _lib
+
+    nq = q.shape[0]
+    if out_idx is None:
+        out_idx = torch.empty((nq, k), dtype=torch.int64, device=q.device)
+        out_d2 = torch.empty((nq, k), dtype=torch.float32, device=q.device)
+    stream = torch.cuda.current_stream(q.device).cuda_stream
+    _lib.check(_lib.lib().gloc_knn_query_sharded_device(index._h, comm._h, q.data_ptr(), nq, k, out_idx.data_ptr(),
+                                                        out_d2.data_ptr(), int(replicated), stream))
+    return out_idx, out_d2
+
+
+def query_sharded_host(index, comm: Comm, q_ptr: int, nq: int, k: int, idx_ptr: int, d2_ptr: int,
+                       replicated: bool = False) -> None:
+    """The same with host buffers (pinned tensors' pointers): H2D and D2H inside the call."""
+    from . import _lib
+
+    _lib.check(_lib.lib().gloc_knn_query_sharded(index._h, comm._h, q_ptr, nq, k, idx_ptr, d2_ptr, int(replicated)))
+
+
+def partition_pairs(idx: np.ndarray, lo: int, hi: int):
+    """Which (query, candidate) pairs a rank verifies in the sharded localizer: those whose
+    retrieved row it owns.  Returns flat positions into the [nq, k] result (host logic mirrored
+    from loc_api.cu, testable without a GPU)."""
+    flat = np.asarray(idx).reshape(-1)
+    return np.nonzero((flat >= lo) & (flat < hi))[0]
+
+
+def combine_pair_keys(keys_per_rank: list[np.ndarray]) -> np.ndarray:
+    """The all-reduce(max) of the sharded localizer: every pair has one owner, the others hold 0."""
+    return np.maximum.reduce([np.asarray(k, np.uint64) for k in keys_per_rank])

@@ -83,6 +83,31 @@ class Localizer:
         check(fn(self._h, q_ptr, nq, pts_ptr, offs.ctypes.data, None, C.byref(params), idx_ptr, d2_ptr,
                  C.cast(cand, C.c_void_p) if cand is not None else None, C.cast(res, C.c_void_p)))
 
+    def localize_sharded(self, comm, queries: np.ndarray, scans, params: LocParams, inits=None,
+                         per_candidate: bool = True) -> LocalizeOutput:
+        """Collective: the same batch on every rank of a row-sharded database (host buffers)."""
+        q = np.ascontiguousarray(queries, np.float32)
+        nq = q.shape[0]
+        pts, offs = scans if isinstance(scans, tuple) else self.pack_scans(scans)
+        init = None if inits is None else np.ascontiguousarray(inits, np.float64).reshape(nq, 3)
+        idx = np.empty((nq, params.k), np.uint64)
+        d2 = np.empty((nq, params.k), np.float32)
+        cand = (CsmResult * (nq * params.k))() if per_candidate else None
+        res = (LocResult * nq)()
+        check(_lib.lib().gloc_loc_localize_sharded(self._h, comm._h, q.ctypes.data, nq, pts.ctypes.data,
+                                                   offs.ctypes.data, None if init is None else init.ctypes.data,
+                                                   C.byref(params), idx.ctypes.data, d2.ctypes.data,
+                                                   C.cast(cand, C.c_void_p) if cand is not None else None,
+                                                   C.cast(res, C.c_void_p), 0))
+        return LocalizeOutput(idx, d2, list(cand) if cand is not None else None, list(res))
+
+    def localize_sharded_ptr(self, comm, q_ptr: int, nq: int, pts_ptr: int, offs: np.ndarray, params: LocParams,
+                             idx_ptr: int, d2_ptr: int, res, cand=None, device: bool = False) -> None:
+        check(_lib.lib().gloc_loc_localize_sharded(self._h, comm._h, q_ptr, nq, pts_ptr, offs.ctypes.data, None,
+                                                   C.byref(params), idx_ptr, d2_ptr,
+                                                   C.cast(cand, C.c_void_p) if cand is not None else None,
+                                                   C.cast(res, C.c_void_p), int(device)))
+
     def set_profiling(self, enabled: bool) -> None:
         check(_lib.lib().gloc_loc_set_profiling(self._h, int(enabled)))
 

@@ -223,6 +223,42 @@ int gloc_csm_get_stats(const gloc_csm_store* store, gloc_csm_stats* stats);
 int gloc_csm_set_profiling(gloc_csm_store* store, int enabled);
 int gloc_csm_get_profile(gloc_csm_store* store, gloc_profile* out);
 
+/* ============================================================ multi-GPU
+ * The database shards by rows over the GPUs of one box (the reference has no
+ * distributed code, F1): every GPU holds the descriptors of rows [offset, offset + n)
+ * (gloc_knn_set_index_offset) and the map grids of those rows.  The communicator is an NCCL
+ * communicator owned by this library (resolved with dlopen at first use), so a C++ host can
+ * drive several GPUs without Python:
+ *   one process per GPU   rank 0: gloc_comm_unique_id -> hand the 128 bytes to the other ranks
+ *                         (any channel) -> every rank: gloc_comm_create
+ *   one process, n GPUs   gloc_comm_create_local (one communicator per device; the collective
+ *                         entry points are then called from one thread per device)
+ */
+typedef struct gloc_comm gloc_comm;
+#define GLOC_COMM_ID_BYTES 128
+int gloc_comm_unique_id(uint8_t* id, size_t capacity);
+int gloc_comm_create(gloc_comm** out, const uint8_t* id, int n_ranks, int rank, int device);
+int gloc_comm_create_local(gloc_comm** out /* n_devices handles */, int n_devices, const int* devices);
+void gloc_comm_destroy(gloc_comm* comm);
+int gloc_comm_rank(const gloc_comm* comm);
+int gloc_comm_size(const gloc_comm* comm);
+int gloc_comm_nccl_version(void);   /* 0 when NCCL cannot be loaded */
+
+/* Row-sharded exact top-k (BASELINE configs[3]); collective, same k on every rank.
+ *   replicated == 0   `queries` is THIS RANK'S SLICE of the batch (nq queries; the same count on
+ *                     every rank): queries are all-gathered over NVLink, every rank searches the
+ *                     whole batch on its shard, the local top-k lists go to the rank that owns the
+ *                     query (all-to-all), which merges them.  Output: this rank's slice, nq x k.
+ *   replicated != 0   every rank passes the same nq queries (online localisation: one query);
+ *                     local search, all-gather of the lists, merge everywhere.  Output: nq x k.
+ * Same result as InvKeyTree::query on the whole database (KDTreeVectorOfVectorsAdaptor.h:95-102):
+ * ascending (d2, idx) with global row indices. */
+int gloc_knn_query_sharded(gloc_knn_index* shard, gloc_comm* comm, const float* queries, size_t nq,
+                           size_t k, uint64_t* out_idx, float* out_d2, int replicated);
+int gloc_knn_query_sharded_device(gloc_knn_index* shard, gloc_comm* comm, const float* d_queries,
+                                  size_t nq, size_t k, uint64_t* d_out_idx, float* d_out_d2,
+                                  int replicated, void* stream);
+
 /* ============================================================ whole query path
  * One call from descriptors + scans to located frames and poses.  Replaces the evaluation loop
  * of the reference driver:
@@ -288,6 +324,17 @@ int gloc_loc_localize_device(gloc_localizer* loc, const float* d_queries, size_t
                              const int64_t* scan_offsets, const double* init_xyyaw,
                              const gloc_loc_params* params, uint64_t* out_idx, float* out_d2,
                              gloc_csm_result* cand_results, gloc_loc_result* results);
+/* The same over a row-sharded database: the localizer's index and store hold this rank's rows
+ * and their grids (grid_of_row is indexed by LOCAL row).  Collective; every rank passes the SAME
+ * batch and gets the same outputs.  Retrieval as gloc_knn_query_sharded (replicated); a (query,
+ * candidate) pair is verified on the rank that owns the candidate's row; one all-reduce of the
+ * 8-byte pair results per wave.  All grids of the map must share one resolution.
+ * buffers_on_device != 0: `queries` and `pts` are device pointers (as gloc_loc_localize_device). */
+int gloc_loc_localize_sharded(gloc_localizer* loc, gloc_comm* comm, const float* queries, size_t nq,
+                              const float* pts, const int64_t* scan_offsets, const double* init_xyyaw,
+                              const gloc_loc_params* params, uint64_t* out_idx, float* out_d2,
+                              gloc_csm_result* cand_results, gloc_loc_result* results,
+                              int buffers_on_device);
 int gloc_loc_get_stats(const gloc_localizer* loc, gloc_loc_stats* out);
 /* Live device-side timing (CUDA events on the stream the work is launched on) of whole calls and
  * of their retrieval stage; the rest of a call is verification.  Summed since the last get. */

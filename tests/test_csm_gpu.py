@@ -214,3 +214,42 @@ def test_kitti_fixture_shape_off_centre_limits(oracle):
     same(r, o)
     assert r.found and abs(r.pose_x - 9.0) <= 0.31 and abs(r.pose_y - 4.2) <= 0.31
     st.close()
+
+
+def test_against_compiled_reference(oracle):
+    """GPU vs the REFERENCE'S OWN matcher (registration/2d compiled unmodified into
+    oracle/_ref/libcsm_ref.so): score always, candidate and pose unless several candidates tie for
+    the best score (std::sort's order among equal scores is unspecified in the reference)."""
+    if not oracle.have_csm_ref():
+        pytest.skip("oracle/_ref/libcsm_ref.so not present")
+    res, step = 0.2, 2 * np.pi / 360
+    st = g.CsmStore(0)
+    cases = []
+    for seed in range(6):
+        rng = np.random.default_rng(500 + seed)
+        nx, ny = int(rng.integers(90, 260)), int(rng.integers(90, 260))
+        grid = synth.make_bev_grid(nx, ny, seed=600 + seed, n_segments=16, n_blobs=8)
+        cells = synth.level1_to_cells(grid)
+        if seed % 2:     # graded costs at the occupied cells
+            occ = cells > 0
+            cells[occ] = rng.integers(1, 32768, int(occ.sum())).astype(np.uint16)
+        mx, my = synth.centered_limits(nx, ny, res)
+        scan = synth.planted_scan(grid, res, mx, my, rng.uniform(-0.6, 0.6), rng.uniform(-3, 3), rng.uniform(-3, 3),
+                                  dropout=0.2, jitter_cells=0.5, seed=seed)
+        init = (float(rng.uniform(-0.4, 0.4)), float(rng.uniform(-0.4, 0.4)), float(rng.uniform(-0.1, 0.1)))
+        cases.append((cells, mx, my, scan, init, st.add_grid_cells(cells, res, mx, my)))
+    n_lin, n_ang, depth, min_score = 30, 40, 5, 0.3
+    out = st.match_batch([c[3] for c in cases], [c[5] for c in cases], list(range(6)), [c[4] for c in cases],
+                         n_lin, n_ang, step, depth, min_score)
+    exact = 0
+    for (cells, mx, my, scan, init, gid), r in zip(cases, out):
+        ref = oracle.ref_csm_match(cells, res, mx, my, depth, scan, init, n_lin, n_ang, step, min_score)
+        assert r.found == ref.found
+        assert np.float32(r.score).view(np.uint32) == np.float32(ref.score).view(np.uint32)
+        for index in (0, 2, 4):
+            assert np.array_equal(st.precomputation_grid(gid, 1 << index), oracle.ref_precomp(cells, 5, index))
+        if ref.found and (r.scan_index, r.x_offset, r.y_offset) == (ref.scan_index, ref.x_offset, ref.y_offset):
+            assert (r.pose_x, r.pose_y, r.pose_yaw) == (ref.pose_x, ref.pose_y, ref.pose_yaw)
+            exact += 1
+    assert exact >= 5        # ties for the maximum are the exception
+    st.close()

@@ -115,3 +115,25 @@ def test_hold_steps_is_a_pure_function():
     spec.loader.exec_module(bench)
     assert bench.hold_steps(1.0) == 250 and bench.hold_steps(5.2) == 48 and bench.hold_steps(1e-9) == 4000
     assert bench.hold_steps(1e9) == 1
+
+
+def test_sharded_localizer_host_logic():
+    """partition_pairs / combine_pair_keys: every (query, candidate) pair has exactly one owner and
+    the all-reduce(max) of the per-rank key arrays (0 = not mine) reassembles all results."""
+    from gloc3d_b200.distributed import combine_pair_keys, partition_pairs, shard_bounds
+
+    rng = np.random.default_rng(0)
+    rows, world, nq, k = 1000, 4, 9, 25
+    idx = rng.integers(0, rows, (nq, k)).astype(np.uint64)
+    keys = rng.integers(1, 1 << 62, nq * k).astype(np.uint64)
+    b = shard_bounds(rows, world)
+    seen = np.zeros(nq * k, int)
+    per_rank = []
+    for r in range(world):
+        mine = partition_pairs(idx, b[r], b[r + 1])
+        seen[mine] += 1
+        kr = np.zeros(nq * k, np.uint64)
+        kr[mine] = keys[mine]
+        per_rank.append(kr)
+    assert (seen == 1).all()
+    assert np.array_equal(combine_pair_keys(per_rank), keys)
