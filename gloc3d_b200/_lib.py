@@ -143,12 +143,19 @@ SIGNATURES = {
     "gloc_bev_project": (_i, [_vp, _vp, _sz, _i, C.POINTER(BevInfo)]),
     "gloc_bev_get_image": (_i, [_vp, _vp, _sz]),
     "gloc_bev_get_cnn_input": (_i, [_vp, _i, _i, _vp]),
+    "gloc_bev_get_cnn_input_roi": (_i, [_vp, _i, _i, _vp, _vp]),
+    "gloc_enc_forward_padded_device": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "gloc_enc_forward_padded": (_i, [_vp, _vp, _vp, _i, _vp]),
+    "gloc_desc_extract_padded": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp]),
     "gloc_bev_get_occupied_points": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "gloc_bev_kernel_launches": (C.c_uint64, [_vp]),
     "gloc_csm_add_grid_from_bev": (_i, [_vp, _vp, _ip]),
     "gloc_csm_add_grid_from_bev_aligned": (_i, [_vp, _vp, _ip]),
     "gloc_csm_get_grid_info": (_i, [_vp, _i, C.POINTER(GridInfo)]),
     "gloc_grid_file_write": (_i, [C.c_char_p, C.POINTER(GridInfo), C.POINTER(_vp), _sz]),
+    "gloc_grid_file_write_tagged": (_i, [C.c_char_p, C.POINTER(GridInfo), C.POINTER(_vp), _sz, C.c_uint32]),
+    "gloc_grid_file_tag": (C.c_uint32, [_vp]),
+    "gloc_csm_save_grids_tagged": (_i, [_vp, C.c_char_p, C.c_uint32]),
     "gloc_grid_file_open": (_i, [C.c_char_p, C.POINTER(_vp), C.POINTER(_sz)]),
     "gloc_grid_file_next": (_i, [_vp, C.POINTER(GridInfo), _vp, _sz]),
     "gloc_grid_file_close": (None, [_vp]),

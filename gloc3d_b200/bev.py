@@ -49,6 +49,13 @@ class BevProjector:
         check(_lib.lib().gloc_bev_get_cnn_input(self._h, width, height, out.ctypes.data))
         return out
 
+    def cnn_input_roi(self, width: int = 768, height: int = 768):
+        """cnn_input plus roi_dst of crop_pad_occupancy (x0, y0, w, h): outside it lies padding."""
+        out = np.empty((height, width), np.uint8)
+        roi = np.zeros(4, np.int32)
+        check(_lib.lib().gloc_bev_get_cnn_input_roi(self._h, width, height, out.ctypes.data, roi.ctypes.data))
+        return out, roi
+
     def occupied_points(self) -> np.ndarray:
         """GridToVirtualPointCloud of the projected grid (fast_..._2d.cpp:78-95): [n, 3] float32."""
         n = C.c_size_t()

@@ -308,6 +308,20 @@ int gloc_bev_get_image(gloc_bev_projector* b, uint8_t* img, size_t capacity) {
   return GLOC_OK;
 }
 
+int gloc_bev_get_cnn_input_roi(gloc_bev_projector* b, int width, int height, uint8_t* out, int32_t roi[4]) {
+  if (!roi) return fail(GLOC_ERR_INVALID, "gloc_bev_get_cnn_input_roi: roi is null");
+  const int rc = gloc_bev_get_cnn_input(b, width, height, out);
+  if (rc != GLOC_OK) return rc;
+  // roi_dst of crop_pad_occupancy, loop_detector.cpp:99-102
+  const int sw = b->info.width, sh = b->info.height;
+  const int cw = sw >= width ? width : sw, ch = sh >= height ? height : sh;
+  roi[0] = (int)std::floor((width - cw) / 2.);
+  roi[1] = (int)std::floor((height - ch) / 2.);
+  roi[2] = cw;
+  roi[3] = ch;
+  return GLOC_OK;
+}
+
 int gloc_bev_get_cnn_input(gloc_bev_projector* b, int width, int height, uint8_t* out) {
   if (!b || !b->valid) return fail(GLOC_ERR_NOT_BUILT, "gloc_bev_get_cnn_input: no projection yet");
   if (!out || width < 1 || height < 1) return fail(GLOC_ERR_INVALID, "gloc_bev_get_cnn_input: bad argument");

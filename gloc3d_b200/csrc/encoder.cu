@@ -221,22 +221,43 @@ enc_conv3x3_kernel(const __grid_constant__ CUtensorMap map_in, const __grid_cons
 
 // conv1_1 folded to one input channel: uint8 image [B][H][W] -> FP16 NHWC [B][H][W][64], ReLU.
 // w1: [64][9] (weights summed over the three identical input channels, times 1/255), thread = pixel.
+// The reference pads its canvas with cv::Mat::ones(h, w, CV_8UC3) * 255 (loop_detector.cpp:84), and
+// Mat::ones sets only channel 0 of a multi-channel matrix: pad pixels are (255, 0, 0), the copied
+// BEV image has three identical channels.  With `rois` ([B][4]: x0, y0, width, height of the copied
+// image inside the plane) the taps that fall on padding use w1p: [64][9], channel 0's weights
+// alone (times 1/255).  rois == nullptr: every pixel is image.
 __global__ void __launch_bounds__(256)
 enc_conv1_kernel(const uint8_t* __restrict__ img, int B, int H, int W, const float* __restrict__ w1,
-                 const float* __restrict__ bias, __half* __restrict__ out) {
-  __shared__ float w_s[64 * 9], b_s[64];
-  for (int i = threadIdx.x; i < 64 * 9; i += 256) w_s[i] = w1[i];
+                 const float* __restrict__ bias, __half* __restrict__ out,
+                 const float* __restrict__ w1p = nullptr, const int* __restrict__ rois = nullptr) {
+  __shared__ float w_s[64 * 9], b_s[64], wp_s[64 * 9];
+  const bool padded = rois != nullptr && w1p != nullptr;
+  for (int i = threadIdx.x; i < 64 * 9; i += 256) {
+    w_s[i] = w1[i];
+    wp_s[i] = padded ? w1p[i] : 0.f;
+  }
   if (threadIdx.x < 64) b_s[threadIdx.x] = bias[threadIdx.x];
   __syncthreads();
   const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (p >= (size_t)B * H * W) return;
   const int x = (int)(p % W), y = (int)((p / W) % H);
   const uint8_t* plane = img + (p - (size_t)y * W - x);
-  float v[9];
+  int rx0 = 0, ry0 = 0, rx1 = W, ry1 = H;
+  if (padded) {
+    const int b = (int)(p / ((size_t)H * W));
+    rx0 = rois[4 * b]; ry0 = rois[4 * b + 1]; rx1 = rx0 + rois[4 * b + 2]; ry1 = ry0 + rois[4 * b + 3];
+  }
+  float v[9], vp[9];
+  bool any_pad = false;
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
     const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-    v[tap] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? (float)plane[(size_t)yy * W + xx] : 0.f;
+    const bool in_img = yy >= 0 && yy < H && xx >= 0 && xx < W;
+    const bool in_roi = in_img && yy >= ry0 && yy < ry1 && xx >= rx0 && xx < rx1;
+    const float val = in_img ? (float)plane[(size_t)yy * W + xx] : 0.f;
+    v[tap] = in_roi ? val : 0.f;
+    vp[tap] = in_img && !in_roi ? val : 0.f;
+    any_pad |= in_img && !in_roi;
   }
   uint4* dst = reinterpret_cast<uint4*>(out + p * 64);
 #pragma unroll 1
@@ -251,6 +272,10 @@ enc_conv1_kernel(const uint8_t* __restrict__ img, int B, int H, int W, const flo
         float acc = b_s[co];
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) acc = fmaf(w_s[co * 9 + tap], v[tap], acc);
+        if (any_pad) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) acc = fmaf(wp_s[co * 9 + tap], vp[tap], acc);
+        }
         f[e] = fmaxf(acc, 0.f);
       }
       h[j] = __floats2half2_rn(f[0], f[1]);
@@ -346,6 +371,9 @@ inline int enc_bn(int cout) { return cout >= 256 ? 256 : cout; }
 struct gloc_encoder {
   int device = 0, H = 0, W = 0;
   float* d_w1 = nullptr;                          // folded conv1_1 [64][9]
+  float* d_w1p = nullptr;                         // conv1_1 on padding: channel 0 alone [64][9]
+  int* d_rois = nullptr;
+  int rois_cap = 0;
   float* d_bias[gloc::kEncLayers] = {nullptr};    // [Cout]
   __half* d_w[gloc::kEncLayers] = {nullptr};      // [Cout][9 Cin] FP16 (layer 0 unused)
   __half* d_act[2] = {nullptr, nullptr};          // ping-pong activations
@@ -378,7 +406,7 @@ cudaError_t launch_conv(const CUtensorMap& map_in, const CUtensorMap& map_w, con
   return cudaGetLastError();
 }
 
-int forward_device(gloc_encoder* e, const uint8_t* d_img, int B, float* d_feat) {
+int forward_device(gloc_encoder* e, const uint8_t* d_img, int B, float* d_feat, const int32_t* rois = nullptr) {
   using namespace gloc;
   const size_t need = (size_t)B * e->H * e->W * 64;   // the largest activation: conv1 output
   if (need > e->act_elems) {
@@ -395,7 +423,24 @@ int forward_device(gloc_encoder* e, const uint8_t* d_img, int B, float* d_feat) 
   int H = e->H, W = e->W, C = 64, cur = 0;
   {
     const size_t px = (size_t)B * H * W;
-    enc_conv1_kernel<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(d_img, B, H, W, e->d_w1, e->d_bias[0], e->d_act[0]);
+    const int* d_rois = nullptr;
+    if (rois) {
+      for (int b = 0; b < B; ++b)
+        if (rois[4 * b] < 0 || rois[4 * b + 1] < 0 || rois[4 * b + 2] < 0 || rois[4 * b + 3] < 0 ||
+            rois[4 * b] + rois[4 * b + 2] > W || rois[4 * b + 1] + rois[4 * b + 3] > H)
+          return fail(GLOC_ERR_INVALID, "gloc_enc_forward: image rectangle outside the plane");
+      if (B > e->rois_cap) {
+        if (e->d_rois) cudaFree(e->d_rois);
+        e->d_rois = nullptr;
+        e->rois_cap = 0;
+        GLOC_CUDA_TRY(cudaMalloc(&e->d_rois, (size_t)B * 16));
+        e->rois_cap = B;
+      }
+      GLOC_CUDA_TRY(cudaMemcpyAsync(e->d_rois, rois, (size_t)B * 16, cudaMemcpyHostToDevice, st));
+      d_rois = e->d_rois;
+    }
+    enc_conv1_kernel<<<(unsigned)((px + 255) / 256), 256, 0, st>>>(d_img, B, H, W, e->d_w1, e->d_bias[0], e->d_act[0],
+                                                                   e->d_w1p, d_rois);
     GLOC_CUDA_TRY(cudaGetLastError());
     ++e->launches;
   }
@@ -476,6 +521,11 @@ int gloc_enc_create(gloc_encoder** out, int device, int height, int width, const
         }
       ce = cudaMalloc(&e->d_w1, w1.size() * 4);
       if (ce == cudaSuccess) ce = cudaMemcpy(e->d_w1, w1.data(), w1.size() * 4, cudaMemcpyHostToDevice);
+      // padding of the reference's canvas is (255, 0, 0): only channel 0 sees it
+      for (int co = 0; co < 64; ++co)
+        for (int tap = 0; tap < 9; ++tap) w1[(size_t)co * 9 + tap] = conv_w[0][((size_t)co * 3 + 0) * 9 + tap] / 255.f;
+      if (ce == cudaSuccess) ce = cudaMalloc(&e->d_w1p, w1.size() * 4);
+      if (ce == cudaSuccess) ce = cudaMemcpy(e->d_w1p, w1.data(), w1.size() * 4, cudaMemcpyHostToDevice);
     } else {        // [Cout][Cin][3][3] float32 -> [Cout][tap][Cin] FP16
       std::vector<__half> w((size_t)cout * 9 * cin);
       for (int co = 0; co < cout; ++co)
@@ -500,6 +550,8 @@ void gloc_enc_destroy(gloc_encoder* e) {
   if (!e) return;
   gloc::DeviceGuard scope(e->device);
   if (e->d_w1) cudaFree(e->d_w1);
+  if (e->d_w1p) cudaFree(e->d_w1p);
+  if (e->d_rois) cudaFree(e->d_rois);
   for (int l = 0; l < gloc::kEncLayers; ++l) {
     if (e->d_bias[l]) cudaFree(e->d_bias[l]);
     if (e->d_w[l]) cudaFree(e->d_w[l]);
@@ -532,7 +584,7 @@ int gloc_enc_forward_device(gloc_encoder* e, const uint8_t* d_images, int batch,
 }
 
 // host planes -> device, encoder -> e->d_feat (both buffers grown on demand); asynchronous on e->stream
-static int stage_and_encode(gloc_encoder* e, const uint8_t* images, int batch) {
+static int stage_and_encode(gloc_encoder* e, const uint8_t* images, int batch, const int32_t* rois = nullptr) {
   const size_t in_bytes = (size_t)batch * e->H * e->W, out_elems = (size_t)batch * 512 * (e->H / 16) * (e->W / 16);
   if (in_bytes > e->img_bytes) {
     if (e->d_img) cudaFree(e->d_img);
@@ -549,16 +601,21 @@ static int stage_and_encode(gloc_encoder* e, const uint8_t* images, int batch) {
     e->feat_elems = out_elems;
   }
   GLOC_CUDA_TRY(cudaMemcpyAsync(e->d_img, images, in_bytes, cudaMemcpyHostToDevice, e->stream));
-  return forward_device(e, e->d_img, batch, e->d_feat);
+  return forward_device(e, e->d_img, batch, e->d_feat, rois);
 }
 
 int gloc_desc_extract(gloc_encoder* e, gloc_vlad_head* head, int out_dim, const uint8_t* images, int batch,
                       float* desc) {
+  return gloc_desc_extract_padded(e, head, out_dim, images, nullptr, batch, desc);
+}
+
+int gloc_desc_extract_padded(gloc_encoder* e, gloc_vlad_head* head, int out_dim, const uint8_t* images,
+                             const int32_t* rois, int batch, float* desc) {
   if (!e || !head || !images || !desc) return fail(GLOC_ERR_INVALID, "gloc_desc_extract: null argument");
   if (batch < 0 || out_dim < 1) return fail(GLOC_ERR_INVALID, "gloc_desc_extract: bad batch / out_dim");
   if (batch == 0) return GLOC_OK;
   gloc::DeviceGuard scope(e->device);
-  int rc = stage_and_encode(e, images, batch);
+  int rc = stage_and_encode(e, images, batch, rois);
   if (rc != GLOC_OK) return rc;
   const size_t n_desc = (size_t)batch * out_dim;
   if (n_desc > e->desc_elems) {
@@ -576,12 +633,28 @@ int gloc_desc_extract(gloc_encoder* e, gloc_vlad_head* head, int out_dim, const 
 }
 
 int gloc_enc_forward(gloc_encoder* e, const uint8_t* images, int batch, float* feat) {
+  return gloc_enc_forward_padded(e, images, nullptr, batch, feat);
+}
+
+int gloc_enc_forward_padded_device(gloc_encoder* e, const uint8_t* d_images, const int32_t* rois, int batch,
+                                   float* d_feat) {
+  if (!e || !d_images || !d_feat) return fail(GLOC_ERR_INVALID, "gloc_enc_forward_device: null argument");
+  if (batch < 0) return fail(GLOC_ERR_INVALID, "gloc_enc_forward_device: negative batch");
+  if (batch == 0) return GLOC_OK;
+  gloc::DeviceGuard scope(e->device);
+  const int rc = forward_device(e, d_images, batch, d_feat, rois);
+  if (rc != GLOC_OK) return rc;
+  GLOC_CUDA_TRY(cudaStreamSynchronize(e->stream));
+  return GLOC_OK;
+}
+
+int gloc_enc_forward_padded(gloc_encoder* e, const uint8_t* images, const int32_t* rois, int batch, float* feat) {
   if (!e || !images || !feat) return fail(GLOC_ERR_INVALID, "gloc_enc_forward: null argument");
   if (batch < 0) return fail(GLOC_ERR_INVALID, "gloc_enc_forward: negative batch");
   if (batch == 0) return GLOC_OK;
   gloc::DeviceGuard scope(e->device);
   const size_t out_elems = (size_t)batch * 512 * (e->H / 16) * (e->W / 16);
-  const int rc = stage_and_encode(e, images, batch);
+  const int rc = stage_and_encode(e, images, batch, rois);
   if (rc != GLOC_OK) return rc;
   GLOC_CUDA_TRY(cudaMemcpyAsync(feat, e->d_feat, out_elems * 4, cudaMemcpyDeviceToHost, e->stream));
   GLOC_CUDA_TRY(cudaStreamSynchronize(e->stream));

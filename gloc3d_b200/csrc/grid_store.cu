@@ -5,6 +5,7 @@
 // points (gloc_csm_get_precomputation_grid / gloc_csm_add_grid_u8).
 #include <cstdio>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -46,6 +47,7 @@ void unpack_bits(const uint8_t* bits, size_t n, uint8_t* v) {
 struct gloc_grid_file {
   FILE* fp = nullptr;
   uint64_t n_grids = 0, next = 0;
+  uint32_t tag = 0;
   std::string path;
   std::vector<uint8_t> scratch;
 };
@@ -56,6 +58,11 @@ extern "C" {
 
 int gloc_grid_file_write(const char* path, const gloc_grid_info* infos, const uint8_t* const* level1,
                          size_t n) {
+  return gloc_grid_file_write_tagged(path, infos, level1, n, 0);
+}
+
+int gloc_grid_file_write_tagged(const char* path, const gloc_grid_info* infos, const uint8_t* const* level1,
+                                size_t n, uint32_t tag) {
   if (!path || (n && (!infos || !level1)))
     return fail(GLOC_ERR_INVALID, "gloc_grid_file_write: null argument");
   for (size_t i = 0; i < n; ++i)
@@ -63,7 +70,7 @@ int gloc_grid_file_write(const char* path, const gloc_grid_info* infos, const ui
       return fail(GLOC_ERR_INVALID, "gloc_grid_file_write: grid " + std::to_string(i) + " is empty");
   FILE* fp = std::fopen(path, "wb");
   if (!fp) return fail(GLOC_ERR_INVALID, std::string("gloc_grid_file_write: cannot open ") + path);
-  const uint32_t head[2] = {kVersion, 0};
+  const uint32_t head[2] = {kVersion, tag};
   const uint64_t count = n;
   bool ok = std::fwrite(kMagic, 1, 8, fp) == 8 && std::fwrite(head, 4, 2, fp) == 2 &&
             std::fwrite(&count, 8, 1, fp) == 1;
@@ -112,9 +119,14 @@ int gloc_grid_file_open(const char* path, gloc_grid_file** out, size_t* n_grids)
     std::fclose(fp);
     return fail(GLOC_ERR_RANGE, "gloc_grid_file_open: unsupported version " + std::to_string(head[0]));
   }
-  gloc_grid_file* f = new gloc_grid_file;
+  gloc_grid_file* f = new (std::nothrow) gloc_grid_file;   // the C ABI never throws
+  if (!f) {
+    std::fclose(fp);
+    return fail(GLOC_ERR_NOMEM, "gloc_grid_file_open: out of host memory");
+  }
   f->fp = fp;
   f->n_grids = count;
+  f->tag = head[1];
   f->path = path;
   *out = f;
   if (n_grids) *n_grids = (size_t)count;
@@ -154,6 +166,8 @@ int gloc_grid_file_next(gloc_grid_file* f, gloc_grid_info* info, uint8_t* level1
   return GLOC_OK;
 }
 
+uint32_t gloc_grid_file_tag(const gloc_grid_file* f) { return f ? f->tag : 0; }
+
 void gloc_grid_file_close(gloc_grid_file* f) {
   if (!f) return;
   if (f->fp) std::fclose(f->fp);
@@ -161,6 +175,10 @@ void gloc_grid_file_close(gloc_grid_file* f) {
 }
 
 int gloc_csm_save_grids(gloc_csm_store* store, const char* path) {
+  return gloc_csm_save_grids_tagged(store, path, 0);
+}
+
+int gloc_csm_save_grids_tagged(gloc_csm_store* store, const char* path, uint32_t tag) {
   if (!store || !path) return fail(GLOC_ERR_INVALID, "gloc_csm_save_grids: null argument");
   const int n = gloc_csm_num_grids(store);
   std::vector<gloc_grid_info> infos((size_t)n);
@@ -174,7 +192,7 @@ int gloc_csm_save_grids(gloc_csm_store* store, const char* path) {
     if (rc != GLOC_OK) return rc;
     ptrs[i] = cells[i].data();
   }
-  return gloc_grid_file_write(path, infos.data(), ptrs.data(), (size_t)n);
+  return gloc_grid_file_write_tagged(path, infos.data(), ptrs.data(), (size_t)n, tag);
 }
 
 int gloc_csm_load_grids(gloc_csm_store* store, const char* path, int* first_grid_id, int* n_grids) {

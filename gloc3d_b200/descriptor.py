@@ -95,12 +95,19 @@ class Encoder:
         check(_lib.lib().gloc_enc_create(C.byref(self._h), device, height, width, wp, bp))
         self.channels, self.n_loc = 512, (height // 16) * (width // 16)
 
-    def forward(self, images: np.ndarray) -> np.ndarray:
+    def forward(self, images: np.ndarray, rois=None) -> np.ndarray:
+        """rois [B, 4] int32 (x0, y0, w, h of the BEV image inside the plane): the rest of the plane is
+        the reference's (255, 0, 0) canvas padding; None: every pixel is image."""
         images = np.ascontiguousarray(images, np.uint8)
         if images.ndim != 3 or images.shape[1:] != (self.height, self.width):
             raise ValueError(f"images must be [B, {self.height}, {self.width}] uint8")
         out = np.empty((images.shape[0], self.channels, self.n_loc), np.float32)
-        check(_lib.lib().gloc_enc_forward(self._h, images.ctypes.data, images.shape[0], out.ctypes.data))
+        if rois is None:
+            check(_lib.lib().gloc_enc_forward(self._h, images.ctypes.data, images.shape[0], out.ctypes.data))
+        else:
+            rois = np.ascontiguousarray(rois, np.int32).reshape(images.shape[0], 4)
+            check(_lib.lib().gloc_enc_forward_padded(self._h, images.ctypes.data, rois.ctypes.data, images.shape[0],
+                                                     out.ctypes.data))
         return out
 
     def forward_device(self, images_ptr: int, batch: int, feat_ptr: int) -> None:

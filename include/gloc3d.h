@@ -381,6 +381,9 @@ int gloc_bev_get_image(gloc_bev_projector* bev, uint8_t* img, size_t capacity);
 /* crop_pad_occupancy: centre crop / 255-pad to width x height (768 x 768 in the
  * reference, loop_detector.cpp:144), one channel. */
 int gloc_bev_get_cnn_input(gloc_bev_projector* bev, int width, int height, uint8_t* out);
+/* The same plus roi_dst of crop_pad_occupancy (loop_detector.cpp:99-102): x0, y0, width, height
+ * of the copied image inside the plane -- everything outside is the canvas's padding. */
+int gloc_bev_get_cnn_input_roi(gloc_bev_projector* bev, int width, int height, uint8_t* out, int32_t roi[4]);
 /* Occupied pixels as GridToVirtualPointCloud produces them from ProjectToGrid's
  * grid (fast_..._2d.cpp:78-95): (ox + i*res, oy + j*res, 0), i outer.  pts may be
  * NULL to query the count. */
@@ -448,6 +451,20 @@ int gloc_enc_forward_device(gloc_encoder* enc, const uint8_t* d_images, int batc
 int gloc_enc_forward(gloc_encoder* enc, const uint8_t* images, int batch, float* feat);
 uint64_t gloc_enc_kernel_launches(const gloc_encoder* enc);
 
+/* The reference pads small BEV images onto its 768 x 768 canvas with cv::Mat::ones(h, w,
+ * CV_8UC3) * 255 (loop_detector.cpp:84); Mat::ones sets only channel 0 of a multi-channel matrix,
+ * so the padding is (255, 0, 0) while the copied image has three identical channels.  The padded
+ * entry points take, per image, the rectangle of the copied image inside the plane (rois:
+ * [batch][4] int32 = x0, y0, width, height, HOST memory; gloc_bev_get_cnn_input_roi returns it)
+ * and give the padding the reference's channel-0-only treatment in conv1_1.  rois == NULL, or the
+ * plain entry points above: every pixel of the plane is image. */
+int gloc_enc_forward_padded_device(gloc_encoder* enc, const uint8_t* d_images, const int32_t* rois,
+                                   int batch, float* d_feat);
+int gloc_enc_forward_padded(gloc_encoder* enc, const uint8_t* images, const int32_t* rois, int batch,
+                            float* feat);
+int gloc_desc_extract_padded(gloc_encoder* enc, gloc_vlad_head* head, int out_dim, const uint8_t* images,
+                             const int32_t* rois, int batch, float* desc);
+
 /* Host convenience over both halves: uint8 planes [batch][H][W] (host) -> descriptors
  * [batch][out_dim] (host); the feature maps stay on the device.  out_dim is the head's. */
 int gloc_desc_extract(gloc_encoder* enc, gloc_vlad_head* head, int out_dim, const uint8_t* images,
@@ -458,7 +475,8 @@ int gloc_desc_extract(gloc_encoder* enc, gloc_vlad_head* head, int out_dim, cons
  * The reference keeps its grids in memory only (db_grids_, loop_detector.h:36-39) and
  * re-projects every scan at start-up (global_localization.cpp:419-449); this is the
  * file that replaces that pass.  Little-endian:
- *   header   "GLOCGRD1" | u32 version = 1 | u32 0 | u64 n_grids
+ *   header   "GLOCGRD1" | u32 version = 1 | u32 tag | u64 n_grids     (tag: the writer's fingerprint
+ *            of what the grids were made from, 0 = none; a reader compares it with its own)
  *   per grid i32 nx | i32 ny | f64 resolution | f64 max_x | f64 max_y | u32 encoding | u32 0 |
  *            u64 payload_bytes | payload
  *   encoding 1  bit-packed binary grid: bit (i & 7) of byte (i >> 3) is set iff level-1 cell
@@ -478,7 +496,10 @@ int gloc_csm_get_grid_info(const gloc_csm_store* store, int grid_id, gloc_grid_i
  * (what gloc_csm_add_grid_u8 takes / gloc_csm_get_precomputation_grid(width = 1) returns). */
 int gloc_grid_file_write(const char* path, const gloc_grid_info* infos,
                          const uint8_t* const* level1, size_t n);
+int gloc_grid_file_write_tagged(const char* path, const gloc_grid_info* infos,
+                                const uint8_t* const* level1, size_t n, uint32_t tag);
 int gloc_grid_file_open(const char* path, gloc_grid_file** out, size_t* n_grids);
+uint32_t gloc_grid_file_tag(const gloc_grid_file* f);
 /* Reads the next grid: info always; the cells into level1 when capacity >= nx*ny, otherwise
  * the record is NOT consumed (call again with a large enough buffer).  GLOC_ERR_RANGE after
  * the last grid. */
@@ -487,6 +508,7 @@ void gloc_grid_file_close(gloc_grid_file* f);
 /* Every grid of the store -> file; file -> grids appended to the store (ids first_grid_id ..
  * first_grid_id + n_grids - 1, in file order). */
 int gloc_csm_save_grids(gloc_csm_store* store, const char* path);
+int gloc_csm_save_grids_tagged(gloc_csm_store* store, const char* path, uint32_t tag);
 int gloc_csm_load_grids(gloc_csm_store* store, const char* path, int* first_grid_id, int* n_grids);
 
 /* ============================================================ measured ceilings

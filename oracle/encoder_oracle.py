@@ -18,13 +18,21 @@ POOL_AFTER = (1, 3, 6, 9)          # 0-based convolution indices followed by a 2
 from gloc3d_b200.synth import hashed_vgg_weights  # noqa: E402,F401
 
 
-def vgg16_features(images_u8, conv_w, conv_b):
-    """images_u8 [B, H, W] uint8 -> [B, 512, H/16, W/16] float32."""
+def vgg16_features(images_u8, conv_w, conv_b, rois=None):
+    """images_u8 [B, H, W] uint8 -> [B, 512, H/16, W/16] float32.  rois [B, 4] (x0, y0, w, h): the
+    rectangle of the BEV image inside the plane; everything outside is the reference's canvas
+    padding, cv::Mat::ones(h, w, CV_8UC3) * 255 = (255, 0, 0) per pixel (loop_detector.cpp:84;
+    Mat::ones sets channel 0 only), so channels 1 and 2 are zero there."""
     import torch
     import torch.nn.functional as F
 
     x = torch.from_numpy(np.asarray(images_u8, np.uint8)).float().div(255.0)
     x = x[:, None, :, :].expand(-1, 3, -1, -1).contiguous()
+    if rois is not None:
+        for b, (x0, y0, w, h) in enumerate(np.asarray(rois).reshape(-1, 4)):
+            keep = torch.zeros(x.shape[2:], dtype=torch.bool)
+            keep[y0:y0 + h, x0:x0 + w] = True
+            x[b, 1:][:, ~keep] = 0.0
     with torch.no_grad():
         for l in range(13):
             x = F.conv2d(x, torch.from_numpy(conv_w[l]), torch.from_numpy(conv_b[l]), padding=1)

@@ -66,6 +66,50 @@ def test_encoder_against_oracle(H, W, B):
 
 
 @pytest.mark.gpu
+def test_reference_canvas_padding():
+    """Small BEV images are padded with the reference's (255, 0, 0) canvas (loop_detector.cpp:84:
+    cv::Mat::ones sets channel 0 only): conv1_1 must treat padding and image differently."""
+    H, W, B = 256, 256, 3
+    ws, bs = eo.hashed_vgg_weights(13)
+    img = bev_like(B, H, W, 6)
+    rois = np.array([[40, 30, 150, 200], [0, 0, 256, 256], [100, 0, 156, 97]], np.int32)
+    for b, (x0, y0, w, h) in enumerate(rois):       # outside the rectangle: the canvas value
+        keep = np.zeros((H, W), bool)
+        keep[y0:y0 + h, x0:x0 + w] = True
+        img[b][~keep] = 255
+    enc = g.Encoder(ws, bs, height=H, width=W)
+    out = enc.forward(img, rois)
+    ref = eo.vgg16_features(img, ws, bs, rois).reshape(B, 512, -1)
+    scale = np.abs(ref).max()
+    assert np.abs(out - ref).max() <= 2e-2 * scale
+    plain = eo.vgg16_features(img, ws, bs).reshape(B, 512, -1)        # all-255 padding: a different network input
+    assert np.abs(ref[0] - plain[0]).max() > 0.1 * scale              # the distinction matters ...
+    assert np.abs(out[0] - plain[0]).max() > 0.05 * scale             # ... and the GPU follows the reference
+    assert np.array_equal(enc.forward(img[1:2]), enc.forward(img[1:2], rois[1:2]))   # full rectangle == no padding
+    with pytest.raises(g.GlocError):
+        enc.forward(img[:1], np.array([[200, 0, 100, 10]], np.int32))
+    enc.close()
+
+
+@pytest.mark.gpu
+def test_reference_input_size_batch_16():
+    """768 x 768 (loop_detector.cpp:144-147), 16 frames per call: two frames against the float32
+    oracle, and every frame bit-identical to the same frame encoded alone."""
+    H = W = 768
+    ws, bs = eo.hashed_vgg_weights(17)
+    img = bev_like(16, H, W, 8)
+    enc = g.Encoder(ws, bs, height=H, width=W)
+    out = enc.forward(img)
+    for b in (0, 15):
+        ref = eo.vgg16_features(img[b:b + 1], ws, bs).reshape(512, -1)
+        err = np.abs(out[b] - ref).max() / np.abs(ref).max()
+        assert err <= 1e-2, err
+    for b in (3, 9):
+        assert np.array_equal(enc.forward(img[b:b + 1])[0], out[b])
+    enc.close()
+
+
+@pytest.mark.gpu
 def test_descriptor_path_on_the_device():
     import torch
 

@@ -15,7 +15,7 @@
 //       - the network's weights in the plain container tools/export_weights.py writes from that
 //         TorchScript file ("GLOCW001": 13 VGG16 convolutions + NetVLAD_fc): descriptors are then
 //         computed like get_place_feature does (loop_detector.cpp:137-172) -- BEV image, crop/pad
-//         to 768 x 768, encoder, pooling head -- through gloc_desc_extract;
+//         to 768 x 768, encoder, pooling head -- through gloc_desc_extract_padded;
 //       - a raw float32 table with (db_num + q_num) x 512 descriptors in valset order (what that
 //         forward would produce), for runs without a network.
 //   * the 4th argument switches ground alignment on like the reference's (:419-449, :482-509,
@@ -250,12 +250,25 @@ class GlocEvaluator {
     // otherwise.  Not used with ground alignment (the per-scan ground transforms are not in it).
     // (a grid store holds no descriptors: with a network every database scan is projected anyway)
     const char* grid_store = (align_ground_ || have_network_) ? nullptr : std::getenv("GLOC_GRID_STORE");
+    // what the stored grids were made from: the database scan list and the projection parameters
+    uint32_t store_tag = 2166136261u;   // FNV-1a
+    auto mix = [&](const void* p, size_t n) {
+      for (size_t b = 0; b < n; ++b) store_tag = (store_tag ^ ((const unsigned char*)p)[b]) * 16777619u;
+    };
+    for (const auto& f : db_files_) mix(f.data(), f.size() + 1);
+    const float proj_params[2] = {0.2f, 100.f};
+    mix(proj_params, sizeof proj_params);
+    if (store_tag == 0) store_tag = 1;
     if (grid_store) {
       gloc_grid_file* gf = nullptr;
       size_t n_stored = 0;
       if (gloc_grid_file_open(grid_store, &gf, &n_stored) == GLOC_OK) {
+        const uint32_t tag = gloc_grid_file_tag(gf);
         gloc_grid_file_close(gf);
-        if (n_stored == db_files_.size()) {
+        if (n_stored == db_files_.size() && tag != store_tag)
+          LOG_INFO << grid_store << " was built from another database or projection (fingerprint " << tag
+                   << ", expected " << store_tag << "): rebuilding";
+        if (n_stored == db_files_.size() && tag == store_tag) {
           int first = 0, n = 0;
           check(gloc_csm_load_grids(store_, grid_store, &first, &n), "gloc_csm_load_grids");
           for (int k = 0; k < n; ++k) db_grid_ids_.push_back(first + k);
@@ -289,7 +302,7 @@ class GlocEvaluator {
     if (have_network_) flush_planes(db_files_.size() - planes_.size() / ((size_t)kCnnSide * kCnnSide));
     check(gloc_knn_set_db(index_, feats_.data(), db_files_.size()), "gloc_knn_set_db");
     if (grid_store) {
-      check(gloc_csm_save_grids(store_, grid_store), "gloc_csm_save_grids");
+      check(gloc_csm_save_grids_tagged(store_, grid_store, store_tag), "gloc_csm_save_grids_tagged");
       LOG_INFO << "wrote " << db_grid_ids_.size() << " database grids to " << grid_store;
     }
     LOG_INFO << "time cost for align to ground: " << t_align / double(i) << "ms.";
@@ -497,15 +510,20 @@ class GlocEvaluator {
   void flush_planes(size_t first_row) {
     const int n = (int)(planes_.size() / ((size_t)kCnnSide * kCnnSide));
     if (n == 0) return;
-    check(gloc_desc_extract(enc_, head_, (int)kDim, planes_.data(), n, feats_.data() + first_row * kDim),
-          "gloc_desc_extract");
+    // padded planes: the reference's canvas padding is (255, 0, 0), loop_detector.cpp:84
+    check(gloc_desc_extract_padded(enc_, head_, (int)kDim, planes_.data(), rois_.data(), n,
+                                   feats_.data() + first_row * kDim),
+          "gloc_desc_extract_padded");
     planes_.clear();
+    rois_.clear();
   }
   // the projector's current image, cropped / padded to the CNN input, appended to the batch
   void push_plane() {
     const size_t at = planes_.size();
     planes_.resize(at + (size_t)kCnnSide * kCnnSide);
-    check(gloc_bev_get_cnn_input(bev_, kCnnSide, kCnnSide, planes_.data() + at), "gloc_bev_get_cnn_input");
+    int32_t roi[4];
+    check(gloc_bev_get_cnn_input_roi(bev_, kCnnSide, kCnnSide, planes_.data() + at, roi), "gloc_bev_get_cnn_input_roi");
+    rois_.insert(rois_.end(), roi, roi + 4);
   }
 
   void load_descriptors(const std::string& path) {
@@ -598,6 +616,7 @@ class GlocEvaluator {
   gloc_encoder* enc_ = nullptr;
   gloc_vlad_head* head_ = nullptr;
   std::vector<uint8_t> planes_;                 // CNN inputs waiting for the next batch
+  std::vector<int32_t> rois_;                   // their image rectangles (x0, y0, w, h)
 };
 
 }  // namespace
