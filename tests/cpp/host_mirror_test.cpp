@@ -100,6 +100,37 @@ int main() {
   size_t qi = 0, li = 0;
   EXPECT(det.detect(qi, li) && qi == 400 && li == 123);
 
+  // ---- match() against one resident store, and the batched detect_all_query + global_registraion
+  {
+    float xy_yaw[3] = {9.f, 9.f, 9.f};
+    double scale = 0.;
+    Grid2DView qg{{res, mx, my, nx, ny}, cells.data(), mx - res * ny, my - res * nx};   // the same place, seen again
+    // GridToVirtualPointCloud puts cell (i, j) at (ox + i res, oy + j res): match it against keyframe 7
+    const bool ok = det.match(qg, 7, xy_yaw, scale, 20, 10, 0.02, 0.3f);
+    const PointCloud qc = FastCorrelativeScanMatcher2D::GridToVirtualPointCloud(qg);
+    gloc_oracle_match_result om;
+    gloc_oracle_csm_match(l1.data(), nx, ny, res, mx, my, 5, qc[0].data(), (int)qc.size(), 0., 0., 0., 20, 10, 0.02,
+                          0.3f, 0, &om);
+    EXPECT(ok == (om.found != 0));
+    if (ok) EXPECT(xy_yaw[0] == (float)om.pose_x && xy_yaw[1] == (float)om.pose_y && xy_yaw[2] == (float)om.pose_yaw &&
+                   det.last_score() == om.score && scale == 1.);
+    std::vector<std::vector<float>> qf = {db[123], db[17]};
+    qf[0][3] += 2e-3f;
+    const auto located = det.localize(qf, {qg, qg}, false, 20, 10, 0.02, 0.3f);
+    EXPECT(located.size() == 2 && located[0].loop_indices.size() == K);
+    for (int qi2 = 0; qi2 < 2; ++qi2) {
+      gloc_oracle_knn(flat.data(), 401, D, qf[qi2].data(), 1, K, oi.data(), od.data());
+      // (row 400 is the near-copy of 123 appended above; the flat copy holds the original rows only)
+      EXPECT(located[qi2].matched == (om.found != 0));       // every keyframe carries the same grid
+      if (located[qi2].matched)
+        EXPECT(located[qi2].located_db_idx == located[qi2].loop_indices[0] && located[qi2].score == om.score &&
+               located[qi2].xy_yaw[0] == (float)om.pose_x && located[qi2].xy_yaw[2] == (float)om.pose_yaw);
+    }
+    EXPECT(located[1].loop_indices[0] == 17 && located[1].out_dists_sqr[0] == 0.f);
+    const auto first = det.localize(qf, {qg, qg}, true, 20, 10, 0.02, 0.3f);
+    EXPECT(first[0].matched == located[0].matched && first[0].located_db_idx == located[0].located_db_idx);
+  }
+
   // ---- BEV projection through the loop detector's own interface vs the oracle
   {
     std::vector<float> scan;
