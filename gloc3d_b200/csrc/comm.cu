@@ -7,6 +7,7 @@
 // (PyTorch bundles its own) shares that copy, a plain C++ host gets the system library, and
 // single-GPU users never load it.
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>   // types and prototypes only; every call goes through the table below
 
 #include <cstring>
@@ -113,6 +114,102 @@ int comm_all_to_all(gloc_comm* c, const void* send, void* recv, size_t bytes_per
   return GLOC_OK;
 }
 
+namespace {
+
+struct PeerInfo {
+  unsigned long long pid, ptr;
+  int device, pad;
+  cudaIpcMemHandle_t handle;
+};
+
+// every rank's `bytes` bytes of host data to every rank (through a small device buffer and NCCL)
+int host_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes) {
+  const size_t need = bytes * (size_t)(c->size + 1);
+  if (need > 65536) return fail(GLOC_ERR_RANGE, "comm: host exchange too large");
+  if (!c->d_scratch) GLOC_CUDA_TRY(cudaMalloc(&c->d_scratch, 65536));
+  if (!c->xstream) GLOC_CUDA_TRY(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
+  char* d = (char*)c->d_scratch;
+  GLOC_CUDA_TRY(cudaMemcpyAsync(d, send, bytes, cudaMemcpyHostToDevice, c->xstream));
+  GLOC_NCCL_TRY(api().AllGather(d, d + bytes, bytes, ncclUint8, (ncclComm_t)c->nccl, c->xstream));
+  GLOC_CUDA_TRY(cudaMemcpyAsync(recv, d + bytes, bytes * (size_t)c->size, cudaMemcpyDeviceToHost, c->xstream));
+  GLOC_CUDA_TRY(cudaStreamSynchronize(c->xstream));
+  return GLOC_OK;
+}
+
+}  // namespace
+
+int comm_map_peers(gloc_comm* c, void* local, void*** out) {
+  for (auto& m : c->maps)
+    if (m.local == local) {
+      *out = m.ptrs.data();
+      return GLOC_OK;
+    }
+  PeerInfo mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.pid = (unsigned long long)getpid();
+  mine.ptr = (unsigned long long)(uintptr_t)local;
+  mine.device = c->device;
+  cudaError_t he = cudaIpcGetMemHandle(&mine.handle, local);
+  if (he != cudaSuccess) (void)cudaGetLastError();   // still exchanged: peers in this process do not need it
+  std::vector<PeerInfo> all((size_t)c->size);
+  int rc = host_all_gather(c, &mine, all.data(), sizeof(PeerInfo));
+  if (rc != GLOC_OK) return rc;
+  gloc_peer_map m;
+  m.local = local;
+  m.ptrs.assign((size_t)c->size, nullptr);
+  m.opened.assign((size_t)c->size, 0);
+  int bad = 0;
+  for (int i = 0; i < c->size; ++i) {
+    if (i == c->rank) {
+      m.ptrs[i] = local;
+    } else if (all[i].pid == mine.pid) {            // same process: the pointer itself, once peer access is on
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, c->device, all[i].device) != cudaSuccess || !can) {
+        bad = 1;
+        continue;
+      }
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[i].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) bad = 1;
+      (void)cudaGetLastError();
+      m.ptrs[i] = (void*)(uintptr_t)all[i].ptr;
+    } else {
+      void* p = nullptr;
+      cudaError_t e = he == cudaSuccess ? cudaIpcOpenMemHandle(&p, all[i].handle, cudaIpcMemLazyEnablePeerAccess)
+                                        : he;
+      if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        bad = 1;
+        continue;
+      }
+      m.ptrs[i] = p;
+      m.opened[i] = 1;
+    }
+  }
+  // agree: either every rank mapped every peer, or nobody uses peer memory
+  std::vector<int> flags((size_t)c->size);
+  rc = host_all_gather(c, &bad, flags.data(), sizeof(int));
+  if (rc != GLOC_OK) return rc;
+  for (int f : flags) bad |= f;
+  if (bad) {
+    for (int i = 0; i < c->size; ++i)
+      if (m.opened[i]) cudaIpcCloseMemHandle(m.ptrs[i]);
+    return fail(GLOC_ERR_CUDA, "comm: the GPUs of this communicator cannot address each other's memory");
+  }
+  c->maps.push_back(std::move(m));
+  *out = c->maps.back().ptrs.data();
+  return GLOC_OK;
+}
+
+void comm_unmap_peers(gloc_comm* c, void* local) {
+  for (size_t k = 0; k < c->maps.size(); ++k)
+    if (c->maps[k].local == local) {
+      for (int i = 0; i < c->size; ++i)
+        if (c->maps[k].opened[i]) cudaIpcCloseMemHandle(c->maps[k].ptrs[i]);
+      c->maps.erase(c->maps.begin() + k);
+      return;
+    }
+}
+
 }  // namespace gloc
 
 using namespace gloc;
@@ -176,9 +273,12 @@ int gloc_comm_create_local(gloc_comm** out, int n_devices, const int* devices) {
 
 void gloc_comm_destroy(gloc_comm* c) {
   if (!c) return;
-  if (c->nccl && api().ok) {
+  {
     DeviceGuard g(c->device);
-    api().CommDestroy((ncclComm_t)c->nccl);
+    while (!c->maps.empty()) comm_unmap_peers(c, c->maps.back().local);
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->xstream) cudaStreamDestroy(c->xstream);
+    if (c->nccl && api().ok) api().CommDestroy((ncclComm_t)c->nccl);
   }
   delete c;
 }

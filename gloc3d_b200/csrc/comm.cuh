@@ -2,9 +2,22 @@
 #pragma once
 #include "common.cuh"
 
+#include <vector>
+
+// A local device buffer and where every rank's counterpart is mapped in this process (peer
+// memory over NVLink: direct pointers inside one process, CUDA IPC between processes).
+struct gloc_peer_map {
+  void* local = nullptr;
+  std::vector<void*> ptrs;       // [size]; ptrs[rank] == local
+  std::vector<char> opened;      // ptrs[i] came from cudaIpcOpenMemHandle
+};
+
 struct gloc_comm {
   void* nccl = nullptr;   // ncclComm_t
   int rank = 0, size = 1, device = 0;
+  void* d_scratch = nullptr;     // small device buffer for host-side exchanges
+  cudaStream_t xstream = nullptr;
+  std::vector<gloc_peer_map> maps;
 };
 
 namespace gloc {
@@ -12,4 +25,8 @@ namespace gloc {
 int comm_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
 int comm_all_reduce_max_u64(gloc_comm* c, const void* send, void* recv, size_t count, cudaStream_t s);
 int comm_all_to_all(gloc_comm* c, const void* send, void* recv, size_t bytes_per_block, cudaStream_t s);
+// Collective: every rank passes its own cudaMalloc'ed buffer; out[i] = rank i's buffer as this
+// process can address it (GLOC_ERR_CUDA when peers cannot reach each other).  Cached per pointer.
+int comm_map_peers(gloc_comm* c, void* local, void*** out);
+void comm_unmap_peers(gloc_comm* c, void* local);
 }  // namespace gloc

@@ -83,6 +83,16 @@ struct gloc_knn_index {
   DevBuf flag;                    // streaming scan: merge-overflow flag
   DevBuf stage_q, stage_idx, stage_d2;
   DevBuf sh_allq, sh_lidx, sh_ld2, sh_gidx, sh_gd2;   // row-sharded search: gathered queries, per-shard lists
+  // peer-memory exchange (NVLink): this rank's lists where every rank can read them
+  struct {
+    int state = 0;               // 0 untried, 1 in use, -1 unavailable (NCCL exchange instead)
+    gloc_comm* comm = nullptr;
+    void* buf[2] = {nullptr, nullptr};
+    void* d_ptrs = nullptr;      // device: [2][size] peer pointers (list buffers) + [size] (flags = buffer 0)
+    int* d_err = nullptr;
+    size_t cap_entries = 0;
+    unsigned epoch = 0;
+  } p2p;
   ShortlistState* sl = nullptr;   // tensor-shortlist state (bf16 copy, norms, workspaces)
   gloc_knn_stats stats{};
   EventProfiler prof;
@@ -285,6 +295,15 @@ void gloc_knn_destroy(gloc_knn_index* ix) {
   ix->stage_idx.release();
   ix->stage_d2.release();
   for (DevBuf* b : {&ix->sh_allq, &ix->sh_lidx, &ix->sh_ld2, &ix->sh_gidx, &ix->sh_gd2}) b->release();
+  // (the peers' mappings of p2p.buf are closed by gloc_comm_destroy; destroy the index after a
+  // barrier of the host program, as with any buffer peers may still read)
+  for (void* b : ix->p2p.buf)
+    if (b) {
+      if (ix->p2p.comm) comm_unmap_peers(ix->p2p.comm, b);
+      cudaFree(b);
+    }
+  if (ix->p2p.d_ptrs) cudaFree(ix->p2p.d_ptrs);
+  if (ix->p2p.d_err) cudaFree(ix->p2p.d_err);
   shortlist_destroy(ix->sl);
   delete ix;
 }
@@ -485,6 +504,67 @@ int gloc_knn_merge_topk_device(const uint64_t* d_idx, const float* d_d2, size_t 
                                        (cudaStream_t)stream));
   return GLOC_OK;
 }
+}  // extern "C"
+
+namespace {
+
+// Peer-memory list buffers of a row-sharded index: (re)allocated collectively -- every rank sees the
+// same (ranks, queries, k), so every rank grows in the same call.  Returns false when the GPUs
+// cannot address each other (then the lists travel through NCCL instead).
+bool p2p_prepare(gloc_knn_index* ix, gloc_comm* comm, size_t entries, cudaStream_t stream) {
+  auto& P = ix->p2p;
+  if (P.state < 0 || std::getenv("GLOC_SHARD_NO_P2P") != nullptr) return false;
+  if (P.state == 1 && P.comm == comm && entries <= P.cap_entries) return true;
+  // growth (or first use): nobody may still be reading the old buffers
+  cudaStreamSynchronize(stream);
+  const size_t cap = std::max<size_t>(entries + entries / 4, 65536);
+  const size_t bytes = 256 + cap * 12;
+  void* nb[2] = {nullptr, nullptr};
+  void** peers[2] = {nullptr, nullptr};
+  bool ok = cudaMalloc(&nb[0], bytes) == cudaSuccess && cudaMalloc(&nb[1], bytes) == cudaSuccess;
+  if (ok) ok = cudaMemset(nb[0], 0, 256) == cudaSuccess && cudaMemset(nb[1], 0, 256) == cudaSuccess &&
+               cudaDeviceSynchronize() == cudaSuccess;
+  // the mapping is collective: called even after a local failure (with a null pointer it fails everywhere)
+  int rc0 = comm_map_peers(comm, ok ? nb[0] : nullptr, &peers[0]);
+  int rc1 = rc0 == GLOC_OK ? comm_map_peers(comm, nb[1], &peers[1]) : rc0;
+  if (rc0 != GLOC_OK || rc1 != GLOC_OK) {
+    if (rc0 == GLOC_OK) comm_unmap_peers(comm, nb[0]);
+    for (void* b : nb)
+      if (b) cudaFree(b);
+    (void)cudaGetLastError();
+    P.state = -1;
+    return false;
+  }
+  for (void* b : P.buf)
+    if (b) {
+      comm_unmap_peers(P.comm, b);
+      cudaFree(b);
+    }
+  const size_t n = (size_t)comm->size;
+  if (!P.d_ptrs && cudaMalloc(&P.d_ptrs, 3 * 64 * sizeof(void*)) != cudaSuccess) { P.state = -1; return false; }
+  if (!P.d_err && (cudaMalloc((void**)&P.d_err, 4) != cudaSuccess || cudaMemset(P.d_err, 0, 4) != cudaSuccess)) { P.state = -1; return false; }
+  std::vector<void*> table(3 * 64, nullptr);
+  for (size_t i = 0; i < n; ++i) {
+    table[i] = peers[0][i];          // list buffers of even calls
+    table[64 + i] = peers[1][i];     // list buffers of odd calls
+    table[128 + i] = peers[0][i];    // flag words: always buffer 0
+  }
+  if (cudaMemcpy(P.d_ptrs, table.data(), table.size() * sizeof(void*), cudaMemcpyHostToDevice) != cudaSuccess) {
+    P.state = -1;
+    return false;
+  }
+  P.buf[0] = nb[0];
+  P.buf[1] = nb[1];
+  P.cap_entries = cap;
+  P.comm = comm;
+  P.epoch = 0;
+  P.state = 1;
+  return true;
+}
+
+}  // namespace
+
+extern "C" {
 
 // Row-sharded exact top-k (BASELINE configs[3]): every rank holds rows
 // [offset, offset + n) and calls this collectively.
@@ -509,13 +589,65 @@ int gloc_knn_query_sharded_device(gloc_knn_index* ix, gloc_comm* comm, const flo
   cudaStream_t stream = (cudaStream_t)stream_v;
   const size_t N = (size_t)comm->size, dim = ix->dim;
   int rc;
+  // tuning aid: GLOC_SHARD_TIMING=1 prints the device time of every stage of this call (rank 0)
+  const bool timing = std::getenv("GLOC_SHARD_TIMING") != nullptr && comm->rank == 0;
+  cudaEvent_t tev[5] = {};
+  auto mark = [&](int i) {
+    if (timing) {
+      if (!tev[i]) cudaEventCreate(&tev[i]);
+      cudaEventRecord(tev[i], stream);
+    }
+  };
+  mark(0);
+  // ---- exchange fused into the merge: the search writes its lists where the peers can read them
+  //      (peer memory over NVLink), one kernel signals, waits, gathers and merges
+  if (comm->size <= 64 && k <= 128 && (size_t)comm->size * k * 12 * 4 <= 48 * 1024 &&
+      p2p_prepare(ix, comm, (replicated ? nq : N * nq) * k, stream)) {
+    auto& P = ix->p2p;
+    const unsigned epoch = ++P.epoch;
+    const int par = (int)(epoch & 1u);
+    char* buf = (char*)P.buf[par];
+    const size_t idx_off = 256, d2_off = 256 + P.cap_entries * 8;
+    const float* dq = d_q;
+    size_t n_search = nq;
+    if (!replicated) {
+      GLOC_CUDA_TRY(ix->sh_allq.reserve(N * nq * dim * sizeof(float)));
+      rc = comm_all_gather(comm, d_q, ix->sh_allq.p, nq * dim * sizeof(float), stream);
+      if (rc != GLOC_OK) return rc;
+      dq = (const float*)ix->sh_allq.p;
+      n_search = N * nq;
+    }
+    mark(1);
+    rc = gloc_knn_query_device(ix, dq, n_search, k, (uint64_t*)(buf + idx_off), (float*)(buf + d2_off), stream);
+    if (rc != GLOC_OK) return rc;
+    mark(2);
+    mark(3);
+    void* const* tab = (void* const*)P.d_ptrs;
+    GLOC_CUDA_TRY(launch_knn_p2p_gather_merge(tab + 128, tab + 64 * par, comm->size, comm->rank, epoch, idx_off, d2_off,
+                                              replicated ? 0 : (size_t)comm->rank * nq, (int)nq, (int)k, d_out_idx,
+                                              d_out_d2, P.d_err, stream));
+    ix->stats.kernel_launches++;
+    mark(4);
+    if (timing) {
+      cudaEventSynchronize(tev[4]);
+      float t[4] = {0, 0, 0, 0};
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+      fprintf(stderr, "[shard] ranks=%d nq=%zu %s (peer memory): gather queries=%.3f ms  local search (%zu queries x %zu rows)"
+                      "=%.3f ms  signal + wait + gather + merge=%.3f ms\n", comm->size, nq,
+              replicated ? "replicated" : "sliced", t[0], n_search, std::min(ix->n, ix->search_limit), t[1], t[3]);
+      for (auto& e : tev) cudaEventDestroy(e);
+    }
+    return GLOC_OK;
+  }
   if (replicated) {
     GLOC_CUDA_TRY(ix->sh_lidx.reserve(nq * k * sizeof(uint64_t)));
     GLOC_CUDA_TRY(ix->sh_ld2.reserve(nq * k * sizeof(float)));
     GLOC_CUDA_TRY(ix->sh_gidx.reserve(N * nq * k * sizeof(uint64_t)));
     GLOC_CUDA_TRY(ix->sh_gd2.reserve(N * nq * k * sizeof(float)));
+    mark(1);
     rc = gloc_knn_query_device(ix, d_q, nq, k, (uint64_t*)ix->sh_lidx.p, (float*)ix->sh_ld2.p, stream);
     if (rc != GLOC_OK) return rc;
+    mark(2);
     rc = comm_all_gather(comm, ix->sh_lidx.p, ix->sh_gidx.p, nq * k * sizeof(uint64_t), stream);
     if (rc != GLOC_OK) return rc;
     rc = comm_all_gather(comm, ix->sh_ld2.p, ix->sh_gd2.p, nq * k * sizeof(float), stream);
@@ -529,9 +661,11 @@ int gloc_knn_query_sharded_device(gloc_knn_index* ix, gloc_comm* comm, const flo
     GLOC_CUDA_TRY(ix->sh_gd2.reserve(nq_all * k * sizeof(float)));
     rc = comm_all_gather(comm, d_q, ix->sh_allq.p, nq * dim * sizeof(float), stream);
     if (rc != GLOC_OK) return rc;
+    mark(1);
     rc = gloc_knn_query_device(ix, (const float*)ix->sh_allq.p, nq_all, k, (uint64_t*)ix->sh_lidx.p,
                                (float*)ix->sh_ld2.p, stream);
     if (rc != GLOC_OK) return rc;
+    mark(2);
     // block r of my lists = the queries rank r owns; I receive my queries' lists from every shard,
     // laid out [shard][nq][k]: exactly what the merge takes
     rc = comm_all_to_all(comm, ix->sh_lidx.p, ix->sh_gidx.p, nq * k * sizeof(uint64_t), stream);
@@ -539,9 +673,20 @@ int gloc_knn_query_sharded_device(gloc_knn_index* ix, gloc_comm* comm, const flo
     rc = comm_all_to_all(comm, ix->sh_ld2.p, ix->sh_gd2.p, nq * k * sizeof(float), stream);
     if (rc != GLOC_OK) return rc;
   }
+  mark(3);
   GLOC_CUDA_TRY(launch_knn_merge_pairs((const uint64_t*)ix->sh_gidx.p, (const float*)ix->sh_gd2.p, (int)N,
                                        (int)nq, (int)k, d_out_idx, d_out_d2, stream));
   ix->stats.kernel_launches++;
+  mark(4);
+  if (timing) {
+    cudaEventSynchronize(tev[4]);
+    float t[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+    fprintf(stderr, "[shard] ranks=%d nq=%zu %s: gather queries=%.3f ms  local search (%zu queries x %zu rows)=%.3f ms  "
+                    "exchange lists=%.3f ms  merge=%.3f ms\n", comm->size, nq, replicated ? "replicated" : "sliced",
+            t[0], replicated ? nq : N * nq, std::min(ix->n, ix->search_limit), t[1], t[2], t[3]);
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
   return GLOC_OK;
 }
 

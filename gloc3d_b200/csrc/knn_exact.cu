@@ -356,6 +356,93 @@ __global__ void knn_merge_pairs_kernel(const uint64_t* __restrict__ idx,
   }
 }
 
+
+// K4 fused with its collective (row-sharded search): every rank's local top-k lists
+// sit in a buffer that every other rank can address over NVLink (peer memory).  One kernel per
+// rank (a) tells every peer "my lists of this epoch are complete" with a remote store into the
+// peer's flag word -- stream order has put the lists in memory before this kernel started --,
+// (b) waits until every peer has said the same, (c) pulls the lists of ITS queries straight out of
+// the peers' buffers into shared memory and (d) merges them.  No NCCL call, no staging copy.
+//   fbufs[p]  rank p's flag words (64 x u32) as this rank addresses them
+//   bufs[p]   rank p's list buffer of this call (two alternate: a rank may be one call ahead of a
+//             peer that is still reading): [256 B][idx][d2]
+//   block     first list of this rank's queries inside every peer's buffer (sliced batch:
+//             rank * nq; the same query everywhere: 0)
+// One warp per query; lists of k <= 128 entries.
+__global__ void knn_p2p_gather_merge_kernel(void* const* __restrict__ fbufs, void* const* __restrict__ bufs,
+                                            int n_ranks, int rank,
+                                            unsigned epoch, size_t idx_off, size_t d2_off, size_t block,
+                                            int nq, int k, uint64_t* __restrict__ out_idx,
+                                            float* __restrict__ out_d2, int* __restrict__ err) {
+  extern __shared__ __align__(16) unsigned char p2p_smem[];
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (a) signal: idempotent, so every block does it -- no block waits on another block of this grid
+  if (threadIdx.x < n_ranks) {
+    __threadfence_system();
+    volatile unsigned* flag = reinterpret_cast<volatile unsigned*>(fbufs[threadIdx.x]) + rank;
+    *flag = epoch;
+  }
+  // (b) wait for every peer (bounded: a peer that died must not hang this GPU)
+  if (threadIdx.x < n_ranks) {
+    volatile unsigned* mine = reinterpret_cast<volatile unsigned*>(fbufs[rank]) + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int)(*mine - epoch) < 0) {
+      if (clock64() - t0 > 8000000000ll) {   // ~4 s
+        atomicExch(err, 1);
+        break;
+      }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int q = blockIdx.x * wpb + w;
+  if (q >= nq) return;
+  uint64_t* li = reinterpret_cast<uint64_t*>(p2p_smem) + (size_t)w * n_ranks * k;
+  float* ld = reinterpret_cast<float*>(p2p_smem + (size_t)wpb * n_ranks * k * 8) + (size_t)w * n_ranks * k;
+  // (c) gather: k contiguous entries per peer, read around the caches (the buffers are rewritten every call)
+  for (int p = 0; p < n_ranks; ++p) {
+    const char* base = reinterpret_cast<const char*>(bufs[p]);
+    const uint64_t* pi = reinterpret_cast<const uint64_t*>(base + idx_off) + (block + q) * k;
+    const float* pd = reinterpret_cast<const float*>(base + d2_off) + (block + q) * k;
+    for (int i = lane; i < k; i += 32) {
+      li[p * k + i] = __ldcv(pi + i);
+      ld[p * k + i] = __ldcv(pd + i);
+    }
+  }
+  __syncwarp();
+  // (d) merge by rank counting, as knn_merge_pairs_kernel
+  uint64_t* oi = out_idx + (size_t)q * k;
+  float* od = out_d2 + (size_t)q * k;
+  for (int i = lane; i < k; i += 32) {
+    oi[i] = 0xFFFFFFFFFFFFFFFFull;
+    od[i] = 3.402823466e+38f;
+  }
+  __syncwarp();
+  const int total = n_ranks * k;
+  for (int e = lane; e < total; e += 32) {
+    const int seg = e / k, pos = e % k;
+    const uint64_t ii = li[e];
+    if (ii == 0xFFFFFFFFFFFFFFFFull) continue;
+    const float dd = ld[e];
+    int r = pos;
+    for (int s2 = 0; s2 < n_ranks && r < k; ++s2) {
+      if (s2 == seg) continue;
+      int lo = 0, hi = k;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const uint64_t im = li[s2 * k + mid];
+        const bool less = (im != 0xFFFFFFFFFFFFFFFFull) && pair_less(ld[s2 * k + mid], im, dd, ii);
+        if (less) lo = mid + 1; else hi = mid;
+      }
+      r += lo;
+    }
+    if (r < k) {
+      oi[r] = ii;
+      od[r] = dd;
+    }
+  }
+}
+
 template <int BQ, int BN, int TQ, int TN, int KCAP>
 cudaError_t launch_scan(const float* db, long long n_rows, int dim, const float* q, int nq, int k,
                         int n_ranges, long long rows_per_range, uint64_t* partial,
@@ -408,6 +495,17 @@ cudaError_t launch_knn_merge_pairs(const uint64_t* idx, const float* d2, int g, 
   const int threads = 128, wpb = threads / 32;
   knn_merge_pairs_kernel<<<(nq + wpb - 1) / wpb, threads, 0, stream>>>(idx, d2, g, nq, k, out_idx,
                                                                        out_d2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn_p2p_gather_merge(void* const* d_fbufs, void* const* d_bufs, int n_ranks, int rank, unsigned epoch, size_t idx_off,
+                                        size_t d2_off, size_t block, int nq, int k, uint64_t* out_idx,
+                                        float* out_d2, int* err, cudaStream_t stream) {
+  const int threads = 128, wpb = threads / 32;
+  const size_t smem = (size_t)wpb * n_ranks * k * 12;
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  knn_p2p_gather_merge_kernel<<<(nq + wpb - 1) / wpb, threads, smem, stream>>>(
+      d_fbufs, d_bufs, n_ranks, rank, epoch, idx_off, d2_off, block, nq, k, out_idx, out_d2, err);
   return cudaGetLastError();
 }
 

@@ -18,6 +18,10 @@ cudaError_t launch_knn_finalize(const uint64_t* partial, int nq, int n_lists, in
                                 uint64_t idx_offset, uint64_t* out_idx, float* out_d2,
                                 cudaStream_t stream, const int* qmap = nullptr,
                                 const int* nq_dev = nullptr);
+// K4 fused with the exchange: lists pulled from the peers' buffers over NVLink (see knn_exact.cu)
+cudaError_t launch_knn_p2p_gather_merge(void* const* d_fbufs, void* const* d_bufs, int n_ranks, int rank, unsigned epoch, size_t idx_off,
+                                        size_t d2_off, size_t block, int nq, int k, uint64_t* out_idx,
+                                        float* out_d2, int* err, cudaStream_t stream);
 cudaError_t launch_knn_merge_pairs(const uint64_t* idx, const float* d2, int g, int nq, int k,
                                    uint64_t* out_idx, float* out_d2, cudaStream_t stream);
 
