@@ -34,38 +34,45 @@ def make_descriptors(n: int, dim: int = DIM, seed: int = 1234, dup_run: int = 0,
     return out
 
 
+MT_BLOCK = 16384     # rows per independent stream of make_descriptors_mt
+
+
 def make_descriptors_mt(n: int, dim: int = DIM, seed: int = 1234, dup_run: int = 8,
-                        dup_sigma: float = 0.001, threads: int = 0) -> np.ndarray:
+                        dup_sigma: float = 0.001, threads: int = 0, rows=None) -> np.ndarray:
     """Same distribution as make_descriptors (iid N(0, 1/dim) run heads, random-walk runs of
     near-duplicates), generated block by block from independent streams `default_rng([seed, block])`
     on a thread pool -- million-row databases in seconds; the result does not depend on the
-    thread count.  Not byte-identical to make_descriptors (different streams)."""
+    thread count.  Not byte-identical to make_descriptors (different streams).  rows = (lo, hi):
+    only rows [lo, hi) of the n-row database (a shard; identical to the slice of the whole)."""
     import os
     from concurrent.futures import ThreadPoolExecutor
 
     run = max(1, dup_run)
-    block = 16384 // run * run
-    out = np.empty((n, dim), np.float32)
+    block = MT_BLOCK // run * run
+    lo, hi = (0, n) if rows is None else rows
+    out = np.empty((hi - lo, dim), np.float32)
     scale = np.float32(1.0 / np.sqrt(dim))
 
     def fill(b):
         s, e = b * block, min(n, (b + 1) * block)
         rng = np.random.default_rng([seed, b])
-        rows = e - s
+        rows = e - s            # noqa: F841 (shadows the parameter on purpose: rows of this block)
         heads = -(-rows // run)
         base = rng.standard_normal((heads, dim), dtype=np.float32) * scale
         if run == 1:
-            out[s:e] = base
-            return
-        steps = rng.standard_normal((heads, run - 1, dim), dtype=np.float32) * np.float32(dup_sigma)
-        full = np.empty((heads, run, dim), np.float32)
-        full[:, 0] = base
-        full[:, 1:] = base[:, None, :] + np.cumsum(steps, axis=1, dtype=np.float32)
-        out[s:e] = full.reshape(heads * run, dim)[:rows]
+            full = base
+        else:
+            steps = rng.standard_normal((heads, run - 1, dim), dtype=np.float32) * np.float32(dup_sigma)
+            full = np.empty((heads, run, dim), np.float32)
+            full[:, 0] = base
+            full[:, 1:] = base[:, None, :] + np.cumsum(steps, axis=1, dtype=np.float32)
+            full = full.reshape(heads * run, dim)[:rows]
+        a, z = max(s, lo), min(e, hi)            # the part of this block inside [lo, hi)
+        out[a - lo:z - lo] = full[a - s:z - s]
 
-    nb = -(-n // block)
+    blocks = range(lo // block, -(-hi // block))
     with ThreadPoolExecutor(max_workers=threads or min(32, os.cpu_count() or 1)) as ex:
-        list(ex.map(fill, range(nb)))
+        list(ex.map(fill, blocks))
     return out
 
 
