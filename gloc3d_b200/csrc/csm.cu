@@ -1037,7 +1037,7 @@ __global__ void csm_filter_kernel(const CsmPairDev* __restrict__ pairs, int n_pa
 
 // ------------------------------------------------------------------- K7 expand
 
-constexpr int kExpChunk = 2048;   // points staged per pass of the expand kernel
+constexpr int kExpChunk = 512;    // points staged per pass of the expand kernel (and the early-exit granularity)
 
 // Survivors of grids without bit planes go to the depth-first refinement unexpanded.
 __global__ void csm_survivors_to_nodes_kernel(const CsmPairDev* __restrict__ pairs, CsmParams prm,
@@ -1135,6 +1135,9 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
     const int ax = xo + wm1, ay = yo + wm1;   // cell -> level frame of child (0, 0)
     int sum[4] = {0, 0, 0, 0};
     if (tid < 128) s_sum[tid >> 2][tid & 3] = 0;
+    // the incumbent as of now: a lower bound of what a child has to beat (it only grows)
+    const unsigned long long incumbent = active ? ld_best(best + pi) : ~0ull;
+    bool group_dead = false;
     for (int p0 = 0; p0 < P; p0 += kExpChunk) {
       const int n = min(kExpChunk, P - p0);
       __syncthreads();
@@ -1193,12 +1196,44 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
           }
         }
       }
+      // early exit: after every chunk but the last, can any child of these 32 survivors still beat the
+      // incumbent if every point left were a hit?  (A matched pair's survivors need ~3/4 of the points
+      // to hit; most are dead after a third of the scan.)
+      if (p0 + n < P) {
+        if (active) {
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            atomicAdd(&s_sum[lane][ch], sum[ch]);
+            sum[ch] = 0;
+          }
+        }
+        __syncthreads();
+        bool alive = false;
+        if (active && slice == 0) {
+          const int left = P - (p0 + n);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const int cx = xo + (ch >> 1) * h, cy = yo + (ch & 1) * h;
+            alive |= cx <= b.max_x && cy <= b.max_y &&
+                     key_of(score_of(255 * (s_sum[lane][ch] + left), P, prm), rank_of(prm, s, cx, cy)) > incumbent;
+          }
+        }
+        if (!__syncthreads_or(alive)) {
+          group_dead = true;
+          break;
+        }
+      }
     }
     if (active) {
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) atomicAdd(&s_sum[lane][ch], sum[ch]);
     }
     __syncthreads();
+    if (group_dead) {                 // partial sums only: nothing here can win, nothing to emit
+      if (active && slice == 0) ++expanded;
+      __syncthreads();
+      continue;
+    }
     if (active && slice == 0) {
       ++expanded;
 #pragma unroll
