@@ -123,7 +123,7 @@ __global__ void csm_level1_from_cells_kernel(const uint16_t* __restrict__ cells,
 // ---- store encodings
 
 // uint8 width-1 grid -> bit-packed rows (bit x of row y at word y * stride + x / 32, stride =
-// (nx + 31) / 32 + 1, zero beyond nx); *not_binary is set when a cell is neither 0 nor 255.
+// csm_bit_stride(nx), zero beyond nx); *not_binary is set when a cell is neither 0 nor 255.
 __global__ void csm_pack_bits_kernel(const uint8_t* __restrict__ level1, int nx, int ny, int stride,
                                      unsigned* __restrict__ out, int* __restrict__ not_binary) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -190,7 +190,6 @@ __global__ void csm_slot_lookup_kernel(CsmPairDev* __restrict__ pairs, int n_pai
   pairs[i].grid = hslot[h];
 }
 
-__device__ __forceinline__ int bit_stride(int wide_nx) { return (wide_nx + 31) / 32 + 1; }
 
 __global__ void csm_prepare_slots_kernel(const CsmGridRec* __restrict__ recs,
                                          const int* __restrict__ slot_gid,
@@ -210,10 +209,10 @@ __global__ void csm_prepare_slots_kernel(const CsmGridRec* __restrict__ recs,
   const int top = plan.depth - 1, w = 1 << top;
   if (plan.bits) {
     g.lvl[0] = reinterpret_cast<const unsigned*>(r.data);
-    g.lvs[0] = bit_stride(r.nx);
+    g.lvs[0] = csm_bit_stride(r.nx);
     for (int l = 1; l < plan.depth; ++l) {
       g.lvl[l] = reinterpret_cast<const unsigned*>(base + plan.lvl_off[l]);
-      g.lvs[l] = bit_stride(r.nx + (1 << l) - 1);
+      g.lvs[l] = csm_bit_stride(r.nx + (1 << l) - 1);
     }
     g.pmb = reinterpret_cast<const unsigned long long*>(base + plan.pmb_off);
     g.pmb_rows = ((r.ny + w - 1 + 3 * plan.n_lin - 1) >> top) + 1 + kBitRowSlack;
@@ -274,7 +273,7 @@ __global__ void csm_slot_level0_u8_kernel(const CsmGridRec* __restrict__ recs,
   const CsmGridRec r = recs[slot_gid[blockIdx.y]];
   const size_t n = (size_t)g.nx * g.ny;
   uint8_t* out = const_cast<uint8_t*>(g.stack);
-  const int stride = (g.nx + 31) / 32 + 1;
+  const int stride = csm_bit_stride(g.nx);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     if (r.enc == 1) {
       const int y = (int)(i / g.nx), x = (int)(i % g.nx);
@@ -674,11 +673,26 @@ __global__ void csm_build_pmb_kernel(const CsmGridDev* __restrict__ slots,
     const int ly = (r << log2w) + ry - py;
     unsigned long long bits = 0;
     if ((unsigned)ly < (unsigned)wide_ny) {
-      const unsigned* row = level + (size_t)ly * stride;
-      for (int c = 0; c < 64; ++c) {
-        const int lx = (c << log2w) + rx - px;
-        if ((unsigned)lx < (unsigned)wide_nx)
-          bits |= (unsigned long long)((__ldg(row + (lx >> 5)) >> (lx & 31)) & 1u) << c;
+      if (log2w == 4) {
+        // bit c of the plane row = level bit 16 c + (rx - px): every 64-bit word of the level row
+        // (rows are 8-byte aligned, zero beyond wide_nx) holds four of them, 16 apart; one multiply
+        // gathers the four into a nibble
+        const unsigned long long* row = reinterpret_cast<const unsigned long long*>(level + (size_t)ly * stride);
+        const int q = rx - px, q16 = q & 15, fq = (q - q16) >> 4;      // column of bit c = 16 (c + fq) + q16
+        unsigned long long gathered = 0;                                // bit c' = level bit 16 c' + q16
+        const int n64 = min(stride >> 1, 16);
+        for (int j = 0; j < n64; ++j) {
+          const unsigned long long t = (__ldg(row + j) >> q16) & 0x0001000100010001ull;
+          gathered |= (((t * 0x0001000200040008ull) >> 48) & 0xFull) << (4 * j);
+        }
+        bits = fq <= 0 ? (-fq < 64 ? gathered << (-fq) : 0ull) : (fq < 64 ? gathered >> fq : 0ull);
+      } else {
+        const unsigned* row = level + (size_t)ly * stride;
+        for (int c = 0; c < 64; ++c) {
+          const int lx = (c << log2w) + rx - px;
+          if ((unsigned)lx < (unsigned)wide_nx)
+            bits |= (unsigned long long)((__ldg(row + (lx >> 5)) >> (lx & 31)) & 1u) << c;
+        }
       }
     }
     out[idx] = bits;
@@ -1015,29 +1029,32 @@ __global__ void csm_filter_kernel(const CsmPairDev* __restrict__ pairs, int n_pa
                                   const unsigned long long* __restrict__ best,
                                   unsigned* __restrict__ survivors,
                                   unsigned* __restrict__ n_survivors) {
-  const size_t per_pair = (size_t)prm.S * prm.maxc;
-  const size_t total = (size_t)n_pairs * per_pair;
-  for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < total;
-       u += (size_t)gridDim.x * blockDim.x) {
-    const int slot = (int)(u % prm.maxc);
-    const size_t ps = u / prm.maxc;
-    const int s = (int)(ps % prm.S), pi = (int)(ps / prm.S);
-    const CsmBounds b = bounds[ps];
-    const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
-    const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
-    if (slot >= ncx * ncy) continue;
-    const int xo = b.min_x + (slot / ncy) * prm.step, yo = b.min_y + (slot % ncy) * prm.step;
-    const float sc = score_of(coarse[u], pairs[pi].n_pts, prm);
-    if (key_of(sc, rank_of(prm, s, xo, yo)) > best[pi]) {
-      const unsigned pos = atomicAdd(n_survivors + pi, 1u);
-      survivors[(size_t)pi * per_pair + pos] = (unsigned)(u - (size_t)pi * per_pair);
+  const unsigned per_pair = (unsigned)prm.S * (unsigned)prm.maxc;   // < 2^32 (checked by the caller)
+  for (int pi = blockIdx.y; pi < n_pairs; pi += gridDim.y) {
+    const int* c = coarse + (size_t)pi * per_pair;
+    const CsmBounds* bp = bounds + (size_t)pi * prm.S;
+    const unsigned long long incumbent = best[pi];
+    const int P = pairs[pi].n_pts;
+    for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < per_pair; u += gridDim.x * blockDim.x) {
+      const unsigned s = u / (unsigned)prm.maxc, slot = u - s * (unsigned)prm.maxc;
+      const CsmBounds b = bp[s];
+      const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
+      const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+      if ((int)slot >= ncx * ncy) continue;
+      const int ix = (int)slot / ncy;
+      const int xo = b.min_x + ix * prm.step, yo = b.min_y + ((int)slot - ix * ncy) * prm.step;
+      const float sc = score_of(c[u], P, prm);
+      if (key_of(sc, rank_of(prm, (int)s, xo, yo)) > incumbent) {
+        const unsigned pos = atomicAdd(n_survivors + pi, 1u);
+        survivors[(size_t)pi * per_pair + pos] = u;
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------- K7 expand
 
-constexpr int kExpChunk = 512;    // points staged per pass of the expand kernel (and the early-exit granularity)
+constexpr int kExpChunk = 2048;   // points staged per pass of the expand kernel
 
 // Survivors of grids without bit planes go to the depth-first refinement unexpanded.
 __global__ void csm_survivors_to_nodes_kernel(const CsmPairDev* __restrict__ pairs, CsmParams prm,
@@ -1099,15 +1116,19 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
   float2* P0 = reinterpret_cast<float2*>(csm_smem);                       // [kExpChunk]
   // rows 16 k apart (neighbouring coarse candidates of one scan) would share two banks with a
   // plain row stride: one extra word every 16 rows spreads them over all banks
-  unsigned* bits = reinterpret_cast<unsigned*>(P0 + kExpChunk);          // [wide_ny][stride] (+ row / 16)
-  for (int i = tid; i < wide_ny * stride; i += 256) {
+  // one zero row after the level and at least one zero word after every row: a lookup clamps an
+  // out-of-level coordinate onto them with one unsigned minimum, no test, no mask
+  unsigned* bits = reinterpret_cast<unsigned*>(P0 + kExpChunk + 4);      // [wide_ny + 1][stride] (+ row / 16)
+  for (int i = tid; i < (wide_ny + 1) * stride; i += 256) {
     const int row = i / stride;
-    bits[i + (row >> 4)] = __ldg(lvb + i);
+    bits[i + (row >> 4)] = row < wide_ny ? __ldg(lvb + i) : 0u;
   }
+  const unsigned wnx_u = (unsigned)wide_nx, wny_u = (unsigned)wide_ny;
   const float mx_f = (float)g.max_x, my_f = (float)g.max_y, ir = (float)(1.0 / g.resolution);
   const float U = (float)(max(g.nx, g.ny) + 2 * prm.n_lin + 64 + 2 * prm.step);
   const float delta = 2.3841858e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
   const float hi1 = 1.f - delta;
+  const float far_pt = -4.f * (fabsf(mx_f) + fabsf(my_f) + fabsf(pr.tx) + fabsf(pr.ty) + U * (float)g.resolution) - 1000.f;
   unsigned long long expanded = 0;
   const unsigned first_base = (unsigned)blockIdx.x * 32u;
 
@@ -1135,9 +1156,6 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
     const int ax = xo + wm1, ay = yo + wm1;   // cell -> level frame of child (0, 0)
     int sum[4] = {0, 0, 0, 0};
     if (tid < 128) s_sum[tid >> 2][tid & 3] = 0;
-    // the incumbent as of now: a lower bound of what a child has to beat (it only grows)
-    const unsigned long long incumbent = active ? ld_best(best + pi) : ~0ull;
-    bool group_dead = false;
     for (int p0 = 0; p0 < P; p0 += kExpChunk) {
       const int n = min(kExpChunk, P - p0);
       __syncthreads();
@@ -1147,6 +1165,9 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
           rot_z(pr.w0, pr.z0, sp[3 * (size_t)(p0 + p)], sp[3 * (size_t)(p0 + p) + 1], x0, y0);
           P0[p] = make_float2(x0, y0);
         }
+        // the last group of four is padded with a point that no rotation and no offset of the window can
+        // bring onto the level: at least one of its coordinates stays `far_pt` - |t| away from the origin
+        if (tid < 4) P0[n + tid] = make_float2(far_pt, far_pt);
       }
       __syncthreads();
       if (active) {
@@ -1158,7 +1179,7 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
           unsigned need = 0u;
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const float2 q = P0[min(p + u, n - 1)];
+            const float2 q = P0[p + u];
             float x1, y1;
             rot_z(r.x, r.y, q.x, q.y, x1, y1);
             wxs[u] = __fadd_rn(x1, pr.tx);
@@ -1168,7 +1189,7 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
             const float dy = uy - fy, dx = ux - fx;
             cxs[u] = (int)fy;
             cys[u] = (int)fx;
-            if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < U && fabsf(ux) < U))
+            if (!(fminf(dy, dx) > delta && fmaxf(dy, dx) < hi1 && fmaxf(fabsf(uy), fabsf(ux)) < U))
               need |= 1u << u;
           }
           if (need) {   // rare: near a rounding boundary
@@ -1182,45 +1203,19 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int lx = cxs[u] + ax, ly = cys[u] + ay;
-            const bool in = p + u < n;
-            const bool x0ok = in && (unsigned)lx < (unsigned)wide_nx, x1ok = in && (unsigned)(lx + h) < (unsigned)wide_nx;
-            const bool y0ok = (unsigned)ly < (unsigned)wide_ny, y1ok = (unsigned)(ly + h) < (unsigned)wide_ny;
-            const unsigned* r0 = bits + ly * stride + (ly >> 4);
-            const unsigned* r1 = bits + (ly + h) * stride + ((ly + h) >> 4);
-            const int w0 = lx >> 5, w1 = (lx + h) >> 5, b0 = lx & 31, b1 = (lx + h) & 31;
-            if (x0ok && y0ok) sum[0] += (r0[w0] >> b0) & 1u;   // child (x, y)
-            if (x0ok && y1ok) sum[1] += (r1[w0] >> b0) & 1u;   // child (x, y + h)
-            if (x1ok && y0ok) sum[2] += (r0[w1] >> b1) & 1u;   // child (x + h, y)
-            if (x1ok && y1ok) sum[3] += (r1[w1] >> b1) & 1u;   // child (x + h, y + h)
+            // children (x, y), (x, y + h), (x + h, y), (x + h, y + h): coordinates outside the level
+            // (negative ones wrap to huge unsigned values) land on the zero row / zero word
+            const unsigned lx = (unsigned)(cxs[u] + ax), ly = (unsigned)(cys[u] + ay);
+            const unsigned cx0 = min(lx, wnx_u), cx1 = min(lx + (unsigned)h, wnx_u);
+            const unsigned ry0 = min(ly, wny_u), ry1 = min(ly + (unsigned)h, wny_u);
+            const unsigned* r0 = bits + ry0 * stride + (ry0 >> 4);
+            const unsigned* r1 = bits + ry1 * stride + (ry1 >> 4);
+            const unsigned w0 = cx0 >> 5, w1 = cx1 >> 5, b0 = cx0 & 31u, b1 = cx1 & 31u;
+            sum[0] += (int)((r0[w0] >> b0) & 1u);
+            sum[1] += (int)((r1[w0] >> b0) & 1u);
+            sum[2] += (int)((r0[w1] >> b1) & 1u);
+            sum[3] += (int)((r1[w1] >> b1) & 1u);
           }
-        }
-      }
-      // early exit: after every chunk but the last, can any child of these 32 survivors still beat the
-      // incumbent if every point left were a hit?  (A matched pair's survivors need ~3/4 of the points
-      // to hit; most are dead after a third of the scan.)
-      if (p0 + n < P) {
-        if (active) {
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            atomicAdd(&s_sum[lane][ch], sum[ch]);
-            sum[ch] = 0;
-          }
-        }
-        __syncthreads();
-        bool alive = false;
-        if (active && slice == 0) {
-          const int left = P - (p0 + n);
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            const int cx = xo + (ch >> 1) * h, cy = yo + (ch & 1) * h;
-            alive |= cx <= b.max_x && cy <= b.max_y &&
-                     key_of(score_of(255 * (s_sum[lane][ch] + left), P, prm), rank_of(prm, s, cx, cy)) > incumbent;
-          }
-        }
-        if (!__syncthreads_or(alive)) {
-          group_dead = true;
-          break;
         }
       }
     }
@@ -1229,11 +1224,6 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
       for (int ch = 0; ch < 4; ++ch) atomicAdd(&s_sum[lane][ch], sum[ch]);
     }
     __syncthreads();
-    if (group_dead) {                 // partial sums only: nothing here can win, nothing to emit
-      if (active && slice == 0) ++expanded;
-      __syncthreads();
-      continue;
-    }
     if (active && slice == 0) {
       ++expanded;
 #pragma unroll
@@ -1389,14 +1379,14 @@ cudaError_t launch_csm_level1_from_cells(const uint16_t* cells, const uint8_t* l
 
 cudaError_t launch_csm_pack_bits(const uint8_t* level1, int nx, int ny, unsigned* out, int* not_binary,
                                  cudaStream_t stream) {
-  const int stride = (nx + 31) / 32 + 1, n = ny * stride;
+  const int stride = csm_bit_stride(nx), n = ny * stride;
   csm_pack_bits_kernel<<<(n + 255) / 256, 256, 0, stream>>>(level1, nx, ny, stride, out, not_binary);
   return cudaGetLastError();
 }
 
 cudaError_t launch_csm_unpack_bits(const unsigned* bits, int nx, int ny, uint8_t* out, cudaStream_t stream) {
   const size_t n = (size_t)nx * ny;
-  csm_unpack_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bits, nx, ny, (nx + 31) / 32 + 1, out);
+  csm_unpack_bits_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(bits, nx, ny, csm_bit_stride(nx), out);
   return cudaGetLastError();
 }
 
@@ -1431,7 +1421,7 @@ cudaError_t launch_csm_build_slots(const CsmGridRec* recs, const int* slot_gid, 
   if (plan.bits) {
     for (int l = 1; l < plan.depth; ++l) {
       const int w = 1 << l;
-      const size_t words = (size_t)(plan.max_ny + w - 1) * (size_t)((plan.max_nx + w - 1 + 31) / 32 + 1);
+      const size_t words = (size_t)(plan.max_ny + w - 1) * (size_t)csm_bit_stride(plan.max_nx + w - 1);
       csm_build_lvl_bits_kernel<<<dim3(blocks(words, 256), max_slots), 256, 0, stream>>>(slots, n_slots, l);
       ++*launches;
     }
@@ -1550,15 +1540,16 @@ cudaError_t launch_csm_filter(const CsmPairDev* pairs, int n_pairs, CsmParams pr
                               const CsmBounds* bounds, const int* coarse,
                               const unsigned long long* best, unsigned* survivors,
                               unsigned* n_survivors, cudaStream_t stream) {
-  const size_t total = (size_t)n_pairs * prm.S * prm.maxc;
-  const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, 148 * 16);
-  csm_filter_kernel<<<blocks, 256, 0, stream>>>(pairs, n_pairs, prm, bounds, coarse, best,
-                                                survivors, n_survivors);
+  const unsigned per_pair = (unsigned)prm.S * (unsigned)prm.maxc;
+  dim3 grd(std::min<unsigned>((per_pair + 255) / 256, 64), (unsigned)std::min(n_pairs, 65535));
+  csm_filter_kernel<<<grd, 256, 0, stream>>>(pairs, n_pairs, prm, bounds, coarse, best,
+                                             survivors, n_survivors);
   return cudaGetLastError();
 }
 
 size_t csm_expand_smem(int wide_ny, int stride) {
-  return (size_t)kExpChunk * sizeof(float2) + ((size_t)wide_ny * stride + (size_t)(wide_ny >> 4) + 1) * 4;
+  return (size_t)(kExpChunk + 4) * sizeof(float2) +
+         ((size_t)(wide_ny + 1) * stride + (size_t)((wide_ny + 1) >> 4) + 1) * 4;
 }
 
 // bits == true: every grid of the batch carries bit-packed levels (binary slots), and

@@ -72,7 +72,7 @@ CsmBuf* all_bufs(gloc_csm_store* st, int i) {
 // not known in advance; none for grids that are binary by construction.
 int add_from_stage(gloc_csm_store* st, int nx, int ny, double resolution, double max_x, double max_y,
                    bool known_binary, int* grid_id, const char* who) {
-  const int stride = (nx + 31) / 32 + 1;
+  const int stride = csm_bit_stride(nx);
   const size_t bit_bytes = (size_t)ny * stride * 4, n = (size_t)nx * ny;
   void* d_bits = nullptr;
   cudaError_t e = st->arena.alloc(bit_bytes, &d_bits);
@@ -191,14 +191,14 @@ int csm_make_plan(int max_nx, int max_ny, bool all_binary, int n_lin, int depth,
     for (int l = 1; l < depth; ++l) {
       const int wl = 1 << l;
       P.dev.lvl_off[l] = off;
-      off += align256((size_t)(max_ny + wl - 1) * (size_t)((max_nx + wl - 1 + 31) / 32 + 1) * 4);
+      off += align256((size_t)(max_ny + wl - 1) * (size_t)csm_bit_stride(max_nx + wl - 1) * 4);
     }
     P.dev.pmb_off = off;
     off += align256((size_t)w * w * (size_t)csm_pmb_rows(wide_ny, n_lin, top) * 8);
     P.dev.slot_bytes = std::max(off, (size_t)256);
     if (depth >= 2) {   // expand stage on the bit-packed level depth-2
       const int l2 = depth - 2, w2 = 1 << l2;
-      const size_t smem = csm_expand_smem(max_ny + w2 - 1, (max_nx + w2 - 1 + 31) / 32 + 1);
+      const size_t smem = csm_expand_smem(max_ny + w2 - 1, csm_bit_stride(max_nx + w2 - 1));
       if (smem <= (size_t)112 * 1024) {
         P.exp_bits = true;
         P.exp_smem = smem;
@@ -349,7 +349,24 @@ int csm_match_core(gloc_csm_store* st, const CsmBatchPlan& plan, const float* d_
               np, hslots, t_build, plan.use_bits ? "bits" : "u8", t[0], t[1], t[2], t[3], t_exp, ns, hn, hc);
       unsigned mx = 0;
       for (unsigned v : hs) mx = std::max(mx, v);
-      fprintf(stderr, "[csm] max survivors in one pair = %u\n", mx);
+      // where the survivors come from: pairs that end up matching vs the rest
+      unsigned long long ns_found = 0, n_found = 0;
+      unsigned hist[6] = {0, 0, 0, 0, 0, 0};   // survivors per pair: 0, <64, <256, <1024, <4096, more
+      for (int i = 0; i < np; ++i) {
+        const unsigned long long key = h_best[p0 + i];
+        uint32_t sb = (uint32_t)(key >> 32);
+        float sc;
+        std::memcpy(&sc, &sb, 4);
+        if (key != 0 && sc > prm.min_score) {
+          ns_found += hs[(size_t)i];
+          ++n_found;
+        }
+        const unsigned v = hs[(size_t)i];
+        hist[v == 0 ? 0 : v < 64 ? 1 : v < 256 ? 2 : v < 1024 ? 3 : v < 4096 ? 4 : 5]++;
+      }
+      fprintf(stderr, "[csm] max survivors in one pair = %u; %llu pairs matched and hold %llu of the survivors; "
+                      "pairs by survivors 0/<64/<256/<1024/<4096/more: %u %u %u %u %u %u\n", mx, n_found, ns_found,
+              hist[0], hist[1], hist[2], hist[3], hist[4], hist[5]);
       for (auto& e : tev) cudaEventDestroy(e);
     }
     st->stats.kernel_launches += depth >= 2 ? 5 : 3;

@@ -7,6 +7,11 @@ namespace gloc {
 
 constexpr int kCsmMaxDepth = 8;  // precomputation widths 1..128
 
+// Words (uint32) per row of a bit-packed level of `wide_nx` cells: at least one zero word after
+// the last cell (lookups clamp out-of-range columns onto it) and an even count, so that rows are
+// 8-byte aligned.
+__host__ __device__ inline int csm_bit_stride(int wide_nx) { return (((wide_nx + 31) >> 5) + 2) & ~1; }
+
 // One map grid as a batch sees it (a "slot" of the batch's working set; built on the device by
 // csm_prepare_slots_kernel from the store's per-grid records).
 //   binary == 0: uint8 precomputation stack, level i = width 2^i, (nx+w-1) x (ny+w-1) cells,
@@ -38,7 +43,7 @@ struct CsmGridDev {
 };
 
 // A grid as the store keeps it: the width-1 precomputation grid only (everything else is
-// derived per batch).  enc 1: bit-packed rows, stride (nx + 31) / 32 + 1 words; enc 0: nx*ny bytes.
+// derived per batch).  enc 1: bit-packed rows, csm_bit_stride(nx) words each; enc 0: nx*ny bytes.
 struct CsmGridRec {
   const void* data;
   int nx, ny, enc, pad;

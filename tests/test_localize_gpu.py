@@ -149,7 +149,7 @@ def test_store_keeps_bits_only_and_rebuilds_per_batch(oracle):
     for gr in grids:
         st.add_grid_u8(gr, res, mx, my)
     grid_bytes, _ = st.store_bytes()
-    per_grid = ny * ((nx + 31) // 32 + 1) * 4
+    per_grid = ny * ((((nx + 31) // 32) + 2) & ~1) * 4     # csm_bit_stride: even, one zero word after the row
     assert grid_bytes <= n * (per_grid + 256)
     assert grid_bytes < n * nx * ny // 6          # far below one byte per cell
     rng = np.random.default_rng(3)
