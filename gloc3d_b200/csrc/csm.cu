@@ -263,6 +263,83 @@ __global__ void csm_build_lvl_bits_kernel(const CsmGridDev* __restrict__ slots,
   const_cast<unsigned*>(g.lvl[l])[idx] = A(j) | sh;
 }
 
+// The whole binary working set of one slot in ONE kernel (a CTA per slot): the stored width-1 grid
+// goes to shared memory once, every coarser level is derived there from the previous one (two
+// buffers alternate), written out for the expand / refine stages, and the coarsest level leaves
+// shared memory as bit planes only.  Replaces depth-1 level launches + the plane launch and their
+// round trips through L2 (1.8 -> 0.5 ms per 1400 slots); grids too large for two levels in shared
+// memory keep the per-level kernels.
+__global__ void __launch_bounds__(512)
+csm_build_slot_fused_kernel(const CsmGridDev* __restrict__ slots, const int* __restrict__ n_slots, int depth,
+                            int buf_words) {
+  if ((int)blockIdx.x >= *n_slots) return;
+  extern __shared__ __align__(16) unsigned char csm_smem[];
+  unsigned* buf[2] = {reinterpret_cast<unsigned*>(csm_smem), reinterpret_cast<unsigned*>(csm_smem) + buf_words};
+  const CsmGridDev& g = slots[blockIdx.x];
+  const int tid = threadIdx.x, top = depth - 1;
+  {   // level 0 as stored
+    const int n0 = g.ny * g.lvs[0];
+    for (int i = tid; i < n0; i += 512) buf[0][i] = __ldg(g.lvl[0] + i);
+  }
+  __syncthreads();
+  for (int l = 1; l <= top; ++l) {
+    const unsigned* prev = buf[(l - 1) & 1];
+    unsigned* cur = buf[l & 1];
+    const int w = 1 << l, h = w >> 1;
+    const int wny = g.ny + w - 1, pny = g.ny + h - 1;
+    const int stride = g.lvs[l], ps = g.lvs[l - 1];
+    const int hs = h >> 5, hb = h & 31;
+    unsigned* out = l < top ? const_cast<unsigned*>(g.lvl[l]) : nullptr;   // the coarsest level is only needed as planes
+    for (int idx = tid; idx < wny * stride; idx += 512) {
+      const int ly = idx / stride, j = idx - ly * stride;
+      auto A = [&](int jj) -> unsigned {
+        if (jj < 0 || jj >= ps) return 0u;
+        unsigned v = 0u;
+        if (ly < pny) v |= prev[ly * ps + jj];
+        if (ly - h >= 0 && ly - h < pny) v |= prev[(ly - h) * ps + jj];
+        return v;
+      };
+      const unsigned sh = hb ? __funnelshift_l(A(j - hs - 1), A(j - hs), hb) : A(j - hs);
+      const unsigned v = A(j) | sh;
+      cur[idx] = v;
+      if (out) out[idx] = v;
+    }
+    __syncthreads();
+  }
+  // bit planes of the coarsest level (see csm_build_pmb_kernel)
+  const unsigned* level = buf[top & 1];
+  const int log2w = g.pmb_log2w, w = 1 << log2w, rows = g.pmb_rows, px = g.pmb_px, py = g.pmb_py;
+  const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1, stride = g.lvs[log2w];
+  unsigned long long* pout = const_cast<unsigned long long*>(g.pmb);
+  const int n = w * w * rows;
+  for (int idx = tid; idx < n; idx += 512) {
+    const int plane = idx / rows, r = idx - plane * rows;
+    const int ry = plane >> log2w, rx = plane & (w - 1);
+    const int ly = (r << log2w) + ry - py;
+    unsigned long long bits = 0;
+    if ((unsigned)ly < (unsigned)wide_ny) {
+      if (log2w == 4) {
+        const unsigned long long* row = reinterpret_cast<const unsigned long long*>(level + ly * stride);
+        const int q = rx - px, q16 = q & 15, fq = (q - q16) >> 4;
+        unsigned long long gathered = 0;
+        const int n64 = min(stride >> 1, 16);
+        for (int j = 0; j < n64; ++j) {
+          const unsigned long long t = (row[j] >> q16) & 0x0001000100010001ull;
+          gathered |= (((t * 0x0001000200040008ull) >> 48) & 0xFull) << (4 * j);
+        }
+        bits = fq <= 0 ? (-fq < 64 ? gathered << (-fq) : 0ull) : (fq < 64 ? gathered >> fq : 0ull);
+      } else {
+        const unsigned* row = level + ly * stride;
+        for (int c = 0; c < 64; ++c) {
+          const int lx = (c << log2w) + rx - px;
+          if ((unsigned)lx < (unsigned)wide_nx) bits |= (unsigned long long)((row[lx >> 5] >> (lx & 31)) & 1u) << c;
+        }
+      }
+    }
+    pout[idx] = bits;
+  }
+}
+
 // uint8 path: width-1 grid of a slot from the store's record (bits or bytes)
 __global__ void csm_slot_level0_u8_kernel(const CsmGridRec* __restrict__ recs,
                                           const int* __restrict__ slot_gid,
@@ -746,27 +823,58 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     }
     __syncthreads();
   };
-  // ---- pass 1: extreme world coordinates of this rotation -> ShrinkToFit bounds
-  float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
-  for (int p0 = 0; p0 < P; p0 += kBitChunk) {
-    const int n = min(kBitChunk, P - p0);
-    stage(p0, n);
-#pragma unroll 4
-    for (int p = half; p < n; p += 2) {
-      const float2 q = P0[p];
-      float x1, y1;
-      rot_z(r.x, r.y, q.x, q.y, x1, y1);
-      const float wx = __fadd_rn(x1, pr.tx), wy = __fadd_rn(y1, pr.ty);
-      mnx = fminf(mnx, wx); mxx = fmaxf(mxx, wx);
-      mny = fminf(mny, wy); mxy = fmaxf(mxy, wy);
-    }
-  }
-  mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, 1));
-  mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, 1));
-  mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, 1));
-  mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, 1));
-  CsmBounds b;
+  // ---- pass 1: ShrinkToFit bounds of this rotation (correlative_scan_matcher_2d.cpp:73-91).
+  // Shortcut: ONE point whose cell lies at least n_lin cells inside the grid on every side makes
+  // all four bounds the full window: min_x = max(-n_lin, min(0, min_p(-cx_p))) and min_p(-cx_p) <=
+  // -cx_w <= -n_lin, likewise for the other three.  The point nearest to the sensor is such a
+  // witness for (nearly) every rotation of a scan taken inside the map; only where it is not do
+  // the threads walk all points for the extreme coordinates.
+  __shared__ unsigned long long s_witness;
+  if (tid == 0) s_witness = ~0ull;
+  __syncthreads();
   {
+    unsigned long long key = ~0ull;
+    for (int p = tid; p < P; p += blockDim.x) {
+      const float x = sp[3 * (size_t)p], y = sp[3 * (size_t)p + 1];
+      const float n2 = x * x + y * y;                                  // >= 0: bit pattern orders like the value
+      key = min(key, ((unsigned long long)__float_as_uint(n2) << 32) | (unsigned)p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if (lane == 0) atomicMin(&s_witness, key);
+  }
+  __syncthreads();
+  bool full = true;
+  if (s_ok) {
+    const int w = (int)(unsigned)(s_witness & 0xFFFFFFFFull);
+    const int2 c = discretize_point(sp + 3 * (size_t)w, pr.w0, pr.z0, r.x, r.y, pr.tx, pr.ty, g.resolution, g.max_x,
+                                    g.max_y);
+    full = c.x >= prm.n_lin && c.x <= g.nx - 1 - prm.n_lin && c.y >= prm.n_lin && c.y <= g.ny - 1 - prm.n_lin;
+  }
+  CsmBounds b;
+  if (__syncthreads_and(full)) {
+    b.min_x = -prm.n_lin; b.max_x = prm.n_lin; b.min_y = -prm.n_lin; b.max_y = prm.n_lin;
+    stage(0, min(kBitChunk, P));        // pass 2 expects the first chunk of points in shared memory
+  } else {
+    // extreme world coordinates of this rotation
+    float mnx = INFINITY, mxx = -INFINITY, mny = INFINITY, mxy = -INFINITY;
+    for (int p0 = 0; p0 < P; p0 += kBitChunk) {
+      const int n = min(kBitChunk, P - p0);
+      stage(p0, n);
+#pragma unroll 4
+      for (int p = half; p < n; p += 2) {
+        const float2 q = P0[p];
+        float x1, y1;
+        rot_z(r.x, r.y, q.x, q.y, x1, y1);
+        const float wx = __fadd_rn(x1, pr.tx), wy = __fadd_rn(y1, pr.ty);
+        mnx = fminf(mnx, wx); mxx = fmaxf(mxx, wx);
+        mny = fminf(mny, wy); mxy = fmaxf(mxy, wy);
+      }
+    }
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, 1));
+    mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, 1));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, 1));
+    mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, 1));
     // cell.x = f(wy), cell.y = f(wx), both monotone non-increasing
     const int cx_max = cell_exact(mny, g.resolution, g.max_y), cx_min = cell_exact(mxy, g.resolution, g.max_y);
     const int cy_max = cell_exact(mnx, g.resolution, g.max_x), cy_min = cell_exact(mxx, g.resolution, g.max_x);
@@ -1029,25 +1137,47 @@ __global__ void csm_filter_kernel(const CsmPairDev* __restrict__ pairs, int n_pa
                                   const unsigned long long* __restrict__ best,
                                   unsigned* __restrict__ survivors,
                                   unsigned* __restrict__ n_survivors) {
+  // One warp per (pair, scan): its survivors are compacted with ballots and appended to the pair's
+  // list with ONE atomicAdd, so the survivors of a scan sit next to each other -- the grouped
+  // expand kernel discretises a scan once for all of them.
   const unsigned per_pair = (unsigned)prm.S * (unsigned)prm.maxc;   // < 2^32 (checked by the caller)
-  for (int pi = blockIdx.y; pi < n_pairs; pi += gridDim.y) {
-    const int* c = coarse + (size_t)pi * per_pair;
-    const CsmBounds* bp = bounds + (size_t)pi * prm.S;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned total = (unsigned)n_pairs * (unsigned)prm.S;
+  for (unsigned gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gw < total; gw += n_warps) {
+    const unsigned pi = gw / (unsigned)prm.S, s = gw - pi * (unsigned)prm.S;
+    const CsmBounds b = bounds[gw];
+    const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
+    const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
+    const int ncand = ncx * ncy;
+    const int* c = coarse + (size_t)pi * per_pair + (size_t)s * prm.maxc;
     const unsigned long long incumbent = best[pi];
     const int P = pairs[pi].n_pts;
-    for (unsigned u = blockIdx.x * blockDim.x + threadIdx.x; u < per_pair; u += gridDim.x * blockDim.x) {
-      const unsigned s = u / (unsigned)prm.maxc, slot = u - s * (unsigned)prm.maxc;
-      const CsmBounds b = bp[s];
-      const int ncx = (b.max_x - b.min_x + prm.step) / prm.step;
-      const int ncy = (b.max_y - b.min_y + prm.step) / prm.step;
-      if ((int)slot >= ncx * ncy) continue;
-      const int ix = (int)slot / ncy;
-      const int xo = b.min_x + ix * prm.step, yo = b.min_y + ((int)slot - ix * ncy) * prm.step;
-      const float sc = score_of(c[u], P, prm);
-      if (key_of(sc, rank_of(prm, (int)s, xo, yo)) > incumbent) {
-        const unsigned pos = atomicAdd(n_survivors + pi, 1u);
-        survivors[(size_t)pi * per_pair + pos] = u;
+    unsigned ballots[8];                       // maxc <= 16 x 16 = 256 slots
+    unsigned n_s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int slot = 32 * k + (int)lane;
+      bool keep = false;
+      if (32 * k < ncand && slot < ncand) {
+        const int ix = slot / ncy;
+        const int xo = b.min_x + ix * prm.step, yo = b.min_y + (slot - ix * ncy) * prm.step;
+        keep = key_of(score_of(c[slot], P, prm), rank_of(prm, (int)s, xo, yo)) > incumbent;
       }
+      ballots[k] = __ballot_sync(0xffffffffu, keep);
+      n_s += __popc(ballots[k]);
+    }
+    if (n_s == 0) continue;
+    unsigned base = 0;
+    if (lane == 0) base = atomicAdd(n_survivors + pi, n_s);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    unsigned* out = survivors + (size_t)pi * per_pair + base;
+    unsigned before = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (ballots[k] & (1u << lane))
+        out[before + __popc(ballots[k] & ((1u << lane) - 1u))] = s * (unsigned)prm.maxc + 32u * k + lane;
+      before += __popc(ballots[k]);
     }
   }
 }
@@ -1419,6 +1549,19 @@ cudaError_t launch_csm_build_slots(const CsmGridRec* recs, const int* slot_gid, 
   };
   const int top = plan.depth - 1;
   if (plan.bits) {
+    // two buffers of the largest level in shared memory: the whole slot in one kernel
+    const size_t buf_words = (size_t)(plan.max_ny + (1 << top) - 1) * (size_t)csm_bit_stride(plan.max_nx + (1 << top) - 1);
+    if (2 * buf_words * 4 <= (size_t)200 * 1024 && std::getenv("GLOC_CSM_NO_FUSED_BUILD") == nullptr) {
+      static unsigned long long attr_mask = 0;
+      if (first_use_on_current_device(attr_mask)) {
+        cudaError_t e = cudaFuncSetAttribute(csm_build_slot_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             200 * 1024);
+        if (e != cudaSuccess) return e;
+      }
+      csm_build_slot_fused_kernel<<<max_slots, 512, 2 * buf_words * 4, stream>>>(slots, n_slots, plan.depth, (int)buf_words);
+      ++*launches;
+      return cudaGetLastError();
+    }
     for (int l = 1; l < plan.depth; ++l) {
       const int w = 1 << l;
       const size_t words = (size_t)(plan.max_ny + w - 1) * (size_t)csm_bit_stride(plan.max_nx + w - 1);
@@ -1540,10 +1683,10 @@ cudaError_t launch_csm_filter(const CsmPairDev* pairs, int n_pairs, CsmParams pr
                               const CsmBounds* bounds, const int* coarse,
                               const unsigned long long* best, unsigned* survivors,
                               unsigned* n_survivors, cudaStream_t stream) {
-  const unsigned per_pair = (unsigned)prm.S * (unsigned)prm.maxc;
-  dim3 grd(std::min<unsigned>((per_pair + 255) / 256, 64), (unsigned)std::min(n_pairs, 65535));
-  csm_filter_kernel<<<grd, 256, 0, stream>>>(pairs, n_pairs, prm, bounds, coarse, best,
-                                             survivors, n_survivors);
+  const size_t warps = (size_t)n_pairs * prm.S;
+  const unsigned blocks = (unsigned)std::min<size_t>((warps + 7) / 8, 148 * 32);
+  csm_filter_kernel<<<blocks, 256, 0, stream>>>(pairs, n_pairs, prm, bounds, coarse, best,
+                                                survivors, n_survivors);
   return cudaGetLastError();
 }
 
