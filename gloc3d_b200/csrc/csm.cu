@@ -829,7 +829,9 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   // -cx_w <= -n_lin, likewise for the other three.  The point nearest to the sensor is such a
   // witness for (nearly) every rotation of a scan taken inside the map; only where it is not do
   // the threads walk all points for the extreme coordinates.
-  __shared__ unsigned long long s_witness;
+  // (kept in the points' staging area, which is filled only afterwards: the kernel's dynamic
+  // shared memory is sized to the opt-in limit, there is no room for a static variable)
+  unsigned long long& s_witness = *reinterpret_cast<unsigned long long*>(P0);
   if (tid == 0) s_witness = ~0ull;
   __syncthreads();
   {
