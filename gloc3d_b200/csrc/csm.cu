@@ -28,6 +28,13 @@ constexpr int kPointChunk = 4096;  // discretised points cached in shared memory
 constexpr int kCoarseThreads = 256;
 constexpr int kCandPerThread = 4;
 constexpr int kBitRowSlack = 17;    // zero plane rows after the last data row (candidate rows read past it)
+// Rows of one bit plane.  The plane stride (rows, or rows / 2 words per half in the paired layout) is
+// kept odd: lanes of a warp sit in different planes, an even stride would fold them onto half of the
+// shared-memory banks (measured: 23 -> 37 ms for the coarse scorer).
+__host__ __device__ inline int csm_pmb_rows_of(int wide_ny, int n_lin, int log2w, bool paired) {
+  const int need = ((wide_ny + 3 * n_lin - 1) >> log2w) + 1 + kBitRowSlack;
+  return paired ? 2 * (((need + 1) >> 1) | 1) : (need | 1);
+}
 
 // Eigen Quaternionf(AngleAxisf(theta, UnitZ)) * v  with vec = (0, 0, z):
 //   uv = vec x v; uv += uv; v' = v + w*uv + vec x uv      (see oracle/csm_oracle.c)
@@ -205,6 +212,7 @@ __global__ void csm_prepare_slots_kernel(const CsmGridRec* __restrict__ recs,
   g.stack = nullptr; g.pm = nullptr; g.pmb = nullptr;
   g.pm_pad = g.pm_pw = g.pm_ph = g.pm_log2w = 0;
   g.pmb_rows = g.pmb_px = g.pmb_py = g.pmb_log2w = 0;
+  g.pmb_b0 = 0; g.pmb_b1 = -1;
   for (int l = 0; l < kCsmMaxDepth; ++l) { g.off[l] = 0; g.lvl[l] = nullptr; g.lvs[l] = 0; }
   const int top = plan.depth - 1, w = 1 << top;
   if (plan.bits) {
@@ -215,8 +223,9 @@ __global__ void csm_prepare_slots_kernel(const CsmGridRec* __restrict__ recs,
       g.lvs[l] = csm_bit_stride(r.nx + (1 << l) - 1);
     }
     g.pmb = reinterpret_cast<const unsigned long long*>(base + plan.pmb_off);
-    g.pmb_rows = ((r.ny + w - 1 + 3 * plan.n_lin - 1) >> top) + 1 + kBitRowSlack;
+    g.pmb_rows = csm_pmb_rows_of(r.ny + w - 1, plan.n_lin, top, plan.pmb_b1 >= 0);
     g.pmb_px = plan.n_lin; g.pmb_py = 2 * plan.n_lin; g.pmb_log2w = top;
+    g.pmb_b0 = plan.pmb_b0; g.pmb_b1 = plan.pmb_b1;
   } else {
     g.stack = base;
     long long total = 0;
@@ -236,6 +245,61 @@ __global__ void csm_prepare_slots_kernel(const CsmGridRec* __restrict__ recs,
     }
   }
   out[j] = g;
+}
+
+// One 64-bit row of a bit plane: bit c = bit (w c + rx - px) of row ly of the coarsest bit level
+// (zero outside the level).
+__device__ __forceinline__ unsigned long long pmb_row_bits(const unsigned* level, int stride, int wide_nx,
+                                                           int wide_ny, int log2w, int ly, int rx, int px) {
+  unsigned long long bits = 0;
+  if ((unsigned)ly >= (unsigned)wide_ny) return bits;
+  if (log2w == 4) {
+    // every 64-bit word of the level row (rows are 8-byte aligned, zero beyond wide_nx) holds four of
+    // the wanted bits, 16 apart; one multiply gathers the four into a nibble
+    const unsigned long long* row = reinterpret_cast<const unsigned long long*>(level + (size_t)ly * stride);
+    const int q = rx - px, q16 = q & 15, fq = (q - q16) >> 4;      // column of bit c = 16 (c + fq) + q16
+    unsigned long long gathered = 0;                                // bit c' = level bit 16 c' + q16
+    const int n64 = min(stride >> 1, 16);
+    for (int j = 0; j < n64; ++j) {
+      const unsigned long long t = (row[j] >> q16) & 0x0001000100010001ull;
+      gathered |= (((t * 0x0001000200040008ull) >> 48) & 0xFull) << (4 * j);
+    }
+    bits = fq <= 0 ? (-fq < 64 ? gathered << (-fq) : 0ull) : (fq < 64 ? gathered >> fq : 0ull);
+  } else {
+    const unsigned* row = level + (size_t)ly * stride;
+    for (int c = 0; c < 64; ++c) {
+      const int lx = (c << log2w) + rx - px;
+      if ((unsigned)lx < (unsigned)wide_nx) bits |= (unsigned long long)((row[lx >> 5] >> (lx & 31)) & 1u) << c;
+    }
+  }
+  return bits;
+}
+
+// The bit planes of slot g from its coarsest bit level (global or shared memory), by the threads
+// first, first + step, ...: either layout of CsmGridDev::pmb.
+__device__ __forceinline__ void pmb_write_planes(const CsmGridDev& g, const unsigned* level, int first, int step) {
+  const int log2w = g.pmb_log2w, w = 1 << log2w, rows = g.pmb_rows, px = g.pmb_px, py = g.pmb_py;
+  const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1, stride = g.lvs[log2w];
+  unsigned long long* out = const_cast<unsigned long long*>(g.pmb);
+  if (g.pmb_b1 < 0) {
+    const int n = w * w * rows;
+    for (int idx = first; idx < n; idx += step) {
+      const int plane = idx / rows, r = idx - plane * rows;
+      const int ry = plane >> log2w, rx = plane & (w - 1);
+      out[idx] = pmb_row_bits(level, stride, wide_nx, wide_ny, log2w, (r << log2w) + ry - py, rx, px);
+    }
+  } else {
+    const int rpc = rows >> 1, n = w * w * rpc, b0 = g.pmb_b0, b1 = g.pmb_b1;
+    for (int idx = first; idx < n; idx += step) {
+      const int plane = idx / rpc, rp = idx - plane * rpc;
+      const int ry = plane >> log2w, rx = plane & (w - 1);
+      const int ly = ((2 * rp) << log2w) + ry - py;
+      const unsigned long long a = pmb_row_bits(level, stride, wide_nx, wide_ny, log2w, ly, rx, px);
+      const unsigned long long b = pmb_row_bits(level, stride, wide_nx, wide_ny, log2w, ly + w, rx, px);
+      out[(size_t)(2 * plane) * rpc + rp] = (unsigned long long)(uint32_t)(a >> b0) | ((unsigned long long)(uint32_t)(b >> b0) << 32);
+      out[(size_t)(2 * plane + 1) * rpc + rp] = (unsigned long long)(uint32_t)(a >> b1) | ((unsigned long long)(uint32_t)(b >> b1) << 32);
+    }
+  }
 }
 
 // bit level l from bit level l-1: the max over a w x w window is the OR of four w/2 x w/2
@@ -307,37 +371,7 @@ csm_build_slot_fused_kernel(const CsmGridDev* __restrict__ slots, const int* __r
     __syncthreads();
   }
   // bit planes of the coarsest level (see csm_build_pmb_kernel)
-  const unsigned* level = buf[top & 1];
-  const int log2w = g.pmb_log2w, w = 1 << log2w, rows = g.pmb_rows, px = g.pmb_px, py = g.pmb_py;
-  const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1, stride = g.lvs[log2w];
-  unsigned long long* pout = const_cast<unsigned long long*>(g.pmb);
-  const int n = w * w * rows;
-  for (int idx = tid; idx < n; idx += 512) {
-    const int plane = idx / rows, r = idx - plane * rows;
-    const int ry = plane >> log2w, rx = plane & (w - 1);
-    const int ly = (r << log2w) + ry - py;
-    unsigned long long bits = 0;
-    if ((unsigned)ly < (unsigned)wide_ny) {
-      if (log2w == 4) {
-        const unsigned long long* row = reinterpret_cast<const unsigned long long*>(level + ly * stride);
-        const int q = rx - px, q16 = q & 15, fq = (q - q16) >> 4;
-        unsigned long long gathered = 0;
-        const int n64 = min(stride >> 1, 16);
-        for (int j = 0; j < n64; ++j) {
-          const unsigned long long t = (row[j] >> q16) & 0x0001000100010001ull;
-          gathered |= (((t * 0x0001000200040008ull) >> 48) & 0xFull) << (4 * j);
-        }
-        bits = fq <= 0 ? (-fq < 64 ? gathered << (-fq) : 0ull) : (fq < 64 ? gathered >> fq : 0ull);
-      } else {
-        const unsigned* row = level + ly * stride;
-        for (int c = 0; c < 64; ++c) {
-          const int lx = (c << log2w) + rx - px;
-          if ((unsigned)lx < (unsigned)wide_nx) bits |= (unsigned long long)((row[lx >> 5] >> (lx & 31)) & 1u) << c;
-        }
-      }
-    }
-    pout[idx] = bits;
-  }
+  pmb_write_planes(g, buf[top & 1], tid, 512);
 }
 
 // uint8 path: width-1 grid of a slot from the store's record (bits or bytes)
@@ -739,41 +773,7 @@ __global__ void csm_build_pmb_kernel(const CsmGridDev* __restrict__ slots,
                                      const int* __restrict__ n_slots) {
   if ((int)blockIdx.y >= *n_slots) return;
   const CsmGridDev& g = slots[blockIdx.y];
-  const int log2w = g.pmb_log2w, w = 1 << log2w, rows = g.pmb_rows, px = g.pmb_px, py = g.pmb_py;
-  const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1, stride = g.lvs[log2w];
-  const unsigned* level = g.lvl[log2w];
-  unsigned long long* out = const_cast<unsigned long long*>(g.pmb);
-  const int n = w * w * rows;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
-    const int plane = idx / rows, r = idx % rows;
-    const int ry = plane >> log2w, rx = plane & (w - 1);
-    const int ly = (r << log2w) + ry - py;
-    unsigned long long bits = 0;
-    if ((unsigned)ly < (unsigned)wide_ny) {
-      if (log2w == 4) {
-        // bit c of the plane row = level bit 16 c + (rx - px): every 64-bit word of the level row
-        // (rows are 8-byte aligned, zero beyond wide_nx) holds four of them, 16 apart; one multiply
-        // gathers the four into a nibble
-        const unsigned long long* row = reinterpret_cast<const unsigned long long*>(level + (size_t)ly * stride);
-        const int q = rx - px, q16 = q & 15, fq = (q - q16) >> 4;      // column of bit c = 16 (c + fq) + q16
-        unsigned long long gathered = 0;                                // bit c' = level bit 16 c' + q16
-        const int n64 = min(stride >> 1, 16);
-        for (int j = 0; j < n64; ++j) {
-          const unsigned long long t = (__ldg(row + j) >> q16) & 0x0001000100010001ull;
-          gathered |= (((t * 0x0001000200040008ull) >> 48) & 0xFull) << (4 * j);
-        }
-        bits = fq <= 0 ? (-fq < 64 ? gathered << (-fq) : 0ull) : (fq < 64 ? gathered >> fq : 0ull);
-      } else {
-        const unsigned* row = level + (size_t)ly * stride;
-        for (int c = 0; c < 64; ++c) {
-          const int lx = (c << log2w) + rx - px;
-          if ((unsigned)lx < (unsigned)wide_nx)
-            bits |= (unsigned long long)((__ldg(row + (lx >> 5)) >> (lx & 31)) & 1u) << c;
-        }
-      }
-    }
-    out[idx] = bits;
-  }
+  pmb_write_planes(g, g.lvl[g.pmb_log2w], blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 // map_limits.h:69-76 on an already transformed point (double arithmetic, lround)
@@ -790,7 +790,14 @@ __device__ __noinline__ int2 cells_exact(float wx, float wy, double res, double 
 // discretises the even points, the odd lane the odd ones, the (row address, shift, mask) of a
 // point travels to the partner lane by shuffle.  Half the counters per thread: twice the
 // warps per SM for the same shared-memory tile.
-template <int NP>
+//
+// PR (paired plane layout, CsmGridDev::pmb_b1 >= 0): one word holds the 32 relevant columns of TWO
+// plane rows, so a lane's 2 NP candidate rows cost NP loads instead of 2 NP -- this kernel is bound
+// by shared-memory wavefronts.  The row pair a point starts in has either parity; lane 0 takes the
+// candidate rows from 0, lane 1 from 2 NP - 1 (odd), so exactly one of the two lanes reads its rows
+// shifted by one against the stored pairs and re-pairs them with one byte permute per word.  The
+// last counter row of either lane is not used (4 NP - 2 candidate rows per rotation).
+template <int NP, bool PR>
 __global__ void __launch_bounds__(kBitThreads, 1)
 csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __restrict__ pairs,
                        const float* __restrict__ pts, const float2* __restrict__ rot, CsmParams prm,
@@ -814,6 +821,10 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   const bool s_ok = s < prm.S;
   const float2 r = rot[s_ok ? s : 0];
   // points after the initial-yaw rotation (fast_..._2d.cpp:278-283), shared by all rotations
+  // A chunk is padded to a multiple of 16 points with a point that no rotation and no offset of the
+  // window brings near the grid: one of its coordinates stays more than `far_pt` - |t| from the origin.
+  const float far_pt = -4.f * (fabsf((float)g.max_x) + fabsf((float)g.max_y) + fabsf(pr.tx) + fabsf(pr.ty) +
+                               (float)(max(g.nx, g.ny) + w + 2 * prm.n_lin + 32) * (float)g.resolution) - 1000.f;
   auto stage = [&](int p0, int n) {
     __syncthreads();
     for (int p = tid; p < n; p += blockDim.x) {
@@ -821,6 +832,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
       rot_z(pr.w0, pr.z0, sp[3 * (size_t)(p0 + p)], sp[3 * (size_t)(p0 + p) + 1], x0, y0);
       P0[p] = make_float2(x0, y0);
     }
+    if (tid < 16) P0[n + tid] = make_float2(far_pt, far_pt);
     __syncthreads();
   };
   // ---- pass 1: ShrinkToFit bounds of this rotation (correlative_scan_matcher_2d.cpp:73-91).
@@ -900,7 +912,12 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   const int offx = wm + b.min_x + g.pmb_px, offy = wm + b.min_y + g.pmb_py;
   const unsigned span_x = (unsigned)(wide_nx + 2 * prm.n_lin), span_y = (unsigned)(wide_ny + 2 * prm.n_lin);
   const int hx0 = wm + prm.n_lin, hy0 = wm + prm.n_lin;
-  const int row0 = half * 2 * NP;   // first candidate row of this lane
+  const int row0 = PR ? half * (2 * NP - 1) : half * 2 * NP;   // first candidate row of this lane
+  // PR: row pairs per plane half, first columns of the halves, first all-zero row, per-lane word offset and
+  // the byte selectors of the re-pairing permute (0x3210 = as stored, 0x5432 = shifted by one row)
+  const int rpc = rows >> 1, b0 = g.pmb_b0, b1 = g.pmb_b1, zrow = rows - 16;
+  const unsigned lane_words = (unsigned)(half * (NP - 1));
+  const uint32_t sel_base = half ? 0x5432u : 0x3210u, sel_step = half ? 0u - 0x2222u : 0x2222u;
 
   // (row address, shift / mask description) of this lane's four points of an 8-point group
   // (points p + 2 i + half): all float discretisations first -- four independent chains with
@@ -911,7 +928,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     unsigned need = 0u;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float2 q = P0[min(p + 2 * i + half, n - 1)];
+      const float2 q = P0[PR ? p + 2 * i + half : min(p + 2 * i + half, n - 1)];
       float x1, y1;
       rot_z(r.x, r.y, q.x, q.y, x1, y1);
       wxs[i] = __fadd_rn(x1, pr.tx);
@@ -921,8 +938,8 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
       const float dy = uy - fy, dx = ux - fx;
       cxs[i] = (int)fy;
       cys[i] = (int)fx;
-      if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1 && fabsf(uy) < 1e7f && fabsf(ux) < 1e7f))
-        need |= 1u << i;
+      // (|u| >= 2^23 or not finite: the fractional part is 0 or NaN, the test fails by itself)
+      if (!(dy > delta && dy < hi1 && dx > delta && dx < hi1)) need |= 1u << i;
     }
     if (need) {   // rare: near a rounding boundary
 #pragma unroll
@@ -936,6 +953,25 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int cx = cxs[i], cy = cys[i];
+      if (PR) {
+        // No test whether the point can land on the grid: the planes are zero outside it, so any address
+        // inside the planes is a correct one.  A row index outside [0, zrow] is clamped onto zrow, the first
+        // of 16 all-zero rows (true rows are all zero there as well); the column window [ax, ax + ncx)
+        // either ends inside half 0 or starts inside half 1 (csm_make_plan admits the layout only then),
+        // a start beyond half 1 reads the zero rows, and the shift count 32 + a in [1, 63] applied to
+        // (row << 32) shifts right for a >= 0 and LEFT (zeros in) for a window that starts before half 0.
+        const int X = (int)((unsigned)cx + (unsigned)offx), Y = (int)((unsigned)cy + (unsigned)offy);
+        const int ax = X >> log2w, ay = Y >> log2w;
+        const int plane = ((Y & wm) << log2w) | (X & wm);
+        const int a0 = ax - b0;
+        const bool second = a0 > 32 - ncx;
+        const int a = second ? a0 - (b1 - b0) : a0;
+        const int ayc = a > 31 ? zrow : (int)min((unsigned)ay, (unsigned)zrow);
+        const int sh = max(a, -31) + 32;
+        addr[i] = (((plane << 1) | (second ? 1 : 0)) * rpc + (ayc >> 1)) | ((sh & 63) << 16) | ((ayc & 1) << 24);
+        meta[i] = 0u;
+        continue;
+      }
       // can the point land on the grid for some offset of the window at all?
       const bool hitable = (unsigned)(cx + hx0) < span_x && (unsigned)(cy + hy0) < span_y && s_ok &&
                            p + 2 * i + half < n;
@@ -951,7 +987,28 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   // the NP packed words (two candidate rows each) a point adds to this lane's counters
   auto point_words = [&](int addr, unsigned meta, uint32_t (&v)[NP]) {
     const int axc = meta & 63u, shl = (meta >> 8) & 31u;
-    const uint32_t m1 = (1u << (meta >> 16)) - 1u, m2 = m1 | (m1 << 16);
+    const uint32_t m1 = (1u << ((meta >> 16) & 31u)) - 1u, m2 = m1 | (m1 << 16);
+    if (PR) {
+      const unsigned A = (unsigned)addr;
+      const unsigned par0 = A >> 24, sh = __byte_perm(A, 0u, 0x4442);
+      // lane 0 starts at candidate row 0, lane 1 at row 2 NP - 1: their first rows have opposite parity
+      // within the stored pairs; the lane whose first row is the odd one re-pairs (t[j].hi, t[j+1].lo)
+      const uint2* rowp = reinterpret_cast<const uint2*>(bits) + ((A & 0xFFFFu) + lane_words + (par0 & (unsigned)half));
+      const uint32_t sel = sel_base + par0 * sel_step;
+      uint32_t t[NP + 1];
+#pragma unroll
+      for (int j = 0; j < NP; ++j) {
+        const uint2 L = rowp[j];
+        const uint32_t lo = (uint32_t)(((unsigned long long)L.x << 32) >> sh);
+        const uint32_t hi = (uint32_t)(((unsigned long long)L.y << 32) >> sh);
+        t[j] = __byte_perm(lo, hi, 0x5410);
+      }
+      t[NP] = 0u;
+      // bits ncx..15 of a 16-bit field hold columns beyond the window: counters nobody reads
+#pragma unroll
+      for (int j = 0; j < NP; ++j) v[j] = __byte_perm(t[j], t[j + 1], sel);
+      return;
+    }
     const unsigned long long* rowp = bits + addr + row0;
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
@@ -985,7 +1042,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     }
     auto pair_words = [&](int addr, unsigned meta, uint32_t (&ta)[NP]) {   // two points -> carry ta, sum into ones
       const int addr_o = __shfl_xor_sync(0xffffffffu, addr, 1);
-      const unsigned meta_o = __shfl_xor_sync(0xffffffffu, meta, 1);
+      const unsigned meta_o = PR ? 0u : __shfl_xor_sync(0xffffffffu, meta, 1);
       uint32_t v0[NP], v1[NP];
       point_words(addr, meta, v0);
       point_words(addr_o, meta_o, v1);
@@ -1030,7 +1087,7 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
     if (s_ok) {
       const bool first = p0 == 0, last = p0 + n >= P;
 #pragma unroll
-      for (int ly = 0; ly < 2 * NP; ++ly) {
+      for (int ly = 0; ly < (PR ? 2 * NP - 1 : 2 * NP); ++ly) {
         const int iy = row0 + ly;
         if (iy < ncy) {
           const int j = ly >> 1, sh0 = (ly & 1) * 16;
@@ -1571,7 +1628,7 @@ cudaError_t launch_csm_build_slots(const CsmGridRec* recs, const int* slot_gid, 
       ++*launches;
     }
     const int w = 1 << top;
-    const size_t words = (size_t)w * w * (size_t)csm_pmb_rows(plan.max_ny + w - 1, plan.n_lin, top);
+    const size_t words = (size_t)w * w * (size_t)csm_pmb_rows(plan.max_ny + w - 1, plan.n_lin, top, plan.pmb_b1 >= 0);
     csm_build_pmb_kernel<<<dim3(blocks(words, 128), max_slots), 128, 0, stream>>>(slots, n_slots);
     ++*launches;
   } else {
@@ -1626,27 +1683,25 @@ cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, 
   return cudaGetLastError();
 }
 
-int csm_pmb_rows(int wide_ny, int n_lin, int log2w) {
-  return ((wide_ny + 3 * n_lin - 1) >> log2w) + 1 + kBitRowSlack;
-}
+int csm_pmb_rows(int wide_ny, int n_lin, int log2w, bool paired) { return csm_pmb_rows_of(wide_ny, n_lin, log2w, paired); }
 
 size_t csm_coarse_bits_smem(int log2w, int rows) {
-  return ((size_t)(1 << (2 * log2w)) * rows + kBitChunk) * 8;
+  return ((size_t)(1 << (2 * log2w)) * rows + kBitChunk + 16) * 8;   // planes + one chunk of points + padding points
 }
 
 namespace {
-template <int NP>
+template <int NP, bool PR>
 cudaError_t launch_bits_np(dim3 grd, int threads, size_t smem, cudaStream_t stream,
                            const CsmGridDev* grids, const CsmPairDev* pairs, const float* pts,
                            const float2* rot, CsmParams prm, CsmBounds* bounds, int* coarse,
                            unsigned long long* top_coarse) {
   static unsigned long long attr_mask = 0;
   if (first_use_on_current_device(attr_mask)) {
-    cudaError_t e = cudaFuncSetAttribute(csm_coarse_bits_kernel<NP>,
+    cudaError_t e = cudaFuncSetAttribute(csm_coarse_bits_kernel<NP, PR>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
-  csm_coarse_bits_kernel<NP><<<grd, threads, smem, stream>>>(grids, pairs, pts, rot, prm, bounds,
+  csm_coarse_bits_kernel<NP, PR><<<grd, threads, smem, stream>>>(grids, pairs, pts, rot, prm, bounds,
                                                              coarse, top_coarse);
   return cudaGetLastError();
 }
@@ -1657,14 +1712,17 @@ cudaError_t launch_bits_np(dim3 grd, int threads, size_t smem, cudaStream_t stre
 cudaError_t launch_csm_coarse_bits(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                                    const float* pts, const float2* rot, CsmParams prm,
                                    CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
-                                   size_t smem, int warps, cudaStream_t stream) {
+                                   size_t smem, int warps, bool paired, cudaStream_t stream) {
   const int threads = 32 * warps;            // two lanes per rotation
   dim3 grd((2 * prm.S + threads - 1) / threads, n_pairs);
-  const int np = (prm.max_side + 3) / 4;     // packed words (two rows each) per lane
-#define GLOC_BITS_CASE(N)                                                                       \
-  case N:                                                                                       \
-    return launch_bits_np<N>(grd, threads, smem, stream, grids, pairs, pts, rot, prm, bounds,   \
-                             coarse, top_coarse);
+  // packed words (two rows each) per lane: 4 NP candidate rows per rotation, 4 NP - 2 when paired
+  const int np = paired ? (prm.max_side + 5) / 4 : (prm.max_side + 3) / 4;
+#define GLOC_BITS_CASE(N)                                                                             \
+  case N:                                                                                             \
+    return paired ? launch_bits_np<N, true>(grd, threads, smem, stream, grids, pairs, pts, rot, prm,  \
+                                            bounds, coarse, top_coarse)                               \
+                  : launch_bits_np<N, false>(grd, threads, smem, stream, grids, pairs, pts, rot, prm, \
+                                             bounds, coarse, top_coarse);
   switch (np) {
     GLOC_BITS_CASE(1) GLOC_BITS_CASE(2) GLOC_BITS_CASE(3) GLOC_BITS_CASE(4)
     default: return cudaErrorInvalidValue;

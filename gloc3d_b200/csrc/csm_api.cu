@@ -177,12 +177,31 @@ int csm_make_plan(int max_nx, int max_ny, bool all_binary, int n_lin, int depth,
   P.dev.max_ny = max_ny;
   // bit-sliced coarse scorer: binary grids whose coarsest level fits 64 columns per plane row
   // and shared memory, at most 16 lattice candidates per axis
-  bool use_bits = all_binary && std::getenv("GLOC_CSM_NO_BITS") == nullptr && max_side <= 16;
+  bool use_bits = all_binary && std::getenv("GLOC_CSM_NO_BITS") == nullptr && max_side <= 16 &&
+                  ((wide_nx + n_lin - 1) >> top) < 64;
+  P.dev.pmb_b0 = 0;
+  P.dev.pmb_b1 = -1;
+  if (use_bits && max_side <= 14 && std::getenv("GLOC_CSM_NO_PAIRED") == nullptr) {
+    // Paired plane layout (CsmGridDev::pmb): the columns that can hold data, [c_lo, c_hi] (plane column
+    // c = level bit w c + rx - px, px = n_lin), must fit two 32-column halves such that every window of
+    // max_side columns ends inside the first or starts inside the second.
+    const int c_lo = n_lin / w, c_hi = (wide_nx - 1 + n_lin) / w;
+    const int b1 = std::max(c_lo, c_hi - 31);
+    if (b1 - c_lo <= 33 - max_side) {
+      P.dev.pmb_b0 = c_lo;
+      P.dev.pmb_b1 = b1;
+      P.bits_paired = true;
+    }
+  }
   if (use_bits) {
-    const int rows = csm_pmb_rows(wide_ny, n_lin, top);
-    const size_t smem = csm_coarse_bits_smem(top, rows);
-    if (((wide_nx + n_lin - 1) >> top) >= 64 || smem > (size_t)225 * 1024) use_bits = false;
-    else P.bits_smem = smem;
+    const size_t smem = csm_coarse_bits_smem(top, csm_pmb_rows(wide_ny, n_lin, top, P.bits_paired));
+    if (smem > (size_t)225 * 1024) {
+      use_bits = false;
+      P.bits_paired = false;
+      P.dev.pmb_b1 = -1;
+    } else {
+      P.bits_smem = smem;
+    }
   }
   P.use_bits = use_bits;
   if (use_bits) {
@@ -194,7 +213,7 @@ int csm_make_plan(int max_nx, int max_ny, bool all_binary, int n_lin, int depth,
       off += align256((size_t)(max_ny + wl - 1) * (size_t)csm_bit_stride(max_nx + wl - 1) * 4);
     }
     P.dev.pmb_off = off;
-    off += align256((size_t)w * w * (size_t)csm_pmb_rows(wide_ny, n_lin, top) * 8);
+    off += align256((size_t)w * w * (size_t)csm_pmb_rows(wide_ny, n_lin, top, P.bits_paired) * 8);
     P.dev.slot_bytes = std::max(off, (size_t)256);
     if (depth >= 2) {   // expand stage on the bit-packed level depth-2
       const int l2 = depth - 2, w2 = 1 << l2;
@@ -296,7 +315,7 @@ int csm_match_core(gloc_csm_store* st, const CsmBatchPlan& plan, const float* d_
     if (plan.use_bits)
       ce = launch_csm_coarse_bits(dg, dp, np, d_pts, d_rot, prm, (CsmBounds*)st->bounds.p,
                                   (int*)st->coarse.p, (unsigned long long*)st->top.p, plan.bits_smem,
-                                  bits_warps, stream);
+                                  bits_warps, plan.bits_paired, stream);
     else
       ce = launch_csm_coarse(dg, dp, np, d_pts, d_rot, prm, (CsmBounds*)st->bounds.p, (int*)st->coarse.p,
                              (unsigned long long*)st->top.p, stream, plan.pm_kernel);
@@ -346,7 +365,7 @@ int csm_match_core(gloc_csm_store* st, const CsmBatchPlan& plan, const float* d_
       if (depth >= 2) cudaEventElapsedTime(&t_exp, tev[3], tev[5]);
       fprintf(stderr, "[csm] pairs=%d grids=%d build=%.3f ms coarse(%s)=%.3f ms seed=%.3f filter=%.3f "
                       "expand+refine=%.3f (expand %.3f) | survivors=%llu nodes=%u expanded=%llu\n",
-              np, hslots, t_build, plan.use_bits ? "bits" : "u8", t[0], t[1], t[2], t[3], t_exp, ns, hn, hc);
+              np, hslots, t_build, plan.use_bits ? (plan.bits_paired ? "bits, paired rows" : "bits") : "u8", t[0], t[1], t[2], t[3], t_exp, ns, hn, hc);
       unsigned mx = 0;
       for (unsigned v : hs) mx = std::max(mx, v);
       // where the survivors come from: pairs that end up matching vs the rest

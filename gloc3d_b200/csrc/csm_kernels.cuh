@@ -38,8 +38,13 @@ struct CsmGridDev {
   // The coarsest level as bit planes (csm.cu "bit-sliced").  Plane (ry, rx), row r = one
   // 64-bit word, bit c = cell (w c + rx - pmb_px, w r + ry - pmb_py) of the level's own
   // (wide) frame; pmb_rows rows per plane, zero outside the grid.
+  // Paired layout (pmb_b1 >= 0; grids whose data columns fit two overlapping 32-column halves
+  // starting at columns pmb_b0 and pmb_b1): plane (ry, rx), half h, row pair p = one 64-bit word,
+  // low 32 bits = columns [b_h, b_h + 32) of row 2p, high 32 bits = the same columns of row 2p + 1;
+  // word index (2 plane + h) * (pmb_rows / 2) + p.  One load then serves two candidate rows.
   const unsigned long long* pmb;
   int pmb_rows, pmb_px, pmb_py, pmb_log2w;
+  int pmb_b0, pmb_b1;
 };
 
 // A grid as the store keeps it: the width-1 precomputation grid only (everything else is
@@ -58,6 +63,7 @@ struct CsmPlan {
   size_t slot_bytes;
   size_t lvl_off[kCsmMaxDepth];   // bits: byte offset of level l inside a slot (l >= 1)
   size_t pmb_off;                 // bits: bit planes
+  int pmb_b0, pmb_b1;             // bits: first columns of the two halves of the paired plane layout (b1 < 0: 64-bit rows)
   size_t pm_off;                  // uint8: phase-major copy (stack at offset 0)
   int max_nx, max_ny;
 };
@@ -116,12 +122,12 @@ cudaError_t launch_csm_unpack_bits(const unsigned* bits, int nx, int ny, uint8_t
 cudaError_t launch_csm_discretize(const float* pts, int n_pts, float w0, float z0, float tx,
                                   float ty, const float2* rot, int S, double resolution,
                                   double max_x, double max_y, int* out_cells, cudaStream_t stream);
-int csm_pmb_rows(int wide_ny, int n_lin, int log2w);
+int csm_pmb_rows(int wide_ny, int n_lin, int log2w, bool paired);
 size_t csm_coarse_bits_smem(int log2w, int rows);
 cudaError_t launch_csm_coarse_bits(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                                    const float* pts, const float2* rot, CsmParams prm,
                                    CsmBounds* bounds, int* coarse, unsigned long long* top_coarse,
-                                   size_t smem, int warps, cudaStream_t stream);
+                                   size_t smem, int warps, bool paired, cudaStream_t stream);
 // K7 pipeline
 cudaError_t launch_csm_coarse(const CsmGridDev* grids, const CsmPairDev* pairs, int n_pairs,
                               const float* pts, const float2* rot, CsmParams prm,

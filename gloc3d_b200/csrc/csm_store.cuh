@@ -84,7 +84,7 @@ struct CsmArena {
 // grid dimensions only -- never from device data).
 struct CsmBatchPlan {
   CsmPlan dev{};
-  bool use_bits = false, exp_bits = false, pm_kernel = false;
+  bool use_bits = false, bits_paired = false, exp_bits = false, pm_kernel = false;
   size_t bits_smem = 0, exp_smem = 0;
 };
 
