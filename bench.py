@@ -1006,7 +1006,13 @@ def run_localize(args, rank, world, local_rank):
     side = (2 * LOC["n_lin"]) // (1 << (LOC["depth"] - 1)) + 1
     S = 2 * LOC["n_ang"] + 1
     pairs_per_launch = pairs_verified / max(coarse_n, 1)
-    lds_per_launch = S * side * P * pairs_per_launch            # one LDS.64 per (rotation, point, candidate row)
+    # one LDS.64 per (rotation, point, candidate row) -- or per PAIR of candidate rows when the grids admit the
+    # paired plane layout (csm_make_plan: the data columns fit two overlapping 32-column halves)
+    wc = 1 << (LOC["depth"] - 1)
+    c_lo, c_hi = LOC["n_lin"] // wc, (LOC["nx"] + wc - 2 + LOC["n_lin"]) // wc
+    paired = side <= 14 and max(c_lo, c_hi - 31) - c_lo <= 33 - side and not os.environ.get("GLOC_CSM_NO_PAIRED")
+    loads_per_point = (side + 2) // 2 if paired else side       # 13 rows, either parity of the first: 7 pairs
+    lds_per_launch = S * loads_per_point * P * pairs_per_launch
     avg_coarse = coarse_ms / max(coarse_n, 1)
     lsu = {}
     try:
@@ -1024,8 +1030,12 @@ def run_localize(args, rank, world, local_rank):
             "traffic": verify_traffic("csm_coarse_bits_localize") if (world == 1 and nq == LOC["q_per_gpu"]) else None,
             "peak_source": "measured live: gloc_bench_smem_gather (random 8-byte shared-memory loads, chip-wide)",
             "kernel_ms": avg_coarse, "kernel_launches_timed": coarse_n,
-            "algorithmic_lookups_per_launch": lds_per_launch * side,
+            "algorithmic_lookups_per_launch": S * side * side * P * pairs_per_launch,
             "algorithmic_lds64_per_launch": lds_per_launch,
+            "plane_layout": ("paired rows: one 8-byte load = 2 candidate rows x 32 columns; %d loads per (rotation, point)"
+                             % loads_per_point) if paired else "one 8-byte load = 1 candidate row x 64 columns",
+            "note": "after the paired layout the scorer is co-limited by shared-memory wavefronts and instruction issue "
+                    "(profiles/r02_ncu_coarse_paired_summary.md); frac is the share of the measured random-LDS.64 ceiling",
             "hbm": {"algorithmic_bytes_per_launch": hbm_bytes,
                     "achieved_gbs": hbm_bytes / (avg_coarse * 1e-3) / 1e9 if avg_coarse else None,
                     "frac_of_peak": hbm_bytes / (avg_coarse * 1e-3) / 1e9 / peaks["hbm_gbs"] if avg_coarse else None},

@@ -905,9 +905,10 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   // ---- pass 2: bit-sliced scoring
   const int wide_nx = g.nx + wm, wide_ny = g.ny + wm;
   const float mx_f = (float)g.max_x, my_f = (float)g.max_y, ir = (float)(1.0 / g.resolution);
-  // |float cell coordinate - exact| <= 2^-24 (|max|/res + 3 |u|) for |u| <= U; 4x safety
+  // |float cell coordinate - exact| <= 2^-24 (|max|/res + 3 |u|) for |u| <= U; 2x safety (a point further out
+  // than U cannot reach any window, there a cell off by one changes nothing)
   const float U = (float)(max(wide_nx, wide_ny) + 2 * prm.n_lin + 32);
-  const float delta = 2.3841858e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
+  const float delta = 1.1920929e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
   const float hi1 = 1.f - delta;
   const int offx = wm + b.min_x + g.pmb_px, offy = wm + b.min_y + g.pmb_py;
   const unsigned span_x = (unsigned)(wide_nx + 2 * prm.n_lin), span_y = (unsigned)(wide_ny + 2 * prm.n_lin);
@@ -1315,7 +1316,7 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
   const unsigned wnx_u = (unsigned)wide_nx, wny_u = (unsigned)wide_ny;
   const float mx_f = (float)g.max_x, my_f = (float)g.max_y, ir = (float)(1.0 / g.resolution);
   const float U = (float)(max(g.nx, g.ny) + 2 * prm.n_lin + 64 + 2 * prm.step);
-  const float delta = 2.3841858e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
+  const float delta = 1.1920929e-07f * (fmaxf(fabsf(mx_f), fabsf(my_f)) * ir + 3.f * U);
   const float hi1 = 1.f - delta;
   const float far_pt = -4.f * (fabsf(mx_f) + fabsf(my_f) + fabsf(pr.tx) + fabsf(pr.ty) + U * (float)g.resolution) - 1000.f;
   unsigned long long expanded = 0;

@@ -2,7 +2,7 @@
 gloc3d_b200/csrc/csm.cu (point_addr4 / the expand kernel): the cell of a transformed point is
 the reference's double-precision GetCellIndex (map_limits.h:69-76: lround((max - w)/res - 0.5));
 the kernels evaluate it in float and accept the float result only when its fractional part is
-further than delta = 2^-22 (|max|/res + 3 U) from 0 and 1.  The model checks that an accepted
+further than delta = 2^-23 (|max|/res + 3 U) from 0 and 1.  The model checks that an accepted
 float cell is never wrong, on random and on adversarial (boundary-hugging) inputs, and that the
 fast path is actually taken most of the time."""
 import re
@@ -26,7 +26,7 @@ def exact_cell(w, res, mx):
 def fast_cell(w, res, mx, U):
     """The kernels' float path: returns (cell, accepted)."""
     mx_f, ir = f32(mx), f32(1.0 / res)
-    delta = f32(2.3841858e-07) * (np.abs(mx_f) * ir + f32(3.0) * f32(U))
+    delta = f32(1.1920929e-07) * (np.abs(mx_f) * ir + f32(3.0) * f32(U))
     hi1 = f32(1.0) - delta
     u = ((mx_f - w).astype(f32) * ir).astype(f32)
     fl = np.floor(u)
@@ -35,10 +35,10 @@ def fast_cell(w, res, mx, U):
     return fl.astype(np.int64), ok, float(delta)
 
 
-def test_constant_in_the_kernel_is_two_to_the_minus_22():
+def test_constant_in_the_kernel_is_two_to_the_minus_23():
     src = open(os.path.join(ROOT, "gloc3d_b200", "csrc", "csm.cu")).read()
     consts = set(re.findall(r"const float delta = ([0-9.e+-]+)f \*", src))
-    assert consts == {"2.3841858e-07"} and abs(float(consts.pop()) - 2.0 ** -22) < 1e-14
+    assert consts == {"1.1920929e-07"} and abs(float(consts.pop()) - 2.0 ** -23) < 1e-14
 
 
 def test_accepted_float_cells_are_exact():
@@ -60,13 +60,13 @@ def test_accepted_float_cells_are_exact():
         cell, ok, delta = fast_cell(w, res, mx, U)
         taken.append((res, mx, delta, ok.mean()))
     # the usual map (KITTI BEV around the origin): the double fallback is rare
-    assert taken[0][3] > 0.997, taken   # 2 delta = 0.17 % of the points take the double path
+    assert taken[0][3] > 0.997, taken   # 2 delta = 0.09 % of the points take the double path
     # far-from-origin maps widen delta but the float path still carries most points
     assert all(t[3] > 0.5 for t in taken if t[2] < 0.2), taken
 
 
-def test_observed_float_error_stays_under_a_quarter_of_delta():
-    """delta carries a 4x safety factor over the proven 2^-24 (|max|/res + 3 |u|) bound."""
+def test_observed_float_error_stays_under_half_of_delta():
+    """delta carries a 2x safety factor over the proven 2^-24 (|max|/res + 3 |u|) bound."""
     rng = np.random.default_rng(1)
     for res, mx, n_cells in ((0.2, 80.0, 800), (0.05, 5000.0, 4000), (0.2, 1.0e5, 800)):
         U = n_cells + 2 * 100 + 32
@@ -75,4 +75,4 @@ def test_observed_float_error_stays_under_a_quarter_of_delta():
         u = ((mx_f - w).astype(f32) * ir).astype(np.float64)
         u_exact = (mx - w.astype(np.float64)) / res
         _, _, delta = fast_cell(w, res, mx, U)
-        assert np.abs(u - u_exact).max() <= 0.25 * delta * 1.0001, (res, mx, np.abs(u - u_exact).max(), delta)
+        assert np.abs(u - u_exact).max() <= 0.5 * delta * 1.0001, (res, mx, np.abs(u - u_exact).max(), delta)
