@@ -276,28 +276,34 @@ __device__ __forceinline__ unsigned long long pmb_row_bits(const unsigned* level
 }
 
 // The bit planes of slot g from its coarsest bit level (global or shared memory), by the threads
-// first, first + step, ...: either layout of CsmGridDev::pmb.
+// first, first + step, ...: either layout of CsmGridDev::pmb.  In GLOBAL memory the words are stored
+// row-major -- word (r, plane) at r w^2 + plane, paired: (p, plane, h) at (p w^2 + plane) 2 + h -- so that
+// neighbouring threads take neighbouring planes: they read the same level row (a broadcast; threads on
+// neighbouring plane ROWS would sit 16 w level rows apart, on the same banks) and write neighbouring
+// words.  The scorer transposes to its plane-major shared-memory layout while staging.
 __device__ __forceinline__ void pmb_write_planes(const CsmGridDev& g, const unsigned* level, int first, int step) {
   const int log2w = g.pmb_log2w, w = 1 << log2w, rows = g.pmb_rows, px = g.pmb_px, py = g.pmb_py;
   const int wide_nx = g.nx + w - 1, wide_ny = g.ny + w - 1, stride = g.lvs[log2w];
   unsigned long long* out = const_cast<unsigned long long*>(g.pmb);
+  const int pm = w * w - 1, lp = 2 * log2w;
   if (g.pmb_b1 < 0) {
-    const int n = w * w * rows;
+    const int n = rows << lp;
     for (int idx = first; idx < n; idx += step) {
-      const int plane = idx / rows, r = idx - plane * rows;
+      const int plane = idx & pm, r = idx >> lp;
       const int ry = plane >> log2w, rx = plane & (w - 1);
       out[idx] = pmb_row_bits(level, stride, wide_nx, wide_ny, log2w, (r << log2w) + ry - py, rx, px);
     }
   } else {
-    const int rpc = rows >> 1, n = w * w * rpc, b0 = g.pmb_b0, b1 = g.pmb_b1;
+    const int n = (rows >> 1) << lp, b0 = g.pmb_b0, b1 = g.pmb_b1;
+    ulonglong2* out2 = reinterpret_cast<ulonglong2*>(out);
     for (int idx = first; idx < n; idx += step) {
-      const int plane = idx / rpc, rp = idx - plane * rpc;
+      const int plane = idx & pm, rp = idx >> lp;
       const int ry = plane >> log2w, rx = plane & (w - 1);
       const int ly = ((2 * rp) << log2w) + ry - py;
       const unsigned long long a = pmb_row_bits(level, stride, wide_nx, wide_ny, log2w, ly, rx, px);
       const unsigned long long b = pmb_row_bits(level, stride, wide_nx, wide_ny, log2w, ly + w, rx, px);
-      out[(size_t)(2 * plane) * rpc + rp] = (unsigned long long)(uint32_t)(a >> b0) | ((unsigned long long)(uint32_t)(b >> b0) << 32);
-      out[(size_t)(2 * plane + 1) * rpc + rp] = (unsigned long long)(uint32_t)(a >> b1) | ((unsigned long long)(uint32_t)(b >> b1) << 32);
+      out2[idx] = make_ulonglong2((unsigned long long)(uint32_t)(a >> b0) | ((unsigned long long)(uint32_t)(b >> b0) << 32),
+                                  (unsigned long long)(uint32_t)(a >> b1) | ((unsigned long long)(uint32_t)(b >> b1) << 32));
     }
   }
 }
@@ -354,8 +360,10 @@ csm_build_slot_fused_kernel(const CsmGridDev* __restrict__ slots, const int* __r
     const int stride = g.lvs[l], ps = g.lvs[l - 1];
     const int hs = h >> 5, hb = h & 31;
     unsigned* out = l < top ? const_cast<unsigned*>(g.lvl[l]) : nullptr;   // the coarsest level is only needed as planes
-    for (int idx = tid; idx < wny * stride; idx += 512) {
-      const int ly = idx / stride, j = idx - ly * stride;
+    // a warp per row: lane = word of the row (strides beyond 32 words take several rounds)
+    for (int ly = tid >> 5; ly < wny; ly += 16)
+    for (int j = tid & 31; j < stride; j += 32) {
+      const int idx = ly * stride + j;
       auto A = [&](int jj) -> unsigned {
         if (jj < 0 || jj >= ps) return 0u;
         unsigned v = 0u;
@@ -813,7 +821,12 @@ csm_coarse_bits_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* _
   const int n_words = (w * w) * rows;
   unsigned long long* bits = reinterpret_cast<unsigned long long*>(csm_smem);
   float2* P0 = reinterpret_cast<float2*>(bits + n_words);
-  for (int i = tid; i < n_words; i += blockDim.x) bits[i] = __ldg(g.pmb + i);
+  // global row-major (see pmb_write_planes) -> plane-major: a lane walks ONE plane (or plane half) for a
+  // point, and the odd plane stride spreads the lanes of a warp over the banks
+  {
+    const int np2 = PR ? 2 * w * w : w * w, lp2 = 2 * log2w + (PR ? 1 : 0), per_plane = PR ? rows >> 1 : rows;
+    for (int i = tid; i < n_words; i += blockDim.x) bits[(i & (np2 - 1)) * per_plane + (i >> lp2)] = __ldg(g.pmb + i);
+  }
 
   const int P = pr.n_pts;
   const float* sp = pts + 3 * (size_t)pr.pt_begin;
@@ -1379,8 +1392,9 @@ csm_expand_kernel(const CsmGridDev* __restrict__ grids, const CsmPairDev* __rest
             const float dy = uy - fy, dx = ux - fx;
             cxs[u] = (int)fy;
             cys[u] = (int)fx;
-            if (!(fminf(dy, dx) > delta && fmaxf(dy, dx) < hi1 && fmaxf(fabsf(uy), fabsf(ux)) < U))
-              need |= 1u << u;
+            // (a coordinate beyond U cells is outside every child's level: its lookups clamp onto the zero
+            // row / word whatever the float cell is, and |u| >= 2^23 or NaN fails the test by itself)
+            if (!(fminf(dy, dx) > delta && fmaxf(dy, dx) < hi1)) need |= 1u << u;
           }
           if (need) {   // rare: near a rounding boundary
 #pragma unroll
