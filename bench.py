@@ -784,7 +784,7 @@ def run_reference_verify(args):
 # ------------------------------------------------------------------- localize
 # The metric itself (BASELINE.json): retrieval + pose verification as ONE measured path,
 # global_localization.cpp:482-574 (detect_all_query -> global_registraion -> match per candidate).
-LOC = dict(rows=1_000_000, grids=8192, base_grids=1024, q_per_gpu=64, nx=800, ny=800, res=0.2,
+LOC = dict(rows=1_000_000, grids=8192, base_grids=1024, q_per_gpu=128, nx=800, ny=800, res=0.2,
            n_lin=100, n_ang=180, step=2 * np.pi / 360, depth=5, min_score=0.3, k=K_NN, batches=24)
 
 
@@ -868,8 +868,8 @@ def loc_config(W, nq_job, sharding):
             "db_rows": W.rows, "distinct_grids": W.n_grids, "queries_per_step": nq_job, "k": LOC["k"],
             "candidates_verified_per_query": LOC["k"], "dim": DIM, "sharding": sharding,
             "grid_store": "bit-packed width-1 grids only; coarser levels rebuilt on the device per batch",
-            "l2": "every step is a new query batch whose ~1600 candidate grids (82 KB each) and 2 GB database "
-                  "exceed L2; no flush"}
+            "l2": f"every step is a new query batch whose ~{int(0.88 * nq_job * LOC['k'])} distinct candidate grids (82 KB each) and "
+                  "2 GB database exceed L2; no flush"}
 
 
 def run_localize(args, rank, world, local_rank):
@@ -1047,7 +1047,7 @@ def run_localize(args, rank, world, local_rank):
                                "achieved_tflops": (2.0 * nq * (hi - lo) * DIM * args.steps / max(gemm_n, 1)) /
                                                   (gemm_ms / max(gemm_n, 1) * 1e-3) / 1e12 if gemm_ms else None,
                                "peak_tflops": peaks["bf16_tflops"],
-                               "note": "64 queries fill half of one 128-row query tile: this launch is latency-, "
+                               "note": f"{nq} queries are one 128-row query tile at most: this launch is latency-, "
                                        "not tensor-bound; see --workload retrieval for the GEMM at batch size"}}
     line = {
         "metric": METRIC, "value": nq_job / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
