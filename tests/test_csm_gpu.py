@@ -253,3 +253,42 @@ def test_against_compiled_reference(oracle):
             exact += 1
     assert exact >= 5        # ties for the maximum are the exception
     st.close()
+
+
+@pytest.mark.parametrize("nx,ny,n_lin", [(800, 800, 100), (813, 500, 100), (500, 813, 104), (640, 700, 60)])
+def test_bit_planes_at_the_borders_both_layouts(oracle, nx, ny, n_lin):
+    """The paired plane layout of the bit-sliced scorer has no hit tests: rows and columns outside the
+    grid are reached through clamped addresses and shifts that pull zeros in.  Grids with occupied
+    borders at the widest sizes the layout admits (52 plane columns), a sensor near a corner, scan
+    points all around and far beyond the map, a shifted initial pose: both layouts must return the
+    oracle's canonical argmax."""
+    res, step, n_ang, depth = 0.2, 2 * np.pi / 360, 8, 5
+    rng = np.random.default_rng(nx * 7 + ny)
+    grid = synth.make_bev_grid(nx, ny, seed=nx + ny, n_segments=30, n_blobs=16)
+    for k in (0, 1, 5):                       # occupied frame: the outermost rows / columns matter
+        grid[k, :] = grid[-1 - k, :] = 255
+        grid[:, k] = grid[:, -1 - k] = 255
+    mx, my = synth.centered_limits(nx, ny, res)
+    ext_x, ext_y = nx * res / 2, ny * res / 2
+    st = g.CsmStore(0)
+    gid = st.add_grid_u8(grid, res, mx, my)
+    import os
+    for corner in ((1, 1), (-1, 1), (1, -1), (-1, -1)):
+        dx, dy = corner[0] * (ext_y - 9.0), corner[1] * (ext_x - 11.0)
+        yaw = float(rng.uniform(-3, 3))
+        scan = synth.planted_scan(grid, res, mx, my, yaw, dx, dy, dropout=0.6, jitter_cells=0.5, seed=nx + corner[0])
+        clutter = np.zeros((1500, 3), np.float32)
+        clutter[:, :2] = rng.uniform(-1.6 * max(ext_x, ext_y), 1.6 * max(ext_x, ext_y), (1500, 2))
+        scan = np.concatenate([scan, clutter]).astype(np.float32)
+        init = (dx + float(rng.uniform(-6, 6)), dy + float(rng.uniform(-6, 6)), yaw + 0.03)
+        o = oracle.csm_match(grid, res, mx, my, depth, scan, init, n_lin, n_ang, step, 0.05, 0)
+        for env in (None, "1"):
+            if env:
+                os.environ["GLOC_CSM_NO_PAIRED"] = env
+            try:
+                r = st.match_batch([scan], [gid], [0], [init], n_lin, n_ang, step, depth, 0.05)[0]
+            finally:
+                os.environ.pop("GLOC_CSM_NO_PAIRED", None)
+            same(r, o)
+        assert o.found
+    st.close()
