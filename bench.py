@@ -902,6 +902,10 @@ def run_localize(args, rank, world, local_rank):
     t_add = time.perf_counter() - t0
     loc = g.Localizer(ix, st)
     loc.set_row_grids(W.grid_of_row(lo, hi))
+    # N > 1: the ranks can read each other's grid stores over NVLink, surplus pairs move to ranks with room
+    shared = world > 1 and not os.environ.get("GLOC_BENCH_NO_SHARE")
+    if shared:
+        loc.share_grids(comm)
     prm = loc.params(LOC["k"], LOC["n_lin"], LOC["n_ang"], LOC["step"], args.verify_depth or LOC["depth"],
                      LOC["min_score"], g.LOC_FIRST_MATCH if args.loc_policy == "first" else g.LOC_VERIFY_ALL)
     n_batches = min(LOC["batches"] if world == 1 else 6, args.steps + args.warmup)
@@ -954,6 +958,7 @@ def run_localize(args, rank, world, local_rank):
     ix.set_profiling(True)
     l0 = st.stats().kernel_launches + ix.stats().kernel_launches + loc.stats().kernel_launches
     pv0 = loc.stats().pairs_verified
+    pm0 = loc.stats().pairs_migrated
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -972,6 +977,8 @@ def run_localize(args, rank, world, local_rank):
     ix.set_profiling(False)
     launches = st.stats().kernel_launches + ix.stats().kernel_launches + loc.stats().kernel_launches - l0
     pairs_verified = loc.stats().pairs_verified - pv0
+    pairs_max = reduce_ranks(float(pairs_verified), dist.ReduceOp.MAX)
+    pairs_migrated = reduce_ranks(float(loc.stats().pairs_migrated - pm0), dist.ReduceOp.SUM)
     ms_total = reduce_ranks(wall_ms, dist.ReduceOp.MAX)        # host clock >= device events (conservative)
     dev_ms = reduce_ranks(total_ms, dist.ReduceOp.MAX)
     for i in range(hold_steps(ms_total / args.steps)):
@@ -1055,8 +1062,10 @@ def run_localize(args, rank, world, local_rank):
         "dtype": "fp16 tensor shortlist + f32 exact re-rank; u8/bit sums -> f32 score", "data": "synthetic",
         "config": loc_config(W, nq_job, "none" if world == 1 else
                              f"rows/{world}: every rank holds {hi - lo} descriptor rows and the {p1 - p0} map grids of their "
-                             f"places; local top-k -> NCCL all-gather + merge; a (query, candidate) pair is verified by the "
-                             f"rank that owns the candidate; all-reduce of the 8-byte pair results (gloc_loc_localize_sharded)"),
+                             f"places; local top-k -> fused peer-memory gather + merge; a (query, candidate) pair is verified by the "
+                             f"rank that owns the candidate" + ("; ranks owning more than 1/N of a step's pairs hand the surplus to "
+                             "ranks with room, which read the owner's bit-packed grid over NVLink (gloc_loc_share_grids)" if shared else "") +
+                             "; all-reduce of the 8-byte pair results (gloc_loc_localize_sharded)"),
         "e2e": {"value": nq_job / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(last["q"].nbytes + last["pts"].nbytes) * world,
                 "d2h_bytes_per_step": int(nq * LOC["k"] * 12 + nq * LOC["k"] * 8) * world,
@@ -1066,6 +1075,8 @@ def run_localize(args, rank, world, local_rank):
                   f"(device events on the library's stream: {dev_ms / args.steps:.3f} ms/step)",
         "stats": {"policy": args.loc_policy, "located": int(located), "located_at_the_right_place": int(right_place),
                   "queries_last_step": nq, "grid_store_bytes": grid_bytes, "grid_store_workspace_bytes": ws_bytes,
+                  "pairs_per_step_busiest_rank": pairs_max / args.steps, "pairs_per_step_mean": nq_job * LOC["k"] / world,
+                  "pairs_migrated_per_step": pairs_migrated / args.steps,
                   "grids_added_s": t_add},
     }
     if world == 1 and not args.no_cpu_baseline:

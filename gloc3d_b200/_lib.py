@@ -69,7 +69,7 @@ class LocResult(C.Structure):
 
 
 class LocStats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("queries", "pairs_verified", "waves", "kernel_launches")]
+    _fields_ = [(n, C.c_uint64) for n in ("queries", "pairs_verified", "waves", "kernel_launches", "pairs_migrated")]
 
 
 class LocProfile(C.Structure):
@@ -127,6 +127,8 @@ SIGNATURES = {
     "gloc_loc_localize": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(LocParams), _vp, _vp, _vp, _vp]),
     "gloc_loc_localize_device": (_i, [_vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(LocParams), _vp, _vp, _vp, _vp]),
     "gloc_loc_get_stats": (_i, [_vp, C.POINTER(LocStats)]),
+    "gloc_loc_share_grids": (_i, [_vp, _vp]),
+    "gloc_loc_unshare_grids": (_i, [_vp, _vp]),
     "gloc_loc_set_profiling": (_i, [_vp, _i]),
     "gloc_loc_get_profile": (_i, [_vp, C.POINTER(LocProfile)]),
     "gloc_csm_get_precomputation_grid": (_i, [_vp, _i, _i, _vp]),

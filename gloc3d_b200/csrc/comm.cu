@@ -138,6 +138,24 @@ int host_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes) {
 
 }  // namespace
 
+int comm_host_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes) {
+  if (bytes == 0) return GLOC_OK;
+  if (bytes * (size_t)(c->size + 1) <= 65536) return host_all_gather(c, send, recv, bytes);
+  if (!c->xstream) GLOC_CUDA_TRY(cudaStreamCreateWithFlags(&c->xstream, cudaStreamNonBlocking));
+  char* d = nullptr;
+  GLOC_CUDA_TRY(cudaMalloc((void**)&d, bytes * (size_t)(c->size + 1)));
+  cudaError_t e = cudaMemcpyAsync(d, send, bytes, cudaMemcpyHostToDevice, c->xstream);
+  ncclResult_t ne = ncclSuccess;
+  if (e == cudaSuccess) ne = api().AllGather(d, d + bytes, bytes, ncclUint8, (ncclComm_t)c->nccl, c->xstream);
+  if (e == cudaSuccess && ne == ncclSuccess)
+    e = cudaMemcpyAsync(recv, d + bytes, bytes * (size_t)c->size, cudaMemcpyDeviceToHost, c->xstream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->xstream);
+  cudaFree(d);
+  if (ne != ncclSuccess) return nccl_fail("comm_host_all_gather: ncclAllGather", ne);
+  GLOC_CUDA_TRY(e);
+  return GLOC_OK;
+}
+
 int comm_map_peers(gloc_comm* c, void* local, void*** out) {
   for (auto& m : c->maps)
     if (m.local == local) {

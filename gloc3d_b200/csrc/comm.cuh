@@ -29,4 +29,6 @@ int comm_all_to_all(gloc_comm* c, const void* send, void* recv, size_t bytes_per
 // process can address it (GLOC_ERR_CUDA when peers cannot reach each other).  Cached per pointer.
 int comm_map_peers(gloc_comm* c, void* local, void*** out);
 void comm_unmap_peers(gloc_comm* c, void* local);
+// Collective: every rank's `bytes` bytes of HOST data to every rank's host (recv holds size * bytes).
+int comm_host_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes);
 }  // namespace gloc

@@ -123,20 +123,25 @@ int check_limits(int nx, int ny, double resolution, const char* who) {
 namespace gloc {
 
 int csm_sync_recs(gloc_csm_store* st) {
-  const size_t n = st->recs.size();
-  if (st->recs_on_device == n) return GLOC_OK;
-  const size_t need = n * sizeof(CsmGridRec);
+  const size_t n = st->recs.size(), m = st->foreign.size();
+  if (st->recs_on_device == n && !st->foreign_dirty) return GLOC_OK;
+  const size_t need = (n + m) * sizeof(CsmGridRec);
   size_t first = st->recs_on_device;
   if (need > st->d_recs.bytes) {   // a growth drops the old contents: upload everything again
     GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
     GLOC_CUDA_TRY(st->d_recs.reserve(std::max(need * 2, (size_t)4096)));
     first = 0;
   }
-  GLOC_CUDA_TRY(cudaMemcpyAsync((char*)st->d_recs.p + first * sizeof(CsmGridRec), st->recs.data() + first,
-                                (n - first) * sizeof(CsmGridRec), cudaMemcpyHostToDevice, st->stream));
-  // the records live in a std::vector that may reallocate: the copy must not outlive this call
+  if (n > first)
+    GLOC_CUDA_TRY(cudaMemcpyAsync((char*)st->d_recs.p + first * sizeof(CsmGridRec), st->recs.data() + first,
+                                  (n - first) * sizeof(CsmGridRec), cudaMemcpyHostToDevice, st->stream));
+  if (m)   // the peers' records follow the local ones
+    GLOC_CUDA_TRY(cudaMemcpyAsync((char*)st->d_recs.p + n * sizeof(CsmGridRec), st->foreign.data(),
+                                  m * sizeof(CsmGridRec), cudaMemcpyHostToDevice, st->stream));
+  // the records live in std::vectors that may reallocate: the copies must not outlive this call
   GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
   st->recs_on_device = n;
+  st->foreign_dirty = false;
   return GLOC_OK;
 }
 

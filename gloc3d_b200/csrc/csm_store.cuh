@@ -96,6 +96,12 @@ struct gloc_csm_store {
   uint8_t* d_lut = nullptr;  // uint16 cost value -> uint8 width-1 cell
   gloc::CsmArena arena;
   std::vector<gloc::CsmGridRec> recs;   // host mirror; rec.data points into the arena
+  // other ranks' grids this store can read through peer memory (gloc_loc_share_grids): records
+  // [recs.size(), recs.size() + foreign.size()) of the device table
+  std::vector<gloc::CsmGridRec> foreign;
+  bool foreign_dirty = false;
+  int f_max_nx = 0, f_max_ny = 0;
+  size_t f_graded = 0;
   gloc::CsmBuf d_recs;
   size_t recs_on_device = 0;
   int max_nx = 0, max_ny = 0;

@@ -59,6 +59,18 @@ struct gloc_localizer {
   CsmBuf d_map, d_q, d_idx, d_d2, d_qs, d_pairs, d_pts, d_keys;
   gloc_loc_stats stats{};
   EventProfiler prof_total, prof_retrieval;   // device-side spans on the store's stream
+  // what gloc_loc_share_grids learnt about the job (all ranks hold the same tables)
+  struct Shared {
+    bool on = false;
+    int size = 0, rank = 0;
+    size_t local_grids = 0, local_rows = 0;          // this rank's store / shard when the tables were built
+    std::vector<uint64_t> row_lo, row_n;             // [size] global row range of every rank
+    std::vector<size_t> n_grids;                     // [size]
+    std::vector<size_t> foreign_base;                // [size] rank r's grids in the store's foreign table
+    std::vector<std::vector<int32_t>> maps;          // [size] row -> grid of every rank (empty: identity)
+    std::vector<void*> chunks;                       // local buffers mapped through the communicator
+    std::vector<void*> dummies;                      // stand-ins where a peer has more arena chunks
+  } shared;
 };
 
 namespace {
@@ -258,6 +270,12 @@ int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, 
   if (n_grids == 0) return fail(GLOC_ERR_NOT_BUILT, "gloc_loc_localize_sharded: the grid store of this shard is empty");
   if (L->h_map.empty() ? n_local > n_grids : n_local > L->h_map.size())
     return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: shard rows without a map grid");
+  // balanced verification needs the tables of gloc_loc_share_grids, still describing this shard
+  // (checked before the first collective of the call)
+  const bool balanced = L->shared.on && L->shared.size == comm->size && L->shared.local_grids == n_grids &&
+                        L->shared.local_rows == n_local;
+  if (L->shared.on && !balanced)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: the shard changed since gloc_loc_share_grids (share again)");
   const double resolution = st->recs[0].resolution;   // one resolution per map (the decode is replicated)
   const int64_t total_pts = scan_offsets[nq];
   std::vector<QueryScan> hq(nq);
@@ -278,7 +296,9 @@ int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, 
   std::vector<float2> rot;
   csm_host_rotations(P->n_ang, P->ang_step, &rot);
   CsmBatchPlan plan;
-  csm_make_plan(st->max_nx, st->max_ny, st->n_graded == 0, P->n_lin, P->depth, &plan);
+  // (with shared grids a rank may meet any rank's grid)
+  csm_make_plan(std::max(st->max_nx, L->shared.on ? st->f_max_nx : 0), std::max(st->max_ny, L->shared.on ? st->f_max_ny : 0),
+                st->n_graded + (L->shared.on ? st->f_graded : 0) == 0, P->n_lin, P->depth, &plan);
   cudaStream_t stream = st->stream;
   const size_t n_pairs = nq * (size_t)k;
   GLOC_CUDA_TRY(L->d_idx.reserve(n_pairs * sizeof(uint64_t)));
@@ -300,7 +320,8 @@ int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, 
   std::vector<unsigned char> verified(n_pairs, 0);
   std::vector<char> done(nq, 0);
   std::vector<CsmPairDev> hp;
-  std::vector<size_t> where;
+  std::vector<size_t> where, wave;
+  std::vector<int> owner_of;
   std::vector<unsigned long long> wb;
   unsigned long long* d_send = (unsigned long long*)L->d_keys.p;
   unsigned long long* d_recv = d_send + n_pairs;
@@ -308,21 +329,73 @@ int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, 
     const int c1 = P->policy == GLOC_LOC_VERIFY_ALL ? k : std::min(k, c0 == 0 ? 1 : 2 * c0);
     hp.clear();
     where.clear();
-    for (size_t q = 0; q < nq; ++q) {
-      if (done[q]) continue;
-      for (int c = c0; c < c1; ++c) {
-        const size_t i = q * k + c;
-        verified[i] = 1;                          // by its owner, somewhere in the job
-        const uint64_t gi = out_idx[i];
-        if (gi < lo || gi >= hi) continue;        // another rank's row (or an empty slot)
-        CsmPairDev p;
-        p.grid = 0;
-        p.gid = L->h_map.empty() ? (int)(gi - lo) : L->h_map[gi - lo];
-        p.pt_begin = hq[q].pt_begin;
-        p.n_pts = hq[q].n_pts;
-        p.w0 = hq[q].w0; p.z0 = hq[q].z0; p.tx = hq[q].tx; p.ty = hq[q].ty;
-        hp.push_back(p);
-        where.push_back(i);
+    auto add_pair = [&](size_t q, size_t i, int gid) {
+      CsmPairDev p;
+      p.grid = 0;
+      p.gid = gid;
+      p.pt_begin = hq[q].pt_begin;
+      p.n_pts = hq[q].n_pts;
+      p.w0 = hq[q].w0; p.z0 = hq[q].z0; p.tx = hq[q].tx; p.ty = hq[q].ty;
+      hp.push_back(p);
+      where.push_back(i);
+    };
+    if (!balanced) {
+      for (size_t q = 0; q < nq; ++q) {
+        if (done[q]) continue;
+        for (int c = c0; c < c1; ++c) {
+          const size_t i = q * k + c;
+          verified[i] = 1;                          // by its owner, somewhere in the job
+          const uint64_t gi = out_idx[i];
+          if (gi < lo || gi >= hi) continue;        // another rank's row (or an empty slot)
+          add_pair(q, i, L->h_map.empty() ? (int)(gi - lo) : L->h_map[gi - lo]);
+        }
+      }
+    } else {
+      // Every rank holds the same retrieval results, so every rank derives the same assignment without
+      // talking: the pairs of the wave in (q, c) order, each owned by the rank that holds its row; a rank
+      // keeps the first `quota` of its own, the rest go, in order, to the ranks with room (lowest first).
+      const auto& SH = L->shared;
+      const int N = SH.size;
+      owner_of.clear();
+      std::vector<size_t> owned((size_t)N, 0);
+      wave.clear();
+      for (size_t q = 0; q < nq; ++q) {
+        if (done[q]) continue;
+        for (int c = c0; c < c1; ++c) {
+          const size_t i = q * k + c;
+          verified[i] = 1;
+          const uint64_t gi = out_idx[i];
+          int r = -1;
+          for (int t = 0; t < N; ++t)
+            if (gi >= SH.row_lo[t] && gi - SH.row_lo[t] < SH.row_n[t]) { r = t; break; }
+          if (r < 0) continue;                      // an empty slot (fewer than k rows in the job)
+          wave.push_back(i);
+          owner_of.push_back(r);
+          owned[(size_t)r]++;
+        }
+      }
+      const size_t quota = (wave.size() + (size_t)N - 1) / (size_t)N;
+      std::vector<size_t> kept((size_t)N, 0), room((size_t)N, 0);
+      for (int t = 0; t < N; ++t) room[(size_t)t] = owned[(size_t)t] < quota ? quota - owned[(size_t)t] : 0;
+      int next = 0;                                 // next rank with room
+      for (size_t w = 0; w < wave.size(); ++w) {
+        const int r = owner_of[w];
+        int by = r;
+        if (kept[(size_t)r] < quota) {
+          kept[(size_t)r]++;
+        } else {
+          while (next < N && room[(size_t)next] == 0) ++next;
+          if (next < N) {
+            by = next;
+            room[(size_t)next]--;
+          }
+        }
+        if (by != SH.rank) continue;
+        const size_t i = wave[w], q = i / (size_t)k;
+        const uint64_t row = out_idx[i] - SH.row_lo[(size_t)r];
+        const int g_local = SH.maps[(size_t)r].empty() ? (int)row : SH.maps[(size_t)r][row];
+        add_pair(q, i, r == SH.rank ? g_local : (int)(SH.local_grids + SH.foreign_base[(size_t)r] + (size_t)g_local));
+        if (r != SH.rank) L->stats.pairs_migrated++;
       }
     }
     if (!hp.empty()) {
@@ -419,6 +492,7 @@ void gloc_loc_destroy(gloc_localizer* L) {
 int gloc_loc_set_row_grids(gloc_localizer* L, const int32_t* grid_of_row, size_t n_rows) {
   if (!L) return fail(GLOC_ERR_INVALID, "gloc_loc_set_row_grids: null localizer");
   DeviceGuard g(L->device);
+  if (L->shared.on) L->shared.local_rows = (size_t)-1;   // the peers hold the old table: share again
   if (!grid_of_row || n_rows == 0) {   // back to the identity (db_grids_[db_idx], loop_detector.h:36-39)
     L->h_map.clear();
     return GLOC_OK;
@@ -503,6 +577,149 @@ int gloc_loc_localize_sharded(gloc_localizer* L, gloc_comm* comm, const float* q
     dp = (const float*)L->d_pts.p;
   }
   return loc_run_sharded(L, comm, dq, nq, dp, scan_offsets, init_xyyaw, prm, out_idx, out_d2, cand_results, results);
+}
+
+namespace {
+struct ShareHeader {
+  unsigned long long n_chunks, n_grids, n_rows, row_lo, has_map, n_graded;
+  int max_nx, max_ny;
+};
+struct ShareGrid {     // a grid record as its owner describes it to its peers
+  unsigned long long offset;
+  int chunk, nx, ny, enc;
+  double resolution, max_x, max_y;
+};
+}  // namespace
+
+int gloc_loc_unshare_grids(gloc_localizer* L, gloc_comm* comm) {
+  if (!L || !comm) return fail(GLOC_ERR_INVALID, "gloc_loc_unshare_grids: null argument");
+  DeviceGuard g(L->device);
+  cudaStreamSynchronize(L->csm->stream);
+  for (void* p : L->shared.chunks) comm_unmap_peers(comm, p);
+  for (void* p : L->shared.dummies) cudaFree(p);
+  L->shared = gloc_localizer::Shared();
+  gloc_csm_store* st = L->csm;
+  st->foreign.clear();
+  st->f_max_nx = st->f_max_ny = 0;
+  st->f_graded = 0;
+  st->foreign_dirty = true;
+  return GLOC_OK;
+}
+
+int gloc_loc_share_grids(gloc_localizer* L, gloc_comm* comm) {
+  if (!L || !comm) return fail(GLOC_ERR_INVALID, "gloc_loc_share_grids: null argument");
+  if (comm->device != L->device) return fail(GLOC_ERR_INVALID, "gloc_loc_share_grids: communicator and localizer live on different devices");
+  DeviceGuard g(L->device);
+  if (L->shared.on) {
+    int rc = gloc_loc_unshare_grids(L, comm);
+    if (rc != GLOC_OK) return rc;
+  }
+  gloc_csm_store* st = L->csm;
+  GLOC_CUDA_TRY(cudaStreamSynchronize(st->stream));
+  const int N = comm->size, me = comm->rank;
+  ShareHeader mine;
+  std::memset(&mine, 0, sizeof(mine));
+  mine.n_chunks = st->arena.chunks.size();
+  mine.n_grids = st->recs.size();
+  mine.n_rows = gloc_knn_size(L->knn);
+  mine.row_lo = knn_offset_of(L->knn);
+  mine.has_map = L->h_map.empty() ? 0 : 1;
+  mine.n_graded = st->n_graded;
+  mine.max_nx = st->max_nx;
+  mine.max_ny = st->max_ny;
+  if (mine.has_map ? L->h_map.size() < mine.n_rows : mine.n_grids < mine.n_rows)
+    return fail(GLOC_ERR_INVALID, "gloc_loc_share_grids: shard rows without a map grid");
+  std::vector<ShareHeader> hd((size_t)N);
+  int rc = comm_host_all_gather(comm, &mine, hd.data(), sizeof(ShareHeader));
+  if (rc != GLOC_OK) return rc;
+  size_t max_chunks = 0, max_grids = 0, max_rows = 0;
+  bool any_map = false;
+  for (const ShareHeader& h : hd) {
+    max_chunks = std::max<size_t>(max_chunks, h.n_chunks);
+    max_grids = std::max<size_t>(max_grids, h.n_grids);
+    max_rows = std::max<size_t>(max_rows, h.n_rows);
+    any_map |= h.has_map != 0;
+  }
+  auto& SH = L->shared;
+  // 1. every arena chunk of every rank, addressable here (ranks with fewer chunks pass stand-ins: the
+  //    mapping is a collective per buffer)
+  std::vector<std::vector<void*>> chunk_at((size_t)N, std::vector<void*>(max_chunks, nullptr));
+  for (size_t i = 0; i < max_chunks; ++i) {
+    void* local = nullptr;
+    if (i < st->arena.chunks.size()) {
+      local = st->arena.chunks[i].p;
+    } else {
+      GLOC_CUDA_TRY(cudaMalloc(&local, 256));
+      SH.dummies.push_back(local);
+    }
+    void** ptrs = nullptr;
+    rc = comm_map_peers(comm, local, &ptrs);
+    if (rc != GLOC_OK) {   // collective outcome: every rank fails here together
+      for (void* p : SH.chunks) comm_unmap_peers(comm, p);
+      for (void* p : SH.dummies) cudaFree(p);
+      SH = gloc_localizer::Shared();
+      return rc;
+    }
+    SH.chunks.push_back(local);
+    for (int r = 0; r < N; ++r) chunk_at[(size_t)r][i] = ptrs[r];
+  }
+  // 2. the grid tables
+  std::vector<ShareGrid> gs(max_grids), all_g((size_t)N * max_grids);
+  std::memset(gs.data(), 0, gs.size() * sizeof(ShareGrid));
+  for (size_t j = 0; j < st->recs.size(); ++j) {
+    const CsmGridRec& r = st->recs[j];
+    int chunk = -1;
+    for (size_t c = 0; c < st->arena.chunks.size(); ++c) {
+      const unsigned char* b = st->arena.chunks[c].p;
+      if ((const unsigned char*)r.data >= b && (const unsigned char*)r.data < b + st->arena.chunks[c].cap) { chunk = (int)c; break; }
+    }
+    if (chunk < 0) return fail(GLOC_ERR_INVALID, "gloc_loc_share_grids: a grid outside the store's arena");
+    gs[j].offset = (unsigned long long)((const unsigned char*)r.data - st->arena.chunks[(size_t)chunk].p);
+    gs[j].chunk = chunk; gs[j].nx = r.nx; gs[j].ny = r.ny; gs[j].enc = r.enc;
+    gs[j].resolution = r.resolution; gs[j].max_x = r.max_x; gs[j].max_y = r.max_y;
+  }
+  rc = comm_host_all_gather(comm, gs.data(), all_g.data(), max_grids * sizeof(ShareGrid));
+  if (rc != GLOC_OK) return rc;
+  // 3. the row -> grid tables (only where some rank has one)
+  SH.maps.assign((size_t)N, std::vector<int32_t>());
+  if (any_map) {
+    std::vector<int32_t> mm(max_rows, 0), all_m((size_t)N * max_rows);
+    for (size_t i = 0; i < mine.n_rows; ++i) mm[i] = L->h_map.empty() ? (int32_t)i : L->h_map[i];
+    rc = comm_host_all_gather(comm, mm.data(), all_m.data(), max_rows * sizeof(int32_t));
+    if (rc != GLOC_OK) return rc;
+    for (int r = 0; r < N; ++r)
+      SH.maps[(size_t)r].assign(all_m.begin() + (size_t)r * max_rows, all_m.begin() + (size_t)r * max_rows + hd[(size_t)r].n_rows);
+  }
+  // 4. the peers' grids as records of this store
+  st->foreign.clear();
+  st->f_max_nx = st->f_max_ny = 0;
+  st->f_graded = 0;
+  SH.row_lo.resize((size_t)N); SH.row_n.resize((size_t)N); SH.n_grids.resize((size_t)N); SH.foreign_base.assign((size_t)N, 0);
+  for (int r = 0; r < N; ++r) {
+    SH.row_lo[(size_t)r] = hd[(size_t)r].row_lo;
+    SH.row_n[(size_t)r] = hd[(size_t)r].n_rows;
+    SH.n_grids[(size_t)r] = hd[(size_t)r].n_grids;
+    if (r == me) continue;
+    SH.foreign_base[(size_t)r] = st->foreign.size();
+    for (size_t j = 0; j < hd[(size_t)r].n_grids; ++j) {
+      const ShareGrid& sg = all_g[(size_t)r * max_grids + j];
+      CsmGridRec rec;
+      rec.data = (const unsigned char*)chunk_at[(size_t)r][(size_t)sg.chunk] + sg.offset;
+      rec.nx = sg.nx; rec.ny = sg.ny; rec.enc = sg.enc; rec.pad = 0;
+      rec.resolution = sg.resolution; rec.max_x = sg.max_x; rec.max_y = sg.max_y;
+      st->foreign.push_back(rec);
+    }
+    st->f_max_nx = std::max(st->f_max_nx, hd[(size_t)r].max_nx);
+    st->f_max_ny = std::max(st->f_max_ny, hd[(size_t)r].max_ny);
+    st->f_graded += hd[(size_t)r].n_graded;
+  }
+  st->foreign_dirty = true;
+  SH.size = N;
+  SH.rank = me;
+  SH.local_grids = st->recs.size();
+  SH.local_rows = mine.n_rows;
+  SH.on = true;
+  return GLOC_OK;
 }
 
 int gloc_loc_set_profiling(gloc_localizer* L, int enabled) {

@@ -108,6 +108,14 @@ class Localizer:
                                                    C.cast(cand, C.c_void_p) if cand is not None else None,
                                                    C.cast(res, C.c_void_p), int(device)))
 
+    def share_grids(self, comm) -> None:
+        """Collective: make every rank's grid store readable by its peers (NVLink peer memory) so that
+        localize_sharded can hand surplus (query, candidate) pairs to ranks with room."""
+        check(_lib.lib().gloc_loc_share_grids(self._h, comm._h))
+
+    def unshare_grids(self, comm) -> None:
+        check(_lib.lib().gloc_loc_unshare_grids(self._h, comm._h))
+
     def set_profiling(self, enabled: bool) -> None:
         check(_lib.lib().gloc_loc_set_profiling(self._h, int(enabled)))
 

@@ -301,6 +301,7 @@ typedef struct {
 
 typedef struct {
   uint64_t queries, pairs_verified, waves, kernel_launches;
+  uint64_t pairs_migrated;   /* of pairs_verified: verified here on a peer's grid (gloc_loc_share_grids) */
 } gloc_loc_stats;
 
 int gloc_loc_create(gloc_localizer** out, gloc_knn_index* knn, gloc_csm_store* csm);
@@ -335,6 +336,17 @@ int gloc_loc_localize_sharded(gloc_localizer* loc, gloc_comm* comm, const float*
                               const gloc_loc_params* params, uint64_t* out_idx, float* out_d2,
                               gloc_csm_result* cand_results, gloc_loc_result* results,
                               int buffers_on_device);
+/* Collective, optional, between building the shards and localizing: every rank makes its grid store
+ * addressable by its peers (NVLink peer memory: direct pointers inside one process, CUDA IPC between
+ * processes) and learns the peers' grid tables.  From then on gloc_loc_localize_sharded balances the
+ * work: ranks that own more than their share of a wave's (query, candidate) pairs hand the excess to
+ * ranks that own less, which build the working set of such a pair straight from the owner's
+ * bit-packed grid over NVLink (83 KB per 800 x 800 grid; nothing is copied ahead of time).  Results
+ * are unchanged.  Call again after any rank added grids or changed its row table; returns
+ * GLOC_ERR_CUDA (and leaves owner-only verification in place) where peers cannot address each other.
+ * gloc_loc_unshare_grids (collective, same communicator) unmaps the peers' stores. */
+int gloc_loc_share_grids(gloc_localizer* loc, gloc_comm* comm);
+int gloc_loc_unshare_grids(gloc_localizer* loc, gloc_comm* comm);
 int gloc_loc_get_stats(const gloc_localizer* loc, gloc_loc_stats* out);
 /* Live device-side timing (CUDA events on the stream the work is launched on) of whole calls and
  * of their retrieval stage; the rest of a call is verification.  Summed since the last get. */

@@ -128,6 +128,69 @@ def main():
     # every rank verified only the pairs it owns
     owned = int(((lref_idx >= lb[rank]) & (lref_idx < lb[rank + 1])).sum())
     assert loc.stats().pairs_verified <= 2 * owned
+
+    # ---- balanced verification over peer memory (gloc_loc_share_grids): queries that all revisit rank
+    # 0's rows, so rank 0 owns most candidates and must hand pairs to its peers, which read rank 0's
+    # bit-packed grids over NVLink.  Same results as the oracle, per-rank work within the quota.
+    nq2 = 9
+    qrows2 = rng.integers(lb[0], lb[1], nq2)
+    lq2 = (ldb[qrows2] + rng.standard_normal((nq2, 512)).astype(np.float32) * 0.01).astype(np.float32)
+    scans2 = [synth.planted_scan(grids[place(int(r))], res, mx, my, rng.uniform(-0.4, 0.4), rng.uniform(-2, 2),
+                                 rng.uniform(-2, 2), dropout=0.2, seed=int(r) + 5) for r in qrows2]
+    ref2_idx, _ = po.knn(ldb, lq2, kk, nthreads=4)
+    ref2 = [[po.csm_match(grids[place(int(ref2_idx[qi, c]))], res, mx, my, depth, scans2[qi], (0, 0, 0), n_lin, n_ang,
+                          step, min_score, 0) for c in range(kk)] for qi in range(nq2)]
+    owned2 = [int(((ref2_idx >= lb[r]) & (ref2_idx < lb[r + 1])).sum()) for r in range(world)]
+    quota = -(-nq2 * kk // world)
+    assert owned2[0] > quota                       # the scenario is skewed
+    loc.share_grids(comm)
+
+    def check_balanced(tag):
+        prm.policy = g.LOC_VERIFY_ALL
+        s0 = loc.stats()
+        o = loc.localize_sharded(comm, lq2, scans2, prm)
+        s1 = loc.stats()
+        assert np.array_equal(o.idx, ref2_idx), tag
+        for qi in range(nq2):
+            for c in range(kk):
+                same(o.candidates[qi * kk + c], ref2[qi][c])
+        mine_now = s1.pairs_verified - s0.pairs_verified
+        assert mine_now <= quota, (tag, rank, mine_now, quota)
+        moved = s1.pairs_migrated - s0.pairs_migrated
+        assert (moved == 0) if rank == 0 else (moved >= 0)
+        tot = torch.tensor([mine_now, moved], device=dev, dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot[0]) == nq2 * kk and int(tot[1]) >= owned2[0] - quota, (tag, tot.tolist())
+        prm.policy = g.LOC_FIRST_MATCH
+        o2 = loc.localize_sharded(comm, lq2, scans2, prm)
+        for qi in range(nq2):
+            A, B = o.results[qi], o2.results[qi]
+            assert (A.located, A.candidate, A.db_index) == (B.located, B.candidate, B.db_index), tag
+            same(B.match, A.match)
+
+    check_balanced("bits over peer memory")
+    # the first batch again: balanced and owner-only verification agree
+    prm.policy = g.LOC_VERIFY_ALL
+    out3 = loc.localize_sharded(comm, lq, scans, prm)
+    assert [c.as_tuple() for c in out3.candidates] == [c.as_tuple() for c in out.candidates]
+    # a graded grid anywhere in the job switches every rank to the uint8 kernels; the tables must be
+    # shared again after a store changed (the stale state is an error, not a silent fallback)
+    if rank == world - 1:
+        st.add_grid_u8(synth.make_bev_grid(nx, ny, seed=77, n_segments=14, n_blobs=8, graded=True), res, mx, my)
+        try:
+            loc.localize_sharded(comm, lq2, scans2, prm)
+            raise AssertionError("a changed shard must be refused")
+        except g.GlocError:
+            pass
+    dist.barrier()
+    loc.share_grids(comm)
+    check_balanced("uint8 kernels over peer memory")
+    loc.unshare_grids(comm)
+    prm.policy = g.LOC_VERIFY_ALL
+    out4 = loc.localize_sharded(comm, lq2, scans2, prm)          # owner-only again
+    for qi in range(nq2):
+        for c in range(kk):
+            same(out4.candidates[qi * kk + c], ref2[qi][c])
     loc.close(); st.close(); lix.close(); ix.close(); comm.close()
     dist.barrier()
     dist.destroy_process_group()
