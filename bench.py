@@ -1067,9 +1067,10 @@ def run_localize(args, rank, world, local_rank):
                              "ranks with room, which read the owner's bit-packed grid over NVLink (gloc_loc_share_grids)" if shared else "") +
                              "; all-reduce of the 8-byte pair results (gloc_loc_localize_sharded)"),
         "e2e": {"value": nq_job / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(last["q"].nbytes + last["pts"].nbytes) * world,
+                "h2d_bytes_per_step": int(last["q"].nbytes + last["pts"].nbytes),
                 "d2h_bytes_per_step": int(nq * LOC["k"] * 12 + nq * LOC["k"] * 8) * world,
-                "note": "N > 1: the batch (descriptors 2 KB + scan ~52 KB per query) is uploaded by every rank"},
+                "note": "N > 1: every rank uploads the descriptors (2 KB) and scans (~52 KB) of 1/N of the queries, the parts "
+                        "travel to the peers over NVLink; every rank downloads all results"},
         "gpu_launches": launches, "clocks": clk, "roofline": roof,
         "timing": "value: host clock around K synchronous C-ABI calls between device synchronisations "
                   f"(device events on the library's stream: {dev_ms / args.steps:.3f} ms/step)",

@@ -35,6 +35,7 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
 };
@@ -68,6 +69,7 @@ NcclApi& api() {
     A.AllReduce = (decltype(A.AllReduce))sym("ncclAllReduce");
     A.Send = (decltype(A.Send))sym("ncclSend");
     A.Recv = (decltype(A.Recv))sym("ncclRecv");
+    A.Broadcast = (decltype(A.Broadcast))sym("ncclBroadcast");
     A.GroupStart = (decltype(A.GroupStart))sym("ncclGroupStart");
     A.GroupEnd = (decltype(A.GroupEnd))sym("ncclGroupEnd");
     A.ok = all;
@@ -94,6 +96,25 @@ int comm_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes_per
 
 int comm_all_reduce_max_u64(gloc_comm* c, const void* send, void* recv, size_t count, cudaStream_t s) {
   GLOC_NCCL_TRY(api().AllReduce(send, recv, count, ncclUint64, ncclMax, (ncclComm_t)c->nccl, s));
+  return GLOC_OK;
+}
+
+// In place: bytes [offsets[r], offsets[r + 1]) of `buf` are valid on rank r; afterwards all of
+// [offsets[0], offsets[size]) is valid everywhere (an all-gather of unequal parts: one grouped
+// broadcast per rank, over NVLink).
+int comm_all_gather_v(gloc_comm* c, void* buf, const size_t* offsets, cudaStream_t s) {
+  GLOC_NCCL_TRY(api().GroupStart());
+  for (int r = 0; r < c->size; ++r) {
+    const size_t n = offsets[r + 1] - offsets[r];
+    if (n == 0) continue;
+    char* p = (char*)buf + offsets[r];
+    ncclResult_t a = api().Broadcast(p, p, n, ncclUint8, r, (ncclComm_t)c->nccl, s);
+    if (a != ncclSuccess) {
+      api().GroupEnd();
+      return nccl_fail("ncclBroadcast", a);
+    }
+  }
+  GLOC_NCCL_TRY(api().GroupEnd());
   return GLOC_OK;
 }
 

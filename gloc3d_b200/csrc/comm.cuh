@@ -25,6 +25,8 @@ namespace gloc {
 int comm_all_gather(gloc_comm* c, const void* send, void* recv, size_t bytes_per_rank, cudaStream_t s);
 int comm_all_reduce_max_u64(gloc_comm* c, const void* send, void* recv, size_t count, cudaStream_t s);
 int comm_all_to_all(gloc_comm* c, const void* send, void* recv, size_t bytes_per_block, cudaStream_t s);
+// in place: rank r holds bytes [offsets[r], offsets[r + 1]) of buf; afterwards every rank holds all of them
+int comm_all_gather_v(gloc_comm* c, void* buf, const size_t* offsets, cudaStream_t s);
 // Collective: every rank passes its own cudaMalloc'ed buffer; out[i] = rank i's buffer as this
 // process can address it (GLOC_ERR_CUDA when peers cannot reach each other).  Cached per pointer.
 int comm_map_peers(gloc_comm* c, void* local, void*** out);

@@ -9,6 +9,7 @@
 // verifier.  Nothing of a batch goes through the host between the stages.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -561,6 +562,14 @@ int gloc_loc_localize_sharded(gloc_localizer* L, gloc_comm* comm, const float* q
   if (comm->device != L->device) return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: communicator on another device");
   DeviceGuard g(L->device);
   if (!g.ok) return fail(GLOC_ERR_CUDA, "gloc_loc_localize_sharded: cudaSetDevice failed");
+  // every local reason to refuse the call comes BEFORE its first collective (the sliced upload below):
+  // a rank that fails alone must not leave its peers waiting inside one
+  if (L->shared.on && !(L->shared.size == comm->size && L->shared.local_grids == L->csm->recs.size() &&
+                        L->shared.local_rows == gloc_knn_size(L->knn)))
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: the shard changed since gloc_loc_share_grids (share again)");
+  if (L->csm->recs.empty()) return fail(GLOC_ERR_NOT_BUILT, "gloc_loc_localize_sharded: the grid store of this shard is empty");
+  if (L->h_map.empty() ? gloc_knn_size(L->knn) > L->csm->recs.size() : gloc_knn_size(L->knn) > L->h_map.size())
+    return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: shard rows without a map grid");
   cudaStream_t stream = L->csm->stream;
   const float* dq = queries;
   const float* dp = pts;
@@ -571,8 +580,29 @@ int gloc_loc_localize_sharded(gloc_localizer* L, gloc_comm* comm, const float* q
     if (total_pts <= 0) return fail(GLOC_ERR_INVALID, "gloc_loc_localize_sharded: bad scan offsets");
     GLOC_CUDA_TRY(L->d_q.reserve(nq * dim * sizeof(float)));
     GLOC_CUDA_TRY(L->d_pts.reserve((size_t)total_pts * 3 * sizeof(float)));
-    GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_q.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
-    GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_pts.p, pts, (size_t)total_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    const int N = comm->size;
+    if (N > 1 && nq >= (size_t)N && std::getenv("GLOC_LOC_FULL_UPLOAD") == nullptr) {
+      // every rank holds the same host batch: each uploads the queries and scans of ITS 1/N of the
+      // queries over PCIe, the parts travel to the peers over NVLink (one upload per byte, not N)
+      std::vector<size_t> oq((size_t)N + 1), op((size_t)N + 1);
+      for (int r = 0; r <= N; ++r) {
+        const size_t q = nq * (size_t)r / (size_t)N;
+        oq[(size_t)r] = q * dim * sizeof(float);
+        op[(size_t)r] = (size_t)scan_offsets[q] * 3 * sizeof(float);
+      }
+      const int me = comm->rank;
+      GLOC_CUDA_TRY(cudaMemcpyAsync((char*)L->d_q.p + oq[(size_t)me], (const char*)queries + oq[(size_t)me],
+                                    oq[(size_t)me + 1] - oq[(size_t)me], cudaMemcpyHostToDevice, stream));
+      if (op[(size_t)me + 1] > op[(size_t)me])
+        GLOC_CUDA_TRY(cudaMemcpyAsync((char*)L->d_pts.p + op[(size_t)me], (const char*)pts + op[(size_t)me],
+                                      op[(size_t)me + 1] - op[(size_t)me], cudaMemcpyHostToDevice, stream));
+      int rc = comm_all_gather_v(comm, L->d_q.p, oq.data(), stream);
+      if (rc == GLOC_OK) rc = comm_all_gather_v(comm, L->d_pts.p, op.data(), stream);
+      if (rc != GLOC_OK) return rc;
+    } else {
+      GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_q.p, queries, nq * dim * sizeof(float), cudaMemcpyHostToDevice, stream));
+      GLOC_CUDA_TRY(cudaMemcpyAsync(L->d_pts.p, pts, (size_t)total_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
     dq = (const float*)L->d_q.p;
     dp = (const float*)L->d_pts.p;
   }

@@ -330,6 +330,8 @@ int gloc_loc_localize_device(gloc_localizer* loc, const float* d_queries, size_t
  * batch and gets the same outputs.  Retrieval as gloc_knn_query_sharded (replicated); a (query,
  * candidate) pair is verified on the rank that owns the candidate's row; one all-reduce of the
  * 8-byte pair results per wave.  All grids of the map must share one resolution.
+ * Host buffers (buffers_on_device == 0): every rank uploads the queries and scans of ITS 1/N of the
+ * queries only, the parts reach the peers over NVLink (one PCIe upload per byte, not one per rank).
  * buffers_on_device != 0: `queries` and `pts` are device pointers (as gloc_loc_localize_device). */
 int gloc_loc_localize_sharded(gloc_localizer* loc, gloc_comm* comm, const float* queries, size_t nq,
                               const float* pts, const int64_t* scan_offsets, const double* init_xyyaw,

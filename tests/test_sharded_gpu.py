@@ -24,7 +24,7 @@ def test_one_process_per_gpu_under_torchrun():
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
            "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "sharded_worker.py")]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=240)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert tail.count("sharded paths ok") == 2, tail
