@@ -2,9 +2,14 @@
  * bev_oracle.c -- CPU restatement of the reference's BEV projection of one scan
  * (the producer of both stages' inputs).
  *
- * TEST INFRASTRUCTURE ONLY (see gloc_oracle.h).  PARITY UNPINNED: the reference path
- * needs Eigen, glog, OpenCV and PCL (none installed) and ships no test vectors; this file
- * follows the sources line by line.  Citations relative to /root/reference/registration/.
+ * TEST INFRASTRUCTURE ONLY (see gloc_oracle.h).  PINNED (round 2): the reference's own
+ * 3d/submap_3d.cpp, 3d/range_data_inserter_3d.cpp, 3d/range_data.cpp and 3d/hybrid_grid.h
+ * compile unmodified against oracle/shim/ into oracle/_ref/libbev_ref.so (oracle/bev_ref.cpp);
+ * tests/test_oracle_bev_ref.py checks this file against it image for image and origin bit
+ * for bit (the reference's KITTI scan, synthetic scans, rounding boundaries, grid growth), and
+ * tests/golden/bev_kitti_subsample.npz is minted from it.  What stays a restatement: the
+ * dozen lines of loop_detector.cpp around it (that file needs PCL and libtorch) and the
+ * arithmetic of the Eigen shim.  Citations relative to /root/reference/registration/.
  *
  * Reference path for ONE scan inserted into a fresh Submap3D with the identity pose
  * (RpyPCLoopDetector::get_projected_grid, loop_detector.cpp:122-135):

@@ -172,7 +172,8 @@ void gloc_oracle_csm_match_batch_mt(const uint8_t* const* grids, int nx, int ny,
 
 /* One scan -> the reference's BEV image (0 = occupied, 255 = free): see bev_oracle.c for
  * the path restated (loop_detector.cpp:108-135, 3d/submap_3d.cpp:238-326,
- * 3d/range_data_inserter_3d.cpp:57-77, 3d/hybrid_grid.h:429-434).  PARITY UNPINNED. */
+ * 3d/range_data_inserter_3d.cpp:57-77, 3d/hybrid_grid.h:429-434).  Pinned against those sources compiled unmodified
+ * (oracle/_ref/libbev_ref.so, tests/test_oracle_bev_ref.py). */
 int gloc_oracle_bev_project(const float* pts, size_t n, int stride, float resolution,
                             float max_range, uint8_t* img, size_t img_capacity, int* w, int* h,
                             int* min_ix, int* min_iy, double* ox, double* oy,

@@ -449,3 +449,44 @@ def ref_csm_match_batch(cells_list, resolution, max_x, max_y, depth, pts_list, i
                                           init.ctypes.data_as(C.POINTER(C.c_double)), n, n_lin, n_ang, ang_step,
                                           min_score, nthreads, out)
     return list(out)
+
+
+# ------------------------------------------------- BEV projection: the REFERENCE's own code
+# oracle/_ref/libbev_ref.so = 3d/submap_3d.cpp (Submap3D, ProjectToCvMat), 3d/range_data_inserter_3d.cpp,
+# 3d/range_data.cpp, 3d/hybrid_grid.h ... compiled unmodified from /root/reference against oracle/shim/
+# (see oracle/bev_ref.cpp).
+_BEV_REF = os.path.join(_HERE, "_ref", "libbev_ref.so")
+_bev_ref = None
+
+
+def have_bev_ref() -> bool:
+    if not os.path.exists(_BEV_REF):
+        try:
+            build(force=os.path.isdir("/root/reference/registration"))
+        except Exception:
+            return False
+    return os.path.exists(_BEV_REF)
+
+
+def ref_bev_project(pts: np.ndarray):
+    """The reference's get_projected_grid for one scan ([n, 3 or 4] float32): (img uint8 [h, w] with
+    0 = occupied / 255 = free, (ox, oy, resolution))."""
+    global _bev_ref
+    if _bev_ref is None:
+        if not have_bev_ref():
+            raise RuntimeError("oracle/_ref/libbev_ref.so is missing")
+        R = C.CDLL(_BEV_REF)
+        R.gloc_ref_bev_project.restype = C.c_int
+        R.gloc_ref_bev_project.argtypes = ([C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t] +
+                                           [C.POINTER(C.c_int)] * 2 + [C.POINTER(C.c_double)] * 3)
+        _bev_ref = R
+    pts = np.ascontiguousarray(pts, np.float32)
+    n, stride = pts.shape
+    w, h = C.c_int(), C.c_int()
+    ox, oy, res = C.c_double(), C.c_double(), C.c_double()
+    args = (C.byref(w), C.byref(h), C.byref(ox), C.byref(oy), C.byref(res))
+    _bev_ref.gloc_ref_bev_project(pts.ctypes.data, n, stride, None, 0, *args)
+    img = np.empty((h.value, w.value), np.uint8)
+    if _bev_ref.gloc_ref_bev_project(pts.ctypes.data, n, stride, img.ctypes.data, img.size, *args) != 0:
+        raise RuntimeError("gloc_ref_bev_project failed")
+    return img, (ox.value, oy.value, res.value)

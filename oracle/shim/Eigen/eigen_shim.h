@@ -1,6 +1,7 @@
 // eigen_shim.h -- TEST INFRASTRUCTURE ONLY (oracle/).  The handful of Eigen types the reference's
-// registration/2d/*.cpp, 3d/point_cloud.cpp and 3d/probability_values.cpp use, so that those files
-// compile UNMODIFIED into oracle/_ref/libcsm_ref.so in an image without Eigen (the build uses
+// registration/2d/*.cpp, 3d/point_cloud.cpp, 3d/probability_values.cpp and (for the BEV projection)
+// 3d/submap_3d.cpp, 3d/range_data_inserter_3d.cpp, 3d/range_data.cpp, 3d/hybrid_grid.h use, so that those
+// files compile UNMODIFIED into oracle/_ref/libcsm_ref.so and oracle/_ref/libbev_ref.so in an image without Eigen (the build uses
 // "Eigen/Core" / "Eigen/Geometry" from PCL's dependency; version unpinned).
 //
 // What is a restatement here and what is not: the control flow of the matcher (precomputation
@@ -19,6 +20,7 @@
 
 #include <algorithm>
 #include <array>
+#include <climits>
 #include <cmath>
 #include <cstddef>
 #include <limits>
@@ -31,11 +33,21 @@ namespace Eigen {
 
 template <typename T, int N> struct Array;
 
-struct BoolArray2 {
-  bool v[2];
-  bool all() const { return v[0] && v[1]; }
-  bool any() const { return v[0] || v[1]; }
+template <int N>
+struct BoolArray {
+  bool v[N];
+  bool all() const {
+    for (int i = 0; i < N; ++i)
+      if (!v[i]) return false;
+    return true;
+  }
+  bool any() const {
+    for (int i = 0; i < N; ++i)
+      if (v[i]) return true;
+    return false;
+  }
 };
+typedef BoolArray<2> BoolArray2;
 
 template <typename T, int N>
 struct CommaInit {
@@ -189,13 +201,64 @@ struct Array {
     for (int i = 0; i < N; ++i) c[i] = T(0);
   }
   Array(T x, T y) : c{x, y} { static_assert(N == 2, "size"); }
+  Array(const Matrix<T, N, 1>& m) {   // Eigen converts between Matrix and Array of one shape
+    for (int i = 0; i < N; ++i) c[i] = m.c[i];
+  }
+  Array(T x, T y, T z) : c{x, y, z} { static_assert(N == 3, "size"); }
+  Array(T x, T y, T z, T w) : c{x, y, z, w} { static_assert(N == 4, "size"); }
   static Array Zero() { return Array(); }
+  static Array Constant(T v) {
+    Array r;
+    for (int i = 0; i < N; ++i) r.c[i] = v;
+    return r;
+  }
   T& x() { return c[0]; }
   T& y() { return c[1]; }
+  T& z() { return c[2]; }
+  T& w() { return c[3]; }
   const T& x() const { return c[0]; }
   const T& y() const { return c[1]; }
+  const T& z() const { return c[2]; }
+  const T& w() const { return c[3]; }
   T& operator[](int i) { return c[i]; }
   const T& operator[](int i) const { return c[i]; }
+  T& operator()(int i) { return c[i]; }
+  const T& operator()(int i) const { return c[i]; }
+  template <int K>
+  Array<T, K> head() const {
+    Array<T, K> r;
+    for (int i = 0; i < K; ++i) r.c[i] = c[i];
+    return r;
+  }
+  Array cwiseMin(const Array& o) const { return min(o); }
+  Array cwiseMax(const Array& o) const { return max(o); }
+  Array cwiseAbs() const {
+    Array r;
+    for (int i = 0; i < N; ++i) r.c[i] = c[i] < T(0) ? -c[i] : c[i];
+    return r;
+  }
+  T maxCoeff() const {
+    T m = c[0];
+    for (int i = 1; i < N; ++i)
+      if (m < c[i]) m = c[i];
+    return m;
+  }
+  T minCoeff() const {
+    T m = c[0];
+    for (int i = 1; i < N; ++i)
+      if (c[i] < m) m = c[i];
+    return m;
+  }
+  template <typename U>
+  Array<U, N> cast() const {
+    Array<U, N> r;
+    for (int i = 0; i < N; ++i) r.c[i] = static_cast<U>(c[i]);
+    return r;
+  }
+  Array& operator+=(const Array& o) {
+    for (int i = 0; i < N; ++i) c[i] += o.c[i];
+    return *this;
+  }
   Array operator-() const {
     Array r;
     for (int i = 0; i < N; ++i) r.c[i] = -c[i];
@@ -229,17 +292,49 @@ Array<T, N> operator-(const Array<T, N>& a, const Array<T, N>& b) {
   for (int i = 0; i < N; ++i) r.c[i] = a.c[i] - b.c[i];
   return r;
 }
-template <typename T>
-BoolArray2 operator<=(const Array<T, 2>& a, const Array<T, 2>& b) {
-  return BoolArray2{{a.c[0] <= b.c[0], a.c[1] <= b.c[1]}};
+#define GLOC_SHIM_ARRAY_CMP(OP)                                            \
+  template <typename T, int N>                                             \
+  BoolArray<N> operator OP(const Array<T, N>& a, const Array<T, N>& b) {   \
+    BoolArray<N> r;                                                        \
+    for (int i = 0; i < N; ++i) r.v[i] = a.c[i] OP b.c[i];                 \
+    return r;                                                              \
+  }
+GLOC_SHIM_ARRAY_CMP(<=)
+GLOC_SHIM_ARRAY_CMP(<)
+GLOC_SHIM_ARRAY_CMP(>=)
+GLOC_SHIM_ARRAY_CMP(>)
+GLOC_SHIM_ARRAY_CMP(==)
+#undef GLOC_SHIM_ARRAY_CMP
+template <typename T, int N, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+BoolArray<N> operator>=(const Array<T, N>& a, S s) {
+  BoolArray<N> r;
+  for (int i = 0; i < N; ++i) r.v[i] = a.c[i] >= static_cast<T>(s);
+  return r;
 }
-template <typename T>
-BoolArray2 operator<(const Array<T, 2>& a, const Array<T, 2>& b) {
-  return BoolArray2{{a.c[0] < b.c[0], a.c[1] < b.c[1]}};
+template <typename T, int N, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+Array<T, N> operator+(const Array<T, N>& a, S s) {
+  Array<T, N> r;
+  for (int i = 0; i < N; ++i) r.c[i] = a.c[i] + static_cast<T>(s);
+  return r;
 }
-template <typename T>
-BoolArray2 operator==(const Array<T, 2>& a, const Array<T, 2>& b) {
-  return BoolArray2{{a.c[0] == b.c[0], a.c[1] == b.c[1]}};
+template <typename T, int N, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+Array<T, N> operator-(const Array<T, N>& a, S s) {
+  Array<T, N> r;
+  for (int i = 0; i < N; ++i) r.c[i] = a.c[i] - static_cast<T>(s);
+  return r;
+}
+// integer arrays: Eigen evaluates coefficient-wise with the scalar's own arithmetic (int * int, int / int)
+template <typename T, int N, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+Array<T, N> operator*(const Array<T, N>& a, S s) {
+  Array<T, N> r;
+  for (int i = 0; i < N; ++i) r.c[i] = a.c[i] * static_cast<T>(s);
+  return r;
+}
+template <typename T, int N, typename S, typename = typename std::enable_if<std::is_arithmetic<S>::value>::type>
+Array<T, N> operator/(const Array<T, N>& a, S s) {
+  Array<T, N> r;
+  for (int i = 0; i < N; ++i) r.c[i] = a.c[i] / static_cast<T>(s);
+  return r;
 }
 template <typename T, int N>
 std::ostream& operator<<(std::ostream& os, const Array<T, N>& m) {
@@ -405,6 +500,9 @@ typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<float, 4, 1> Vector4f;
 typedef Array<int, 2> Array2i;
+typedef Array<int, 3> Array3i;
+typedef Array<float, 3> Array3f;
+typedef Array<int, 4> Array4i;
 typedef AlignedBox<int, 2> AlignedBox2i;
 typedef Rotation2D<double> Rotation2Dd;
 typedef Rotation2D<float> Rotation2Df;

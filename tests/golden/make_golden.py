@@ -63,9 +63,13 @@ def csm_case(name, nx, ny, seed, yaw, dx, dy, n_lin, n_ang, step, depth, min_sco
 
 def bev_case(name, every=4):
     """Every `every`-th point of the reference's only real scan (s2s_libtorch/000000.bin, a
-    KITTI frame) and the BEV image the oracle computes for it (needs /root/reference)."""
+    KITTI frame) and the BEV image the REFERENCE's own projection code computes for it (needs /root/reference)."""
     pts = np.fromfile("/root/reference/s2s_libtorch/000000.bin", np.float32).reshape(-1, 4)[::every].copy()
     img, (ox, oy, res), (mx, my), nv, no = po.bev_project(pts)
+    # minted from the reference's own projection (oracle/_ref/libbev_ref.so): the oracle must agree
+    rimg, rgeo = po.ref_bev_project(pts)
+    assert np.array_equal(rimg, img) and rgeo == (ox, oy, res)
+    img = rimg
     np.savez_compressed(os.path.join(OUT, name), pts=pts, occupied_bits=np.packbits(img == 0),
                         shape=np.array(img.shape), min_and_count=np.array([mx, my, no]))
     print(name, pts.shape, img.shape, no)

@@ -85,3 +85,24 @@ def test_occupied_points_and_projected_grid(oracle):
     assert r.as_tuple() == ro.as_tuple()
     st.close()
     bev.close()
+
+
+def test_against_compiled_reference(oracle):
+    """GPU vs the REFERENCE'S OWN projection (3d/submap_3d.cpp, range_data_inserter_3d.cpp, hybrid_grid.h
+    compiled unmodified into oracle/_ref/libbev_ref.so): image and double-precision origin identical."""
+    if not oracle.have_bev_ref():
+        pytest.skip("oracle/_ref/libbev_ref.so not present")
+    bev = g.BevProjector(0)
+    rng = np.random.default_rng(2)
+    scans = [synth.make_lidar_scan(seed=40 + s, n_walls=20 + 15 * s) for s in range(3)]
+    k = rng.integers(-450, 450, (3000, 3)).astype(np.float32)
+    half = (k + np.float32(0.5)) * np.float32(0.2)          # coordinates on voxel boundaries
+    half[:, 2] = np.clip(half[:, 2], -3, 3)
+    scans.append(np.concatenate([half, np.zeros((3000, 1), np.float32)], 1))
+    for scan in scans:
+        info = bev.project(scan)
+        rimg, (rox, roy, rres) = oracle.ref_bev_project(scan)
+        assert (info.height, info.width) == rimg.shape
+        assert (info.ox, info.oy, info.resolution) == (rox, roy, rres)
+        assert np.array_equal(bev.image(), rimg)
+    bev.close()
