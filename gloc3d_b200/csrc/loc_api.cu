@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <vector>
 
 #include "comm.cuh"
@@ -487,6 +488,8 @@ void gloc_loc_destroy(gloc_localizer* L) {
   if (!L) return;
   DeviceGuard g(L->device);
   for (CsmBuf* b : {&L->d_map, &L->d_q, &L->d_idx, &L->d_d2, &L->d_qs, &L->d_pairs, &L->d_pts, &L->d_keys}) b->release();
+  // (peer mappings of a still shared store belong to the communicator: gloc_loc_unshare_grids or its destruction)
+  for (void* p : L->shared.dummies) cudaFree(p);
   delete L;
 }
 
@@ -613,6 +616,7 @@ namespace {
 struct ShareHeader {
   unsigned long long n_chunks, n_grids, n_rows, row_lo, has_map, n_graded;
   int max_nx, max_ny;
+  int ok, pad;   // 0: this rank cannot take part (every rank then fails together, nobody waits)
 };
 struct ShareGrid {     // a grid record as its owner describes it to its peers
   unsigned long long offset;
@@ -657,11 +661,14 @@ int gloc_loc_share_grids(gloc_localizer* L, gloc_comm* comm) {
   mine.n_graded = st->n_graded;
   mine.max_nx = st->max_nx;
   mine.max_ny = st->max_ny;
-  if (mine.has_map ? L->h_map.size() < mine.n_rows : mine.n_grids < mine.n_rows)
-    return fail(GLOC_ERR_INVALID, "gloc_loc_share_grids: shard rows without a map grid");
+  mine.ok = (mine.has_map ? L->h_map.size() >= mine.n_rows : mine.n_grids >= mine.n_rows) && mine.n_grids > 0;
   std::vector<ShareHeader> hd((size_t)N);
   int rc = comm_host_all_gather(comm, &mine, hd.data(), sizeof(ShareHeader));
   if (rc != GLOC_OK) return rc;
+  for (int r = 0; r < N; ++r)
+    if (!hd[(size_t)r].ok)
+      return fail(GLOC_ERR_INVALID, "gloc_loc_share_grids: rank " + std::to_string(r) +
+                                        " has shard rows without a map grid (or an empty grid store)");
   size_t max_chunks = 0, max_grids = 0, max_rows = 0;
   bool any_map = false;
   for (const ShareHeader& h : hd) {
