@@ -714,20 +714,32 @@ def run_verify(args, rank, world, local_rank):
                 "h2d_bytes_per_step": int(sum(s.nbytes for s in scans)) * world,
                 "d2h_bytes_per_step": len(pairs) * 8},
         "gpu_launches": int(launches) * world, "clocks": clk,
-        "roofline": {"bound": "hbm", "kernel": "csm_coarse_bits_kernel",
-                     "achieved": hbm_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None,
-                     "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": (hbm_bytes / (avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if avg_ms else None,
-                     "traffic": verify_traffic(), "kernel_ms": avg_ms,
-                     "note": "compulsory HBM bytes are tiny; the binding limit is the shared-memory gather "
-                             "rate of the LSU (ncu: l1tex throughput 78 %)",
-                     "gather_lookups_per_s": lookups / (avg_ms * 1e-3) if avg_ms else None,
-                     "lsu_gather": lsu},
+        "roofline": None,
         "stats": {"found": int(found), "pairs": len(mine)},
     }
+    hbm = {"algorithmic_bytes_per_launch": hbm_bytes,
+           "achieved_gbs": hbm_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms else None,
+           "frac_of_peak": (hbm_bytes / (avg_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if avg_ms else None}
     if lsu and "peak_random_lds64_per_s" in lsu and avg_ms:
-        lsu["achieved_lds64_per_s"] = lookups / side / (avg_ms * 1e-3)   # one load serves a row of `side` candidates
-        lsu["frac"] = lsu["achieved_lds64_per_s"] / lsu["peak_random_lds64_per_s"]
+        # as the localize workload: the scorer is bound by shared-memory gathers, one 8-byte load per (rotation,
+        # point, candidate row) -- per PAIR of candidate rows in the paired plane layout 800-cell grids get
+        wc = 1 << (VER["depth"] - 1)
+        c_lo, c_hi = VER["n_lin"] // wc, (VER["nx"] + wc - 2 + VER["n_lin"]) // wc
+        paired = side <= 14 and max(c_lo, c_hi - 31) - c_lo <= 33 - side and not os.environ.get("GLOC_CSM_NO_PAIRED")
+        loads = lookups / side / side * ((side + 2) // 2 if paired else side)
+        ach = loads / (avg_ms * 1e-3)
+        line["roofline"] = {"bound": "lsu", "kernel": "csm_coarse_bits_kernel", "achieved": ach / 1e9,
+                            "peak": lsu["peak_random_lds64_per_s"] / 1e9, "unit": "G LDS.64/s",
+                            "frac": ach / lsu["peak_random_lds64_per_s"], "traffic": None, "kernel_ms": avg_ms,
+                            "peak_source": "measured live: gloc_bench_smem_gather (random 8-byte shared-memory loads, chip-wide)",
+                            "algorithmic_lookups_per_launch": lookups, "algorithmic_lds64_per_launch": loads,
+                            "note": "200 pairs = 400 CTAs do not fill the chip for long: see the localize workload "
+                                    "(3200 pairs per launch) for the scorer's steady state", "hbm": hbm}
+    else:
+        line["roofline"] = {"bound": "hbm", "kernel": "csm_coarse_bits_kernel", "achieved": hbm["achieved_gbs"],
+                            "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm["frac_of_peak"], "traffic": verify_traffic(),
+                            "kernel_ms": avg_ms, "lsu_gather": lsu,
+                            "note": "the LSU ceiling could not be measured; compulsory HBM bytes are tiny"}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_verify(maps, mx, my, scans, pairs, args.cpu_budget)
     st.close()
