@@ -129,6 +129,7 @@ SIGNATURES = {
     "gloc_loc_get_stats": (_i, [_vp, C.POINTER(LocStats)]),
     "gloc_loc_share_grids": (_i, [_vp, _vp]),
     "gloc_loc_unshare_grids": (_i, [_vp, _vp]),
+    "gloc_loc_assign_pairs": (_i, [_vp, _sz, _i, _vp]),
     "gloc_loc_set_profiling": (_i, [_vp, _i]),
     "gloc_loc_get_profile": (_i, [_vp, C.POINTER(LocProfile)]),
     "gloc_csm_get_precomputation_grid": (_i, [_vp, _i, _i, _vp]),

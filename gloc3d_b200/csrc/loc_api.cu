@@ -51,6 +51,42 @@ __global__ void loc_make_pairs_kernel(const uint64_t* __restrict__ idx, int nq, 
   pairs[i] = p;
 }
 
+// Which rank verifies which pair of a wave (the balanced form of "the owner verifies"): pairs in
+// (query, candidate) order, owner[i] = the rank that holds pair i's row (or -1: no such row).  A rank
+// keeps the first quota = ceil(pairs / n_ranks) of the pairs it owns; the rest go, in order, to the
+// ranks with room, lowest rank first.  Pure function of its arguments: every rank derives the same
+// assignment from the same retrieval results without communication.
+void loc_assign_pairs(const int32_t* owner, size_t n, int n_ranks, int32_t* verifier) {
+  std::vector<size_t> owned((size_t)n_ranks, 0), kept((size_t)n_ranks, 0), room((size_t)n_ranks, 0);
+  size_t total = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (owner[i] >= 0 && owner[i] < n_ranks) {
+      owned[(size_t)owner[i]]++;
+      total++;
+    }
+  const size_t quota = (total + (size_t)n_ranks - 1) / (size_t)n_ranks;
+  for (int t = 0; t < n_ranks; ++t) room[(size_t)t] = owned[(size_t)t] < quota ? quota - owned[(size_t)t] : 0;
+  int next = 0;                                 // next rank with room
+  for (size_t i = 0; i < n; ++i) {
+    const int r = owner[i];
+    if (r < 0 || r >= n_ranks) {
+      verifier[i] = -1;
+      continue;
+    }
+    int by = r;
+    if (kept[(size_t)r] < quota) {
+      kept[(size_t)r]++;
+    } else {
+      while (next < n_ranks && room[(size_t)next] == 0) ++next;
+      if (next < n_ranks) {
+        by = next;
+        room[(size_t)next]--;
+      }
+    }
+    verifier[i] = by;
+  }
+}
+
 }  // namespace
 
 struct gloc_localizer {
@@ -323,7 +359,7 @@ int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, 
   std::vector<char> done(nq, 0);
   std::vector<CsmPairDev> hp;
   std::vector<size_t> where, wave;
-  std::vector<int> owner_of;
+  std::vector<int32_t> owner_of, verifier;
   std::vector<unsigned long long> wb;
   unsigned long long* d_send = (unsigned long long*)L->d_keys.p;
   unsigned long long* d_recv = d_send + n_pairs;
@@ -359,7 +395,6 @@ int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, 
       const auto& SH = L->shared;
       const int N = SH.size;
       owner_of.clear();
-      std::vector<size_t> owned((size_t)N, 0);
       wave.clear();
       for (size_t q = 0; q < nq; ++q) {
         if (done[q]) continue;
@@ -373,26 +408,13 @@ int loc_run_sharded(gloc_localizer* L, gloc_comm* comm, const float* d_queries, 
           if (r < 0) continue;                      // an empty slot (fewer than k rows in the job)
           wave.push_back(i);
           owner_of.push_back(r);
-          owned[(size_t)r]++;
         }
       }
-      const size_t quota = (wave.size() + (size_t)N - 1) / (size_t)N;
-      std::vector<size_t> kept((size_t)N, 0), room((size_t)N, 0);
-      for (int t = 0; t < N; ++t) room[(size_t)t] = owned[(size_t)t] < quota ? quota - owned[(size_t)t] : 0;
-      int next = 0;                                 // next rank with room
+      verifier.resize(wave.size());
+      loc_assign_pairs(owner_of.data(), wave.size(), N, verifier.data());
       for (size_t w = 0; w < wave.size(); ++w) {
         const int r = owner_of[w];
-        int by = r;
-        if (kept[(size_t)r] < quota) {
-          kept[(size_t)r]++;
-        } else {
-          while (next < N && room[(size_t)next] == 0) ++next;
-          if (next < N) {
-            by = next;
-            room[(size_t)next]--;
-          }
-        }
-        if (by != SH.rank) continue;
+        if (verifier[w] != SH.rank) continue;
         const size_t i = wave[w], q = i / (size_t)k;
         const uint64_t row = out_idx[i] - SH.row_lo[(size_t)r];
         const int g_local = SH.maps[(size_t)r].empty() ? (int)row : SH.maps[(size_t)r][row];
@@ -624,6 +646,13 @@ struct ShareGrid {     // a grid record as its owner describes it to its peers
   double resolution, max_x, max_y;
 };
 }  // namespace
+
+int gloc_loc_assign_pairs(const int32_t* owner, size_t n_pairs, int n_ranks, int32_t* verifier) {
+  if (n_pairs && (!owner || !verifier)) return fail(GLOC_ERR_INVALID, "gloc_loc_assign_pairs: null argument");
+  if (n_ranks < 1) return fail(GLOC_ERR_INVALID, "gloc_loc_assign_pairs: n_ranks must be positive");
+  loc_assign_pairs(owner, n_pairs, n_ranks, verifier);
+  return GLOC_OK;
+}
 
 int gloc_loc_unshare_grids(gloc_localizer* L, gloc_comm* comm) {
   if (!L || !comm) return fail(GLOC_ERR_INVALID, "gloc_loc_unshare_grids: null argument");

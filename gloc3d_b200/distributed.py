@@ -177,6 +177,20 @@ def partition_pairs(idx: np.ndarray, lo: int, hi: int):
     return np.nonzero((flat >= lo) & (flat < hi))[0]
 
 
+def assign_pairs(idx: np.ndarray, bounds) -> np.ndarray:
+    """Which rank verifies which (query, candidate) pair once the ranks share their grid stores
+    (gloc_loc_share_grids): `bounds` = the row ranges [bounds[r], bounds[r + 1]) of the ranks.  Calls the
+    library's own rule (gloc_loc_assign_pairs, host only -- no GPU needed); -1 = a slot without a row."""
+    from . import _lib
+    flat = np.ascontiguousarray(np.asarray(idx).reshape(-1).astype(np.int64))
+    b = np.asarray(bounds, np.int64)
+    owner = (np.searchsorted(b, flat, side="right") - 1).astype(np.int32)
+    owner[(flat < b[0]) | (flat >= b[-1])] = -1
+    out = np.empty(flat.size, np.int32)
+    _lib.check(_lib.lib().gloc_loc_assign_pairs(owner.ctypes.data, flat.size, len(b) - 1, out.ctypes.data))
+    return out
+
+
 def combine_pair_keys(keys_per_rank: list[np.ndarray]) -> np.ndarray:
     """The all-reduce(max) of the sharded localizer: every pair has one owner, the others hold 0."""
     return np.maximum.reduce([np.asarray(k, np.uint64) for k in keys_per_rank])

@@ -348,6 +348,11 @@ int gloc_loc_localize_sharded(gloc_localizer* loc, gloc_comm* comm, const float*
  * GLOC_ERR_CUDA (and leaves owner-only verification in place) where peers cannot address each other.
  * gloc_loc_unshare_grids (collective, same communicator) unmaps the peers' stores. */
 int gloc_loc_share_grids(gloc_localizer* loc, gloc_comm* comm);
+/* The assignment rule itself (host only, no device needed; what gloc_loc_localize_sharded applies per
+ * wave once grids are shared): owner[i] = the rank holding pair i's row (or -1), pairs in (query,
+ * candidate) order; verifier[i] = the rank that verifies it.  A rank keeps the first
+ * ceil(pairs / n_ranks) of its own pairs, the surplus goes in order to the ranks with room. */
+int gloc_loc_assign_pairs(const int32_t* owner, size_t n_pairs, int n_ranks, int32_t* verifier);
 int gloc_loc_unshare_grids(gloc_localizer* loc, gloc_comm* comm);
 int gloc_loc_get_stats(const gloc_localizer* loc, gloc_loc_stats* out);
 /* Live device-side timing (CUDA events on the stream the work is launched on) of whole calls and

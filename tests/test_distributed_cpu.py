@@ -137,3 +137,44 @@ def test_sharded_localizer_host_logic():
         per_rank.append(kr)
     assert (seen == 1).all()
     assert np.array_equal(combine_pair_keys(per_rank), keys)
+
+
+def test_balanced_pair_assignment_rule():
+    """gloc_loc_assign_pairs -- the library's own rule (host only) for which rank verifies which pair once the
+    ranks share their grid stores: every pair exactly once, nobody above the quota, an owner keeps its first
+    quota pairs, surplus goes in order to the ranks with room; owner-only when nothing is skewed."""
+    from gloc3d_b200.distributed import assign_pairs, partition_pairs, shard_bounds
+
+    rng = np.random.default_rng(1)
+    for world in (1, 2, 3, 8):
+        rows, nq, k = 4000, 37, 25
+        b = np.asarray(shard_bounds(rows, world))
+        # skewed: most candidates of a query come from one shard (the place it revisits)
+        home = rng.integers(0, world, nq)
+        idx = np.where(rng.random((nq, k)) < 0.8,
+                       b[home][:, None] + rng.integers(0, rows // world, (nq, k)),
+                       rng.integers(0, rows, (nq, k))).astype(np.uint64)
+        idx[3, 7] = rows + 5                        # a slot without a row (fewer than k rows in the job)
+        ver = assign_pairs(idx, b)
+        flat = idx.reshape(-1)
+        n = int((flat < rows).sum())
+        quota = -(-n // world)
+        assert ver[3 * k + 7] == -1 and (ver >= 0).sum() == n
+        counts = np.bincount(ver[ver >= 0], minlength=world)
+        assert counts.sum() == n and counts.max() <= quota
+        for r in range(world):
+            own = partition_pairs(idx, b[r], b[r + 1])
+            kept = own[ver[own] == r]
+            # a rank keeps a PREFIX of its own pairs, and takes foreign pairs only if it owns less than the quota
+            assert np.array_equal(kept, own[:len(kept)]) and len(kept) == min(len(own), quota)
+            foreign = np.nonzero(ver == r)[0]
+            foreign = foreign[~np.isin(foreign, own)]
+            assert len(foreign) == 0 or len(own) < quota
+        if world == 1:
+            assert (ver[ver >= 0] == 0).all()
+    # nothing to balance: exactly quota pairs per owner -> everybody verifies its own
+    b = np.asarray(shard_bounds(800, 4))
+    idx = np.concatenate([np.full(10, b[r] + 1) for r in range(4)]).astype(np.uint64)
+    assert np.array_equal(assign_pairs(idx, b), np.repeat(np.arange(4), 10))
+    # deterministic
+    assert np.array_equal(assign_pairs(idx[::-1].copy(), b), np.repeat(np.arange(4)[::-1], 10))
