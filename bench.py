@@ -917,7 +917,12 @@ def run_localize(args, rank, world, local_rank):
     # N > 1: the ranks can read each other's grid stores over NVLink, surplus pairs move to ranks with room
     shared = world > 1 and not os.environ.get("GLOC_BENCH_NO_SHARE")
     if shared:
-        loc.share_grids(comm)
+        try:
+            loc.share_grids(comm)
+        except g.GlocError as e:     # peers cannot address each other (the failure is collective): owner-only
+            shared = False
+            if rank == 0:
+                print(f"[bench] gloc_loc_share_grids unavailable, owner-only verification: {e}", file=sys.stderr, flush=True)
     prm = loc.params(LOC["k"], LOC["n_lin"], LOC["n_ang"], LOC["step"], args.verify_depth or LOC["depth"],
                      LOC["min_score"], g.LOC_FIRST_MATCH if args.loc_policy == "first" else g.LOC_VERIFY_ALL)
     n_batches = min(LOC["batches"] if world == 1 else 6, args.steps + args.warmup)
