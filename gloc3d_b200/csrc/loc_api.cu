@@ -744,15 +744,21 @@ int gloc_loc_share_grids(gloc_localizer* L, gloc_comm* comm) {
     gs[j].chunk = chunk; gs[j].nx = r.nx; gs[j].ny = r.ny; gs[j].enc = r.enc;
     gs[j].resolution = r.resolution; gs[j].max_x = r.max_x; gs[j].max_y = r.max_y;
   }
+  auto undo = [&](int code) {   // a failed exchange leaves nothing mapped behind
+    for (void* p : SH.chunks) comm_unmap_peers(comm, p);
+    for (void* p : SH.dummies) cudaFree(p);
+    SH = gloc_localizer::Shared();
+    return code;
+  };
   rc = comm_host_all_gather(comm, gs.data(), all_g.data(), max_grids * sizeof(ShareGrid));
-  if (rc != GLOC_OK) return rc;
+  if (rc != GLOC_OK) return undo(rc);
   // 3. the row -> grid tables (only where some rank has one)
   SH.maps.assign((size_t)N, std::vector<int32_t>());
   if (any_map) {
     std::vector<int32_t> mm(max_rows, 0), all_m((size_t)N * max_rows);
     for (size_t i = 0; i < mine.n_rows; ++i) mm[i] = L->h_map.empty() ? (int32_t)i : L->h_map[i];
     rc = comm_host_all_gather(comm, mm.data(), all_m.data(), max_rows * sizeof(int32_t));
-    if (rc != GLOC_OK) return rc;
+    if (rc != GLOC_OK) return undo(rc);
     for (int r = 0; r < N; ++r)
       SH.maps[(size_t)r].assign(all_m.begin() + (size_t)r * max_rows, all_m.begin() + (size_t)r * max_rows + hd[(size_t)r].n_rows);
   }
