@@ -93,3 +93,30 @@ def test_lane_row_split_covers_the_lattice():
                 for j in range(NP):
                     lo_row = 2 * first_word + 2 * j + par
                     assert lo_row == ay + row0 + 2 * j
+
+
+def test_row_major_storage_transposes_to_plane_major_staging():
+    """pmb_write_planes stores word (rp, plane, h) at (rp w^2 + plane) 2 + h (64-bit rows: (r, plane) at
+    r w^2 + plane); the scorer stages global word i at (i & (np2 - 1)) * per_plane + (i >> lp2) and addresses
+    ((plane << 1) | h) * rpc + rp (64-bit rows: plane * rows + r)."""
+    for log2w in (1, 2, 4):
+        w2 = 1 << (2 * log2w)
+        for rows in (6, 18, 90):
+            rpc = rows // 2
+            # paired
+            np2, lp2, per_plane = 2 * w2, 2 * log2w + 1, rpc
+            seen = set()
+            for rp in range(rpc):
+                for plane in range(w2):
+                    for h in (0, 1):
+                        i = (rp * w2 + plane) * 2 + h
+                        staged = (i & (np2 - 1)) * per_plane + (i >> lp2)
+                        assert staged == ((plane << 1) | h) * rpc + rp
+                        seen.add(staged)
+            assert seen == set(range(w2 * rows))
+            # 64-bit rows
+            np2, lp2, per_plane = w2, 2 * log2w, rows
+            for r in range(rows):
+                for plane in range(w2):
+                    i = r * w2 + plane
+                    assert (i & (np2 - 1)) * per_plane + (i >> lp2) == plane * rows + r
